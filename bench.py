@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the block-diagonal QR hot path (BASELINE.json configs[1]).
+
+Workload (N = 1): 1,000,000 diagonal blocks of 8x4 FP64 (matrix 8M x 4M), one step = ONE fused pass
+"factorize every block + Q^T b + back substitution + column permutation" (compute() + solve(b) of the
+reference's BlockDiagonalSparseQR) through the C ABI.  N > 1: every rank owns its own contiguous range of
+1M blocks of an N-times larger matrix (weak scaling, no data-path collective: the blocks are independent).
+
+One JSON line on stdout (rank 0):
+  value      rows/s with A and b resident in HBM (device pointers through qrk_compute_solve)
+  e2e        rows/s through the same C-ABI call with HOST (pinned) buffers: H2D of A and b and D2H of x inside
+             the timed region
+  roofline   algorithmic bytes (16rc+8r+16c = 640 B/block, +4c with pivoting) / measured kernel time vs the
+             measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restatement of the reference's algorithm; Eigen is absent, the reference itself
+             cannot be built) timed on this box's host cores on a bounded sample
+
+`--impl reference` times the CPU restatement alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED_A = 0x51524B49
+NB, R, CC = 1_000_000, 8, 4
+METRIC = "rows/sec, FP64 block-diagonal QR+solve (1M blocks 8x4 per GPU)"
+UNIT = "rows/s"
+WORKLOAD = "block-diagonal FP64, 1M blocks of 8x4 per GPU: fused batched Householder QR + Q^T b + back substitution"
+
+
+def algorithmic_bytes_per_block(r, c, piv):
+    return 16 * r * c + 8 * r + 16 * c + (4 * c if piv else 0)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/), else None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(name)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(nb_sample, steps, warmup, piv):
+    """The reference's own algorithm (explicit Q_i, sparse Q/R assembly, sparse Q^T b, sparse triangular solve —
+    BlockDiagonalSparseQR.h:415-547, 258-280) restated in oracle/, single thread like the reference's serial loop."""
+    from helpers import uniform_blocks, vector
+    from oracle import oracle as orc
+    orc.build()
+    vals = uniform_blocks(nb_sample, R, CC)
+    b = vector(nb_sample * R, seed=SEED_A + 5)
+    times = []
+    for i in range(warmup + steps):
+        res = orc.bd_reference_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv))
+        if i >= warmup:
+            times.append(res["seconds"])
+    # the compact variant on all host cores, for context (what a tuned CPU port of OUR algorithm would do)
+    threads = os.cpu_count() or 1
+    orc.bd_compact_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv), threads=threads)
+    tc = min(orc.bd_compact_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv), threads=threads)["seconds"] for _ in range(3))
+    return sum(times) / len(times), tc, threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb_sample = 250_000
+    t, tc, threads = cpu_reference_run(nb_sample, args.steps, args.warmup, args.pivoting)
+    value = nb_sample * R / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (counter-based U[0.5,5), shared with the GPU arm)",
+        "config": {"workload": WORKLOAD, "pivoting": "colpiv" if args.pivoting else "none",
+                   "note": "Eigen is not in this image: the reference cannot be compiled; this is the CPU restatement of its "
+                           "algorithm (oracle/), serial like the reference's block loop"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{nb_sample} of {NB} blocks per step (reference-faithful explicit-Q variant)",
+                         "compact_all_cores": {"value": nb_sample * R / tc, "cores": threads}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pivoting", type=int, default=0, help="0 = HouseholderQR per block (headline), 1 = ColPivHouseholderQR")
+    ap.add_argument("--blocks", type=int, default=NB)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QRK_HOST, QrkDesc, check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: qrkit_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = capi.lib()
+    nb = args.blocks
+    piv = args.pivoting
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_handle(pivoting):
+        d = QrkDesc()
+        d.kind, d.device, d.num_blocks, d.block_rows, d.block_cols, d.pivoting = 0, local_rank, nb, R, CC, pivoting
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream)), h)
+        return h
+
+    # ---- synthetic inputs, generated on the device by the shared counter-based generator (rank r owns blocks
+    #      [r*nb, (r+1)*nb) of the N-times larger matrix)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dA = torch.empty(nb * R * CC, dtype=torch.float64, device="cuda")
+    db = torch.empty(nb * R, dtype=torch.float64, device="cuda")
+    dx = torch.empty(nb * CC, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(C.c_void_p(dA.data_ptr()), SEED_A, rank * nb, nb, R, CC, 0.5, 5.0, stream))
+    check(L.qrk_synth_fill(C.c_void_p(db.data_ptr()), SEED_A + 5, rank * nb, nb, R, 0, -1.0, 1.0, stream))
+    torch.cuda.synchronize()
+
+    def launches(h):
+        v = C.c_int64()
+        L.qrk_launch_count(h, C.byref(v))
+        return v.value
+
+    def timed_device(pivoting, steps, warmup, sample_clocks=False):
+        h = make_handle(pivoting)
+
+        def step():
+            check(L.qrk_compute_solve(h, C.c_void_p(dA.data_ptr()), C.c_void_p(db.data_ptr()), C.c_void_p(dx.data_ptr()), QRK_DEVICE), h)
+        for _ in range(warmup):
+            step()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            t_wait = time.time()
+            while not sampler.rows and time.time() - t_wait < 5.0:    # nvidia-smi is up and sampling
+                time.sleep(0.05)
+            sampler.rows.clear()
+        barrier()
+        l0 = launches(h)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        nl = launches(h) - l0
+        clocks = None
+        if sampler:
+            # the K-step region lasts a few ms, shorter than one nvidia-smi period: keep the same kernel running
+            # back to back for ~1.5 s right behind it so that the sampler sees the clocks under this load
+            burst = int(min(50000, max(steps, 1500.0 / max(ms / steps, 1e-3))))
+            for _ in range(burst):
+                step()
+            torch.cuda.synchronize()
+            clocks = sampler.stop()
+            clocks["note"] = f"sampled every 100 ms over the timed region plus a {burst}-step burst of the same kernel behind it"
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        L.qrk_destroy(h)
+        return ms / steps, nl, clocks
+
+    ms_step, n_launch, clocks = timed_device(piv, args.steps, args.warmup, sample_clocks=True)
+    ms_other, _, _ = timed_device(1 - piv, args.steps, args.warmup)
+
+    # ---- sanity: the timed step really solved the systems (cheap residual check on a window, on the device)
+    h = make_handle(piv)
+    check(L.qrk_compute_solve(h, C.c_void_p(dA.data_ptr()), C.c_void_p(db.data_ptr()), C.c_void_p(dx.data_ptr()), QRK_DEVICE), h)
+    torch.cuda.synchronize()
+    w = 4096
+    Aw = dA[: w * R * CC].view(w, CC, R).transpose(1, 2)
+    resid = torch.einsum("bij,bj->bi", Aw, dx[: w * CC].view(w, CC)) - db[: w * R].view(w, R)
+    normal = torch.einsum("bij,bi->bj", Aw, resid)          # A^T (A x - b) = 0 at the least-squares solution
+    ls_check = float(normal.abs().max() / (Aw.abs().max() * db[: w * R].abs().max()))
+    L.qrk_destroy(h)
+    if not ls_check < 1e-10:
+        raise SystemExit(f"bench sanity check failed: normal-equation residual {ls_check}")
+
+    # ---- e2e: the same call with HOST buffers (pinned), H2D of A and b and D2H of x inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hA = torch.empty(nb * R * CC, dtype=torch.float64).pin_memory()
+        hb = torch.empty(nb * R, dtype=torch.float64).pin_memory()
+        hx = torch.empty(nb * CC, dtype=torch.float64).pin_memory()
+        hA.copy_(dA); hb.copy_(db)
+        h = make_handle(piv)
+
+        def step_host():
+            check(L.qrk_compute_solve(h, C.c_void_p(hA.data_ptr()), C.c_void_p(hb.data_ptr()), C.c_void_p(hx.data_ptr()), QRK_HOST), h)
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e_steps):
+            step_host()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(e0.elapsed_time(e1), wall) / e_steps   # the call is synchronous: wall time bounds it from above
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        assert torch.allclose(hx[: w * CC].cuda(), dx[: w * CC], rtol=0, atol=0), "host and device paths disagree"
+        L.qrk_destroy(h)
+        e2e = {"value": world * nb * R / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hA.numel() * 8 + hb.numel() * 8),
+               "d2h_bytes_per_step": int(hx.numel() * 8), "ms_per_step": ms_e2e, "steps": e_steps,
+               "note": "qrk_compute_solve(QRK_HOST): pinned host A, b -> device, fused kernel, x -> host, per step"}
+        del hA, hb, hx
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = algorithmic_bytes_per_block(R, CC, piv) * nb
+    achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9
+    kname = f"bd_small_factor_kernel<8,4,{'true' if piv else 'false'},true>"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(kname), "kernel": kname, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "note": "one kernel launch per step; duration = CUDA events over the timed region / steps"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        nb_sample = 250_000
+        t, tc, threads = cpu_reference_run(nb_sample, 3, 1, piv)
+        cpu = {"value": nb_sample * R / t, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{nb_sample} of {nb} blocks, 3 repetitions; reference-faithful variant (explicit Q_i, sparse Q/R assembly, "
+                         "sparse Q^T b + triangular solve), serial like the reference's block loop",
+               "compact_all_cores": {"value": nb_sample * R / tc, "cores": threads,
+                                     "note": "packed reflectors + fused solve with OpenMP over blocks (not what the reference does)"}}
+
+    line = {
+        "metric": METRIC, "value": world * nb * R / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (counter-based U[0.5,5) blocks, U[-1,1) rhs, generated on device)",
+        "config": {"workload": WORKLOAD, "blocks_per_gpu": nb, "block": [R, CC], "pivoting": "colpiv" if piv else "none",
+                   "l2": "per-step footprint 640 MB (A 256 + b 64 in, packed 256 + tau 32 + x 32 out) exceeds the 126 MB L2; no flush needed",
+                   "parallelism": f"{world} x contiguous block ranges, no collective"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks,
+        "other_pivoting": {"pivoting": "none" if piv else "colpiv", "ms_per_step": ms_other,
+                           "value": world * nb * R / (ms_other * 1e-3),
+                           "roofline_frac": algorithmic_bytes_per_block(R, CC, 1 - piv) * nb / (ms_other * 1e-3) / 1e9 / peak},
+        "ls_normal_residual": ls_check,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

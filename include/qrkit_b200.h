@@ -1,0 +1,170 @@
+/* qrkit_b200.h — C ABI of the B200-native structured-sparse QR hot path (drop-in boundary).
+ *
+ * This is the only surface the host side binds: plain pointers and sizes, no C++/torch types.
+ * A C++ façade with the reference's Eigen-style method names (include/qrkit_b200/QRKit.hpp) forwards
+ * to it; INTEGRATION.md shows the stub a QRKit maintainer would add on the reference side.
+ *
+ * Each entry point names the reference interface it replaces (file:line relative to the
+ * jasvob/QRKit tree).  All functions
+ *   - return a qrk_status (0 = OK) and never throw,
+ *   - are ordered on the handle's CUDA stream (qrk_set_stream); host-pointer variants return after
+ *     the result is in the caller's buffer, device-pointer variants return after enqueueing,
+ *   - use one handle from one host thread at a time (as the reference's solver objects,
+ *     BlockDiagonalSparseQR.h:316 `mutable m_info`).
+ * There is no CPU fallback: without a CUDA device every compute entry point returns
+ * QRK_STATUS_NO_DEVICE.
+ *
+ * Data layout ("block-COO", the device form of SparseBlockCOO.h:37-50 / SparseBlockDiagonal.h:44-163):
+ *   values[]  one flat FP64 array, block i at values + val_off(i), column-major r_i x c_i inside
+ *             the block (Eigen's Matrix<double,r,c> layout, so a std::vector of fixed-size
+ *             blocks IS this array);
+ *   block i sits at matrix position (base_row(i), base_col(i)) = prefix sums of the block sizes
+ *             (BlockDiagonalSparseQR.h:524-525; SparseQRUtils.h:255-272 for the uniform case).
+ * All indices are int32 (StorageIndex = int, test/test-qrkit.cpp:40), all values FP64.
+ */
+#ifndef QRKIT_B200_H_
+#define QRKIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define QRK_API
+#else
+#define QRK_API __attribute__((visibility("default")))
+#endif
+
+typedef struct qrk_solver* qrk_handle_t;
+
+typedef enum {
+  QRK_STATUS_OK = 0,
+  QRK_STATUS_INVALID_ARGUMENT = 1,
+  QRK_STATUS_NOT_FACTORIZED = 2,   /* eigen_assert "The factorization should be called first" (BlockDiagonalSparseQR.h:260) */
+  QRK_STATUS_CUDA_ERROR = 3,
+  QRK_STATUS_NO_DEVICE = 4,
+  QRK_STATUS_ALLOC_FAILED = 5,
+  QRK_STATUS_UNSUPPORTED = 6
+} qrk_status;
+
+/* Eigen::ComputationInfo values, as returned by info() (BlockDiagonalSparseQR.h:309-313). */
+typedef enum { QRK_INFO_SUCCESS = 0, QRK_INFO_NUMERICAL_ISSUE = 1, QRK_INFO_NO_CONVERGENCE = 2, QRK_INFO_INVALID_INPUT = 3 } qrk_computation_info;
+
+/* Which reference solver the handle stands for. */
+typedef enum {
+  QRK_BLOCK_DIAGONAL = 0,  /* BlockDiagonalSparseQR  (BlockDiagonalSparseQR.h:37-335)  */
+  QRK_BLOCK_ANGULAR = 1,   /* BlockAngularSparseQR   (BlockAngularSparseQR.h:79-281), left = block diagonal */
+  QRK_BANDED_BLOCKED = 2   /* BandedBlockedSparseQR  (BandedBlockedSparseQR.h:122-344) */
+} qrk_kind;
+
+/* The per-block dense solver (template parameter _BlockQRSolver, BlockDiagonalSparseQR.h:37). */
+typedef enum {
+  QRK_PIVOT_NONE = 0,   /* Eigen::HouseholderQR        */
+  QRK_PIVOT_COLPIV = 1  /* Eigen::ColPivHouseholderQR (test/test-qrkit.cpp:49-51) */
+} qrk_pivoting;
+
+/* MatrixQFormat (BlockDiagonalSparseQR.h:59-62). */
+typedef enum { QRK_FULL_Q = 0, QRK_BLOCK_DIAGONAL_Q = 1 } qrk_qformat;
+
+/* Where a caller's buffer lives. */
+typedef enum { QRK_HOST = 0, QRK_DEVICE = 1 } qrk_memspace;
+
+typedef struct {
+  int32_t kind;            /* qrk_kind */
+  int32_t device;          /* CUDA device ordinal */
+  int64_t num_blocks;      /* nb */
+  int32_t block_rows;      /* uniform block size (fromBlockDiagonalPattern, SparseBlockDiagonal.h:72-89); */
+  int32_t block_cols;      /*   both 0 => per-block sizes come from rows[] / cols[] */
+  const int32_t* rows;     /* host arrays of length nb (copied), or NULL when uniform */
+  const int32_t* cols;
+  int64_t n_rows;          /* matrix rows; 0 => sum of block rows.  Rows beyond the blocks get Q(i,i)=1 (BlockDiagonalSparseQR.h:530-533) */
+  int64_t n_cols;          /* matrix cols; 0 => sum of block cols */
+  int32_t pivoting;        /* qrk_pivoting */
+  int32_t q_format;        /* qrk_qformat */
+  int32_t border_cols;     /* block angular: m2 = columns of the dense right block (BlockAngularSparseQR.h:464); else 0 */
+  int32_t block_overlap;   /* banded: column overlap of consecutive blocks (_BlockOverlap, BandedBlockedSparseQR.h:122); else 0 */
+  int32_t reserved[4];
+} qrk_desc_t;
+
+/* ---- library ------------------------------------------------------------------------------- */
+QRK_API int qrk_version(void);
+QRK_API const char* qrk_status_string(int status);
+QRK_API const char* qrk_last_error(qrk_handle_t h);          /* lastErrorMessage() (BlockAngularSparseQR.h:199) but actually filled */
+QRK_API int qrk_device_count(int* count);
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+/* Solver construction (default ctor BlockDiagonalSparseQR.h:74) + the structure half of
+ * analyzePattern (:392-405): sizes R, builds the prefix-sum block index on the device. */
+QRK_API int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out);
+QRK_API int qrk_destroy(qrk_handle_t h);
+QRK_API int qrk_set_stream(qrk_handle_t h, void* cuda_stream);   /* NULL => the handle's own stream */
+QRK_API int qrk_synchronize(qrk_handle_t h);
+
+/* ---- SparseBlockCOO assembly / upload (SparseBlockDiagonal.h:44-163) --------------------------- */
+/* Copy the blocks into the handle's device storage (host: H2D on the handle's stream;
+ * device: D2D).  `values` holds total_values doubles in the block-COO layout above. */
+QRK_API int qrk_set_blocks(qrk_handle_t h, const double* values, int memspace);
+/* Zero-copy: adopt a caller-owned device buffer; factorize() then overwrites it in place with the
+ * packed factors (R in the upper triangle, essential Householder parts below). */
+QRK_API int qrk_adopt_blocks(qrk_handle_t h, double* device_values);
+QRK_API int qrk_total_values(qrk_handle_t h, int64_t* n);
+
+/* ---- compute / factorize (BlockDiagonalSparseQR.h:94-104, 415-547) ----------------------------- */
+/* row_perm: optional int32[n_rows] host array, the rowPerm argument of compute()/analyzePattern()
+ * (:94,:392-400); NULL => identity.  It is stored and returned by rowsPermutation() only — as in
+ * the reference, _solve_impl does not apply it (:266; callers do, test-qrkit.cpp:235,274). */
+QRK_API int qrk_analyze_pattern(qrk_handle_t h, const int32_t* row_perm);
+QRK_API int qrk_factorize(qrk_handle_t h);                                   /* on the blocks set above */
+QRK_API int qrk_compute(qrk_handle_t h, const double* values, int memspace); /* set_blocks + analyze + factorize */
+/* Fused factorize + Q^T b + back substitution + column permutation in ONE pass over the blocks
+ * (what compute() followed by solve(b) returns; 16rc+8r+16c bytes per block instead of two passes). */
+QRK_API int qrk_compute_solve(qrk_handle_t h, const double* values, const double* b, double* x, int memspace);
+/* Same on blocks already resident (qrk_set_blocks / qrk_adopt_blocks); b, x in `memspace`. */
+QRK_API int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace);
+
+/* ---- accessors (BlockDiagonalSparseQR.h:108-112, 156-165, 242-254, 309-313) --------------------- */
+QRK_API int qrk_rows(qrk_handle_t h, int64_t* rows);
+QRK_API int qrk_cols(qrk_handle_t h, int64_t* cols);
+QRK_API int qrk_rank(qrk_handle_t h, int64_t* rank);   /* = sum of block cols, as the reference (:439-444,:543) */
+QRK_API int qrk_info(qrk_handle_t h, int32_t* info);   /* qrk_computation_info */
+QRK_API int qrk_cols_permutation(qrk_handle_t h, int32_t* indices, int memspace);  /* int32[n_cols], P.indices() with A*P = Q*R (:519-521) */
+QRK_API int qrk_rows_permutation(qrk_handle_t h, int32_t* indices, int memspace);  /* int32[n_rows] */
+
+/* matrixR() (:156): column-major compressed sparse, n_rows x n_cols, int32 indices, exactly the
+ * entries the reference emits (:475-479 FullQ, :496-500 BlockDiagonalQ) after setFromTriplets. */
+QRK_API int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz);
+QRK_API int qrk_matrix_r(qrk_handle_t h, int32_t* outer /* n_cols+1 */, int32_t* inner, double* values, int memspace);
+/* matrixQ() (:235-237): the explicit row-major sparse Q, n_rows x n_rows, index rule :455-470
+ * (FullQ) / :483-491 (BlockDiagonalQ) plus the identity tail (:530-533).  Built on demand from the
+ * compact reflectors; the solve / apply paths never materialise it. */
+QRK_API int qrk_matrix_q_nnz(qrk_handle_t h, int64_t* nnz);
+QRK_API int qrk_matrix_q(qrk_handle_t h, int32_t* outer /* n_rows+1 */, int32_t* inner, double* values, int memspace);
+
+/* Compact factors (the device-native form): packed V\R in the block-COO layout, tau[n_cols]. */
+QRK_API int qrk_packed_factors(qrk_handle_t h, double* packed, double* tau, int memspace);
+
+/* ---- matrixQ().transpose() * B and matrixQ() * B (:235-237 used at :266; BlockAngularSparseQR.h:365) */
+/* B, Y: n_rows x nrhs column-major with leading dimensions ldb, ldy.  The result uses the index
+ * layout of the reference's Q format (FullQ: thin part first, complement after n_cols, :455-470). */
+QRK_API int qrk_apply_qt(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace);
+QRK_API int qrk_apply_q(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace);
+
+/* ---- solve (_solve_impl :258-280, solve :287-299) ------------------------------------------------ */
+/* X = P * R^-1 * (Q^T B)[0:rank]; B: n_rows x nrhs (ldb), X: n_cols x nrhs (ldx). */
+QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace);
+
+/* ---- measurement hooks ---------------------------------------------------------------------------- */
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+QRK_API int qrk_launch_count(qrk_handle_t h, int64_t* launches);
+/* Fill nb uniform r x c blocks (or a vector when c == 0) on the device with the shared counter-based
+ * generator of the test-suite (splitmix64, U[lo,hi)); lets the bench create HBM-resident inputs
+ * without a host copy. */
+QRK_API int qrk_synth_fill(double* device_out, uint64_t seed, int64_t block0, int64_t nb, int32_t r, int32_t c,
+                           double lo, double hi, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRKIT_B200_H_ */

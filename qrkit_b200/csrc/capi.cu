@@ -1,0 +1,756 @@
+// capi.cu — the C ABI of qrkit_b200 (include/qrkit_b200.h): handle management, block-COO upload,
+// kernel dispatch.  Host logic only; every floating-point operation of the hot path runs in the
+// CUDA kernels of bd_small.cuh / bd_generic.cuh.  There is deliberately no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <numeric>
+
+#include "bd_generic.cuh"
+#include "bd_small.cuh"
+#include "export.cuh"
+#include "solver.hpp"
+
+using namespace qrk;
+
+namespace {
+
+#define QRK_TRY_CUDA(h, expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      if (h) (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                    \
+      return e__ == cudaErrorMemoryAllocation ? QRK_STATUS_ALLOC_FAILED : QRK_STATUS_CUDA_ERROR; \
+    }                                                                                           \
+  } while (0)
+
+#define QRK_REQUIRE(h, cond, msg)                 \
+  do {                                            \
+    if (!(cond)) {                                \
+      if (h) (h)->err = (msg);                    \
+      return QRK_STATUS_INVALID_ARGUMENT;         \
+    }                                             \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- thread-per-block kernels: the (r, c) shapes instantiated at compile time -------------------
+#define QRK_SMALL_SHAPES(X) X(2, 1) X(3, 1) X(4, 2) X(6, 3) X(7, 2) X(8, 2) X(8, 4) X(9, 2)
+constexpr int kSmallTPB = 128;
+constexpr int kSmallMinBlocks = 4;
+
+// opt in to > 48 KB dynamic shared memory, once per (kernel instantiation, device)
+template <typename K>
+cudaError_t ensure_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
+template <int R, int C, bool PIV, bool SOLVE>
+cudaError_t launch_small_factor(const double* A, double* packed, double* tau, int* perm, const double* b, double* x,
+                                long long nb, cudaStream_t s) {
+  auto kernel = bd_small_factor_kernel<R, C, PIV, SOLVE, kSmallTPB, kSmallMinBlocks>;
+  constexpr size_t smem = SmallSmem<R, C, kSmallTPB>::bytes;
+  cudaError_t attr = ensure_smem(kernel, smem);
+  if (attr != cudaSuccess) return attr;
+  const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
+  kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(A, packed, tau, perm, b, x, nb);
+  return cudaGetLastError();
+}
+
+template <int R, int C, int OP, bool PERM>
+cudaError_t launch_small_op_t(const double* packed, const double* tau, const int* perm, const double* B, long long ldb,
+                              double* X, long long ldx, int nrhs, long long nb, long long n_cols, int full_q,
+                              cudaStream_t s) {
+  auto kernel = bd_small_op_kernel<R, C, OP, PERM, kSmallTPB, kSmallMinBlocks>;
+  constexpr size_t smem = SmallOpSmem<R, C, kSmallTPB>::bytes;
+  cudaError_t attr = ensure_smem(kernel, smem);
+  if (attr != cudaSuccess) return attr;
+  const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
+  kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q);
+  return cudaGetLastError();
+}
+
+bool small_shape_available(int r, int c) {
+#define X(R_, C_) if (r == R_ && c == C_) return true;
+  QRK_SMALL_SHAPES(X)
+#undef X
+  return false;
+}
+
+cudaError_t launch_small_factor_dyn(int r, int c, bool piv, bool solve, const double* A, double* packed, double* tau,
+                                    int* perm, const double* b, double* x, long long nb, cudaStream_t s) {
+#define X(R_, C_)                                                                                     \
+  if (r == R_ && c == C_) {                                                                           \
+    if (piv) return solve ? launch_small_factor<R_, C_, true, true>(A, packed, tau, perm, b, x, nb, s) \
+                          : launch_small_factor<R_, C_, true, false>(A, packed, tau, perm, b, x, nb, s); \
+    return solve ? launch_small_factor<R_, C_, false, true>(A, packed, tau, perm, b, x, nb, s)        \
+                 : launch_small_factor<R_, C_, false, false>(A, packed, tau, perm, b, x, nb, s);      \
+  }
+  QRK_SMALL_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_small_op_dyn(int r, int c, int op, bool use_perm, const double* packed, const double* tau,
+                                const int* perm, const double* B, long long ldb, double* X, long long ldx, int nrhs,
+                                long long nb, long long n_cols, int full_q, cudaStream_t s) {
+#define X(R_, C_)                                                                                                   \
+  if (r == R_ && c == C_) {                                                                                         \
+    if (op == OP_SOLVE)                                                                                             \
+      return use_perm ? launch_small_op_t<R_, C_, OP_SOLVE, true>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q, s)  \
+                      : launch_small_op_t<R_, C_, OP_SOLVE, false>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q, s); \
+    if (op == OP_APPLY_QT)                                                                                          \
+      return launch_small_op_t<R_, C_, OP_APPLY_QT, false>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q, s);        \
+    return launch_small_op_t<R_, C_, OP_APPLY_Q, false>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q, s);           \
+  }
+  QRK_SMALL_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// ---- generic (team-per-block) kernels ------------------------------------------------------------
+template <int W>
+cudaError_t launch_generic_factor_w(bool piv, bool solve, const BlockIndex& bi, const SizeClass& sc, const double* A,
+                                    double* packed, double* tau, int* perm, const double* b, double* x, cudaStream_t s) {
+#define LAUNCH(PIV, SOLVE)                                                                        \
+  {                                                                                               \
+    auto kernel = bd_generic_factor_kernel<W, PIV, SOLVE>;                                        \
+    if (sc.smem > 48 * 1024) {                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.smem); \
+      if (e != cudaSuccess) return e;                                                             \
+    }                                                                                             \
+    kernel<<<(unsigned)sc.count, 32 * W, sc.smem, s>>>(bi, sc.d_ids, A, packed, tau, perm, b, x);  \
+  }
+  if (piv && solve) LAUNCH(true, true)
+  else if (piv) LAUNCH(true, false)
+  else if (solve) LAUNCH(false, true)
+  else LAUNCH(false, false)
+#undef LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_generic_factor(bool piv, bool solve, const BlockIndex& bi, const SizeClass& sc, const double* A,
+                                  double* packed, double* tau, int* perm, const double* b, double* x, cudaStream_t s) {
+  switch (sc.warps) {
+    case 1: return launch_generic_factor_w<1>(piv, solve, bi, sc, A, packed, tau, perm, b, x, s);
+    case 4: return launch_generic_factor_w<4>(piv, solve, bi, sc, A, packed, tau, perm, b, x, s);
+    default: return launch_generic_factor_w<8>(piv, solve, bi, sc, A, packed, tau, perm, b, x, s);
+  }
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+int team_warps_for(int r, int c) {
+  const long long e = (long long)r * c;
+  if (e <= 1024) return 1;
+  if (e <= 4096) return 4;
+  return 8;
+}
+
+BlockIndex block_index(const qrk_solver* h) {
+  BlockIndex bi;
+  bi.rows = h->uniform ? nullptr : h->d_rows;
+  bi.cols = h->d_cols; bi.voff = h->d_voff; bi.roff = h->d_roff; bi.coff = h->d_coff;
+  bi.ur = h->ur; bi.uc = h->uc;
+  return bi;
+}
+
+void free_dev(qrk_solver* h) {
+  auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+  F(h->d_rows); F(h->d_cols); F(h->d_voff); F(h->d_roff); F(h->d_coff);
+  if (h->own_values) F(h->d_values);
+  h->d_values = nullptr;
+  F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
+  for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
+  h->classes.clear();
+}
+
+int ensure_buffer(qrk_solver* h, double*& p, size_t& cap, size_t n) {
+  if (cap >= n && p) return QRK_STATUS_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  QRK_TRY_CUDA(h, cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)));
+  cap = n;
+  return QRK_STATUS_OK;
+}
+
+int ensure_own_values(qrk_solver* h) {
+  if (h->own_values && h->d_values) return QRK_STATUS_OK;
+  h->d_values = nullptr;
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_values, std::max<long long>(h->total_values, 1) * sizeof(double)));
+  h->own_values = true;
+  return QRK_STATUS_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// One factorisation pass over all blocks (optionally fused with the solve of one right-hand side).
+// A_in: where the blocks are read from (h->d_values itself: in place; a caller's device buffer: out of
+// place, no staging copy); the packed factors always land in h->d_values.
+int run_factor(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
+  const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
+  const bool solve = d_b != nullptr;
+  if (h->nb == 0) return QRK_STATUS_OK;
+  if (h->small_path) {
+    QRK_TRY_CUDA(h, launch_small_factor_dyn(h->ur, h->uc, piv, solve, A_in, h->d_values, h->d_tau, h->d_perm, d_b,
+                                            d_x, h->nb, h->stream));
+    h->launches++;
+  } else {
+    const BlockIndex bi = block_index(h);
+    for (const auto& sc : h->classes) {
+      QRK_TRY_CUDA(h, launch_generic_factor(piv, solve, bi, sc, A_in, h->d_values, h->d_tau, h->d_perm, d_b, d_x,
+                                            h->stream));
+      h->launches++;
+    }
+  }
+  return QRK_STATUS_OK;
+}
+
+int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X, long long ldx, int nrhs) {
+  if (h->nb == 0 || nrhs == 0) return QRK_STATUS_OK;
+  const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
+  const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
+  const bool in_full_layout = (op == OP_APPLY_Q) && full_q;
+  const bool vec_ok = aligned16(d_B) && aligned16(d_X) && (ldb % 2 == 0) && (ldx % 2 == 0) &&
+                      (!(in_full_layout || (op == OP_APPLY_QT && full_q)) || (h->n_cols % 2 == 0));
+  if (h->small_path && vec_ok) {
+    QRK_TRY_CUDA(h, launch_small_op_dyn(h->ur, h->uc, op, piv, h->d_values, h->d_tau, h->d_perm, d_B, ldb, d_X, ldx, nrhs,
+                                        h->nb, h->n_cols, full_q, h->stream));
+  } else {
+    constexpr int WPC = 4;
+    const long long items = h->nb * (long long)nrhs;
+    const long long grid = (items + WPC - 1) / WPC;
+    const size_t smem = (size_t)WPC * h->max_r * sizeof(double);
+    auto kernel = bd_generic_op_kernel<WPC>;
+    if (smem > 48 * 1024) QRK_TRY_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, 32 * WPC, smem, h->stream>>>(block_index(h), h->nb, h->d_values, h->d_tau,
+                                                          piv ? h->d_perm : nullptr, d_B, ldb, d_X, ldx, nrhs, h->n_cols, op,
+                                                          full_q, h->max_r);
+    QRK_TRY_CUDA(h, cudaGetLastError());
+  }
+  h->launches++;
+  return QRK_STATUS_OK;
+}
+
+// rows of Q / R not covered by a block (BlockDiagonalSparseQR.h:530-533): Q(i,i) = 1, so Q^T b and
+// Q b copy b there.  In the FullQ layout these rows sit at the same index i (columns n_cols+m1 .. map
+// to themselves only when the index rule says so; the reference writes Q(i,i)=1 literally).
+__global__ void copy_tail_kernel(const double* B, long long ldb, double* Y, long long ldy, int nrhs, long long from, long long to) {
+  const long long n = to - from;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nrhs; i += (long long)gridDim.x * blockDim.x) {
+    const long long col = i / n, row = from + i % n;
+    Y[col * ldy + row] = B[col * ldb + row];
+  }
+}
+
+__global__ void iota_kernel(int* p, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = (int)i;
+}
+
+__global__ void synth_fill_kernel(double* out, uint64_t seed, long long block0, long long nb, int r, int c, double lo, double hi) {
+  const long long per = (long long)r * (c > 0 ? c : 1);
+  const long long total = nb * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long blk = i / per;
+    const int w = (int)(i - blk * per);
+    if (c > 0) { const int col = w / r, row = w - col * r; out[i] = synth_value(seed, (uint64_t)(block0 + blk), row, col, lo, hi); }
+    else out[i] = synth_value(seed, (uint64_t)(block0 * r + i), 0, 0, lo, hi);
+  }
+}
+
+
+}  // namespace
+
+extern "C" {
+
+int qrk_version(void) { return 100; }
+
+const char* qrk_status_string(int status) {
+  switch (status) {
+    case QRK_STATUS_OK: return "ok";
+    case QRK_STATUS_INVALID_ARGUMENT: return "invalid argument";
+    case QRK_STATUS_NOT_FACTORIZED: return "the factorization should be called first, use compute()";
+    case QRK_STATUS_CUDA_ERROR: return "CUDA error";
+    case QRK_STATUS_NO_DEVICE: return "no CUDA device (qrkit_b200 has no CPU fallback)";
+    case QRK_STATUS_ALLOC_FAILED: return "device allocation failed";
+    case QRK_STATUS_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* qrk_last_error(qrk_handle_t h) { return h ? h->err.c_str() : ""; }
+
+int qrk_device_count(int* count) {
+  if (!count) return QRK_STATUS_INVALID_ARGUMENT;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *count = n;
+  return QRK_STATUS_OK;
+}
+
+int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
+  if (!desc || !out) return QRK_STATUS_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (desc->kind != QRK_BLOCK_DIAGONAL) return QRK_STATUS_UNSUPPORTED;
+  if (desc->num_blocks < 0) return QRK_STATUS_INVALID_ARGUMENT;
+  const bool uniform = desc->block_rows > 0 && desc->block_cols > 0;
+  if (!uniform && desc->num_blocks > 0 && (!desc->rows || !desc->cols)) return QRK_STATUS_INVALID_ARGUMENT;
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  if (desc->device < 0 || desc->device >= ndev) return QRK_STATUS_INVALID_ARGUMENT;
+
+  qrk_solver* h = new (std::nothrow) qrk_solver;
+  if (!h) return QRK_STATUS_ALLOC_FAILED;
+  h->desc = *desc;
+  h->desc.rows = h->desc.cols = nullptr;
+  h->device = desc->device;
+  h->nb = desc->num_blocks;
+  h->uniform = uniform;
+  DeviceGuard g(h->device);
+  auto fail = [&](int st) { free_dev(h); if (h->own_stream) cudaStreamDestroy(h->own_stream); delete h; return st; };
+
+  // prefix sums = block origins (BlockDiagonalSparseQR.h:524-525)
+  bool landscape = false;
+  if (uniform) {
+    h->ur = desc->block_rows; h->uc = desc->block_cols;
+    h->max_r = h->ur; h->max_c = h->uc;
+    h->sum_rows = h->nb * h->ur; h->sum_cols = h->nb * h->uc;
+    h->total_values = h->nb * (long long)h->ur * h->uc;
+    landscape = h->ur < h->uc;
+  } else {
+    h->h_rows.assign(desc->rows, desc->rows + h->nb);
+    h->h_cols.assign(desc->cols, desc->cols + h->nb);
+    h->h_voff.resize(h->nb); h->h_roff.resize(h->nb); h->h_coff.resize(h->nb);
+    long long vo = 0, ro = 0, co = 0;
+    for (long long i = 0; i < h->nb; i++) {
+      const int r = h->h_rows[i], c = h->h_cols[i];
+      if (r <= 0 || c <= 0) return fail(QRK_STATUS_INVALID_ARGUMENT);
+      if (r < c) landscape = true;
+      h->h_voff[i] = vo; h->h_roff[i] = ro; h->h_coff[i] = co;
+      vo += (long long)r * c; ro += r; co += c;
+      h->max_r = std::max(h->max_r, r); h->max_c = std::max(h->max_c, c);
+    }
+    h->total_values = vo; h->sum_rows = ro; h->sum_cols = co;
+  }
+  h->n_rows = desc->n_rows > 0 ? desc->n_rows : h->sum_rows;
+  h->n_cols = desc->n_cols > 0 ? desc->n_cols : h->sum_cols;
+  if (h->n_rows < h->sum_rows || h->n_cols < h->sum_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
+  if (h->n_rows > INT32_MAX || h->n_cols > INT32_MAX) return fail(QRK_STATUS_UNSUPPORTED);  // StorageIndex = int
+  if (desc->q_format != QRK_FULL_Q && desc->q_format != QRK_BLOCK_DIAGONAL_Q) h->info = QRK_INFO_INVALID_INPUT;  // :501-505
+  if (landscape) h->info = QRK_INFO_INVALID_INPUT;                                                               // :509-516
+
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);
+  h->stream = h->own_stream;
+
+  h->small_path = uniform && small_shape_available(h->ur, h->uc);
+  auto up = [&](auto*& dptr, const auto& vec) -> cudaError_t {
+    using T = typename std::remove_reference<decltype(vec[0])>::type;
+    cudaError_t e = cudaMalloc(&dptr, std::max<size_t>(vec.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(dptr, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+  };
+  if (!uniform && h->nb > 0) {
+    if (up(h->d_rows, h->h_rows) != cudaSuccess || up(h->d_cols, h->h_cols) != cudaSuccess ||
+        up(h->d_voff, h->h_voff) != cudaSuccess || up(h->d_roff, h->h_roff) != cudaSuccess ||
+        up(h->d_coff, h->h_coff) != cudaSuccess)
+      return fail(QRK_STATUS_ALLOC_FAILED);
+  }
+  if (!h->small_path && h->nb > 0 && h->info == QRK_INFO_SUCCESS) {
+    // size classes of the generic kernel: (team warps, shared memory rounded up to 8 KB steps)
+    if (uniform) {
+      SizeClass sc;
+      sc.warps = team_warps_for(h->ur, h->uc);
+      sc.smem = generic_smem_bytes(h->ur, h->uc);
+      sc.count = h->nb;
+      if (sc.smem > kMaxSmem) return fail(QRK_STATUS_UNSUPPORTED);
+      h->classes.push_back(sc);
+    } else {
+      std::map<std::pair<int, size_t>, std::vector<int>> bins;
+      for (long long i = 0; i < h->nb; i++) {
+        const size_t need = generic_smem_bytes(h->h_rows[i], h->h_cols[i]);
+        if (need > kMaxSmem) return fail(QRK_STATUS_UNSUPPORTED);
+        const size_t cls = std::min(kMaxSmem, (need + 8191) / 8192 * 8192);
+        bins[{team_warps_for(h->h_rows[i], h->h_cols[i]), cls}].push_back((int)i);
+      }
+      for (auto it = bins.rbegin(); it != bins.rend(); ++it) {   // largest first: long CTAs start early
+        SizeClass sc;
+        sc.warps = it->first.first; sc.smem = it->first.second; sc.count = (long long)it->second.size();
+        if (up(sc.d_ids, it->second) != cudaSuccess) return fail(QRK_STATUS_ALLOC_FAILED);
+        h->classes.push_back(sc);
+      }
+    }
+  }
+  if (cudaMalloc(&h->d_tau, std::max<long long>(h->n_cols, 1) * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_perm, std::max<long long>(h->n_cols, 1) * sizeof(int)) != cudaSuccess)
+    return fail(QRK_STATUS_ALLOC_FAILED);
+  cudaMemsetAsync(h->d_tau, 0, std::max<long long>(h->n_cols, 1) * sizeof(double), h->stream);
+  iota_kernel<<<256, 256, 0, h->stream>>>(h->d_perm, h->n_cols);   // m_outputPerm_c.setIdentity (:417)
+  h->launches++;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);  // host vectors may go away
+  *out = h;
+  return QRK_STATUS_OK;
+}
+
+int qrk_destroy(qrk_handle_t h) {
+  if (!h) return QRK_STATUS_OK;
+  {
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_dev(h);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  }
+  delete h;
+  return QRK_STATUS_OK;
+}
+
+int qrk_set_stream(qrk_handle_t h, void* cuda_stream) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return QRK_STATUS_OK;
+}
+
+int qrk_synchronize(qrk_handle_t h) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  DeviceGuard g(h->device);
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QRK_STATUS_OK;
+}
+
+int qrk_total_values(qrk_handle_t h, int64_t* n) {
+  if (!h || !n) return QRK_STATUS_INVALID_ARGUMENT;
+  *n = h->total_values;
+  return QRK_STATUS_OK;
+}
+
+int qrk_set_blocks(qrk_handle_t h, const double* values, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, values || h->total_values == 0, "values is null");
+  DeviceGuard g(h->device);
+  {
+    int st = ensure_own_values(h);
+    if (st != QRK_STATUS_OK) return st;
+  }
+  QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_values, values, h->total_values * sizeof(double),
+                                  memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  h->has_blocks = true;
+  h->factorized = false;
+  return QRK_STATUS_OK;
+}
+
+int qrk_adopt_blocks(qrk_handle_t h, double* device_values) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, device_values || h->total_values == 0, "device_values is null");
+  QRK_REQUIRE(h, aligned16(device_values), "device_values must be 16-byte aligned");
+  DeviceGuard g(h->device);
+  if (h->own_values && h->d_values) cudaFree(h->d_values);
+  h->d_values = device_values;
+  h->own_values = false;
+  h->has_blocks = true;
+  h->factorized = false;
+  return QRK_STATUS_OK;
+}
+
+int qrk_analyze_pattern(qrk_handle_t h, const int32_t* row_perm) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  h->h_rowperm.resize(h->n_rows);
+  if (row_perm) std::copy(row_perm, row_perm + h->n_rows, h->h_rowperm.begin());
+  else std::iota(h->h_rowperm.begin(), h->h_rowperm.end(), 0);
+  h->analyzed = true;
+  return QRK_STATUS_OK;
+}
+
+int qrk_factorize(qrk_handle_t h) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, h->has_blocks, "no blocks set: call qrk_set_blocks / qrk_adopt_blocks first");
+  if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
+  if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;   // reported through info(), as the reference
+  DeviceGuard g(h->device);
+  int st = run_factor(h, h->d_values, nullptr, nullptr);
+  if (st != QRK_STATUS_OK) return st;
+  h->factorized = true;
+  return QRK_STATUS_OK;
+}
+
+// Device-resident input: the kernels read the caller's blocks directly and write the packed factors
+// into the handle's storage (the input is borrowed const for the call, as compute(const MatrixType&)).
+static int compute_from_device(qrk_solver* h, const double* values, const double* d_b, double* d_x) {
+  QRK_REQUIRE(h, values || h->total_values == 0, "values is null");
+  QRK_REQUIRE(h, aligned16(values), "device values must be 16-byte aligned");
+  DeviceGuard g(h->device);
+  int st = ensure_own_values(h);
+  if (st != QRK_STATUS_OK) return st;
+  h->has_blocks = true;
+  h->factorized = false;
+  if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
+  if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
+  if (d_x && h->n_cols > h->sum_cols)
+    QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
+  st = run_factor(h, values, d_b, d_x);
+  if (st != QRK_STATUS_OK) return st;
+  h->factorized = true;
+  return QRK_STATUS_OK;
+}
+
+int qrk_compute(qrk_handle_t h, const double* values, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  if (memspace == QRK_DEVICE) return compute_from_device(h, values, nullptr, nullptr);
+  int st = qrk_set_blocks(h, values, memspace);
+  if (st != QRK_STATUS_OK) return st;
+  st = qrk_analyze_pattern(h, nullptr);
+  if (st != QRK_STATUS_OK) return st;
+  return qrk_factorize(h);
+}
+
+int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, h->has_blocks, "no blocks set: call qrk_set_blocks / qrk_adopt_blocks first");
+  QRK_REQUIRE(h, b && x, "b / x is null");
+  if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
+  if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
+  DeviceGuard g(h->device);
+  const double* d_b = b;
+  double* d_x = x;
+  if (memspace == QRK_HOST) {
+    int st = ensure_buffer(h, h->d_b, h->cap_b, (size_t)h->n_rows);
+    if (st != QRK_STATUS_OK) return st;
+    st = ensure_buffer(h, h->d_x, h->cap_x, (size_t)h->n_cols);
+    if (st != QRK_STATUS_OK) return st;
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_b, b, h->n_rows * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    d_b = h->d_b; d_x = h->d_x;
+  } else {
+    QRK_REQUIRE(h, aligned16(b) && aligned16(x), "device b / x must be 16-byte aligned");
+  }
+  if (h->n_cols > h->sum_cols)
+    QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
+  int st = run_factor(h, h->d_values, d_b, d_x);
+  if (st != QRK_STATUS_OK) return st;
+  h->factorized = true;
+  if (memspace == QRK_HOST) {
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(x, h->d_x, h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return QRK_STATUS_OK;
+}
+
+int qrk_compute_solve(qrk_handle_t h, const double* values, const double* b, double* x, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  if (memspace == QRK_DEVICE) {
+    QRK_REQUIRE(h, b && x, "b / x is null");
+    QRK_REQUIRE(h, aligned16(b) && aligned16(x), "device b / x must be 16-byte aligned");
+    return compute_from_device(h, values, b, x);
+  }
+  int st = qrk_set_blocks(h, values, memspace);
+  if (st != QRK_STATUS_OK) return st;
+  return qrk_factorize_solve(h, b, x, memspace);
+}
+
+int qrk_rows(qrk_handle_t h, int64_t* rows) { if (!h || !rows) return QRK_STATUS_INVALID_ARGUMENT; *rows = h->n_rows; return QRK_STATUS_OK; }
+int qrk_cols(qrk_handle_t h, int64_t* cols) { if (!h || !cols) return QRK_STATUS_INVALID_ARGUMENT; *cols = h->n_cols; return QRK_STATUS_OK; }
+int qrk_rank(qrk_handle_t h, int64_t* rank) {
+  if (!h || !rank) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  *rank = h->sum_cols;   // rank += blockSolver.cols() (BlockDiagonalSparseQR.h:440)
+  return QRK_STATUS_OK;
+}
+int qrk_info(qrk_handle_t h, int32_t* info) { if (!h || !info) return QRK_STATUS_INVALID_ARGUMENT; *info = h->info; return QRK_STATUS_OK; }
+
+int qrk_cols_permutation(qrk_handle_t h, int32_t* indices, int memspace) {
+  if (!h || !indices) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  DeviceGuard g(h->device);
+  QRK_TRY_CUDA(h, cudaMemcpyAsync(indices, h->d_perm, h->n_cols * sizeof(int),
+                                  memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (memspace == QRK_HOST) QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QRK_STATUS_OK;
+}
+
+int qrk_rows_permutation(qrk_handle_t h, int32_t* indices, int memspace) {
+  if (!h || !indices) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->analyzed) return QRK_STATUS_NOT_FACTORIZED;
+  DeviceGuard g(h->device);
+  if (memspace == QRK_DEVICE) {
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(indices, h->h_rowperm.data(), h->n_rows * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else {
+    std::copy(h->h_rowperm.begin(), h->h_rowperm.end(), indices);
+  }
+  return QRK_STATUS_OK;
+}
+
+int qrk_packed_factors(qrk_handle_t h, double* packed, double* tau, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  DeviceGuard g(h->device);
+  const cudaMemcpyKind kind = memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (packed) QRK_TRY_CUDA(h, cudaMemcpyAsync(packed, h->d_values, h->total_values * sizeof(double), kind, h->stream));
+  if (tau) QRK_TRY_CUDA(h, cudaMemcpyAsync(tau, h->d_tau, h->n_cols * sizeof(double), kind, h->stream));
+  if (memspace == QRK_HOST) QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QRK_STATUS_OK;
+}
+
+// ---- matrixR / matrixQ export --------------------------------------------------------------------
+int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz) {
+  if (!h || !nnz) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  long long n = 0;
+  if (h->uniform) n = h->nb * ((long long)h->uc * (h->uc + 1) / 2);
+  else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
+  *nnz = n;
+  return QRK_STATUS_OK;
+}
+
+int qrk_matrix_q_nnz(qrk_handle_t h, int64_t* nnz) {
+  if (!h || !nnz) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  long long n = 0;
+  if (h->uniform) n = h->nb * ((long long)h->ur * h->ur);
+  else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_rows[i] * h->h_rows[i];
+  *nnz = n + (h->n_rows - h->sum_rows);
+  return QRK_STATUS_OK;
+}
+
+static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* inner, double* values, int memspace) {
+  if (!h || !outer || !inner || !values) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  int64_t nnz = 0;
+  if (want_q) qrk_matrix_q_nnz(h, &nnz); else qrk_matrix_r_nnz(h, &nnz);
+  QRK_REQUIRE(h, nnz <= INT32_MAX, "matrix has more than 2^31-1 stored entries (StorageIndex = int)");
+  DeviceGuard g(h->device);
+  const long long n_outer = (want_q ? h->n_rows : h->n_cols) + 1;
+  int32_t *d_outer = outer, *d_inner = inner;
+  double* d_vals = values;
+  if (memspace == QRK_HOST) {
+    d_outer = d_inner = nullptr; d_vals = nullptr;
+    QRK_TRY_CUDA(h, cudaMalloc(&d_outer, n_outer * sizeof(int32_t)));
+    if (cudaMalloc(&d_inner, std::max<long long>(nnz, 1) * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&d_vals, std::max<long long>(nnz, 1) * sizeof(double)) != cudaSuccess) {
+      cudaFree(d_outer); if (d_inner) cudaFree(d_inner);
+      h->err = "export: device allocation failed";
+      return QRK_STATUS_ALLOC_FAILED;
+    }
+  }
+  // per-block start of its entries in the compressed arrays (non-uniform: prefix sums on the host)
+  long long* d_eoff = nullptr;
+  if (!h->uniform && h->nb > 0) {
+    std::vector<long long> eoff(h->nb);
+    long long acc = 0;
+    for (long long i = 0; i < h->nb; i++) {
+      eoff[i] = acc;
+      acc += want_q ? (long long)h->h_rows[i] * h->h_rows[i] : (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
+    }
+    cudaMalloc(&d_eoff, h->nb * sizeof(long long));
+    cudaMemcpyAsync(d_eoff, eoff.data(), h->nb * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  const BlockIndex bi = block_index(h);
+  const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
+  cudaError_t e;
+  if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->n_cols, h->sum_rows,
+                                  nnz - (h->n_rows - h->sum_rows), full_q, h->max_r, d_outer, d_inner, d_vals, h->stream);
+  else e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->n_cols, h->sum_cols, nnz, full_q, d_outer, d_inner, d_vals, h->stream);
+  h->launches += 2;
+  int st = QRK_STATUS_OK;
+  if (e != cudaSuccess) { h->err = std::string("export kernel: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
+  if (st == QRK_STATUS_OK && memspace == QRK_HOST) {
+    cudaMemcpyAsync(outer, d_outer, n_outer * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(inner, d_inner, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(values, d_vals, nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  }
+  e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess && st == QRK_STATUS_OK) { h->err = std::string("export: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
+  if (memspace == QRK_HOST) { cudaFree(d_outer); cudaFree(d_inner); cudaFree(d_vals); }
+  if (d_eoff) cudaFree(d_eoff);
+  return st;
+}
+
+int qrk_matrix_r(qrk_handle_t h, int32_t* outer, int32_t* inner, double* values, int memspace) {
+  return export_sparse(h, false, outer, inner, values, memspace);
+}
+int qrk_matrix_q(qrk_handle_t h, int32_t* outer, int32_t* inner, double* values, int memspace) {
+  return export_sparse(h, true, outer, inner, values, memspace);
+}
+
+// ---- Q^T B, Q B, solve ----------------------------------------------------------------------------
+static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  QRK_REQUIRE(h, B && X && nrhs >= 0, "B / X is null or nrhs < 0");
+  const long long in_rows = h->n_rows;
+  const long long out_rows = (op == OP_SOLVE) ? h->n_cols : h->n_rows;
+  QRK_REQUIRE(h, ldb >= in_rows && ldx >= out_rows, "leading dimension smaller than the number of rows");
+  DeviceGuard g(h->device);
+  const double* d_B = B;
+  double* d_X = X;
+  long long dldb = ldb, dldx = ldx;
+  if (memspace == QRK_HOST) {
+    dldb = (in_rows + 1) & ~1LL; dldx = (out_rows + 1) & ~1LL;
+    int st = ensure_buffer(h, h->d_b, h->cap_b, (size_t)dldb * nrhs);
+    if (st != QRK_STATUS_OK) return st;
+    st = ensure_buffer(h, h->d_x, h->cap_x, (size_t)dldx * nrhs);
+    if (st != QRK_STATUS_OK) return st;
+    QRK_TRY_CUDA(h, cudaMemcpy2DAsync(h->d_b, dldb * sizeof(double), B, ldb * sizeof(double), in_rows * sizeof(double), nrhs,
+                                      cudaMemcpyHostToDevice, h->stream));
+    d_B = h->d_b; d_X = h->d_x;
+  }
+  if (op == OP_SOLVE) {
+    if (h->n_cols > h->sum_cols)   // y.bottomRows(...).setZero() (:272)
+      QRK_TRY_CUDA(h, cudaMemset2DAsync(d_X + h->sum_cols, dldx * sizeof(double), 0, (h->n_cols - h->sum_cols) * sizeof(double),
+                                        nrhs, h->stream));
+  } else if (h->n_rows > h->sum_rows) {
+    copy_tail_kernel<<<64, 256, 0, h->stream>>>(d_B, dldb, d_X, dldx, nrhs, h->sum_rows, h->n_rows);
+    h->launches++;
+  }
+  int st = run_op(h, op, d_B, dldb, d_X, dldx, nrhs);
+  if (st != QRK_STATUS_OK) return st;
+  if (memspace == QRK_HOST) {
+    QRK_TRY_CUDA(h, cudaMemcpy2DAsync(X, ldx * sizeof(double), h->d_x, dldx * sizeof(double), out_rows * sizeof(double), nrhs,
+                                      cudaMemcpyDeviceToHost, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->info = QRK_INFO_SUCCESS;   // m_info = Success (:278)
+  return QRK_STATUS_OK;
+}
+
+int qrk_apply_qt(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace) {
+  return op_entry(h, OP_APPLY_QT, B, ldb, Y, ldy, nrhs, memspace);
+}
+int qrk_apply_q(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace) {
+  return op_entry(h, OP_APPLY_Q, B, ldb, Y, ldy, nrhs, memspace);
+}
+int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace) {
+  return op_entry(h, OP_SOLVE, B, ldb, X, ldx, nrhs, memspace);
+}
+
+int qrk_launch_count(qrk_handle_t h, int64_t* launches) {
+  if (!h || !launches) return QRK_STATUS_INVALID_ARGUMENT;
+  *launches = h->launches;
+  return QRK_STATUS_OK;
+}
+
+int qrk_synth_fill(double* device_out, uint64_t seed, int64_t block0, int64_t nb, int32_t r, int32_t c, double lo, double hi,
+                   void* cuda_stream) {
+  if (!device_out || nb < 0 || r <= 0 || c < 0) return QRK_STATUS_INVALID_ARGUMENT;
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  if (nb == 0) return QRK_STATUS_OK;
+  synth_fill_kernel<<<148 * 8, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(device_out, seed, block0, nb, r, c, lo, hi);
+  return cudaGetLastError() == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// common.cuh — shared device helpers of the qrkit_b200 kernels (sm_100a only).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "qrkit_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace qrk {
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory staging of "groups": a tile is `count` groups of N doubles, contiguous in global
+// memory (the block-COO layout: consecutive blocks are adjacent).  In shared memory every group gets
+// a stride of S doubles chosen so that thread t reading *its own* group t is bank-conflict free:
+//   N even -> 16-byte accesses; a quarter-warp (8 threads x 16 B) is conflict free iff S/2 is odd;
+//   N odd  ->  8-byte accesses; a half-warp (16 threads x 8 B) is conflict free iff S is odd.
+// Global traffic is always fully coalesced 16-byte (8-byte for odd N) accesses.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct Group {
+  static constexpr int vec = (N % 2 == 0) ? 2 : 1;
+  static constexpr int stride = (N % 2 == 1) ? N : ((N % 4 == 2) ? N : N + 2);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
+
+// global (contiguous) -> shared (strided groups), asynchronous (LDGSTS): no register staging.
+template <int N, int S, int TPB>
+__device__ __forceinline__ void stage_in_async(double* s, const double* __restrict__ g, int count) {
+  constexpr int V = Group<N>::vec;
+  if (count == TPB) {
+    constexpr int total = TPB * N / V;
+#pragma unroll
+    for (int q0 = 0; q0 < total; q0 += TPB) {
+      const int q = q0 + threadIdx.x;
+      if (total % TPB == 0 || q < total) {
+        const int d = q * V, grp = d / N, within = d - grp * N;
+        if (V == 2) cp_async16(s + grp * S + within, g + d);
+        else cp_async8(s + grp * S + within, g + d);
+      }
+    }
+  } else {
+    const int total = count * N / V + ((count * N) % V ? 1 : 0);
+    for (int q = threadIdx.x; q < total; q += TPB) {
+      const int d = q * V, grp = d / N, within = d - grp * N;
+      if (V == 2) cp_async16(s + grp * S + within, g + d);   // count*N is even whenever N is
+      else cp_async8(s + grp * S + within, g + d);
+    }
+  }
+}
+
+// shared (strided groups) -> global (contiguous), coalesced vector stores.
+template <int N, int S, int TPB>
+__device__ __forceinline__ void stage_out(double* __restrict__ g, const double* s, int count) {
+  constexpr int V = Group<N>::vec;
+  const int total = (count == TPB) ? TPB * N / V : count * N / V;
+#pragma unroll 4
+  for (int q = threadIdx.x; q < total; q += TPB) {
+    const int d = q * V, grp = d / N, within = d - grp * N;
+    if (V == 2) *reinterpret_cast<double2*>(g + d) = *reinterpret_cast<const double2*>(s + grp * S + within);
+    else g[d] = s[grp * S + within];
+  }
+}
+
+// int32 groups (column permutation): stride odd => conflict free 4-byte accesses.
+template <int N>
+struct GroupI32 { static constexpr int stride = (N % 2 == 1) ? N : N + 1; };
+
+template <int N, int S, int TPB>
+__device__ __forceinline__ void stage_out_i32(int* __restrict__ g, const int* s, int count) {
+  const int total = count * N;
+  for (int d = threadIdx.x; d < total; d += TPB) {
+    const int grp = d / N, within = d - grp * N;
+    g[d] = s[grp * S + within];
+  }
+}
+
+// per-thread group <-> registers
+template <int N>
+__device__ __forceinline__ void load_group(double (&dst)[N], const double* s) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      const double2 v = reinterpret_cast<const double2*>(s)[i];
+      dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) dst[i] = s[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_group(double* s, const double (&src)[N]) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) reinterpret_cast<double2*>(s)[i] = make_double2(src[2 * i], src[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) s[i] = src[i];
+  }
+}
+
+// splitmix64 counter-based generator shared with the test-suite (tests/helpers.py)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ double synth_value(uint64_t seed, uint64_t block, uint64_t row, uint64_t col,
+                                                       double lo, double hi) {
+  const uint64_t u = splitmix64(seed ^ (block << 20) ^ (row << 10) ^ col);
+  return lo + (hi - lo) * (double)(u >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace qrk

@@ -1,0 +1,54 @@
+// solver.hpp — internal state behind the opaque qrk_handle_t (host side of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qrkit_b200.h"
+
+namespace qrk {
+
+struct SizeClass {          // one launch of the generic kernel: blocks with a similar shared-memory need
+  int warps = 1;            // team size W
+  size_t smem = 0;          // dynamic shared memory per CTA
+  long long count = 0;
+  int* d_ids = nullptr;     // block numbers of this class (nullptr: all blocks, identity order)
+};
+
+}  // namespace qrk
+
+struct qrk_solver {
+  qrk_desc_t desc{};
+  int device = 0;
+  cudaStream_t stream = nullptr;      // the stream work is enqueued on
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // ---- block structure (SparseBlockDiagonal / block-COO index) ----
+  long long nb = 0;
+  bool uniform = true;
+  int ur = 0, uc = 0, max_r = 0, max_c = 0;
+  std::vector<int> h_rows, h_cols;
+  std::vector<long long> h_voff, h_roff, h_coff;
+  int *d_rows = nullptr, *d_cols = nullptr;
+  long long *d_voff = nullptr, *d_roff = nullptr, *d_coff = nullptr;
+  long long n_rows = 0, n_cols = 0, sum_rows = 0, sum_cols = 0, total_values = 0;
+  bool small_path = false;            // thread-per-block kernels instantiated for (ur, uc)
+  std::vector<qrk::SizeClass> classes;
+
+  // ---- factorisation state ----
+  double* d_values = nullptr;         // blocks, overwritten by the packed factors
+  bool own_values = false;
+  double* d_tau = nullptr;
+  int* d_perm = nullptr;              // colsPermutation().indices(), int32[n_cols]
+  std::vector<int> h_rowperm;         // rowsPermutation().indices()
+  bool analyzed = false, has_blocks = false, factorized = false;
+  int info = QRK_INFO_SUCCESS;
+
+  // ---- staging buffers for host-memspace calls ----
+  double *d_b = nullptr, *d_x = nullptr;
+  size_t cap_b = 0, cap_x = 0;
+};
