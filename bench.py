@@ -182,6 +182,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = capi.lib()
+    # a non-default torch stream: the handle enqueues on it and torch.cuda.Event records on it (events only see
+    # torch's current stream; the legacy default stream has handle 0, which qrk_set_stream reads as "own stream")
+    bench_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(bench_stream)
+    assert bench_stream.cuda_stream != 0
     nb = args.blocks
     piv = args.pivoting
 

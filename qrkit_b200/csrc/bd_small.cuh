@@ -167,12 +167,12 @@ __device__ __forceinline__ void back_substitute(const double (&a)[R * C], const 
 template <int R, int C, int TPB>
 struct SmallSmem {
   static constexpr int SA = Group<R * C>::stride;
-  static constexpr int SB = Group<R>::stride;       // rhs in; x out reuses the slot (C <= R)
-  static constexpr int ST = Group<C>::stride;
+  static constexpr int SB = Group<R>::stride;       // rhs in
+  static constexpr int ST = Group<C>::stride;       // tau out; x out (aliases the rhs region, own stride)
   static constexpr int SP = GroupI32<C>::stride;
   static constexpr int offA = 0;
   static constexpr int offB = offA + TPB * SA;
-  static constexpr int offT = offB + TPB * SB;
+  static constexpr int offT = offB + TPB * (SB > ST ? SB : ST);
   static constexpr int offP = offT + TPB * ST;      // in doubles
   static constexpr size_t bytes = (size_t)offP * 8 + (size_t)TPB * SP * 4;
 };
@@ -199,11 +199,14 @@ bd_small_factor_kernel(const double* A_in, double* packed, double* __restrict__ 
   cp_async_wait<0>();
   __syncthreads();
 
+  double a[R * C], rhs[R], tau[C], inv_diag[C];
+  int perm[C];
   if (t < count) {
-    double a[R * C], rhs[R], tau[C], inv_diag[C];
-    int perm[C];
     load_group<R * C>(a, sA + t * L::SA);
     if (SOLVE) load_group<R>(rhs, sB + t * L::SB);
+  }
+  if (SOLVE) __syncthreads();   // every rhs is in registers: the region is reused for x with a different stride
+  if (t < count) {
     BlockQR<R, C, PIV, SOLVE>::run(a, tau, inv_diag, perm, rhs);
     store_group<R * C>(sA + t * L::SA, a);
     store_group<C>(sT + t * L::ST, tau);
@@ -214,7 +217,7 @@ bd_small_factor_kernel(const double* A_in, double* packed, double* __restrict__ 
     }
     if (SOLVE) {
       back_substitute<R, C>(a, inv_diag, rhs);
-      double* xs = sB + t * L::SB;
+      double* xs = sB + t * L::ST;
       if (PIV) {
 #pragma unroll
         for (int j = 0; j < C; j++) xs[perm[j]] = rhs[j];
@@ -230,7 +233,7 @@ bd_small_factor_kernel(const double* A_in, double* packed, double* __restrict__ 
   stage_out<R * C, L::SA, TPB>(packed + tile0 * (R * C), sA, count);
   stage_out<C, L::ST, TPB>(tau_out + tile0 * C, sT, count);
   if (PIV) stage_out_i32<C, L::SP, TPB>(perm_out + tile0 * C, sP, count);
-  if (SOLVE) stage_out<C, L::SB, TPB>(x + tile0 * C, sB, count);
+  if (SOLVE) stage_out<C, L::ST, TPB>(x + tile0 * C, sB, count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,7 +254,7 @@ struct SmallOpSmem {
   static constexpr int SC = Group<(R - C > 0 ? R - C : 1)>::stride;
   static constexpr int offA = 0;
   static constexpr int offB = offA + TPB * SA;
-  static constexpr int offT = offB + TPB * SB;
+  static constexpr int offT = offB + TPB * (SB > ST ? SB : ST);
   static constexpr int offC = offT + TPB * ST;
   static constexpr size_t bytes = (size_t)(offC + TPB * SC) * 8;
 };
@@ -298,8 +301,8 @@ bd_small_op_kernel(const double* __restrict__ packed, const double* __restrict__
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    double v[R];
     if (t < count) {
-      double v[R];
       if (OP == OP_APPLY_Q && full_q) {
 #pragma unroll
         for (int k = 0; k < C; k++) v[k] = sT[t * L::ST + k];
@@ -308,6 +311,9 @@ bd_small_op_kernel(const double* __restrict__ packed, const double* __restrict__
       } else {
         load_group<R>(v, sB + t * L::SB);
       }
+    }
+    if (OP == OP_SOLVE) __syncthreads();   // the rhs region is reused for x with a different stride
+    if (t < count) {
       if (OP == OP_APPLY_Q) {
         // Q v = H_0 ... H_{C-1} v : last reflector first
         apply_q_chain<R, C>(a, tau, v);
@@ -319,7 +325,7 @@ bd_small_op_kernel(const double* __restrict__ packed, const double* __restrict__
 #pragma unroll
         for (int j = 0; j < C; j++) inv_diag[j] = 1.0 / a[j * R + j];
         back_substitute<R, C>(a, inv_diag, v);
-        double* xs = sB + t * L::SB;
+        double* xs = sB + t * L::ST;
 #pragma unroll
         for (int j = 0; j < C; j++) xs[PERM ? p[j] : j] = v[j];
       } else if (OP == OP_APPLY_QT && full_q) {
@@ -333,7 +339,7 @@ bd_small_op_kernel(const double* __restrict__ packed, const double* __restrict__
     }
     __syncthreads();
     if (OP == OP_SOLVE) {
-      stage_out<C, L::SB, TPB>(Xc + tile0 * C, sB, count);
+      stage_out<C, L::ST, TPB>(Xc + tile0 * C, sB, count);
     } else if (OP == OP_APPLY_QT && full_q) {
       stage_out<C, L::ST, TPB>(Xc + tile0 * C, sT, count);
       if (M1 > 0) stage_out<(M1 > 0 ? M1 : 1), L::SC, TPB>(Xc + n_cols + tile0 * M1, sC, count);

@@ -46,10 +46,11 @@ constexpr int kSmallTPB = 128;
 constexpr int kSmallMinBlocks = 4;
 
 // opt in to > 48 KB dynamic shared memory, once per (kernel instantiation, device)
+// (`done` must be a static of the calling launch template: the kernel pointer TYPE is shared by all
+// instantiations with the same signature)
 template <typename K>
-cudaError_t ensure_smem(K kernel, size_t bytes) {
+cudaError_t ensure_smem(K kernel, size_t bytes, bool (&done)[64]) {
   if (bytes <= 48 * 1024) return cudaSuccess;
-  static bool done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
@@ -63,7 +64,8 @@ cudaError_t launch_small_factor(const double* A, double* packed, double* tau, in
                                 long long nb, cudaStream_t s) {
   auto kernel = bd_small_factor_kernel<R, C, PIV, SOLVE, kSmallTPB, kSmallMinBlocks>;
   constexpr size_t smem = SmallSmem<R, C, kSmallTPB>::bytes;
-  cudaError_t attr = ensure_smem(kernel, smem);
+  static bool smem_opt_in[64] = {};
+  cudaError_t attr = ensure_smem(kernel, smem, smem_opt_in);
   if (attr != cudaSuccess) return attr;
   const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
   kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(A, packed, tau, perm, b, x, nb);
@@ -76,7 +78,8 @@ cudaError_t launch_small_op_t(const double* packed, const double* tau, const int
                               cudaStream_t s) {
   auto kernel = bd_small_op_kernel<R, C, OP, PERM, kSmallTPB, kSmallMinBlocks>;
   constexpr size_t smem = SmallOpSmem<R, C, kSmallTPB>::bytes;
-  cudaError_t attr = ensure_smem(kernel, smem);
+  static bool smem_opt_in[64] = {};
+  cudaError_t attr = ensure_smem(kernel, smem, smem_opt_in);
   if (attr != cudaSuccess) return attr;
   const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
   kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q);

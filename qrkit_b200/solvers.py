@@ -216,7 +216,7 @@ class BlockDiagonalSparseQR:
     def _apply(self, fn, B, out_rows):
         B = np.asarray(B, dtype=np.float64)
         vec = B.ndim == 1
-        Bf = np.asfortranarray(B.reshape(len(B), -1))
+        Bf = np.asfortranarray(B.reshape(len(B), 1) if vec else B)
         nrhs = Bf.shape[1]
         Y = np.empty((out_rows, nrhs), order="F")
         check(fn(self._h, _ptr(Bf), Bf.shape[0], _ptr(Y), out_rows, nrhs, QRK_HOST), self._h)
