@@ -30,17 +30,17 @@ __device__ __forceinline__ double make_reflector_k(double (&a)[R * C], double& i
   for (int i = K + 1; i < R; i++) tailSq = fma(a[K * R + i], a[K * R + i], tailSq);
   const double c0 = a[K * R + K];
   const bool degenerate = (K + 1 >= R) || (tailSq <= DBL_MIN);   // Eigen: tailSqNorm <= (numeric_limits::min)()
-  double beta = sqrt(fma(c0, c0, tailSq));
-  if (c0 >= 0.0) beta = -beta;
-  double inv = 1.0 / (c0 - beta);
-  double ib = 1.0 / beta;
-  if (degenerate) { inv = 0.0; ib = 0.0; }
-  const double tau = (beta - c0) * ib;
-  if (degenerate) beta = c0;
+  double norm;
+  const double rnorm = fast_rsqrt(fma(c0, c0, tailSq), norm);    // 1/||x||, ||x||
+  double beta = (c0 >= 0.0) ? -norm : norm;                      // beta = -sign(x0) ||x||
+  double ib = (c0 >= 0.0) ? -rnorm : rnorm;                      // 1/beta
+  double inv = fast_rcp(c0 - beta);
+  double tau = (beta - c0) * ib;
+  if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; ib = fast_rcp(c0); }
 #pragma unroll
   for (int i = K + 1; i < R; i++) a[K * R + i] *= inv;
   a[K * R + K] = beta;
-  inv_beta = degenerate ? 1.0 / c0 : ib;
+  inv_beta = ib;
   return tau;
 }
 
@@ -79,7 +79,7 @@ struct BlockQR {
   static __device__ __forceinline__ void step(double (&a)[R * C], double (&tau)[C], double (&inv_diag)[C], int (&perm)[C],
                                              double (&rhs)[R], double (&upd)[C], double (&dir)[C]) {
     if (PIV) {
-      // first maximum of the downdated norms (strict '>' keeps the lowest index on ties)
+      // first maximum of the downdated (squared) norms; strict '>' keeps the lowest index on ties
       int big = K;
       double bigv = upd[K];
 #pragma unroll
@@ -100,26 +100,29 @@ struct BlockQR {
 #pragma unroll
     for (int j = K + 1; j < C; j++) apply_reflector_k<R, C, K>(a, tau[K], &a[j * R]);
     if (RHS) apply_reflector_k<R, C, K>(a, tau[K], rhs);
-    if (PIV) {
-      // LAWN-176 norm downdate (Eigen ColPivHouseholderQR::computeInPlace)
+    if (PIV && K + 1 < NV) {
+      // LAWN-176 norm downdate (Eigen ColPivHouseholderQR::computeInPlace) carried in SQUARED form:
+      //   Eigen:  t = |a_kj|/upd_j; temp = (1+t)(1-t); temp2 = temp (upd_j/dir_j)^2;
+      //           temp2 <= sqrt(eps) ? upd_j = dir_j = ||a[k+1:,j]|| : upd_j *= sqrt(temp)
+      //   here :  U_j = upd_j^2, rho_j = (upd_j/dir_j)^2: temp = 1 - a_kj^2/U_j; temp2 = temp rho_j;
+      //           temp2 <= sqrt(eps) ? (U_j = ||a[k+1:,j]||^2, rho_j = 1) : (U_j *= temp, rho_j *= temp)
+      // The same quantities in exact arithmetic, with no square root and one reciprocal per column;
+      // they only feed comparisons (pivot choice), never the factors.
       const double thr = 1.4901161193847656e-08;  // sqrt(DBL_EPSILON)
 #pragma unroll
       for (int j = K + 1; j < C; j++) {
-        if (upd[j] != 0.0) {
-          double t = fabs(a[j * R + K]) / upd[j];
-          t = (1.0 + t) * (1.0 - t);
-          t = t < 0.0 ? 0.0 : t;
-          const double q = upd[j] / dir[j];
-          const double t2 = t * (q * q);
-          if (t2 <= thr) {
-            double s = 0.0;
+        const double akj = a[j * R + K];
+        double temp = fmax(fma(-(akj * akj), fast_rcp(upd[j]), 1.0), 0.0);   // U_j = 0 -> NaN -> 0 -> recompute (= 0)
+        const double temp2 = temp * dir[j];
+        if (temp2 <= thr) {
+          double s = 0.0;
 #pragma unroll
-            for (int i = K + 1; i < R; i++) s = fma(a[j * R + i], a[j * R + i], s);
-            dir[j] = sqrt(s);
-            upd[j] = dir[j];
-          } else {
-            upd[j] *= sqrt(t);
-          }
+          for (int i = K + 1; i < R; i++) s = fma(a[j * R + i], a[j * R + i], s);
+          upd[j] = s;
+          dir[j] = 1.0;
+        } else {
+          upd[j] *= temp;
+          dir[j] *= temp;
         }
       }
     }
@@ -137,7 +140,8 @@ struct BlockQR {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < R; i++) s = fma(a[j * R + i], a[j * R + i], s);
-        upd[j] = dir[j] = sqrt(s);
+        upd[j] = s;      // squared norm U_j
+        dir[j] = 1.0;    // rho_j = (upd_j/dir_j)^2
       }
     }
     step<0>(a, tau, inv_diag, perm, rhs, upd, dir);

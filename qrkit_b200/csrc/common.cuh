@@ -112,6 +112,43 @@ __device__ __forceinline__ void store_group(double* s, const double (&src)[N]) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FP64 reciprocal / reciprocal square root without the slow-path branches of the IEEE sequences:
+// MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 good bits) + Newton steps -> ~1 ulp (not correctly rounded).
+// The per-block QR needs, per reflector, norm, 1/beta and 1/(x0 - beta); with the IEEE sqrt and two
+// IEEE divisions those three take ~40 instructions and three branches, here ~17 straight-line ones.
+// Zero / infinite inputs keep the seed's inf / 0 (as the IEEE operations would give).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  double e = fma(-x, r0, 1.0);
+  double r = fma(r0, e, r0);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return (r0 == 0.0 || fabs(r0) == __longlong_as_double(0x7ff0000000000000LL)) ? r0 : r;
+}
+// returns 1/sqrt(x); sqrt_out = sqrt(x).  x must be >= 0.
+__device__ __forceinline__ double fast_rsqrt(double x, double& sqrt_out) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double h = 0.5 * x;
+  double y = y0;
+#pragma unroll
+  for (int it = 0; it < 3; it++) {
+    const double t = y * y;
+    const double e = fma(-h, t, 0.5);
+    y = fma(y, e, y);
+  }
+  double s = x * y;
+  s = fma(fma(-s, s, x), 0.5 * y, s);     // one Heron correction of the square root
+  const bool special = (y0 == 0.0) || (y0 == __longlong_as_double(0x7ff0000000000000LL));
+  sqrt_out = special ? ((x == 0.0) ? 0.0 : x) : s;   // x = 0 -> 0, x = inf -> inf
+  return special ? y0 : y;
+}
+
 // splitmix64 counter-based generator shared with the test-suite (tests/helpers.py)
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
