@@ -155,6 +155,29 @@ QRK_API int qrk_apply_q(qrk_handle_t h, const double* B, int64_t ldb, double* Y,
 /* X = P * R^-1 * (Q^T B)[0:rank]; B: n_rows x nrhs (ldb), X: n_cols x nrhs (ldx). */
 QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace);
 
+/* ---- block angular: A = [J1 | J2] (BlockAngularSparseQR.h:79-281; BlockMatrix1x2.h:31-67) ----------------------
+ * A handle of kind QRK_BLOCK_ANGULAR describes the LEFT block J1 (block diagonal, desc as above) and
+ * border_cols = m2 columns of the dense RIGHT block J2.  The generic entry points then mean:
+ *   qrk_compute / qrk_factorize      leftSolver.compute(J1); J2' = Q1^T J2; TSQR of the residual rows of J2'
+ *                                    (replaces rightSolver.compute(Abot), :368, Right = ColPivHouseholderQR);
+ *                                    R = [R1, Atop P2; 0, R2] (:285-308), P_c = [P1; m1 + P2] (:498-503)
+ *   qrk_compute_solve / qrk_factorize_solve / qrk_solve   _solve_impl (:203-227); b: n, x: m1 + m2
+ *   qrk_matrix_r(_nnz), qrk_cols_permutation, qrk_rank (= rank1 + rank2, :510), qrk_rows, qrk_cols (= m1 + m2)
+ * qrk_apply_qt / qrk_apply_q / qrk_matrix_q / qrk_packed_factors keep referring to the LEFT factor Q1.
+ * Supported now: uniform left blocks of 2x1, 3x1, 4x2, 7x2 and 1 <= m2 <= 8 (else QRK_STATUS_UNSUPPORTED). */
+/* J2: n x m2 column-major with leading dimension ld (BlockMatrix1x2::rightBlock()).  Host: copied to the
+ * device on the handle's stream; device: borrowed until the next compute returns. */
+QRK_API int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace);
+/* Multi-GPU (one handle per GPU, each owning a contiguous range of diagonal blocks and the matching rows of
+ * J2 and b): with world_size > 1 the compute/solve calls stop after the per-GPU m2 x (m2+1) TSQR triangle;
+ * the caller all-gathers the triangles (NCCL) and every rank calls qrk_angular_merge, which runs the TSQR
+ * root redundantly and finishes the local part of the solution (x: m1_local + m2, the m2 shared
+ * parameters last). */
+QRK_API int qrk_angular_set_world(qrk_handle_t h, int32_t world_size);
+QRK_API int qrk_angular_triangle_size(qrk_handle_t h, int64_t* doubles);
+QRK_API int qrk_angular_local_triangle(qrk_handle_t h, double* tri, int memspace);
+QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int memspace);
+
 /* ---- measurement hooks ---------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 QRK_API int qrk_launch_count(qrk_handle_t h, int64_t* launches);

@@ -30,10 +30,6 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: qrkit_b200 has no CPU fallback and cannot be built without the CUDA toolkit")
 
 
-def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
-
-
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -43,19 +39,48 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+ANGULAR_M2 = range(1, 9)      # border widths instantiated for the block-angular kernels (angular_inst.cu)
+
+
+def translation_units():
+    """(object name, source, extra flags): capi.cu once, angular_inst.cu once per border width."""
+    tus = [("capi.o", os.path.join(CSRC, "capi.cu"), [])]
+    tus += [(f"angular_m{k}.o", os.path.join(CSRC, "angular_inst.cu"), [f"-DQRK_M2={k}"]) for k in ANGULAR_M2]
+    return tus
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into one shared library exporting the C ABI of include/qrkit_b200.h."""
+    """Compile csrc/*.cu (in parallel, one nvcc per translation unit) and link one shared library exporting
+    the C ABI of include/qrkit_b200.h."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *sources()]
+    obj_dir = os.path.join(_PKG, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+
+    def compile_one(tu):
+        name, src, extra = tu
+        obj = os.path.join(obj_dir, name)
+        cmd = [_nvcc(), *compile_flags, *extra, "-I", INCLUDE, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, translation_units()))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        for _, err in results:
+            print(err)
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC",
+            "-o", LIB_PATH, *[o for o, _ in results]]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -84,6 +84,9 @@ def lib():
             "qrk_apply_q": [vp, vp, i64, vp, i64, i32, C.c_int],
             "qrk_solve": [vp, vp, i64, vp, i64, i32, C.c_int],
             "qrk_launch_count": [vp, C.POINTER(i64)],
+            "qrk_set_border": [vp, vp, i64, C.c_int], "qrk_angular_set_world": [vp, i32],
+            "qrk_angular_triangle_size": [vp, C.POINTER(i64)], "qrk_angular_local_triangle": [vp, vp, C.c_int],
+            "qrk_angular_merge": [vp, vp, i32, C.c_int],
             "qrk_synth_fill": [vp, C.c_uint64, i64, i64, i32, i32, C.c_double, C.c_double, vp],
             "qrk_device_count": [C.POINTER(C.c_int)],
         }

@@ -1,0 +1,115 @@
+// angular_inst.cu — instantiations of the block-angular kernels for ONE border width (-DQRK_M2=k).
+#include "angular.cuh"
+#include "angular_dispatch.hpp"
+
+#ifndef QRK_M2
+#error "compile with -DQRK_M2=<border columns>"
+#endif
+
+namespace qrk {
+namespace {
+
+constexpr int M2 = QRK_M2;
+constexpr int TPB = 128;
+
+// left block shapes available to the block-angular path (r > c)
+#define QRK_ANGULAR_SHAPES(X) X(2, 1) X(3, 1) X(4, 2) X(7, 2)
+
+template <int R, int C>
+constexpr int minb() { return ((R * C + (R - C) * (M2 + 1) + Tri<M2>::N) <= 40) ? 4 : 2; }
+
+template <typename K>
+cudaError_t opt_in(K kernel, size_t smem) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int R, int C, bool PIV>
+cudaError_t factor_t(const AngularArgs& a, cudaStream_t s) {
+  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, minb<R, C>()>;
+  const size_t smem = AngularSmem<R, C, TPB>::template bytes<M2>();
+  cudaError_t e = opt_in(kernel, smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<a.grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
+  return cudaGetLastError();
+}
+
+template <int R, int C, bool PIV>
+cudaError_t max_grid_t(int* grid) {
+  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, minb<R, C>()>;
+  const size_t smem = AngularSmem<R, C, TPB>::template bytes<M2>();
+  cudaError_t e = opt_in(kernel, smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, smem);
+  if (e != cudaSuccess) return e;
+  *grid = sms * (per_sm > 0 ? per_sm : 1);
+  return cudaSuccess;
+}
+
+template <int R, int C>
+cudaError_t rhs_t(const AngularArgs& a, cudaStream_t s) {
+  auto kernel = angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>;
+  const size_t smem = ((size_t)TPB * (Group<R * C>::stride + Group<C>::stride) + (TPB / 32) * Tri<M2>::N) * 8;
+  cudaError_t e = opt_in(kernel, smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<a.grid, TPB, smem, s>>>(a.packed, a.tau, a.b, a.y1, a.abot, a.partials, a.nb);
+  return cudaGetLastError();
+}
+
+template <int R, int C>
+cudaError_t backsolve_t(const AngularArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)TPB * Group<R * C>::stride * 8;
+  const unsigned grid = (unsigned)((a.nb + TPB - 1) / TPB);
+  if (a.piv) angular_backsolve_kernel<R, C, M2, true, TPB><<<grid, TPB, smem, s>>>(a.packed, a.perm, a.atop, a.y1, a.root, a.x, a.nb);
+  else angular_backsolve_kernel<R, C, M2, false, TPB><<<grid, TPB, smem, s>>>(a.packed, a.perm, a.atop, a.y1, a.root, a.x, a.nb);
+  return cudaGetLastError();
+}
+
+bool shape_ok(int r, int c) {
+#define X(R_, C_) if (r == R_ && c == C_) return true;
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return false;
+}
+
+cudaError_t max_grid(int r, int c, bool piv, int* grid) {
+#define X(R_, C_) if (r == R_ && c == C_) return piv ? max_grid_t<R_, C_, true>(grid) : max_grid_t<R_, C_, false>(grid);
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+cudaError_t factor(const AngularArgs& a, cudaStream_t s) {
+#define X(R_, C_) if (a.r == R_ && a.c == C_) return a.piv ? factor_t<R_, C_, true>(a, s) : factor_t<R_, C_, false>(a, s);
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+cudaError_t rhs(const AngularArgs& a, cudaStream_t s) {
+#define X(R_, C_) if (a.r == R_ && a.c == C_) return rhs_t<R_, C_>(a, s);
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+cudaError_t backsolve(const AngularArgs& a, cudaStream_t s) {
+#define X(R_, C_) if (a.r == R_ && a.c == C_) return backsolve_t<R_, C_>(a, s);
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+cudaError_t root(const AngularArgs& a, cudaStream_t s) {
+  angular_root_kernel<M2, 256><<<1, 256, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only);
+  return cudaGetLastError();
+}
+
+const AngularVTable kTable = {M2, Tri<M2>::N, shape_ok, max_grid, factor, rhs, root, backsolve};
+
+}  // namespace
+
+#define QRK_CAT2(a, b) a##b
+#define QRK_CAT(a, b) QRK_CAT2(a, b)
+const AngularVTable* QRK_CAT(angular_vtable_m, QRK_M2)() { return &kTable; }
+
+}  // namespace qrk

@@ -15,6 +15,25 @@
 
 using namespace qrk;
 
+namespace qrk {
+#define QRK_DECL_VT(k) const AngularVTable* angular_vtable_m##k();
+QRK_DECL_VT(1) QRK_DECL_VT(2) QRK_DECL_VT(3) QRK_DECL_VT(4) QRK_DECL_VT(5) QRK_DECL_VT(6) QRK_DECL_VT(7) QRK_DECL_VT(8)
+#undef QRK_DECL_VT
+const AngularVTable* angular_vtable(int m2) {
+  switch (m2) {
+    case 1: return angular_vtable_m1();
+    case 2: return angular_vtable_m2();
+    case 3: return angular_vtable_m3();
+    case 4: return angular_vtable_m4();
+    case 5: return angular_vtable_m5();
+    case 6: return angular_vtable_m6();
+    case 7: return angular_vtable_m7();
+    case 8: return angular_vtable_m8();
+    default: return nullptr;
+  }
+}
+}  // namespace qrk
+
 namespace {
 
 #define QRK_TRY_CUDA(h, expr)                                                                   \
@@ -177,6 +196,7 @@ void free_dev(qrk_solver* h) {
   if (h->own_values) F(h->d_values);
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
+  F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
 }
@@ -227,11 +247,12 @@ int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X,
   const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
   const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
   const bool in_full_layout = (op == OP_APPLY_Q) && full_q;
+  const long long q_nstart = h->avt ? h->sum_cols : h->n_cols;   // N_start = mat.cols() of the block-diagonal matrix (:430)
   const bool vec_ok = aligned16(d_B) && aligned16(d_X) && (ldb % 2 == 0) && (ldx % 2 == 0) &&
-                      (!(in_full_layout || (op == OP_APPLY_QT && full_q)) || (h->n_cols % 2 == 0));
+                      (!(in_full_layout || (op == OP_APPLY_QT && full_q)) || (q_nstart % 2 == 0));
   if (h->small_path && vec_ok) {
     QRK_TRY_CUDA(h, launch_small_op_dyn(h->ur, h->uc, op, piv, h->d_values, h->d_tau, h->d_perm, d_B, ldb, d_X, ldx, nrhs,
-                                        h->nb, h->n_cols, full_q, h->stream));
+                                        h->nb, q_nstart, full_q, h->stream));
   } else {
     constexpr int WPC = 4;
     const long long items = h->nb * (long long)nrhs;
@@ -240,7 +261,7 @@ int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X,
     auto kernel = bd_generic_op_kernel<WPC>;
     if (smem > 48 * 1024) QRK_TRY_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<(unsigned)grid, 32 * WPC, smem, h->stream>>>(block_index(h), h->nb, h->d_values, h->d_tau,
-                                                          piv ? h->d_perm : nullptr, d_B, ldb, d_X, ldx, nrhs, h->n_cols, op,
+                                                          piv ? h->d_perm : nullptr, d_B, ldb, d_X, ldx, nrhs, q_nstart, op,
                                                           full_q, h->max_r);
     QRK_TRY_CUDA(h, cudaGetLastError());
   }
@@ -275,6 +296,105 @@ __global__ void synth_fill_kernel(double* out, uint64_t seed, long long block0, 
 }
 
 
+
+// ---- block angular ---------------------------------------------------------------------------------
+__global__ void angular_finish_perm_kernel(int* perm_tail, const int* root_i, int m1, int m2) {
+  const int j = threadIdx.x;
+  if (j < m2) perm_tail[j] = m1 + root_i[j];     // m_outputPerm_c(m1 + j) = m1 + P2(j) (BlockAngularSparseQR.h:501-503)
+}
+
+// border columns of R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:296-305)
+__global__ void export_angular_border_kernel(const double* __restrict__ atop, const double* __restrict__ root,
+                                             const int* __restrict__ root_i, long long m1, int m2, long long base,
+                                             int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals) {
+  const long long per_col_max = m1 + m2;
+  const long long total = (long long)m2 * per_col_max;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / per_col_max);
+    const long long r = i - (long long)c * per_col_max;
+    const long long start = base + (long long)c * m1 + (long long)c * (c + 1) / 2;
+    if (r == 0) outer[m1 + c] = (int)start;
+    if (r < m1) {
+      inner[start + r] = (int)r;
+      vals[start + r] = atop[(long long)root_i[c] * m1 + r];
+    } else if (r - m1 <= c) {
+      inner[start + r] = (int)r;
+      vals[start + r] = root[(long long)c * m2 + (r - m1)];
+    }
+    if (i == 0) outer[m1 + m2] = (int)(base + (long long)m2 * m1 + (long long)m2 * (m2 + 1) / 2);
+  }
+}
+
+AngularArgs angular_args(qrk_solver* h) {
+  AngularArgs a;
+  a.r = h->ur; a.c = h->uc; a.piv = h->desc.pivoting == QRK_PIVOT_COLPIV; a.nb = h->nb;
+  a.packed = h->d_values; a.tau = h->d_tau; a.perm = h->d_perm;
+  a.J2 = h->d_border; a.ldj = h->ld_border;
+  a.atop = h->d_atop; a.y1 = h->d_y1; a.abot = nullptr;
+  a.partials = h->d_partials;
+  const long long ntiles = (h->nb + 127) / 128;
+  a.grid = (int)std::max<long long>(1, std::min<long long>(h->a_grid, ntiles));
+  a.tris = h->d_partials; a.tri_count = a.grid;
+  a.out_tri = h->d_tri; a.root = h->d_root; a.root_i = h->d_root_i;
+  return a;
+}
+
+// TSQR root (+ back substitution when a right-hand side is present).  world > 1: stop at the per-GPU triangle.
+int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* d_x, int keep_rhs_only) {
+  if (h->world > 1) {
+    a.root_mode = 0;
+    QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
+    h->launches++;
+    h->root_done = false;
+    h->pending = true;
+    h->pending_keep_rhs_only = keep_rhs_only;
+    h->pending_x = have_rhs ? d_x : nullptr;
+    return QRK_STATUS_OK;
+  }
+  a.root_mode = 1;
+  a.keep_rhs_only = keep_rhs_only;
+  QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
+  h->launches++;
+  if (!keep_rhs_only) {
+    angular_finish_perm_kernel<<<1, 32, 0, h->stream>>>(h->d_perm + h->sum_cols, h->d_root_i, (int)h->sum_cols, h->m2);
+    h->launches++;
+  }
+  h->root_done = true;
+  if (have_rhs) {
+    a.x = d_x;
+    QRK_TRY_CUDA(h, h->avt->backsolve(a, h->stream));
+    h->launches++;
+  }
+  return QRK_STATUS_OK;
+}
+
+// compute (+ fused solve when d_b != nullptr).  keep_abot: store the residual panel for later solve(b) calls.
+int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x, bool keep_abot) {
+  QRK_REQUIRE(h, h->d_border, "no border set: call qrk_set_border first (BlockMatrix1x2 right block)");
+  AngularArgs a = angular_args(h);
+  a.A_in = A_in;
+  a.b = d_b;
+  if (keep_abot) {
+    if (!h->d_abot) QRK_TRY_CUDA(h, cudaMalloc(&h->d_abot, std::max<long long>(1, (h->n_rows - h->sum_cols) * (long long)(h->m2 + 1)) * sizeof(double)));
+    a.abot = h->d_abot;
+  }
+  QRK_TRY_CUDA(h, h->avt->factor(a, h->stream));
+  h->launches++;
+  h->have_abot = keep_abot;
+  return angular_root_and_back(h, a, d_b != nullptr, d_x, 0);
+}
+
+// solve(b) on a stored factorisation: Q1^T b, TSQR redone over [Abot | b_bot], root, back substitution
+int angular_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
+  QRK_REQUIRE(h, h->have_abot, "solve() after a fused compute_solve(): the residual panel was not kept; call compute() first");
+  AngularArgs a = angular_args(h);
+  a.b = d_b;
+  a.abot = h->d_abot;
+  QRK_TRY_CUDA(h, h->avt->rhs(a, h->stream));
+  h->launches++;
+  return angular_root_and_back(h, a, true, d_x, 1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -308,7 +428,8 @@ int qrk_device_count(int* count) {
 int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   if (!desc || !out) return QRK_STATUS_INVALID_ARGUMENT;
   *out = nullptr;
-  if (desc->kind != QRK_BLOCK_DIAGONAL) return QRK_STATUS_UNSUPPORTED;
+  if (desc->kind != QRK_BLOCK_DIAGONAL && desc->kind != QRK_BLOCK_ANGULAR) return QRK_STATUS_UNSUPPORTED;
+  const bool angular = desc->kind == QRK_BLOCK_ANGULAR;
   if (desc->num_blocks < 0) return QRK_STATUS_INVALID_ARGUMENT;
   const bool uniform = desc->block_rows > 0 && desc->block_cols > 0;
   if (!uniform && desc->num_blocks > 0 && (!desc->rows || !desc->cols)) return QRK_STATUS_INVALID_ARGUMENT;
@@ -352,6 +473,14 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   }
   h->n_rows = desc->n_rows > 0 ? desc->n_rows : h->sum_rows;
   h->n_cols = desc->n_cols > 0 ? desc->n_cols : h->sum_cols;
+  if (angular) {
+    // left block: uniform small blocks covering all rows, FullQ; border: 1..8 dense columns
+    h->m2 = desc->border_cols;
+    h->avt = angular_vtable(h->m2);
+    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc) || desc->q_format != QRK_FULL_Q) return fail(QRK_STATUS_UNSUPPORTED);
+    if (h->n_rows != h->sum_rows || (desc->n_cols > 0 && desc->n_cols != h->sum_cols + h->m2)) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    h->n_cols = h->sum_cols + h->m2;     // cols() = m1 + m2
+  }
   if (h->n_rows < h->sum_rows || h->n_cols < h->sum_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
   if (h->n_rows > INT32_MAX || h->n_cols > INT32_MAX) return fail(QRK_STATUS_UNSUPPORTED);  // StorageIndex = int
   if (desc->q_format != QRK_FULL_Q && desc->q_format != QRK_BLOCK_DIAGONAL_Q) h->info = QRK_INFO_INVALID_INPUT;  // :501-505
@@ -404,6 +533,20 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   cudaMemsetAsync(h->d_tau, 0, std::max<long long>(h->n_cols, 1) * sizeof(double), h->stream);
   iota_kernel<<<256, 256, 0, h->stream>>>(h->d_perm, h->n_cols);   // m_outputPerm_c.setIdentity (:417)
   h->launches++;
+  if (angular) {
+    const bool piv = desc->pivoting == QRK_PIVOT_COLPIV;
+    if (h->avt->max_grid(h->ur, h->uc, piv, &h->a_grid) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);
+    const size_t tri = (size_t)h->avt->tri_doubles;
+    if (cudaMalloc(&h->d_partials, std::max<size_t>(1, (size_t)h->a_grid * tri) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_tri, tri * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_root, (size_t)(h->m2 * h->m2 + 3 * h->m2) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_root_i, (size_t)(h->m2 + 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_atop, std::max<long long>(1, h->sum_cols * (long long)h->m2) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_y1, std::max<long long>(1, h->sum_cols) * sizeof(double)) != cudaSuccess)
+      return fail(QRK_STATUS_ALLOC_FAILED);
+    cudaMemsetAsync(h->d_root, 0, (size_t)(h->m2 * h->m2 + 3 * h->m2) * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_root_i, 0, (size_t)(h->m2 + 1) * sizeof(int), h->stream);
+  }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);  // host vectors may go away
   *out = h;
   return QRK_STATUS_OK;
@@ -483,7 +626,7 @@ int qrk_factorize(qrk_handle_t h) {
   if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;   // reported through info(), as the reference
   DeviceGuard g(h->device);
-  int st = run_factor(h, h->d_values, nullptr, nullptr);
+  int st = h->avt ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr);
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -501,9 +644,9 @@ static int compute_from_device(qrk_solver* h, const double* values, const double
   h->factorized = false;
   if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
-  if (d_x && h->n_cols > h->sum_cols)
+  if (d_x && h->n_cols > h->sum_cols && !h->avt)
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  st = run_factor(h, values, d_b, d_x);
+  st = h->avt ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x);
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -538,11 +681,16 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   } else {
     QRK_REQUIRE(h, aligned16(b) && aligned16(x), "device b / x must be 16-byte aligned");
   }
-  if (h->n_cols > h->sum_cols)
+  if (h->n_cols > h->sum_cols && !h->avt)
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  int st = run_factor(h, h->d_values, d_b, d_x);
+  int st = h->avt ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x);
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
+  if (h->pending) {            // multi-GPU block angular: x is produced by qrk_angular_merge
+    h->pending_space = memspace;
+    if (memspace == QRK_HOST) h->pending_x = x;
+    return QRK_STATUS_OK;
+  }
   if (memspace == QRK_HOST) {
     QRK_TRY_CUDA(h, cudaMemcpyAsync(x, h->d_x, h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -568,13 +716,21 @@ int qrk_rank(qrk_handle_t h, int64_t* rank) {
   if (!h || !rank) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
   *rank = h->sum_cols;   // rank += blockSolver.cols() (BlockDiagonalSparseQR.h:440)
+  if (h->avt) {          // + rightSolver.rank() (BlockAngularSparseQR.h:510)
+    if (!h->root_done) return QRK_STATUS_NOT_FACTORIZED;
+    DeviceGuard g(h->device);
+    int r2 = 0;
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(&r2, h->d_root_i + h->m2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+    *rank += r2;
+  }
   return QRK_STATUS_OK;
 }
 int qrk_info(qrk_handle_t h, int32_t* info) { if (!h || !info) return QRK_STATUS_INVALID_ARGUMENT; *info = h->info; return QRK_STATUS_OK; }
 
 int qrk_cols_permutation(qrk_handle_t h, int32_t* indices, int memspace) {
   if (!h || !indices) return QRK_STATUS_INVALID_ARGUMENT;
-  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  if (!h->factorized || (h->avt && !h->root_done)) return QRK_STATUS_NOT_FACTORIZED;
   DeviceGuard g(h->device);
   QRK_TRY_CUDA(h, cudaMemcpyAsync(indices, h->d_perm, h->n_cols * sizeof(int),
                                   memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
@@ -613,6 +769,7 @@ int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz) {
   long long n = 0;
   if (h->uniform) n = h->nb * ((long long)h->uc * (h->uc + 1) / 2);
   else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
+  if (h->avt) n += h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2;   // border columns (makeR :296-305)
   *nnz = n;
   return QRK_STATUS_OK;
 }
@@ -630,6 +787,7 @@ int qrk_matrix_q_nnz(qrk_handle_t h, int64_t* nnz) {
 static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* inner, double* values, int memspace) {
   if (!h || !outer || !inner || !values) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  if (h->avt && !want_q && !h->root_done) return QRK_STATUS_NOT_FACTORIZED;
   int64_t nnz = 0;
   if (want_q) qrk_matrix_q_nnz(h, &nnz); else qrk_matrix_r_nnz(h, &nnz);
   QRK_REQUIRE(h, nnz <= INT32_MAX, "matrix has more than 2^31-1 stored entries (StorageIndex = int)");
@@ -663,9 +821,16 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
   const BlockIndex bi = block_index(h);
   const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
   cudaError_t e;
-  if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->n_cols, h->sum_rows,
+  if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->avt ? h->sum_cols : h->n_cols, h->sum_rows,
                                   nnz - (h->n_rows - h->sum_rows), full_q, h->max_r, d_outer, d_inner, d_vals, h->stream);
-  else e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->n_cols, h->sum_cols, nnz, full_q, d_outer, d_inner, d_vals, h->stream);
+  else if (h->avt) {
+    const long long nnz_r1 = nnz - (h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2);
+    e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->sum_cols, h->sum_cols, nnz_r1, 1, d_outer, d_inner, d_vals, h->stream);
+    export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->d_atop, h->d_root, h->d_root_i, h->sum_cols, h->m2, nnz_r1, d_outer,
+                                                             d_inner, d_vals);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    h->launches++;
+  } else e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->n_cols, h->sum_cols, nnz, full_q, d_outer, d_inner, d_vals, h->stream);
   h->launches += 2;
   int st = QRK_STATUS_OK;
   if (e != cudaSuccess) { h->err = std::string("export kernel: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
@@ -711,14 +876,25 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     d_B = h->d_b; d_X = h->d_x;
   }
   if (op == OP_SOLVE) {
-    if (h->n_cols > h->sum_cols)   // y.bottomRows(...).setZero() (:272)
+    if (h->n_cols > h->sum_cols && !h->avt)   // y.bottomRows(...).setZero() (:272)
       QRK_TRY_CUDA(h, cudaMemset2DAsync(d_X + h->sum_cols, dldx * sizeof(double), 0, (h->n_cols - h->sum_cols) * sizeof(double),
                                         nrhs, h->stream));
   } else if (h->n_rows > h->sum_rows) {
     copy_tail_kernel<<<64, 256, 0, h->stream>>>(d_B, dldb, d_X, dldx, nrhs, h->sum_rows, h->n_rows);
     h->launches++;
   }
-  int st = run_op(h, op, d_B, dldb, d_X, dldx, nrhs);
+  int st = QRK_STATUS_OK;
+  if (h->avt && op == OP_SOLVE) {
+    QRK_REQUIRE(h, h->world == 1 || nrhs == 1, "multi-GPU block-angular solve takes one right-hand side per call");
+    for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) st = angular_solve_stored(h, d_B + j * dldb, d_X + j * dldx);
+    if (st == QRK_STATUS_OK && h->pending) {
+      h->pending_space = memspace;
+      if (memspace == QRK_HOST) h->pending_x = X;
+      return QRK_STATUS_OK;
+    }
+  } else {
+    st = run_op(h, op, d_B, dldb, d_X, dldx, nrhs);
+  }
   if (st != QRK_STATUS_OK) return st;
   if (memspace == QRK_HOST) {
     QRK_TRY_CUDA(h, cudaMemcpy2DAsync(X, ldx * sizeof(double), h->d_x, dldx * sizeof(double), out_rows * sizeof(double), nrhs,
@@ -737,6 +913,89 @@ int qrk_apply_q(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t
 }
 int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace) {
   return op_entry(h, OP_SOLVE, B, ldb, X, ldx, nrhs, memspace);
+}
+
+// ---- block angular entry points --------------------------------------------------------------------
+int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace) {
+  if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, h->avt, "qrk_set_border: the handle is not of kind QRK_BLOCK_ANGULAR");
+  QRK_REQUIRE(h, J2 && ld >= h->n_rows, "border is null or its leading dimension is smaller than the number of rows");
+  DeviceGuard g(h->device);
+  if (memspace == QRK_DEVICE) {
+    QRK_REQUIRE(h, (reinterpret_cast<uintptr_t>(J2) & 7) == 0, "border must be 8-byte aligned");
+    h->d_border = J2;
+    h->ld_border = ld;
+  } else {
+    const size_t need = (size_t)h->n_rows * h->m2;
+    int st = ensure_buffer(h, h->d_border_own, h->cap_border, need);
+    if (st != QRK_STATUS_OK) return st;
+    QRK_TRY_CUDA(h, cudaMemcpy2DAsync(h->d_border_own, h->n_rows * sizeof(double), J2, ld * sizeof(double),
+                                      h->n_rows * sizeof(double), h->m2, cudaMemcpyHostToDevice, h->stream));
+    h->d_border = h->d_border_own;
+    h->ld_border = h->n_rows;
+  }
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_set_world(qrk_handle_t h, int32_t world_size) {
+  if (!h || !h->avt || world_size < 1) return QRK_STATUS_INVALID_ARGUMENT;
+  h->world = world_size;
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_triangle_size(qrk_handle_t h, int64_t* doubles) {
+  if (!h || !h->avt || !doubles) return QRK_STATUS_INVALID_ARGUMENT;
+  *doubles = h->avt->tri_doubles;
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_local_triangle(qrk_handle_t h, double* tri, int memspace) {
+  if (!h || !h->avt || !tri) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  QRK_REQUIRE(h, h->world > 1, "the per-GPU triangle is only kept when qrk_angular_set_world(world > 1) was called");
+  DeviceGuard g(h->device);
+  QRK_TRY_CUDA(h, cudaMemcpyAsync(tri, h->d_tri, h->avt->tri_doubles * sizeof(double),
+                                  memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (memspace == QRK_HOST) QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int memspace) {
+  if (!h || !h->avt || !tris || count < 1) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!h->factorized || !h->pending) return QRK_STATUS_NOT_FACTORIZED;
+  DeviceGuard g(h->device);
+  const size_t n = (size_t)count * h->avt->tri_doubles;
+  const double* d_tris = tris;
+  double* tmp = nullptr;
+  if (memspace == QRK_HOST) {
+    QRK_TRY_CUDA(h, cudaMalloc(&tmp, n * sizeof(double)));
+    cudaMemcpyAsync(tmp, tris, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    d_tris = tmp;
+  }
+  AngularArgs a = angular_args(h);
+  a.tris = d_tris; a.tri_count = count; a.root_mode = 1; a.keep_rhs_only = h->pending_keep_rhs_only;
+  int st = QRK_STATUS_OK;
+  cudaError_t e = h->avt->root(a, h->stream);
+  h->launches++;
+  if (e == cudaSuccess && !a.keep_rhs_only) {
+    angular_finish_perm_kernel<<<1, 32, 0, h->stream>>>(h->d_perm + h->sum_cols, h->d_root_i, (int)h->sum_cols, h->m2);
+    h->launches++;
+  }
+  h->root_done = true;
+  if (e == cudaSuccess && h->pending_x) {
+    double* d_x = (h->pending_space == QRK_HOST) ? h->d_x : h->pending_x;
+    a.x = d_x;
+    e = h->avt->backsolve(a, h->stream);
+    h->launches++;
+    if (e == cudaSuccess && h->pending_space == QRK_HOST)
+      e = cudaMemcpyAsync(h->pending_x, h->d_x, h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess && (memspace == QRK_HOST || h->pending_space == QRK_HOST)) e = cudaStreamSynchronize(h->stream);
+  if (tmp) { cudaStreamSynchronize(h->stream); cudaFree(tmp); }
+  if (e != cudaSuccess) { h->err = std::string("qrk_angular_merge: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
+  h->pending = false;
+  h->pending_x = nullptr;
+  return st;
 }
 
 int qrk_launch_count(qrk_handle_t h, int64_t* launches) {

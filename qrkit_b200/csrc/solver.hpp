@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/qrkit_b200.h"
+#include "angular_dispatch.hpp"
 
 namespace qrk {
 
@@ -47,6 +48,24 @@ struct qrk_solver {
   std::vector<int> h_rowperm;         // rowsPermutation().indices()
   bool analyzed = false, has_blocks = false, factorized = false;
   int info = QRK_INFO_SUCCESS;
+
+  // ---- block angular (kind == QRK_BLOCK_ANGULAR): dense border of m2 columns ----
+  int m2 = 0;
+  const qrk::AngularVTable* avt = nullptr;
+  int a_grid = 0;                      // CTAs of the factor kernel = partial triangles
+  int world = 1;                       // > 1: compute stops at the per-GPU triangle, qrk_angular_merge finishes
+  const double* d_border = nullptr;    // n x m2 column-major (borrowed device pointer or d_border_own)
+  long long ld_border = 0;
+  double* d_border_own = nullptr;
+  size_t cap_border = 0;
+  double *d_atop = nullptr, *d_y1 = nullptr, *d_abot = nullptr, *d_partials = nullptr, *d_tri = nullptr, *d_root = nullptr;
+  int* d_root_i = nullptr;
+  bool have_abot = false;              // the residual panel of the last compute() is resident (solve(b) possible)
+  bool root_done = false;
+  bool pending = false;                // a right-hand side waits for qrk_angular_merge
+  double* pending_x = nullptr;
+  int pending_space = 0;
+  int pending_keep_rhs_only = 0;
 
   // ---- staging buffers for host-memspace calls ----
   double *d_b = nullptr, *d_x = nullptr;

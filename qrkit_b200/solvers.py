@@ -237,3 +237,95 @@ class BlockDiagonalSparseQR:
         v = C.c_int64()
         check(lib().qrk_launch_count(self._h, C.byref(v)), self._h)
         return v.value
+
+
+class BlockMatrix1x2:
+    """BlockMatrix1x2<Left, Right> (BlockMatrix1x2.h:31-67): references to a left block-diagonal matrix and a
+    dense right block (n x m2, column-major) with the same number of rows."""
+
+    def __init__(self, left: SparseBlockDiagonal, right):
+        self.left = left
+        self.right = np.asfortranarray(right, dtype=np.float64) if isinstance(right, np.ndarray) else right
+        if isinstance(right, np.ndarray):
+            assert self.right.shape[0] == left.rows(), "blocks must have the same number of rows (BlockMatrix1x2.h:37)"
+
+    def leftBlock(self):
+        return self.left
+
+    def rightBlock(self):
+        return self.right
+
+    def rows(self):
+        return self.left.rows()
+
+    def cols(self):
+        return self.left.cols() + self.right.shape[1]
+
+
+class BlockAngularSparseQR(BlockDiagonalSparseQR):
+    """BlockAngularSparseQR<BlockDiagonalSparseQR<...>, ColPivHouseholderQR<MatrixXd>> (BlockAngularSparseQR.h:79-281):
+    left block diagonal, dense border factored by a TSQR tree + Eigen's ColPiv rule at the root."""
+
+    def __init__(self, mat: BlockMatrix1x2 | None = None, *, pivoting=QRK_PIVOT_COLPIV, device=0, stream=None, world=1):
+        self._world = world
+        super().__init__(None, pivoting=pivoting, q_format=QRK_FULL_Q, device=device, stream=stream)
+        if mat is not None:
+            self.compute(mat)
+
+    def _ensure_handle_angular(self, mat: BlockMatrix1x2):
+        left, m2 = mat.left, mat.right.shape[1]
+        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2)
+        if self._h and key == self._shape_key:
+            return
+        self.close()
+        d = QrkDesc()
+        d.kind, d.device, d.num_blocks = capi.QRK_BLOCK_ANGULAR, self._device, left.num_blocks
+        d.block_rows, d.block_cols = left.block_rows, left.block_cols
+        d.pivoting, d.q_format, d.border_cols = self._pivoting, QRK_FULL_Q, m2
+        h = C.c_void_p()
+        check(lib().qrk_create(C.byref(d), C.byref(h)))
+        self._h, self._shape_key = h, key
+        if self._stream is not None:
+            check(lib().qrk_set_stream(self._h, C.c_void_p(int(self._stream))), self._h)
+        if self._world > 1:
+            check(lib().qrk_angular_set_world(self._h, self._world), self._h)
+
+    def compute(self, mat: BlockMatrix1x2):
+        self._ensure_handle_angular(mat)
+        self._mat = mat
+        check(lib().qrk_set_border(self._h, _ptr(mat.right), mat.right.shape[0], QRK_HOST), self._h)
+        check(lib().qrk_compute(self._h, _ptr(mat.left.values), QRK_HOST), self._h)
+        return self
+
+    def compute_solve(self, mat: BlockMatrix1x2, b):
+        self._ensure_handle_angular(mat)
+        self._mat = mat
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self._x = np.empty(mat.cols())
+        check(lib().qrk_set_border(self._h, _ptr(mat.right), mat.right.shape[0], QRK_HOST), self._h)
+        check(lib().qrk_compute_solve(self._h, _ptr(mat.left.values), _ptr(b), _ptr(self._x), QRK_HOST), self._h)
+        return self._x          # world > 1: filled by merge()
+
+    def solve(self, B):
+        if self._world > 1:
+            B = np.ascontiguousarray(B, dtype=np.float64)
+            self._x = np.empty(self.cols())
+            check(lib().qrk_solve(self._h, _ptr(B), len(B), _ptr(self._x), self.cols(), 1, QRK_HOST), self._h)
+            return self._x
+        return super().solve(B)
+
+    # ---- multi-GPU TSQR exchange ------------------------------------------------------------------
+    def triangle_size(self):
+        v = C.c_int64()
+        check(lib().qrk_angular_triangle_size(self._h, C.byref(v)), self._h)
+        return v.value
+
+    def local_triangle(self):
+        t = np.empty(self.triangle_size())
+        check(lib().qrk_angular_local_triangle(self._h, _ptr(t), QRK_HOST), self._h)
+        return t
+
+    def merge(self, triangles):
+        t = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1)
+        check(lib().qrk_angular_merge(self._h, _ptr(t), len(t) // self.triangle_size(), QRK_HOST), self._h)
+        return getattr(self, "_x", None)

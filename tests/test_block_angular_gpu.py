@@ -1,0 +1,148 @@
+"""GPU parity tests of the block-angular path (left block diagonal + dense border, TSQR merge) against the CPU oracle's
+restatement of BlockAngularSparseQR<BlockDiagonalSparseQR, ColPivHouseholderQR<MatrixXd>> (BlockAngularSparseQR.h:459-514).
+Inputs: the ellipse-fit Jacobian of bench/bench_sparse_qr_extra.cpp:79-114 (BASELINE configs 1 and 3) and random blocks
+with a dense random border (the shape of test/test-qrkit.cpp:135-165)."""
+import numpy as np
+import pytest
+
+from helpers import SEED_A, blocks_to_dense, dense_border, ellipse_problem, rel, uniform_blocks, vector
+
+pytestmark = pytest.mark.gpu
+TOL_R, TOL_X = 1e-12, 1e-10
+
+
+@pytest.fixture(scope="module")
+def qk():
+    import qrkit_b200 as q
+    if q.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests must run on the B200 box (there is no CPU fallback)")
+    return q
+
+
+def _sign_fix(R2, R2ref):
+    s = np.sign(np.diag(R2)) * np.sign(np.diag(R2ref))
+    s[s == 0] = 1.0
+    return R2 * s[:, None]
+
+
+def _check(qk, oracle, vals, r, c, J2, b, piv, tol_x=TOL_X):
+    nb = len(vals) // (r * c)
+    m1, m2 = nb * c, J2.shape[1]
+    left = qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c)
+    mat = qk.BlockMatrix1x2(left, J2)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=bool(piv), right_kind=0)
+    x_ref = ref.solve(b)
+    # fused one-pass compute + solve
+    s1 = qk.BlockAngularSparseQR(pivoting=piv)
+    x1 = s1.compute_solve(mat, b)
+    assert rel(x1, x_ref) <= tol_x
+    # compute(), then accessors and solve()
+    s2 = qk.BlockAngularSparseQR(mat, pivoting=piv)
+    assert s2.rows() == nb * r and s2.cols() == m1 + m2
+    assert s2.rank() == ref.rank and s2.info() == qk.QRK_INFO_SUCCESS
+    P = s2.colsPermutation()
+    assert np.array_equal(P, ref.colsPermutation()), "P_c = [P1; m1 + P2] must be bit-exact"
+    R, Rr = s2.matrixR(), ref.matrixR()
+    assert np.array_equal(R.outer, Rr.outer) and np.array_equal(R.inner, Rr.inner)
+    Rd, Rrd = R.toarray(), Rr.toarray()
+    assert rel(Rd[:m1, :], Rrd[:m1, :]) <= TOL_R                     # [R1, Atop*P2]: determined by Q1, sign included
+    R2 = _sign_fix(Rd[m1:m1 + m2, m1:], Rrd[m1:m1 + m2, m1:])         # R2 equal up to per-row sign
+    assert rel(R2, Rrd[m1:m1 + m2, m1:]) <= TOL_R * 10
+    A = np.hstack([blocks_to_dense(vals, np.full(nb, r), np.full(nb, c)), J2])
+    AP = A[:, P]
+    Rt = Rd[:m1 + m2, :]
+    assert rel(Rt.T @ Rt, AP.T @ AP) <= 1e-12                         # (AP)^T AP = R^T R  <=>  AP = QR with Q orthonormal
+    assert rel(s2.solve(b), x_ref) <= tol_x
+    x_true = vector(m1 + m2, seed=77)
+    assert rel(s2.solve(A @ x_true), x_true) <= tol_x
+    # Q1 accessors still refer to the left factor
+    y = s2.applyQt(b)
+    yref = ref.apply_qt(b)
+    assert rel(y[:m1], yref[:m1]) <= TOL_R
+
+
+@pytest.mark.parametrize("n", [500, 2000, 10000])
+@pytest.mark.parametrize("piv", [0, 1])
+def test_ellipse_jacobian_vs_oracle(qk, oracle, n, piv):
+    """BASELINE config 1: ellipse Jacobian, N blocks of 2x1 + 2N x 5 border, rhs = residual at the initial iterate."""
+    J1, J2, rhs = ellipse_problem(n)
+    _check(qk, oracle, J1, 2, 1, J2, rhs, piv, tol_x=1e-9 if n >= 10000 else TOL_X)
+
+
+@pytest.mark.parametrize("r,c", [(2, 1), (3, 1), (4, 2), (7, 2)])
+@pytest.mark.parametrize("m2", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_border_vs_oracle(qk, oracle, r, c, m2):
+    nb = 333
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    b = vector(nb * r, seed=5)
+    _check(qk, oracle, vals, r, c, J2, b, piv=1)
+
+
+def test_multi_gpu_exchange_on_one_device(qk, oracle):
+    """The N-GPU algorithm with the ranks emulated as handles on one device: contiguous block ranges per rank,
+    per-rank TSQR triangles 'all-gathered' on the host, root merged redundantly by every rank."""
+    n, world = 4000, 4
+    J1, J2, rhs = ellipse_problem(n)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(n, 2), bc=np.full(n, 1), values=J1, left_colpiv=True, right_kind=0)
+    x_ref = ref.solve(rhs)
+    per = n // world
+    solvers, tris = [], []
+    for g in range(world):
+        sl = slice(g * per, (g + 1) * per)
+        rows = slice(2 * g * per, 2 * (g + 1) * per)
+        mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(J1[2 * g * per:2 * (g + 1) * per].copy(), block_rows=2, block_cols=1),
+                                J2[rows, :].copy())
+        s = qk.BlockAngularSparseQR(world=world)
+        s.compute_solve(mat, rhs[rows].copy())
+        tris.append(s.local_triangle())
+        solvers.append(s)
+    gathered = np.concatenate(tris)
+    x2s = []
+    for g, s in enumerate(solvers):
+        xg = s.merge(gathered)
+        assert rel(xg[:per], x_ref[g * per:(g + 1) * per]) <= 1e-9
+        assert rel(xg[per:], x_ref[n:]) <= 1e-9
+        x2s.append(xg[per:].copy())
+        assert np.array_equal(s.colsPermutation()[per:] - per, ref.rightPermutation())
+    for g in range(1, world):
+        assert np.array_equal(x2s[g], x2s[0]), "the redundantly computed shared parameters must be bit-identical on every rank"
+
+
+def test_unsupported_border_width_is_reported(qk):
+    import ctypes as C
+    from qrkit_b200 import capi
+    d = capi.QrkDesc()
+    d.kind, d.num_blocks, d.block_rows, d.block_cols, d.border_cols = capi.QRK_BLOCK_ANGULAR, 10, 2, 1, 9
+    h = C.c_void_p()
+    assert capi.lib().qrk_create(C.byref(d), C.byref(h)) == capi.QRK_STATUS_UNSUPPORTED
+
+
+def test_config3_full_size_properties(qk, oracle):
+    """BASELINE config 3: ellipse Jacobian at N = 1M (2M x (1M+5)).  Size-independent checks: normal equations of the
+    least-squares solution, x2 against a float128-free reference (numpy lstsq on the Schur-reduced 5-column problem)."""
+    n = 1_000_000
+    J1, J2, rhs = ellipse_problem(n)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(J1, block_rows=2, block_cols=1), J2)
+    s = qk.BlockAngularSparseQR(pivoting=0)
+    x = s.compute_solve(mat, rhs)
+    x1, x2 = x[:n], x[n:]
+    # eliminate the diagonal blocks analytically: for each point, project out the 2x1 block direction
+    a = J1.reshape(n, 2)
+    nrm2 = (a * a).sum(axis=1)
+    Jb = J2.reshape(n, 2, 5)
+    proj = np.einsum("ni,nij->nj", a, Jb) / nrm2[:, None]
+    Ared = (Jb - a[:, :, None] * proj[:, None, :]).reshape(2 * n, 5)
+    rb = rhs.reshape(n, 2)
+    rred = (rb - a * ((a * rb).sum(axis=1) / nrm2)[:, None]).reshape(-1)
+    x2_ref = np.linalg.lstsq(Ared, rred, rcond=None)[0]
+    assert rel(x2, x2_ref) <= 1e-8
+    x1_ref = ((a * (rb - np.einsum("nij,j->ni", Jb, x2))).sum(axis=1)) / nrm2
+    assert rel(x1, x1_ref) <= 1e-9
+    # window against the oracle's packed left factor is covered by the block-diagonal tests; here the residual's
+    # orthogonality to every column: A^T (A x - b) = 0
+    res = (a * x1[:, None] + np.einsum("nij,j->ni", Jb, x2) - rb)
+    g1 = (a * res).sum(axis=1)
+    g2 = np.einsum("nij,ni->j", Jb, res)
+    scale = np.abs(J2).max() * np.linalg.norm(rhs)
+    assert np.abs(g1).max() <= 1e-9 * scale and np.abs(g2).max() <= 1e-7 * scale
