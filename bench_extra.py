@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""bench_extra.py — device-timed measurements of the other BASELINE configs (3: block-angular ellipse Jacobian at
+1M points, 5: mixed 32x16..128x64 blocks, 2 as two API calls).  One JSON line per workload; the headline line
+the driver reads is bench.py's.  Inputs are generated on the device; every call goes through the C ABI."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+
+from bench import measured_peaks
+from qrkit_b200 import capi
+from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
+
+SEED_A = 0x51524B49
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def time_steps(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def ellipse_device(n):
+    """Ellipse-fit Jacobian at the initial LM iterate (bench/bench_sparse_qr_extra.cpp:79-114, 221-282) on the device."""
+    a, b, x0, y0, r = 7.5, 2.0, 17.0, 23.0, 0.23
+    t = torch.arange(n, dtype=torch.float64, device="cuda") * (1.3 * math.pi / n)
+    px = x0 + a * torch.cos(t) * math.cos(r) - b * torch.sin(t) * math.sin(r)
+    py = y0 + a * torch.cos(t) * math.sin(r) + b * torch.sin(t) * math.cos(r)
+    pa = 0.5 * (px.max() - px.min()); pb = 0.5 * (py.max() - py.min())
+    cx = 0.5 * (px.max() + px.min()); cy = 0.5 * (py.max() + py.min())
+    ct, st, cr, sr = torch.cos(t), torch.sin(t), 1.0, 0.0
+    J1 = torch.empty(n, 2, dtype=torch.float64, device="cuda")
+    J1[:, 0] = pa * cr * st + pb * sr * ct
+    J1[:, 1] = pa * sr * st - pb * cr * ct
+    J2 = torch.zeros(5, 2 * n, dtype=torch.float64, device="cuda")      # column-major 2n x 5
+    J2[0, 0::2] = -ct * cr; J2[1, 0::2] = st * sr; J2[2, 0::2] = -1; J2[4, 0::2] = pa * ct * sr + pb * st * cr
+    J2[0, 1::2] = -ct * sr; J2[1, 1::2] = -st * cr; J2[3, 1::2] = -1; J2[4, 1::2] = -pa * ct * cr + pb * st * sr
+    rhs = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+    rhs[0::2] = px - (pa * ct * cr - pb * st * sr + cx)
+    rhs[1::2] = py - (pa * ct * sr + pb * st * cr + cy)
+    return J1.reshape(-1).contiguous(), J2, rhs
+
+
+def bench_angular(args, L, stream):
+    n = args.points
+    J1, J2, rhs = ellipse_device(n)
+    x = torch.empty(n + 5, dtype=torch.float64, device="cuda")
+    out = {}
+    for piv in (0, 1):
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, n, 2, 1, piv, 5
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_set_stream(h, stream), h)
+        check(L.qrk_set_border(h, vp(J2), 2 * n, QRK_DEVICE), h)
+
+        def step():
+            check(L.qrk_compute_solve(h, vp(J1), vp(rhs), vp(x), QRK_DEVICE), h)
+        l0 = C.c_int64(); L.qrk_launch_count(h, C.byref(l0))
+        ms = time_steps(step, args.steps, args.warmup)
+        l1 = C.c_int64(); L.qrk_launch_count(h, C.byref(l1))
+        out[piv] = (ms, (l1.value - l0.value) // (args.steps + args.warmup))
+        L.qrk_destroy(h)
+    peak, src = measured_peaks()
+    ms, launches = out[0]
+    bytes_per_point = 248          # J1 16 + J2 80 + b 16 in; packed 16(+tau 8) ... second pass; see DESIGN.md
+    achieved = bytes_per_point * n / (ms * 1e-3) / 1e9
+    line = {"workload": f"block-angular ellipse Jacobian, N={n} points: {2*n} x ({n}+5), fused compute+solve (BASELINE config 3)",
+            "metric": "rows/s", "value": 2 * n / (ms * 1e-3), "ms_per_step": ms, "launches_per_step": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_point": bytes_per_point, "peak_source": src},
+            "colpiv_left": {"ms_per_step": out[1][0], "value": 2 * n / (out[1][0] * 1e-3)},
+            "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}
+    print(json.dumps(line), flush=True)
+
+
+def mixed_sizes(nb, seed=SEED_A):
+    from helpers import splitmix64
+    hsh = splitmix64(np.arange(nb, dtype=np.uint64) ^ np.uint64(seed))
+    br = (32 + 16 * (hsh % np.uint64(7)).astype(np.int64)).astype(np.int32)
+    return br, (br // 2).astype(np.int32)
+
+
+def bench_mixed(args, L, stream):
+    nb = args.mixed_blocks
+    br, bc = mixed_sizes(nb)
+    total = int((br.astype(np.int64) * bc).sum())
+    rows, cols = int(br.sum()), int(bc.sum())
+    A = torch.empty(total, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(A), SEED_A, 0, total, 1, 0, 0.5, 5.0, stream))
+    b = torch.empty(rows, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(b), SEED_A + 5, 0, rows, 1, 0, -1.0, 1.0, stream))
+    x = torch.empty(cols, dtype=torch.float64, device="cuda")
+    res = {}
+    for piv in (0, 1):
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.pivoting = 0, nb, piv
+        d.rows = br.ctypes.data_as(C.POINTER(C.c_int32)); d.cols = bc.ctypes.data_as(C.POINTER(C.c_int32))
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_set_stream(h, stream), h)
+
+        def step():
+            check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h)
+        res[piv] = time_steps(step, args.steps, args.warmup)
+        L.qrk_destroy(h)
+    peak, src = measured_peaks()
+    r64, c64 = br.astype(np.float64), bc.astype(np.float64)
+    alg_bytes = float((16 * r64 * c64 + 8 * r64 + 16 * c64).sum())
+    flops = float((2 * r64 * c64 * c64 - (2.0 / 3.0) * c64 ** 3 + 4 * r64 * c64 + c64 * c64).sum())
+    ms = res[0]
+    line = {"workload": f"mixed block-diagonal, {nb} blocks 32x16..128x64 (BASELINE config 5), fused QR+solve",
+            "metric": "rows/s", "value": rows / (ms * 1e-3), "ms_per_step": ms, "rows": rows,
+            "roofline": {"hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak},
+                         "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": 37.0, "unit": "TFLOP/s (nominal FP64 vector peak)",
+                                  "frac": flops / (ms * 1e-3) / 1e12 / 37.0},
+                         "algorithmic_bytes": alg_bytes, "flops": flops, "peak_source": src},
+            "colpiv": {"ms_per_step": res[1], "value": rows / (res[1] * 1e-3)}, "steps": args.steps, "dtype": "f64"}
+    print(json.dumps(line), flush=True)
+
+
+def bench_two_call(args, L, stream):
+    nb, r, c = 1_000_000, 8, 4
+    A = torch.empty(nb * r * c, dtype=torch.float64, device="cuda")
+    b = torch.empty(nb * r, dtype=torch.float64, device="cuda")
+    x = torch.empty(nb * c, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(A), SEED_A, 0, nb, r, c, 0.5, 5.0, stream))
+    check(L.qrk_synth_fill(vp(b), SEED_A + 5, 0, nb, r, 0, -1.0, 1.0, stream))
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting = 0, nb, r, c, 0
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_stream(h, stream), h)
+    ms_f = time_steps(lambda: check(L.qrk_compute(h, vp(A), QRK_DEVICE), h), args.steps, args.warmup)
+    ms_s = time_steps(lambda: check(L.qrk_solve(h, vp(b), nb * r, vp(x), nb * c, 1, QRK_DEVICE), h), args.steps, args.warmup)
+    y = torch.empty_like(b)
+    ms_q = time_steps(lambda: check(L.qrk_apply_qt(h, vp(b), nb * r, vp(y), nb * r, 1, QRK_DEVICE), h), args.steps, args.warmup)
+    L.qrk_destroy(h)
+    peak, _ = measured_peaks()
+    line = {"workload": "config 2 as separate API calls: compute(), solve(b), matrixQ().transpose()*b",
+            "factor": {"ms": ms_f, "bytes_per_block": 544, "frac": 544 * nb / (ms_f * 1e-3) / 1e9 / peak},
+            "solve": {"ms": ms_s, "bytes_per_block": 384, "frac": 384 * nb / (ms_s * 1e-3) / 1e9 / peak},
+            "apply_qt": {"ms": ms_q, "bytes_per_block": 256 + 32 + 128, "frac": 416 * nb / (ms_q * 1e-3) / 1e9 / peak}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="angular,mixed,two_call")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--mixed-blocks", type=int, default=100_000)
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device: qrkit_b200 has no CPU fallback")
+    torch.cuda.set_device(0)
+    s = torch.cuda.Stream()
+    torch.cuda.set_stream(s)
+    stream = C.c_void_p(s.cuda_stream)
+    L = capi.lib()
+    for w in args.workload.split(","):
+        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call}[w](args, L, stream)
+
+
+if __name__ == "__main__":
+    main()

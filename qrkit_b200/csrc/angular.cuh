@@ -103,15 +103,60 @@ __device__ __forceinline__ void fold_tri(double (&T)[Tri<M2>::N], double (&S)[Tr
   }
 }
 
-// Warp butterfly: after the call lane 0 holds the QR-merge of all 32 lanes' triangles.
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Cooperative warp merge of the 32 lanes' triangles: ONE Householder QR of the stacked (32*M2) x (M2+1)
+// matrix, rows spread over the lanes (lane l owns the M2 rows of its triangle), reflector norms and the
+// v^T A dot products are warp-shuffle reductions.  Lane 0's row k is the pivot row of column k, so the
+// result triangle ends up in lane 0; the other lanes' triangles are consumed.  Compared with a pairwise
+// butterfly (5 dependent 2-triangle merges) this has one fifth of the dependent rsqrt/rcp chains.
 template <int M2>
 __device__ __forceinline__ void warp_merge_tri(double (&T)[Tri<M2>::N]) {
+  using TR = Tri<M2>;
+  const bool lead = (threadIdx.x & 31) == 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double S[Tri<M2>::N];
+  for (int k = 0; k < M2; k++) {
+    double tail = 0.0;
 #pragma unroll
-    for (int i = 0; i < Tri<M2>::N; i++) S[i] = __shfl_xor_sync(0xffffffffu, T[i], o);
-    fold_tri<M2>(T, S);
+    for (int p = 0; p <= k; p++) tail = fma(T[TR::idx(p, k)], T[TR::idx(p, k)], tail);
+    tail = lead ? 0.0 : tail;                     // lane 0 contributes only the pivot entry
+    const double tailSq = warp_sum_f64(tail);
+    const double c0 = __shfl_sync(0xffffffffu, T[TR::idx(k, k)], 0);
+    const bool degenerate = tailSq <= DBL_MIN;
+    double norm;
+    const double rnorm = fast_rsqrt(fma(c0, c0, tailSq), norm);
+    double beta = (c0 >= 0.0) ? -norm : norm;
+    const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
+    double inv = fast_rcp(c0 - beta);
+    double tau = (beta - c0) * ib;
+    if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
+    double v[M2];
+#pragma unroll
+    for (int p = 0; p <= k; p++) v[p] = T[TR::idx(p, k)] * inv;
+    double dot[M2 + 1];
+#pragma unroll
+    for (int j = k + 1; j <= M2; j++) {
+      double d = 0.0;
+#pragma unroll
+      for (int p = 0; p <= k; p++) d = fma(v[p], T[TR::idx(p, j)], d);
+      dot[j] = lead ? T[TR::idx(k, j)] : d;
+    }
+#pragma unroll
+    for (int j = k + 1; j <= M2; j++) dot[j] = warp_sum_f64(dot[j]) * tau;
+#pragma unroll
+    for (int j = k + 1; j <= M2; j++) {
+      if (lead) {
+        T[TR::idx(k, j)] -= dot[j];
+      } else {
+#pragma unroll
+        for (int p = 0; p <= k; p++) T[TR::idx(p, j)] = fma(-v[p], dot[j], T[TR::idx(p, j)]);
+      }
+    }
+    if (lead) T[TR::idx(k, k)] = beta;
   }
 }
 
@@ -121,21 +166,17 @@ __device__ __forceinline__ void cta_merge_tri(double (&T)[Tri<M2>::N], double* s
   constexpr int N = Tri<M2>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   warp_merge_tri<M2>(T);
+  if (NWARPS == 1) return;
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < N; i++) scratch[warp * N + i] = T[i];
   }
   __syncthreads();
   if (warp == 0) {
+    static_assert(NWARPS <= 32, "one triangle per lane in the second stage");
 #pragma unroll
     for (int i = 0; i < N; i++) T[i] = (lane < NWARPS) ? scratch[lane * N + i] : 0.0;
-#pragma unroll
-    for (int o = 1; o < NWARPS; o <<= 1) {
-      double S[N];
-#pragma unroll
-      for (int i = 0; i < N; i++) S[i] = __shfl_xor_sync(0xffffffffu, T[i], o);
-      fold_tri<M2>(T, S);
-    }
+    warp_merge_tri<M2>(T);
   }
 }
 
@@ -147,36 +188,39 @@ __device__ __forceinline__ void cta_merge_tri(double (&T)[Tri<M2>::N], double* s
 //   abot : optional (n-m1) x (M2+1) column-major panel [Abot | Q1^T b bottom] (leading dimension n-m1),
 //          kept for later solve(b') calls; null in the fused compute+solve path
 //   partials : gridDim.x triangles (Tri<M2>::N doubles each)
+// Persistent CTAs; a tile is U*TPB blocks (thread t owns blocks t, t+TPB, ... of the tile, so the U*(r-c)
+// residual rows of one thread are folded with ONE reflector per border column).  The tile's slices of A,
+// of every J2 column and of b are contiguous in HBM and are brought in by cp.async (LDGSTS) into a
+// NSTAGE-deep ring of shared-memory buffers: the loads of tile i+1 are in flight while tile i is computed.
 // ---------------------------------------------------------------------------------------------
-template <int R, int C, int TPB>
+template <int R, int C, int M2, int TPB, int U, int NSTAGE>
 struct AngularSmem {
+  static constexpr int TILE = U * TPB;
+  static constexpr int W = M2 + 1;
   static constexpr int SA = Group<R * C>::stride;
+  static constexpr int SR = Group<R>::stride;
   static constexpr int ST = Group<C>::stride;
   static constexpr int SP = GroupI32<C>::stride;
-  static constexpr int offA = 0;
-  static constexpr int offT = offA + TPB * SA;
-  static constexpr int offP = offT + TPB * ST;
-  template <int M2>
-  static constexpr size_t bytes() {
-    size_t perm_bytes = ((size_t)TPB * SP * 4 + 15) & ~(size_t)15;
-    return (size_t)offP * 8 + perm_bytes + (size_t)(TPB / 32) * Tri<M2>::N * 8;
-  }
+  static constexpr int stage_doubles = TILE * (SA + W * SR);        // A tile + W border/rhs column slices
+  static constexpr int offT = NSTAGE * stage_doubles;               // tau out
+  static constexpr int offTri = offT + TILE * ST;
+  static constexpr int offP = offTri + (TPB / 32) * Tri<M2>::N + ((TPB / 32) * Tri<M2>::N % 2);
+  static constexpr size_t bytes = (size_t)offP * 8 + (size_t)TILE * SP * 4;
 };
 
-template <int R, int C, bool PIV, int M2, int TPB, int MINB>
+template <int R, int C, bool PIV, int M2, int TPB, int U, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
 angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, int* __restrict__ perm_out,
                       const double* __restrict__ J2, long long ldj, const double* __restrict__ b,
                       double* __restrict__ atop, double* __restrict__ y1, double* __restrict__ abot,
                       double* __restrict__ partials, long long nb) {
   static_assert(R > C, "the border merge needs residual rows (r > c)");
-  using L = AngularSmem<R, C, TPB>;
-  constexpr int M1 = R - C, W = M2 + 1;
+  using L = AngularSmem<R, C, M2, TPB, U, NSTAGE>;
+  constexpr int M1 = R - C, W = M2 + 1, TILE = L::TILE;
   extern __shared__ __align__(16) double smem[];
-  double* sA = smem + L::offA;
   double* sT = smem + L::offT;
+  double* sTri = smem + L::offTri;
   int* sP = reinterpret_cast<int*>(smem + L::offP);
-  double* sTri = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sP) + (((size_t)TPB * L::SP * 4 + 15) & ~(size_t)15));
   const int t = threadIdx.x;
   const long long m1 = nb * C, nres = nb * M1;
 
@@ -184,60 +228,91 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
 #pragma unroll
   for (int i = 0; i < Tri<M2>::N; i++) T[i] = 0.0;
 
-  const long long ntiles = (nb + TPB - 1) / TPB;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long tile0 = tile * TPB;
-    const int count = (int)((nb - tile0 < TPB) ? (nb - tile0) : TPB);
-    __syncthreads();                       // previous tile's stage_out has drained the staging buffers
-    stage_in_async<R * C, L::SA, TPB>(sA, A_in + tile0 * (R * C), count);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    if (t < count) {
-      const long long blk = tile0 + t;
-      double a[R * C], tau[C], inv_diag[C], dummy[R];
-      int perm[C];
-      load_group<R * C>(a, sA + t * L::SA);
-      BlockQR<R, C, PIV, false>::run(a, tau, inv_diag, perm, dummy);
-      store_group<R * C>(sA + t * L::SA, a);
-      store_group<C>(sT + t * L::ST, tau);
-      if (PIV) {
+  const long long ntiles = (nb + TILE - 1) / TILE;
+  auto issue = [&](long long tile, int stage) {
+    const long long tile0 = tile * TILE;
+    const int count = (int)((nb - tile0 < TILE) ? (nb - tile0) : TILE);
+    double* buf = smem + (size_t)stage * L::stage_doubles;
+    stage_in_async<R * C, L::SA, TPB, TILE>(buf, A_in + tile0 * (R * C), count);
 #pragma unroll
-        for (int j = 0; j < C; j++) sP[t * L::SP + j] = (int)(blk * C) + perm[j];
-      }
-      // border rows of this block: column by column through the reflectors
-      double w[M1][W];
-#pragma unroll
-      for (int j = 0; j < W; j++) {
-        double col[R];
-        if (j < M2) {
-          const double* src = J2 + (long long)j * ldj + blk * R;
-#pragma unroll
-          for (int i = 0; i < R; i++) col[i] = __ldg(src + i);
-        } else {
-#pragma unroll
-          for (int i = 0; i < R; i++) col[i] = b ? __ldg(b + blk * R + i) : 0.0;
-        }
-        apply_qt_chain<R, C>(a, tau, col);
-        double* top = (j < M2) ? atop + (long long)j * m1 + blk * C : y1 + blk * C;
-#pragma unroll
-        for (int i = 0; i < C; i++) top[i] = col[i];
-#pragma unroll
-        for (int i = 0; i < M1; i++) w[i][j] = col[C + i];
-        if (abot) {
-          double* dst = abot + (long long)j * nres + blk * M1;
-#pragma unroll
-          for (int i = 0; i < M1; i++) dst[i] = col[C + i];
-        }
-      }
-      fold_rows<M2, M1>(T, w);
+    for (int j = 0; j < M2; j++)
+      stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + j * TILE * L::SR, J2 + (long long)j * ldj + tile0 * R, count);
+    if (b) stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + M2 * TILE * L::SR, b + tile0 * R, count);
+  };
+
+  long long tile = blockIdx.x;
+  if (NSTAGE > 1 && tile < ntiles) issue(tile, 0);
+  if (NSTAGE > 1) cp_async_commit();
+  int it = 0;
+  for (; tile < ntiles; tile += gridDim.x, it++) {
+    const int stage = (NSTAGE > 1) ? (it & 1) : 0;
+    const long long tile0 = tile * TILE;
+    const int count = (int)((nb - tile0 < TILE) ? (nb - tile0) : TILE);
+    double* buf = smem + (size_t)stage * L::stage_doubles;
+    if (NSTAGE > 1) {
+      const long long next = tile + gridDim.x;
+      if (next < ntiles) issue(next, stage ^ 1);     // the other buffer was drained before the barrier ending the previous iteration
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      issue(tile, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
     }
     __syncthreads();
-    stage_out<R * C, L::SA, TPB>(packed + tile0 * (R * C), sA, count);
-    stage_out<C, L::ST, TPB>(tau_out + tile0 * C, sT, count);
-    if (PIV) stage_out_i32<C, L::SP, TPB>(perm_out + tile0 * C, sP, count);
+    double w[U * M1][W];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int slot = u * TPB + t;
+      if (slot < count) {
+        const long long blk = tile0 + slot;
+        double a[R * C], tau[C], inv_diag[C], dummy[R];
+        int perm[C];
+        load_group<R * C>(a, buf + slot * L::SA);
+        BlockQR<R, C, PIV, false>::run(a, tau, inv_diag, perm, dummy);
+        store_group<R * C>(buf + slot * L::SA, a);
+        store_group<C>(sT + slot * L::ST, tau);
+        if (PIV) {
+#pragma unroll
+          for (int j = 0; j < C; j++) sP[slot * L::SP + j] = (int)(blk * C) + perm[j];
+        }
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          double col[R];
+          if (j < M2 || b) load_group<R>(col, buf + TILE * L::SA + j * TILE * L::SR + slot * L::SR);
+          else {
+#pragma unroll
+            for (int i = 0; i < R; i++) col[i] = 0.0;
+          }
+          apply_qt_chain<R, C>(a, tau, col);
+          double* top = (j < M2) ? atop + (long long)j * m1 + blk * C : y1 + blk * C;
+#pragma unroll
+          for (int i = 0; i < C; i++) top[i] = col[i];
+#pragma unroll
+          for (int i = 0; i < M1; i++) w[u * M1 + i][j] = col[C + i];
+          if (abot) {
+            double* dst = abot + (long long)j * nres + blk * M1;
+#pragma unroll
+            for (int i = 0; i < M1; i++) dst[i] = col[C + i];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < M1; i++)
+#pragma unroll
+          for (int j = 0; j < W; j++) w[u * M1 + i][j] = 0.0;
+      }
+    }
+    fold_rows<M2, U * M1>(T, w);
+    __syncthreads();
+    stage_out<R * C, L::SA, TPB, TILE>(packed + tile0 * (R * C), buf, count);
+    stage_out<C, L::ST, TPB, TILE>(tau_out + tile0 * C, sT, count);
+    if (PIV) {
+      for (int d = t; d < count * C; d += TPB) perm_out[tile0 * C + d] = sP[(d / C) * L::SP + (d % C)];
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  if (NSTAGE > 1) cp_async_wait<0>();
   cta_merge_tri<M2, TPB / 32>(T, sTri);
   if (t == 0) {
 #pragma unroll
@@ -320,11 +395,20 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   double T[N];
 #pragma unroll
   for (int i = 0; i < N; i++) T[i] = 0.0;
-  for (int q = threadIdx.x; q < count; q += TPB) {
-    double S[N];
+  // every thread takes one triangle per round; a round is merged cooperatively (warp, then CTA)
+  for (int q0 = 0; q0 < count; q0 += TPB) {
+    const int q = q0 + threadIdx.x;
+    if (q0 == 0) {
+      if (q < count) {
 #pragma unroll
-    for (int i = 0; i < N; i++) S[i] = tris[(long long)q * N + i];
-    fold_tri<M2>(T, S);
+        for (int i = 0; i < N; i++) T[i] = tris[(long long)q * N + i];
+      }
+    } else {
+      double S[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) S[i] = (q < count) ? tris[(long long)q * N + i] : 0.0;
+      fold_tri<M2>(T, S);
+    }
   }
   cta_merge_tri<M2, TPB / 32>(T, scratch);
   if (threadIdx.x != 0) return;

@@ -40,6 +40,7 @@ struct AngularVTable {
   int tri_doubles;                                                 // Tri<M2>::N
   bool (*shape_ok)(int r, int c);
   cudaError_t (*max_grid)(int r, int c, bool piv, int* grid);       // resident CTAs of the factor kernel on this device
+  int (*tile_blocks)(int r, int c);                                // diagonal blocks per tile of the factor kernel
   cudaError_t (*factor)(const AngularArgs&, cudaStream_t);
   cudaError_t (*rhs)(const AngularArgs&, cudaStream_t);
   cudaError_t (*root)(const AngularArgs&, cudaStream_t);

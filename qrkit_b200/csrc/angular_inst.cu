@@ -15,8 +15,21 @@ constexpr int TPB = 128;
 // left block shapes available to the block-angular path (r > c)
 #define QRK_ANGULAR_SHAPES(X) X(2, 1) X(3, 1) X(4, 2) X(7, 2)
 
+// tile shape of the factor kernel: U blocks per thread so that one fold covers >= 2 residual rows where the
+// footprint allows, and a double-buffered cp.async ring when two stages fit comfortably in shared memory
 template <int R, int C>
-constexpr int minb() { return ((R * C + (R - C) * (M2 + 1) + Tri<M2>::N) <= 40) ? 4 : 2; }
+struct Cfg {
+  static constexpr int M1 = R - C;
+  static constexpr int U = (M1 >= 2) ? 1 : 2;
+  static constexpr size_t stage_bytes = (size_t)AngularSmem<R, C, M2, TPB, U, 1>::stage_doubles * 8;
+  static constexpr int NSTAGE = (2 * stage_bytes <= 96 * 1024) ? 2 : 1;
+  static constexpr int regs_doubles = R * C + U * M1 * (M2 + 1) + Tri<M2>::N;
+  static constexpr int MINB = (regs_doubles <= 44) ? 3 : 2;
+  using Smem = AngularSmem<R, C, M2, TPB, U, NSTAGE>;
+};
+
+template <int R, int C>
+constexpr int minb() { return Cfg<R, C>::MINB; }
 
 template <typename K>
 cudaError_t opt_in(K kernel, size_t smem) {
@@ -26,8 +39,9 @@ cudaError_t opt_in(K kernel, size_t smem) {
 
 template <int R, int C, bool PIV>
 cudaError_t factor_t(const AngularArgs& a, cudaStream_t s) {
-  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, minb<R, C>()>;
-  const size_t smem = AngularSmem<R, C, TPB>::template bytes<M2>();
+  using G = Cfg<R, C>;
+  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, G::U, G::NSTAGE, G::MINB>;
+  const size_t smem = G::Smem::bytes;
   cudaError_t e = opt_in(kernel, smem);
   if (e != cudaSuccess) return e;
   kernel<<<a.grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
@@ -36,8 +50,9 @@ cudaError_t factor_t(const AngularArgs& a, cudaStream_t s) {
 
 template <int R, int C, bool PIV>
 cudaError_t max_grid_t(int* grid) {
-  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, minb<R, C>()>;
-  const size_t smem = AngularSmem<R, C, TPB>::template bytes<M2>();
+  using G = Cfg<R, C>;
+  auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, G::U, G::NSTAGE, G::MINB>;
+  const size_t smem = G::Smem::bytes;
   cudaError_t e = opt_in(kernel, smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0, per_sm = 0;
@@ -75,6 +90,13 @@ bool shape_ok(int r, int c) {
   return false;
 }
 
+int tile_blocks(int r, int c) {
+#define X(R_, C_) if (r == R_ && c == C_) return Cfg<R_, C_>::U * TPB;
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return TPB;
+}
+
 cudaError_t max_grid(int r, int c, bool piv, int* grid) {
 #define X(R_, C_) if (r == R_ && c == C_) return piv ? max_grid_t<R_, C_, true>(grid) : max_grid_t<R_, C_, false>(grid);
   QRK_ANGULAR_SHAPES(X)
@@ -104,7 +126,7 @@ cudaError_t root(const AngularArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-const AngularVTable kTable = {M2, Tri<M2>::N, shape_ok, max_grid, factor, rhs, root, backsolve};
+const AngularVTable kTable = {M2, Tri<M2>::N, shape_ok, max_grid, tile_blocks, factor, rhs, root, backsolve};
 
 }  // namespace
 

@@ -332,7 +332,8 @@ AngularArgs angular_args(qrk_solver* h) {
   a.J2 = h->d_border; a.ldj = h->ld_border;
   a.atop = h->d_atop; a.y1 = h->d_y1; a.abot = nullptr;
   a.partials = h->d_partials;
-  const long long ntiles = (h->nb + 127) / 128;
+  const long long tile = h->avt->tile_blocks(h->ur, h->uc);
+  const long long ntiles = (h->nb + tile - 1) / tile;
   a.grid = (int)std::max<long long>(1, std::min<long long>(h->a_grid, ntiles));
   a.tris = h->d_partials; a.tri_count = a.grid;
   a.out_tri = h->d_tri; a.root = h->d_root; a.root_i = h->d_root_i;
@@ -923,6 +924,8 @@ int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace) {
   DeviceGuard g(h->device);
   if (memspace == QRK_DEVICE) {
     QRK_REQUIRE(h, (reinterpret_cast<uintptr_t>(J2) & 7) == 0, "border must be 8-byte aligned");
+    QRK_REQUIRE(h, (h->ur % 2) || (aligned16(J2) && ld % 2 == 0),
+                "even block_rows: the device border must be 16-byte aligned with an even leading dimension");
     h->d_border = J2;
     h->ld_border = ld;
   } else {

@@ -37,11 +37,12 @@ template <int K>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
 
 // global (contiguous) -> shared (strided groups), asynchronous (LDGSTS): no register staging.
-template <int N, int S, int TPB>
+// TPB threads copy a tile of up to TILE groups (`count` of them valid).
+template <int N, int S, int TPB, int TILE = TPB>
 __device__ __forceinline__ void stage_in_async(double* s, const double* __restrict__ g, int count) {
   constexpr int V = Group<N>::vec;
-  if (count == TPB) {
-    constexpr int total = TPB * N / V;
+  if (count == TILE) {
+    constexpr int total = TILE * N / V;
 #pragma unroll
     for (int q0 = 0; q0 < total; q0 += TPB) {
       const int q = q0 + threadIdx.x;
@@ -62,10 +63,10 @@ __device__ __forceinline__ void stage_in_async(double* s, const double* __restri
 }
 
 // shared (strided groups) -> global (contiguous), coalesced vector stores.
-template <int N, int S, int TPB>
+template <int N, int S, int TPB, int TILE = TPB>
 __device__ __forceinline__ void stage_out(double* __restrict__ g, const double* s, int count) {
   constexpr int V = Group<N>::vec;
-  const int total = (count == TPB) ? TPB * N / V : count * N / V;
+  const int total = (count == TILE) ? TILE * N / V : count * N / V;
 #pragma unroll 4
   for (int q = threadIdx.x; q < total; q += TPB) {
     const int d = q * V, grp = d / N, within = d - grp * N;
