@@ -388,7 +388,8 @@ angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__
 template <int M2, int TPB>
 __global__ void __launch_bounds__(TPB)
 angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
-                    double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only) {
+                    double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only, int* __restrict__ perm_tail,
+                    int m1) {
   using TR = Tri<M2>;
   constexpr int N = TR::N;
   __shared__ double scratch[(TPB / 32) * N];
@@ -441,6 +442,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
 #pragma unroll
       for (int i = 0; i < M2; i++) root[j * M2 + i] = (i <= j) ? a[j * M2 + i] : 0.0;
       root_i[j] = perm[j];
+      perm_tail[j] = m1 + perm[j];     // m_outputPerm_c(m1 + j) = m1 + P2(j) (BlockAngularSparseQR.h:501-503)
     }
     root_i[M2] = rank;
   }

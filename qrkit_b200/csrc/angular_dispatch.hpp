@@ -31,6 +31,8 @@ struct AngularArgs {
   double* out_tri = nullptr;
   double* root = nullptr;
   int* root_i = nullptr;
+  int* perm_tail = nullptr;  // colsPermutation()[m1 .. m1+m2)
+  int m1 = 0;
   // solution
   double* x = nullptr;
 };

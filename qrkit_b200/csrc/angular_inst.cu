@@ -122,7 +122,8 @@ cudaError_t backsolve(const AngularArgs& a, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 cudaError_t root(const AngularArgs& a, cudaStream_t s) {
-  angular_root_kernel<M2, 256><<<1, 256, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only);
+  angular_root_kernel<M2, 512><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
+                                                 a.perm_tail, a.m1);
   return cudaGetLastError();
 }
 

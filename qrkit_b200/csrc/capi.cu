@@ -298,11 +298,6 @@ __global__ void synth_fill_kernel(double* out, uint64_t seed, long long block0, 
 
 
 // ---- block angular ---------------------------------------------------------------------------------
-__global__ void angular_finish_perm_kernel(int* perm_tail, const int* root_i, int m1, int m2) {
-  const int j = threadIdx.x;
-  if (j < m2) perm_tail[j] = m1 + root_i[j];     // m_outputPerm_c(m1 + j) = m1 + P2(j) (BlockAngularSparseQR.h:501-503)
-}
-
 // border columns of R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:296-305)
 __global__ void export_angular_border_kernel(const double* __restrict__ atop, const double* __restrict__ root,
                                              const int* __restrict__ root_i, long long m1, int m2, long long base,
@@ -337,6 +332,7 @@ AngularArgs angular_args(qrk_solver* h) {
   a.grid = (int)std::max<long long>(1, std::min<long long>(h->a_grid, ntiles));
   a.tris = h->d_partials; a.tri_count = a.grid;
   a.out_tri = h->d_tri; a.root = h->d_root; a.root_i = h->d_root_i;
+  a.perm_tail = h->d_perm + h->sum_cols; a.m1 = (int)h->sum_cols;
   return a;
 }
 
@@ -356,10 +352,6 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
   a.keep_rhs_only = keep_rhs_only;
   QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
   h->launches++;
-  if (!keep_rhs_only) {
-    angular_finish_perm_kernel<<<1, 32, 0, h->stream>>>(h->d_perm + h->sum_cols, h->d_root_i, (int)h->sum_cols, h->m2);
-    h->launches++;
-  }
   h->root_done = true;
   if (have_rhs) {
     a.x = d_x;
@@ -980,10 +972,6 @@ int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int mem
   int st = QRK_STATUS_OK;
   cudaError_t e = h->avt->root(a, h->stream);
   h->launches++;
-  if (e == cudaSuccess && !a.keep_rhs_only) {
-    angular_finish_perm_kernel<<<1, 32, 0, h->stream>>>(h->d_perm + h->sum_cols, h->d_root_i, (int)h->sum_cols, h->m2);
-    h->launches++;
-  }
   h->root_done = true;
   if (e == cudaSuccess && h->pending_x) {
     double* d_x = (h->pending_space == QRK_HOST) ? h->d_x : h->pending_x;

@@ -115,7 +115,7 @@ __device__ __forceinline__ void store_group(double* s, const double (&src)[N]) {
 
 // ---------------------------------------------------------------------------------------------
 // FP64 reciprocal / reciprocal square root without the slow-path branches of the IEEE sequences:
-// MUFU.RCP64H / MUFU.RSQ64H seed (>= 20 good bits) + Newton steps -> ~1 ulp (not correctly rounded).
+// MUFU.RCP64H / MUFU.RSQ64H seed (20 good bits) + two Newton steps -> <= 1 ulp (not correctly rounded).
 // The per-block QR needs, per reflector, norm, 1/beta and 1/(x0 - beta); with the IEEE sqrt and two
 // IEEE divisions those three take ~40 instructions and three branches, here ~17 straight-line ones.
 // Zero / infinite inputs keep the seed's inf / 0 (as the IEEE operations would give).
@@ -123,10 +123,8 @@ __device__ __forceinline__ void store_group(double* s, const double (&src)[N]) {
 __device__ __forceinline__ double fast_rcp(double x) {
   double r0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
-  double e = fma(-x, r0, 1.0);
+  double e = fma(-x, r0, 1.0);      // seed: 19.9 good bits (measured, tools/seed_accuracy.cu) -> 40 -> 80
   double r = fma(r0, e, r0);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return (r0 == 0.0 || fabs(r0) == __longlong_as_double(0x7ff0000000000000LL)) ? r0 : r;
@@ -138,7 +136,7 @@ __device__ __forceinline__ double fast_rsqrt(double x, double& sqrt_out) {
   const double h = 0.5 * x;
   double y = y0;
 #pragma unroll
-  for (int it = 0; it < 3; it++) {
+  for (int it = 0; it < 2; it++) {     // seed: 20.0 good bits (measured) -> 39 -> 78
     const double t = y * y;
     const double e = fma(-h, t, 0.5);
     y = fma(y, e, y);
