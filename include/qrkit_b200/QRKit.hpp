@@ -1,0 +1,409 @@
+// QRKit.hpp — header-only C++17 host façade over the C ABI (qrkit_b200.h) with the reference's solver
+// interface: same class names, method names, argument meaning and error behaviour as
+//   BlockDiagonalSparseQR  (reference src/QRKit/BlockDiagonalSparseQR.h:37-335)
+//   BlockAngularSparseQR   (reference src/QRKit/BlockAngularSparseQR.h:79-281)
+//   SparseBlockDiagonal    (reference src/QRKit/SparseBlockDiagonal.h:44-163)
+//   BlockMatrix1x2         (reference src/QRKit/BlockMatrix1x2.h:31-67)
+// so that code written against QRKit's Eigen-style API (compute(), matrixQ().transpose() * b, matrixR(),
+// solve(), rank(), info(), colsPermutation(), rowsPermutation()) switches by changing a namespace.
+// Eigen is NOT required: the small value types below stand in for Eigen::VectorXd / MatrixXd /
+// SparseMatrix / PermutationMatrix.  When <Eigen/Sparse> is available, include qrkit_b200/EigenAdapter.hpp
+// for zero-copy maps between the two (untested in this image, which has no Eigen).
+//
+// All arithmetic happens in libqrkit_b200.so on the GPU; there is no CPU fallback: without a CUDA device
+// every solver reports info() == InvalidInput and lastErrorMessage() says so.
+#pragma once
+#include <cassert>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../qrkit_b200.h"
+
+namespace QRKit_b200 {
+
+// Eigen::ComputationInfo
+enum ComputationInfo { Success = 0, NumericalIssue = 1, NoConvergence = 2, InvalidInput = 3 };
+
+using Index = std::int64_t;
+using StorageIndex = int;   // test/test-qrkit.cpp:40
+
+// ---- value types standing in for Eigen's --------------------------------------------------------------
+using VectorXd = std::vector<double>;
+
+struct MatrixXd {           // column-major dense matrix
+  Index m_rows = 0, m_cols = 0;
+  std::vector<double> m_data;
+  MatrixXd() {}
+  MatrixXd(Index r, Index c) : m_rows(r), m_cols(c), m_data((size_t)r * c, 0.0) {}
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  double& operator()(Index i, Index j) { return m_data[(size_t)j * m_rows + i]; }
+  double operator()(Index i, Index j) const { return m_data[(size_t)j * m_rows + i]; }
+  double* data() { return m_data.data(); }
+  const double* data() const { return m_data.data(); }
+};
+
+template <int Rows, int Cols>
+struct Matrix {              // Eigen::Matrix<double, Rows, Cols>: fixed-size column-major block, no padding
+  enum { RowsAtCompileTime = Rows, ColsAtCompileTime = Cols };
+  double m_data[Rows * Cols];
+  static constexpr Index rows() { return Rows; }
+  static constexpr Index cols() { return Cols; }
+  double& operator()(Index i, Index j) { return m_data[j * Rows + i]; }
+  double operator()(Index i, Index j) const { return m_data[j * Rows + i]; }
+  const double* data() const { return m_data; }
+};
+
+template <int Major>        // 0 = ColMajor, 1 = RowMajor (Eigen's option values)
+struct SparseMatrix {       // compressed storage, int32 indices
+  Index m_rows = 0, m_cols = 0;
+  std::vector<StorageIndex> outer, inner;
+  std::vector<double> values;
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index nonZeros() const { return (Index)values.size(); }
+  const StorageIndex* outerIndexPtr() const { return outer.data(); }
+  const StorageIndex* innerIndexPtr() const { return inner.data(); }
+  const double* valuePtr() const { return values.data(); }
+  double coeff(Index i, Index j) const {
+    const Index o = Major ? i : j, in = Major ? j : i;
+    for (StorageIndex p = outer[o]; p < outer[o + 1]; p++)
+      if (inner[p] == in) return values[p];
+    return 0.0;
+  }
+};
+enum { ColMajor = 0, RowMajor = 1 };
+
+struct PermutationMatrix {
+  std::vector<StorageIndex> m_indices;
+  const std::vector<StorageIndex>& indices() const { return m_indices; }
+  std::vector<StorageIndex>& indices() { return m_indices; }
+  Index size() const { return (Index)m_indices.size(); }
+  Index rows() const { return size(); }
+  void setIdentity(Index n) { m_indices.resize(n); for (Index i = 0; i < n; i++) m_indices[i] = (StorageIndex)i; }
+  // (P * v)(indices(i)) = v(i), as Eigen
+  VectorXd operator*(const VectorXd& v) const {
+    VectorXd r(v.size());
+    for (size_t i = 0; i < v.size(); i++) r[m_indices[i]] = v[i];
+    return r;
+  }
+};
+
+// per-block dense solver tags (template parameter _BlockQRSolver of the reference)
+template <typename BlockMatrix> struct HouseholderQR { using MatrixType = BlockMatrix; static constexpr int pivoting = QRK_PIVOT_NONE; };
+template <typename BlockMatrix> struct ColPivHouseholderQR { using MatrixType = BlockMatrix; static constexpr int pivoting = QRK_PIVOT_COLPIV; };
+
+// ---- SparseBlockDiagonal (SparseBlockDiagonal.h:44-163) ------------------------------------------------
+template <typename BlockMatrixType>
+class SparseBlockDiagonal {
+ public:
+  using Scalar = double;
+  using BlockVec = std::vector<BlockMatrixType>;
+  SparseBlockDiagonal() {}
+  SparseBlockDiagonal(Index rows, Index cols) : nRows(rows), nCols(cols) {}
+  void insertBack(const BlockMatrixType& b) { blocks.push_back(b); }            // :141-143
+  void reserve(Index n) { blocks.reserve((size_t)n); }
+  Index size() const { return (Index)blocks.size(); }
+  Index rows() const { return nRows; }
+  Index cols() const { return nCols; }
+  void setDims(Index r, Index c) { nRows = r; nCols = c; }
+  const BlockMatrixType& operator[](Index i) const { return blocks[(size_t)i]; }
+  BlockMatrixType& operator[](Index i) { return blocks[(size_t)i]; }
+  // fromBlockDiagonalPattern (:72-89) for a column-major compressed sparse matrix with equal blocks at (i*br, i*bc)
+  void fromBlockDiagonalPattern(const SparseMatrix<ColMajor>& mat, Index blockRows, Index blockCols) {
+    nRows = mat.rows(); nCols = mat.cols();
+    const Index numBlocks = nCols / blockCols;                                   // SparseQRUtils.h:260
+    blocks.assign((size_t)numBlocks, BlockMatrixType());
+    for (Index i = 0; i < numBlocks; i++)
+      for (Index j = 0; j < blockCols; j++)
+        for (Index k = 0; k < blockRows; k++) blocks[(size_t)i](k, j) = mat.coeff(i * blockRows + k, i * blockCols + j);
+  }
+  const BlockVec& blockVector() const { return blocks; }
+
+ private:
+  BlockVec blocks;
+  Index nRows = 0, nCols = 0;
+};
+
+namespace detail {
+inline void throw_if(int status, qrk_handle_t h, const char* what) {
+  if (status != QRK_STATUS_OK && status != QRK_STATUS_NO_DEVICE)
+    throw std::runtime_error(std::string(what) + ": " + qrk_status_string(status) + (h ? std::string(" — ") + qrk_last_error(h) : ""));
+}
+}  // namespace detail
+
+// ---- BlockDiagonalSparseQR (BlockDiagonalSparseQR.h:37-335) ---------------------------------------------
+template <typename _BlockQRSolver, int _QFormat = 0>
+class BlockDiagonalSparseQR {
+ public:
+  using BlockQRSolver = _BlockQRSolver;
+  using BlockMatrixType = typename BlockQRSolver::MatrixType;
+  using MatrixType = SparseBlockDiagonal<BlockMatrixType>;
+  using Scalar = double;
+  using MatrixQType = SparseMatrix<RowMajor>;
+  using MatrixRType = SparseMatrix<ColMajor>;
+  using PermutationType = PermutationMatrix;
+  enum MatrixQFormat { FullQ = 0, BlockDiagonalQ = 1 };
+
+  BlockDiagonalSparseQR() {}
+  explicit BlockDiagonalSparseQR(const MatrixType& mat) { compute(mat); }
+  ~BlockDiagonalSparseQR() { qrk_destroy(m_h); }
+  BlockDiagonalSparseQR(const BlockDiagonalSparseQR&) = delete;
+  BlockDiagonalSparseQR& operator=(const BlockDiagonalSparseQR&) = delete;
+
+  void compute(const MatrixType& mat, const PermutationType& rowPerm = PermutationType(), bool = false) {   // :94-102
+    analyzePattern(mat, rowPerm);
+    m_isInitialized = false;
+    factorize(mat);
+  }
+  void analyzePattern(const MatrixType& mat, const PermutationType& rowPerm = PermutationType()) {           // :392-405
+    ensureHandle(mat);
+    if (!m_h) return;
+    detail::throw_if(qrk_analyze_pattern(m_h, rowPerm.size() ? rowPerm.indices().data() : nullptr), m_h, "analyzePattern");
+  }
+  void factorize(const MatrixType& mat) {                                                                     // :415-547
+    ensureHandle(mat);
+    if (!m_h) return;
+    static_assert(sizeof(BlockMatrixType) == sizeof(double) * BlockMatrixType::RowsAtCompileTime * BlockMatrixType::ColsAtCompileTime,
+                  "fixed-size blocks are stored back to back: the std::vector of blocks IS the block-COO value array");
+    const double* values = mat.size() ? mat[0].data() : nullptr;
+    detail::throw_if(qrk_set_blocks(m_h, values, QRK_HOST), m_h, "factorize/upload");
+    detail::throw_if(qrk_factorize(m_h), m_h, "factorize");
+    m_R = MatrixRType(); m_haveR = false;
+    m_isInitialized = true;
+  }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  const MatrixRType& matrixR() const {                                                                        // :156
+    assert(m_isInitialized && "Decomposition is not initialized.");
+    if (!m_haveR) {
+      int64_t nnz = 0;
+      detail::throw_if(qrk_matrix_r_nnz(m_h, &nnz), m_h, "matrixR");
+      m_R.m_rows = m_rows; m_R.m_cols = m_cols;
+      m_R.outer.resize((size_t)m_cols + 1); m_R.inner.resize((size_t)nnz); m_R.values.resize((size_t)nnz);
+      detail::throw_if(qrk_matrix_r(m_h, m_R.outer.data(), m_R.inner.data(), m_R.values.data(), QRK_HOST), m_h, "matrixR");
+      m_haveR = true;
+    }
+    return m_R;
+  }
+  Index rank() const {                                                                                        // :161-165
+    assert(m_isInitialized && "The factorization should be called first, use compute()");
+    int64_t r = 0;
+    qrk_rank(m_h, &r);
+    return r;
+  }
+
+  // matrixQ(): an operator with transpose() and operator*; the explicit sparse matrix on request (toSparse()).
+  class QProxy {
+   public:
+    QProxy(const BlockDiagonalSparseQR& qr, bool transposed) : m_qr(qr), m_t(transposed) {}
+    QProxy transpose() const { return QProxy(m_qr, !m_t); }
+    QProxy adjoint() const { return transpose(); }
+    Index rows() const { return m_qr.rows(); }
+    Index cols() const { return m_qr.rows(); }
+    VectorXd operator*(const VectorXd& v) const {
+      VectorXd y((size_t)m_qr.rows());
+      detail::throw_if((m_t ? qrk_apply_qt : qrk_apply_q)(m_qr.m_h, v.data(), m_qr.rows(), y.data(), m_qr.rows(), 1, QRK_HOST), m_qr.m_h, "matrixQ()*v");
+      return y;
+    }
+    MatrixXd operator*(const MatrixXd& B) const {
+      MatrixXd Y(m_qr.rows(), B.cols());
+      detail::throw_if((m_t ? qrk_apply_qt : qrk_apply_q)(m_qr.m_h, B.data(), B.rows(), Y.data(), Y.rows(), (int32_t)B.cols(), QRK_HOST), m_qr.m_h, "matrixQ()*B");
+      return Y;
+    }
+    MatrixQType toSparse() const {             // the reference's explicit row-major sparse Q (:455-470, 483-491, 530-533)
+      MatrixQType Q;
+      int64_t nnz = 0;
+      detail::throw_if(qrk_matrix_q_nnz(m_qr.m_h, &nnz), m_qr.m_h, "matrixQ");
+      Q.m_rows = Q.m_cols = m_qr.rows();
+      Q.outer.resize((size_t)m_qr.rows() + 1); Q.inner.resize((size_t)nnz); Q.values.resize((size_t)nnz);
+      detail::throw_if(qrk_matrix_q(m_qr.m_h, Q.outer.data(), Q.inner.data(), Q.values.data(), QRK_HOST), m_qr.m_h, "matrixQ");
+      return Q;
+    }
+   private:
+    const BlockDiagonalSparseQR& m_qr;
+    bool m_t;
+  };
+  QProxy matrixQ() const { return QProxy(*this, false); }                                                     // :235-237
+
+  const PermutationType& colsPermutation() const {                                                            // :242-246
+    assert(m_isInitialized && "Decomposition is not initialized.");
+    m_outputPerm_c.indices().resize((size_t)m_cols);
+    detail::throw_if(qrk_cols_permutation(m_h, m_outputPerm_c.indices().data(), QRK_HOST), m_h, "colsPermutation");
+    return m_outputPerm_c;
+  }
+  const PermutationType& rowsPermutation() const {                                                            // :251-254
+    assert(m_isInitialized && "Decomposition is not initialized.");
+    m_rowPerm.indices().resize((size_t)m_rows);
+    detail::throw_if(qrk_rows_permutation(m_h, m_rowPerm.indices().data(), QRK_HOST), m_h, "rowsPermutation");
+    return m_rowPerm;
+  }
+  VectorXd solve(const VectorXd& B) const {                                                                   // :258-299
+    assert(m_isInitialized && "The factorization should be called first, use compute()");
+    assert(rows() == (Index)B.size() && "SparseQR::solve() : invalid number of rows in the right hand side matrix");
+    VectorXd x((size_t)m_cols);
+    detail::throw_if(qrk_solve(m_h, B.data(), m_rows, x.data(), m_cols, 1, QRK_HOST), m_h, "solve");
+    return x;
+  }
+  MatrixXd solve(const MatrixXd& B) const {
+    MatrixXd X(m_cols, B.cols());
+    detail::throw_if(qrk_solve(m_h, B.data(), B.rows(), X.data(), m_cols, (int32_t)B.cols(), QRK_HOST), m_h, "solve");
+    return X;
+  }
+  // one fused pass: compute(mat) followed by solve(b)
+  VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {
+    ensureHandle(mat);
+    VectorXd x((size_t)m_cols);
+    if (!m_h) return x;
+    detail::throw_if(qrk_compute_solve(m_h, mat.size() ? mat[0].data() : nullptr, b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
+    m_haveR = false; m_isInitialized = true;
+    return x;
+  }
+  ComputationInfo info() const {                                                                              // :309-313
+    if (!m_h) return InvalidInput;
+    int32_t i = 0;
+    qrk_info(m_h, &i);
+    return (ComputationInfo)i;
+  }
+  std::string lastErrorMessage() const { return m_h ? qrk_last_error(m_h) : m_lastError; }
+  qrk_handle_t handle() const { return m_h; }
+
+ protected:
+  void ensureHandle(const MatrixType& mat) {
+    const Index br = BlockMatrixType::RowsAtCompileTime, bc = BlockMatrixType::ColsAtCompileTime;
+    if (m_h && m_nb == mat.size() && m_rows == mat.rows() && m_cols == mat.cols()) return;
+    qrk_destroy(m_h);
+    m_h = nullptr;
+    qrk_desc_t d{};
+    d.kind = QRK_BLOCK_DIAGONAL; d.num_blocks = mat.size(); d.block_rows = (int32_t)br; d.block_cols = (int32_t)bc;
+    d.n_rows = mat.rows(); d.n_cols = mat.cols(); d.pivoting = BlockQRSolver::pivoting; d.q_format = _QFormat;
+    const int st = qrk_create(&d, &m_h);
+    m_nb = mat.size(); m_rows = mat.rows() ? mat.rows() : mat.size() * br; m_cols = mat.cols() ? mat.cols() : mat.size() * bc;
+    if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
+    detail::throw_if(st, nullptr, "BlockDiagonalSparseQR");
+  }
+  qrk_handle_t m_h = nullptr;
+  Index m_nb = -1, m_rows = 0, m_cols = 0;
+  bool m_isInitialized = false;
+  mutable bool m_haveR = false;
+  mutable MatrixRType m_R;
+  mutable PermutationType m_outputPerm_c, m_rowPerm;
+  std::string m_lastError;
+};
+
+// ---- BlockMatrix1x2 (BlockMatrix1x2.h:31-67) -----------------------------------------------------------------
+template <typename LeftBlock, typename RightBlock>
+class BlockMatrix1x2 {
+ public:
+  BlockMatrix1x2(const LeftBlock& l, const RightBlock& r) : m_left(l), m_right(r) {
+    assert(l.rows() == r.rows() && "blocks must have the same number of rows");                               // :37
+  }
+  Index rows() const { return m_left.rows(); }
+  Index cols() const { return m_left.cols() + m_right.cols(); }
+  const LeftBlock& leftBlock() const { return m_left; }
+  const RightBlock& rightBlock() const { return m_right; }
+ private:
+  const LeftBlock& m_left;       // references, as the reference (:65-66): both blocks must outlive this object
+  const RightBlock& m_right;
+};
+
+// ---- BlockAngularSparseQR (BlockAngularSparseQR.h:79-281), Left = BlockDiagonalSparseQR<...>, Right = dense ColPiv ---------
+template <typename BlockQRSolverLeftTag>
+class BlockAngularSparseQR {
+ public:
+  using LeftBlockMatrixType = SparseBlockDiagonal<typename BlockQRSolverLeftTag::MatrixType>;
+  using RightBlockMatrixType = MatrixXd;
+  using MatrixType = BlockMatrix1x2<LeftBlockMatrixType, RightBlockMatrixType>;
+  using MatrixRType = SparseMatrix<ColMajor>;
+  using PermutationType = PermutationMatrix;
+
+  BlockAngularSparseQR() {}
+  explicit BlockAngularSparseQR(const MatrixType& mat) { compute(mat); }
+  ~BlockAngularSparseQR() { qrk_destroy(m_h); }
+  BlockAngularSparseQR(const BlockAngularSparseQR&) = delete;
+  BlockAngularSparseQR& operator=(const BlockAngularSparseQR&) = delete;
+
+  void compute(const MatrixType& mat) {                                                                       // :134-138
+    ensureHandle(mat);
+    if (!m_h) return;
+    const auto& L = mat.leftBlock();
+    detail::throw_if(qrk_set_border(m_h, mat.rightBlock().data(), mat.rightBlock().rows(), QRK_HOST), m_h, "compute/border");
+    detail::throw_if(qrk_compute(m_h, L.size() ? L[0].data() : nullptr, QRK_HOST), m_h, "compute");
+    m_haveR = false; m_isInitialized = true;
+  }
+  VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {
+    ensureHandle(mat);
+    VectorXd x((size_t)mat.cols());
+    if (!m_h) return x;
+    const auto& L = mat.leftBlock();
+    detail::throw_if(qrk_set_border(m_h, mat.rightBlock().data(), mat.rightBlock().rows(), QRK_HOST), m_h, "border");
+    detail::throw_if(qrk_compute_solve(m_h, L.size() ? L[0].data() : nullptr, b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
+    m_haveR = false; m_isInitialized = true;
+    return x;
+  }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index leftBlockRows() const { return m_rows; }                                                              // :276-280
+  Index leftBlockCols() const { return m_cols - m_m2; }
+  const MatrixRType& matrixR() const {                                                                        // :163
+    if (!m_haveR) {
+      int64_t nnz = 0;
+      detail::throw_if(qrk_matrix_r_nnz(m_h, &nnz), m_h, "matrixR");
+      m_R.m_rows = m_rows; m_R.m_cols = m_cols;
+      m_R.outer.resize((size_t)m_cols + 1); m_R.inner.resize((size_t)nnz); m_R.values.resize((size_t)nnz);
+      detail::throw_if(qrk_matrix_r(m_h, m_R.outer.data(), m_R.inner.data(), m_R.values.data(), QRK_HOST), m_h, "matrixR");
+      m_haveR = true;
+    }
+    return m_R;
+  }
+  Index rank() const { int64_t r = 0; qrk_rank(m_h, &r); return r; }                                         // :510
+  const PermutationType& colsPermutation() const {
+    m_outputPerm_c.indices().resize((size_t)m_cols);
+    detail::throw_if(qrk_cols_permutation(m_h, m_outputPerm_c.indices().data(), QRK_HOST), m_h, "colsPermutation");
+    return m_outputPerm_c;
+  }
+  const PermutationType& rowsPermutation() const {
+    m_rowPerm.setIdentity(m_rows);                                                                            // :440-442, identity left and right
+    return m_rowPerm;
+  }
+  VectorXd solve(const VectorXd& B) const {                                                                   // :203-227
+    assert(m_isInitialized && "The factorization should be called first, use compute()");
+    VectorXd x((size_t)m_cols);
+    detail::throw_if(qrk_solve(m_h, B.data(), m_rows, x.data(), m_cols, 1, QRK_HOST), m_h, "solve");
+    return x;
+  }
+  void setPivotThreshold(double) {}                                                                           // no-op in the reference too (:234-237)
+  ComputationInfo info() const { if (!m_h) return InvalidInput; int32_t i = 0; qrk_info(m_h, &i); return (ComputationInfo)i; }
+  std::string lastErrorMessage() const { return m_h ? qrk_last_error(m_h) : m_lastError; }
+  qrk_handle_t handle() const { return m_h; }
+
+ private:
+  void ensureHandle(const MatrixType& mat) {
+    using Blk = typename BlockQRSolverLeftTag::MatrixType;
+    const auto& L = mat.leftBlock();
+    const Index m2 = mat.rightBlock().cols();
+    assert(L.cols() > m2 && "the left block should be the bigger one");                                        // :434
+    if (m_h && m_nb == L.size() && m_m2 == m2) return;
+    qrk_destroy(m_h);
+    m_h = nullptr;
+    qrk_desc_t d{};
+    d.kind = QRK_BLOCK_ANGULAR; d.num_blocks = L.size(); d.block_rows = Blk::RowsAtCompileTime; d.block_cols = Blk::ColsAtCompileTime;
+    d.pivoting = BlockQRSolverLeftTag::pivoting; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2;
+    const int st = qrk_create(&d, &m_h);
+    m_nb = L.size(); m_m2 = m2; m_rows = mat.rows(); m_cols = mat.cols();
+    if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
+    detail::throw_if(st, nullptr, "BlockAngularSparseQR");
+  }
+  qrk_handle_t m_h = nullptr;
+  Index m_nb = -1, m_m2 = 0, m_rows = 0, m_cols = 0;
+  bool m_isInitialized = false;
+  mutable bool m_haveR = false;
+  mutable MatrixRType m_R;
+  mutable PermutationType m_outputPerm_c, m_rowPerm;
+  std::string m_lastError;
+};
+
+}  // namespace QRKit_b200
