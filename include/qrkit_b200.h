@@ -178,6 +178,22 @@ QRK_API int qrk_angular_triangle_size(qrk_handle_t h, int64_t* doubles);
 QRK_API int qrk_angular_local_triangle(qrk_handle_t h, double* tri, int memspace);
 QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int memspace);
 
+/* ---- banded blocked (BandedBlockedSparseQR.h:122-344) ---------------------------------------------------------------
+ * A handle of kind QRK_BANDED_BLOCKED describes num_blocks block rows of block_rows x block_cols; block row k sits at
+ * rows [k*block_rows, ...) and columns [k*S, k*S + block_cols), S = block_cols - block_overlap
+ * (fromBlockBandedPattern, SparseQRUtils.h:274-302).  values = the slabs, column-major, back to back.
+ * Single GPU by construction (sequential window recurrence, BandedBlockedSparseQR.h:463-508).  Generic entry points:
+ *   qrk_compute / qrk_factorize / qrk_compute_solve / qrk_factorize_solve    factorize (:443-519) (+ fused solve)
+ *   qrk_solve                         Q^T b by the window sweep (:655-670 / SparseBlockYTY.h:102-139), banded back
+ *                                     substitution (:299-304)
+ *   qrk_apply_qt                      matrixQ().transpose() * b: the thin part [0, n_cols) (what solve and LM use); rows
+ *                                     beyond n_cols are returned as zero (the reference's complement depends on its own
+ *                                     window blocking and is not unique)
+ *   qrk_matrix_r(_nnz)                R as CSC with its natural band pattern (values as the reference up to row signs;
+ *                                     the reference additionally stores explicit zeros of its merged windows, :484-491)
+ *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation
+ * Supported (block_rows, block_cols, overlap): (16,24,16), (7,4,2), (7,2,0), (8,8,4), (12,8,4), (4,6,4). */
+
 /* ---- measurement hooks ---------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 QRK_API int qrk_launch_count(qrk_handle_t h, int64_t* launches);

@@ -1,0 +1,247 @@
+// banded.cuh — block-banded QR (BandedBlockedSparseQR, reference src/QRKit/BandedBlockedSparseQR.h:443-519):
+// a strictly sequential sliding-window Householder recurrence (window recurrence :494-507), hence ONE GPU,
+// one SM, and a latency-bound kernel by construction (SURVEY §7 hard part 5).
+//
+// Input: nb block rows; block row k is a dense BR x BC slab at rows [k*BR, (k+1)*BR), columns
+// [k*S, k*S + BC), S = BC - OV (fromBlockBandedPattern(rows, cols, BR, BC, OV), SparseQRUtils.h:274-302),
+// stored as block-COO slabs (column-major BR x BC, back to back).
+//
+// Window k = [carry (OV rows, upper triangular, left over from window k-1) ; slab k] is (OV+BR) x BC.
+// A full Householder QR of the window makes its first S rows final rows of R (rows k*S .. k*S+S-1, BC
+// entries each), annihilates OV+BR-BC rows, and leaves rows S..BC-1 as the next carry — the same
+// recurrence as the reference (which first merges block rows into larger windows; R is unique up to row
+// signs for a fixed column order, so the blocking is free).
+//
+// One warp, the whole window in registers, COLUMNS ACROSS LANES: lane j owns column j of the window (lane
+// BC owns the right-hand side), so every v^T a_j dot product and every rank-1 update is lane-local with no
+// reduction; the only cross-lane traffic is the broadcast of each reflector (<= BR values) from its lane.
+// Because the carry is upper triangular, reflector c < OV touches only the pivot entry and the BR slab
+// rows.  The next slab is prefetched into registers while the current window is factored.
+// Outputs: band R (n_cols x BC, row g holds columns [w(g)*S, w(g)*S+BC)), y = (Q^T b) thin part, the
+// packed windows (reflectors below the diagonal, in place over the slabs) and tau for later Q^T applications.
+#pragma once
+#include "common.cuh"
+
+namespace qrk {
+
+template <int BR, int BC, int OV>
+struct BandedCfg {
+  static constexpr int S = BC - OV;          // column step = rows finalised per window
+  static constexpr int M = OV + BR;          // window rows
+  static constexpr int DIE = M - BC;         // rows annihilated per window
+  static_assert(BC + 1 <= 32, "one lane per window column plus the right-hand side");
+  static_assert(OV >= 0 && OV < BC && M >= BC, "window must have at least as many rows as columns");
+};
+
+// window row r (0 <= r < M) of this lane's column lives in cw[r] (r < OV) or bw[r - OV]
+#define QRK_WROW(r) ((r) < OV ? cw[(r) < OV ? (r) : 0] : bw[(r) >= OV ? (r) - OV : 0])
+
+template <int BR, int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, double* __restrict__ rband,
+                     const double* __restrict__ b, double* __restrict__ y, double* __restrict__ ycomp, long long nb, int last_cols) {
+  using G = BandedCfg<BR, BC, OV>;
+  constexpr int S = G::S, M = G::M;
+  const int lane = threadIdx.x;
+  const bool is_col = lane < BC, is_rhs = (lane == BC) && (b != nullptr);
+  double cw[OV > 0 ? OV : 1], bw[BR], nxt[BR], tau_mine = 0.0;
+#pragma unroll
+  for (int i = 0; i < (OV > 0 ? OV : 1); i++) cw[i] = 0.0;
+
+  auto load_slab = [&](long long k, double (&dst)[BR]) {
+    if (is_col) {
+      const double* src = A_in + (k * BC + lane) * (long long)BR;
+#pragma unroll
+      for (int i = 0; i < BR; i++) dst[i] = src[i];
+    } else if (is_rhs) {
+#pragma unroll
+      for (int i = 0; i < BR; i++) dst[i] = b[k * BR + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < BR; i++) dst[i] = 0.0;
+    }
+  };
+  load_slab(0, nxt);
+
+  for (long long k = 0; k < nb; k++) {
+#pragma unroll
+    for (int i = 0; i < BR; i++) bw[i] = nxt[i];
+    if (k + 1 < nb) load_slab(k + 1, nxt);       // in flight while this window is factored
+    const int ncols_w = (k == nb - 1) ? last_cols : BC;   // the last slab may be narrower (fromBlockBandedPattern, SparseQRUtils.h:284)
+
+#pragma unroll
+    for (int c = 0; c < BC; c++) {
+      if (c >= ncols_w) continue;                  // columns beyond the matrix: no reflector
+      const int P0 = (c < OV) ? 0 : c - OV + 1;   // first participating slab row (compile time after unrolling)
+      // ---- reflector of column c, computed in lane c (every lane runs the arithmetic, lane c's result is used)
+      double tailSq = 0.0;
+#pragma unroll
+      for (int i = 0; i < BR; i++) if (i >= P0) tailSq = fma(bw[i], bw[i], tailSq);
+      const double c0 = QRK_WROW(c);
+      const bool degenerate = (P0 >= BR) || (tailSq <= DBL_MIN);
+      double norm;
+      const double rnorm = fast_rsqrt(fma(c0, c0, tailSq), norm);
+      double beta = (c0 >= 0.0) ? -norm : norm;
+      const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
+      double inv = fast_rcp(c0 - beta);
+      double tau = (beta - c0) * ib;
+      if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
+      tau = __shfl_sync(0xffffffffu, tau, c);
+      // ---- broadcast v = [1; inv * tail] from lane c; dot product and rank-1 update are lane-local
+      const bool upd = lane > c;                  // columns right of c and the right-hand side
+      double pv = QRK_WROW(c);
+      double dot = pv;
+      double v[BR];
+#pragma unroll
+      for (int i = 0; i < BR; i++) {
+        if (i >= P0) {
+          v[i] = __shfl_sync(0xffffffffu, bw[i] * inv, c);
+          dot = fma(v[i], bw[i], dot);
+        }
+      }
+      const double w = upd ? tau * dot : 0.0;
+      pv -= w;
+      if (lane == c) { pv = beta; tau_mine = tau; }
+      if (c < OV) cw[c < OV ? c : 0] = pv; else bw[c >= OV ? c - OV : 0] = pv;
+#pragma unroll
+      for (int i = 0; i < BR; i++) {
+        if (i >= P0) {
+          if (lane == c) bw[i] = v[i];            // store the essential part in place (LAPACK packing)
+          else bw[i] = fma(-v[i], w, bw[i]);
+        }
+      }
+    }
+
+    // ---- outputs of this window
+    const bool last = (k == nb - 1);
+    if (is_col) {
+      double* dst = packed + (k * BC + lane) * (long long)BR;
+#pragma unroll
+      for (int i = 0; i < BR; i++) dst[i] = bw[i];
+      tau_out[k * BC + lane] = tau_mine;
+    }
+#pragma unroll
+    for (int r = 0; r < BC; r++) {
+      if (last ? (r < last_cols) : (r < S)) {
+        const double val = QRK_WROW(r);
+        const long long g = k * S + r;
+        if (is_col) rband[g * BC + lane] = (lane >= r) ? val : 0.0;
+        else if (is_rhs) y[g] = val;
+      }
+    }
+    if (is_rhs && ycomp) {
+#pragma unroll
+      for (int r = BC; r < M; r++) ycomp[k * (M - BC) + (r - BC)] = QRK_WROW(r);
+    }
+    // ---- next carry: window rows S..BC-1, columns shifted left by S (the right-hand side lane keeps its own)
+    if (OV > 0) {
+      double ncw[OV > 0 ? OV : 1];
+#pragma unroll
+      for (int i = 0; i < OV; i++) {
+        const double val = QRK_WROW(S + i);
+        const double shifted = __shfl_down_sync(0xffffffffu, val, S);
+        ncw[i] = (lane == BC) ? val : ((lane < BC - S && lane >= i) ? shifted : 0.0);   // keep the carry upper triangular
+      }
+#pragma unroll
+      for (int i = 0; i < OV; i++) cw[i] = ncw[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q^T applied to a new right-hand side on a stored factorisation (packed windows + tau): the same window
+// sweep with only the vector; lane i owns slab row i, the OV carried entries are replicated in every lane.
+// ---------------------------------------------------------------------------------------------
+template <int BR, int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
+                       double* __restrict__ y, double* __restrict__ ycomp, long long nb, int last_cols) {
+  using G = BandedCfg<BR, BC, OV>;
+  constexpr int S = G::S, M = G::M;
+  static_assert(BR <= 32, "one lane per slab row");
+  const int lane = threadIdx.x;
+  double cy[OV > 0 ? OV : 1];
+#pragma unroll
+  for (int i = 0; i < (OV > 0 ? OV : 1); i++) cy[i] = 0.0;
+  for (long long k = 0; k < nb; k++) {
+    double bi = (lane < BR) ? b[k * BR + lane] : 0.0;
+    double vv[BC], tt[BC];
+#pragma unroll
+    for (int c = 0; c < BC; c++) {               // independent of the chain: issued up front
+      vv[c] = (lane < BR) ? packed[(k * BC + c) * (long long)BR + lane] : 0.0;
+      tt[c] = tau_in[k * BC + c];
+    }
+    const int ncols_w = (k == nb - 1) ? last_cols : BC;
+#pragma unroll
+    for (int c = 0; c < BC; c++) {
+      if (c >= ncols_w) continue;
+      const int P0 = (c < OV) ? 0 : c - OV + 1;
+      double part = (lane >= P0 && lane < BR) ? vv[c] * bi : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const double pivot = (c < OV) ? cy[c < OV ? c : 0] : __shfl_sync(0xffffffffu, bi, c >= OV ? c - OV : 0);
+      const double w = tt[c] * (pivot + part);
+      if (c < OV) cy[c < OV ? c : 0] -= w;
+      else if (lane == c - OV) bi -= w;
+      if (lane >= P0 && lane < BR) bi = fma(-vv[c], w, bi);
+    }
+    const bool last = (k == nb - 1);
+#pragma unroll
+    for (int r = 0; r < BC; r++) {
+      if (last ? (r < last_cols) : (r < S)) {
+        const double val = (r < OV) ? cy[r < OV ? r : 0] : __shfl_sync(0xffffffffu, bi, r >= OV ? r - OV : 0);
+        if (lane == 0) y[k * S + r] = val;
+      }
+    }
+    if (ycomp) {
+#pragma unroll
+      for (int r = BC; r < M; r++) {
+        const double val = __shfl_sync(0xffffffffu, bi, r - OV);
+        if (lane == 0) ycomp[k * (M - BC) + (r - BC)] = val;
+      }
+    }
+    if (OV > 0) {
+      double ncy[OV > 0 ? OV : 1];
+#pragma unroll
+      for (int i = 0; i < OV; i++)
+        ncy[i] = (S + i < OV) ? cy[(S + i < OV) ? S + i : 0] : __shfl_sync(0xffffffffu, bi, (S + i >= OV) ? S + i - OV : 0);
+#pragma unroll
+      for (int i = 0; i < OV; i++) cy[i] = ncy[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Back substitution with the band R, window by window from the bottom (R.topLeftCorner(rank, rank)
+// .triangularView<Upper>().solve, BandedBlockedSparseQR.h:299-304).  Lane j owns x[w*S + j].
+// ---------------------------------------------------------------------------------------------
+template <int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_backsolve_kernel(const double* __restrict__ rband, const double* __restrict__ y, double* __restrict__ x, long long nb,
+                        int last_cols) {
+  constexpr int S = BC - OV;
+  const int lane = threadIdx.x;
+  double xj = 0.0;                                // x of window column `lane`
+  for (long long w = nb - 1; w >= 0; --w) {
+    const int nrows = (w == nb - 1) ? last_cols : S;
+    if (w != nb - 1) {
+      const double up = __shfl_up_sync(0xffffffffu, xj, S);   // column (w+1)*S + j  ==  w*S + (j + S)
+      xj = (lane >= S) ? up : 0.0;
+    }
+    for (int r = nrows - 1; r >= 0; --r) {
+      const long long g = w * S + r;
+      const double rv = (lane < BC) ? rband[g * BC + lane] : 0.0;
+      double part = (lane > r && lane < BC) ? rv * xj : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const double diag = __shfl_sync(0xffffffffu, rv, r);
+      const double xr = (y[g] - part) / diag;
+      if (lane == r) xj = xr;
+    }
+    if (lane < nrows) x[w * S + lane] = xj;
+  }
+}
+
+#undef QRK_WROW
+
+}  // namespace qrk

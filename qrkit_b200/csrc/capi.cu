@@ -196,6 +196,7 @@ void free_dev(qrk_solver* h) {
   if (h->own_values) F(h->d_values);
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
+  F(h->d_rband); F(h->d_btau); F(h->d_ythin);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
@@ -388,6 +389,61 @@ int angular_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
   return angular_root_and_back(h, a, true, d_x, 1);
 }
 
+
+// ---- banded blocked ----------------------------------------------------------------------------------
+BandedArgs banded_args(qrk_solver* h) {
+  BandedArgs a;
+  a.nb = h->nb; a.packed = h->d_values; a.tau = h->d_btau; a.rband = h->d_rband; a.y = h->d_ythin;
+  a.last_cols = (int)(h->n_cols - (h->nb - 1) * (long long)h->b_step);
+  return a;
+}
+
+// window sweep (+ fused Q^T b and back substitution when d_b != nullptr)
+int banded_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
+  BandedArgs a = banded_args(h);
+  a.A_in = A_in; a.b = d_b;
+  QRK_TRY_CUDA(h, h->bvt->factor(a, h->stream));
+  h->launches++;
+  if (d_b) {
+    a.x = d_x;
+    QRK_TRY_CUDA(h, h->bvt->backsolve(a, h->stream));
+    h->launches++;
+  }
+  return QRK_STATUS_OK;
+}
+
+// natural band pattern of R as CSC: column j holds rows [gmin(j), j]
+__global__ void export_banded_r_kernel(const double* __restrict__ rband, const int* __restrict__ outer, int* __restrict__ inner,
+                                       double* __restrict__ vals, long long n_cols, long long nb, int bc, int step) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_cols; j += (long long)gridDim.x * blockDim.x) {
+    const int p0 = outer[j], cnt = outer[j + 1] - p0;
+    const long long g0 = j - cnt + 1;
+    for (int q = 0; q < cnt; q++) {
+      const long long g = g0 + q;
+      long long w = g / step;
+      if (w > nb - 1) w = nb - 1;
+      inner[p0 + q] = (int)g;
+      vals[p0 + q] = rband[g * bc + (j - w * step)];
+    }
+  }
+}
+
+std::vector<int> banded_r_outer(const qrk_solver* h) {
+  const long long n = h->n_cols, S = h->b_step, BC = h->uc, nb = h->nb;
+  std::vector<int> outer(n + 1, 0);
+  long long acc = 0;
+  for (long long j = 0; j < n; j++) {
+    // rows g <= j whose window covers column j: w(g) >= wmin, w(g) = min(g / S, nb - 1)
+    long long wmin = (j - BC) >= 0 ? (j - BC) / S + 1 : 0;
+    if (wmin > nb - 1) wmin = nb - 1;
+    const long long gmin = wmin * S;
+    outer[j] = (int)acc;
+    acc += j - gmin + 1;
+  }
+  outer[n] = (int)acc;
+  return outer;
+}
+
 }  // namespace
 
 extern "C" {
@@ -421,7 +477,8 @@ int qrk_device_count(int* count) {
 int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   if (!desc || !out) return QRK_STATUS_INVALID_ARGUMENT;
   *out = nullptr;
-  if (desc->kind != QRK_BLOCK_DIAGONAL && desc->kind != QRK_BLOCK_ANGULAR) return QRK_STATUS_UNSUPPORTED;
+  if (desc->kind != QRK_BLOCK_DIAGONAL && desc->kind != QRK_BLOCK_ANGULAR && desc->kind != QRK_BANDED_BLOCKED) return QRK_STATUS_UNSUPPORTED;
+  const bool banded = desc->kind == QRK_BANDED_BLOCKED;
   const bool angular = desc->kind == QRK_BLOCK_ANGULAR;
   if (desc->num_blocks < 0) return QRK_STATUS_INVALID_ARGUMENT;
   const bool uniform = desc->block_rows > 0 && desc->block_cols > 0;
@@ -466,6 +523,25 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   }
   h->n_rows = desc->n_rows > 0 ? desc->n_rows : h->sum_rows;
   h->n_cols = desc->n_cols > 0 ? desc->n_cols : h->sum_cols;
+  if (banded) {
+    // nb block rows of block_rows x block_cols, consecutive blocks shifted by S = block_cols - overlap columns
+    // (BlockBandedMatrixInfo::fromBlockBandedPattern, SparseQRUtils.h:274-302)
+    if (!uniform || h->nb < 1) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    h->b_ov = desc->block_overlap;
+    h->b_step = h->uc - h->b_ov;
+    h->bvt = banded_vtable(h->ur, h->uc, h->b_ov);
+    if (!h->bvt) return fail(QRK_STATUS_UNSUPPORTED);
+    h->n_rows = h->sum_rows;
+    // n_cols defaults to the full width of the last slab; a narrower last slab (the reference's pattern gives the last
+    // block block_cols - overlap columns, SparseQRUtils.h:284) is selected by passing n_cols explicitly
+    const long long full = (h->nb - 1) * (long long)h->b_step + h->uc;
+    h->n_cols = desc->n_cols > 0 ? desc->n_cols : full;
+    if (h->n_cols > full || h->n_cols <= (h->nb - 1) * (long long)h->b_step) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    h->sum_cols = h->n_cols;
+    if (h->n_rows < h->n_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    if (desc->n_rows > 0 && desc->n_rows != h->n_rows) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    h->info = QRK_INFO_SUCCESS;      // landscape slabs are normal here
+  }
   if (angular) {
     // left block: uniform small blocks covering all rows, FullQ; border: 1..8 dense columns
     h->m2 = desc->border_cols;
@@ -477,12 +553,12 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   if (h->n_rows < h->sum_rows || h->n_cols < h->sum_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
   if (h->n_rows > INT32_MAX || h->n_cols > INT32_MAX) return fail(QRK_STATUS_UNSUPPORTED);  // StorageIndex = int
   if (desc->q_format != QRK_FULL_Q && desc->q_format != QRK_BLOCK_DIAGONAL_Q) h->info = QRK_INFO_INVALID_INPUT;  // :501-505
-  if (landscape) h->info = QRK_INFO_INVALID_INPUT;                                                               // :509-516
+  if (landscape && !banded) h->info = QRK_INFO_INVALID_INPUT;                                                               // :509-516
 
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);
   h->stream = h->own_stream;
 
-  h->small_path = uniform && small_shape_available(h->ur, h->uc);
+  h->small_path = uniform && !banded && small_shape_available(h->ur, h->uc);
   auto up = [&](auto*& dptr, const auto& vec) -> cudaError_t {
     using T = typename std::remove_reference<decltype(vec[0])>::type;
     cudaError_t e = cudaMalloc(&dptr, std::max<size_t>(vec.size(), 1) * sizeof(T));
@@ -495,7 +571,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         up(h->d_coff, h->h_coff) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);
   }
-  if (!h->small_path && h->nb > 0 && h->info == QRK_INFO_SUCCESS) {
+  if (!h->small_path && !banded && h->nb > 0 && h->info == QRK_INFO_SUCCESS) {
     // size classes of the generic kernel: (team warps, shared memory rounded up to 8 KB steps)
     if (uniform) {
       SizeClass sc;
@@ -526,6 +602,12 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   cudaMemsetAsync(h->d_tau, 0, std::max<long long>(h->n_cols, 1) * sizeof(double), h->stream);
   iota_kernel<<<256, 256, 0, h->stream>>>(h->d_perm, h->n_cols);   // m_outputPerm_c.setIdentity (:417)
   h->launches++;
+  if (banded) {
+    if (cudaMalloc(&h->d_rband, (size_t)h->n_cols * h->uc * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_btau, (size_t)h->nb * h->uc * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_ythin, (size_t)h->n_cols * sizeof(double)) != cudaSuccess)
+      return fail(QRK_STATUS_ALLOC_FAILED);
+  }
   if (angular) {
     const bool piv = desc->pivoting == QRK_PIVOT_COLPIV;
     if (h->avt->max_grid(h->ur, h->uc, piv, &h->a_grid) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);
@@ -619,7 +701,8 @@ int qrk_factorize(qrk_handle_t h) {
   if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;   // reported through info(), as the reference
   DeviceGuard g(h->device);
-  int st = h->avt ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr);
+  int st = h->bvt ? banded_run(h, h->d_values, nullptr, nullptr)
+                  : (h->avt ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -639,7 +722,7 @@ static int compute_from_device(qrk_solver* h, const double* values, const double
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
   if (d_x && h->n_cols > h->sum_cols && !h->avt)
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  st = h->avt ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x);
+  st = h->bvt ? banded_run(h, values, d_b, d_x) : (h->avt ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -676,7 +759,7 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   }
   if (h->n_cols > h->sum_cols && !h->avt)
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  int st = h->avt ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x);
+  int st = h->bvt ? banded_run(h, h->d_values, d_b, d_x) : (h->avt ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   if (h->pending) {            // multi-GPU block angular: x is produced by qrk_angular_merge
@@ -763,6 +846,7 @@ int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz) {
   if (h->uniform) n = h->nb * ((long long)h->uc * (h->uc + 1) / 2);
   else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
   if (h->avt) n += h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2;   // border columns (makeR :296-305)
+  if (h->bvt) n = banded_r_outer(h).back();
   *nnz = n;
   return QRK_STATUS_OK;
 }
@@ -814,7 +898,16 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
   const BlockIndex bi = block_index(h);
   const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
   cudaError_t e;
-  if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->avt ? h->sum_cols : h->n_cols, h->sum_rows,
+  if (h->bvt) {
+    if (want_q) { h->err = "banded matrixQ() as an explicit sparse matrix is not provided"; e = cudaErrorNotSupported; }
+    else {
+      const std::vector<int> ho = banded_r_outer(h);
+      cudaMemcpyAsync(d_outer, ho.data(), ho.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->n_cols, h->nb, h->uc, h->b_step);
+      e = cudaGetLastError();
+      cudaStreamSynchronize(h->stream);     // ho must outlive the copy
+    }
+  } else if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->avt ? h->sum_cols : h->n_cols, h->sum_rows,
                                   nnz - (h->n_rows - h->sum_rows), full_q, h->max_r, d_outer, d_inner, d_vals, h->stream);
   else if (h->avt) {
     const long long nnz_r1 = nnz - (h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2);
@@ -872,12 +965,30 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     if (h->n_cols > h->sum_cols && !h->avt)   // y.bottomRows(...).setZero() (:272)
       QRK_TRY_CUDA(h, cudaMemset2DAsync(d_X + h->sum_cols, dldx * sizeof(double), 0, (h->n_cols - h->sum_cols) * sizeof(double),
                                         nrhs, h->stream));
-  } else if (h->n_rows > h->sum_rows) {
+  } else if (h->n_rows > h->sum_rows && !h->bvt) {
     copy_tail_kernel<<<64, 256, 0, h->stream>>>(d_B, dldb, d_X, dldx, nrhs, h->sum_rows, h->n_rows);
     h->launches++;
   }
   int st = QRK_STATUS_OK;
-  if (h->avt && op == OP_SOLVE) {
+  if (h->bvt) {
+    // Q^T b by the window sweep over the stored reflectors (BandedBlockedSparseQR.h:655-670 applies the YTY blocks in
+    // the same order), then the banded back substitution (:299-304).  Q^T b: thin part [0, n_cols), zeros after it.
+    // matrixQ() * v is not provided yet.
+    if (op == OP_APPLY_Q) { h->err = "banded matrixQ() * v is not implemented"; return QRK_STATUS_UNSUPPORTED; }
+    for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) {
+      BandedArgs a = banded_args(h);
+      a.b = d_B + j * dldb;
+      if (op == OP_APPLY_QT) {
+        a.y = d_X + j * dldx;      // thin part; the window sweep works on [0 (overlap rows); A], whose annihilated-row
+        a.ycomp = nullptr;         // components do not map one-to-one onto the n_rows - n_cols complement: left zero
+        if (h->n_rows > h->n_cols) cudaMemsetAsync(d_X + j * dldx + h->n_cols, 0, (h->n_rows - h->n_cols) * sizeof(double), h->stream);
+      }
+      cudaError_t e = h->bvt->apply_qt(a, h->stream);
+      h->launches++;
+      if (e == cudaSuccess && op == OP_SOLVE) { a.x = d_X + j * dldx; e = h->bvt->backsolve(a, h->stream); h->launches++; }
+      if (e != cudaSuccess) { h->err = std::string("banded op: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
+    }
+  } else if (h->avt && op == OP_SOLVE) {
     QRK_REQUIRE(h, h->world == 1 || nrhs == 1, "multi-GPU block-angular solve takes one right-hand side per call");
     for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) st = angular_solve_stored(h, d_B + j * dldb, d_X + j * dldx);
     if (st == QRK_STATUS_OK && h->pending) {

@@ -8,6 +8,7 @@
 
 #include "../../include/qrkit_b200.h"
 #include "angular_dispatch.hpp"
+#include "banded_dispatch.hpp"
 
 namespace qrk {
 
@@ -66,6 +67,13 @@ struct qrk_solver {
   double* pending_x = nullptr;
   int pending_space = 0;
   int pending_keep_rhs_only = 0;
+
+  // ---- banded blocked (kind == QRK_BANDED_BLOCKED): sequential window sweep on one SM ----
+  const qrk::BandedVTable* bvt = nullptr;
+  int b_ov = 0, b_step = 0;            // overlap, column step S = block_cols - overlap
+  double *d_rband = nullptr;           // band R: n_cols x block_cols
+  double *d_btau = nullptr;            // tau: num_blocks x block_cols
+  double *d_ythin = nullptr;           // (Q^T b)[0:n_cols]
 
   // ---- staging buffers for host-memspace calls ----
   double *d_b = nullptr, *d_x = nullptr;

@@ -329,3 +329,50 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
         t = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1)
         check(lib().qrk_angular_merge(self._h, _ptr(t), len(t) // self.triangle_size(), QRK_HOST), self._h)
         return getattr(self, "_x", None)
+
+
+class BandedBlockedSparseQR(BlockDiagonalSparseQR):
+    """BandedBlockedSparseQR<SparseMatrix, HouseholderQR<MatrixXd>, BlockOverlap, ...> (BandedBlockedSparseQR.h:122-344) for
+    the fixed block-banded pattern: ``slabs`` is the block-COO array of nb dense block_rows x block_cols slabs (column-major),
+    slab k at rows [k*block_rows, ...), columns [k*(block_cols-overlap), ...)."""
+
+    def __init__(self, slabs=None, *, num_blocks=None, block_rows=0, block_cols=0, overlap=0, n_cols=0, device=0, stream=None):
+        self._geom = (block_rows, block_cols, overlap)
+        self._n_cols = n_cols                # 0: full last slab; else the matrix ends inside the last slab
+        super().__init__(None, pivoting=QRK_PIVOT_NONE, q_format=QRK_FULL_Q, device=device, stream=stream)
+        if slabs is not None:
+            self.compute(slabs, num_blocks)
+
+    def _ensure_handle_banded(self, nb):
+        br, bc, ov = self._geom
+        key = ("banded", nb, br, bc, ov)
+        if self._h and key == self._shape_key:
+            return
+        self.close()
+        d = QrkDesc()
+        d.kind, d.device, d.num_blocks = capi.QRK_BANDED_BLOCKED, self._device, nb
+        d.block_rows, d.block_cols, d.block_overlap = br, bc, ov
+        d.n_cols = self._n_cols
+        h = C.c_void_p()
+        check(lib().qrk_create(C.byref(d), C.byref(h)))
+        self._h, self._shape_key = h, key
+        if self._stream is not None:
+            check(lib().qrk_set_stream(self._h, C.c_void_p(int(self._stream))), self._h)
+
+    def _nb(self, slabs, num_blocks):
+        br, bc, _ = self._geom
+        return int(num_blocks) if num_blocks is not None else len(slabs) // (br * bc)
+
+    def compute(self, slabs, num_blocks=None):
+        slabs = np.ascontiguousarray(slabs, dtype=np.float64)
+        self._ensure_handle_banded(self._nb(slabs, num_blocks))
+        check(lib().qrk_compute(self._h, _ptr(slabs), QRK_HOST), self._h)
+        return self
+
+    def compute_solve(self, slabs, b, num_blocks=None):
+        slabs = np.ascontiguousarray(slabs, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self._ensure_handle_banded(self._nb(slabs, num_blocks))
+        x = np.empty(self.cols())
+        check(lib().qrk_compute_solve(self._h, _ptr(slabs), _ptr(b), _ptr(x), QRK_HOST), self._h)
+        return x

@@ -121,3 +121,26 @@ def sign_normalize_rows(R):
         if R[i, i] < 0:
             R[i, :] = -R[i, :]
     return R
+
+
+def reference_style_windows(nb, br, bc, ov, suggested=2):
+    """Windows the reference would factor for nb block rows of br x bc shifted by s = bc - ov columns: consecutive block rows
+    are merged until the window is portrait and at least `suggested` columns wide (mergeBlocks rule, SparseQRUtils.h:357),
+    a leftover that cannot form such a window is merged into the last one (:370-383).  Rows: (idxRow, idxCol, numRows, numCols)."""
+    s = bc - ov
+    out, first, rows, cols = [], None, 0, 0
+    for k in range(nb):
+        if first is None:
+            first, rows, cols = k, br, bc
+        else:
+            rows, cols = (k + 1 - first) * br, (k - first) * s + bc
+        if rows > cols and cols >= s and cols >= suggested:
+            out.append([first * br, first * s, rows, cols])
+            first = None
+    if first is not None:
+        if out:
+            last = out[-1]
+            out[-1] = [last[0], last[1], last[2] + rows, first * s + cols - last[1]]
+        else:
+            out.append([first * br, first * s, rows, cols])
+    return np.array(out, dtype=np.int32)
