@@ -142,6 +142,34 @@ def bench_mixed(args, L, stream):
     print(json.dumps(line), flush=True)
 
 
+def bench_classes(args, L, stream):
+    """Config 5 one size class at a time (uniform r x r/2 blocks, nb/7 each): where the mixed time goes."""
+    peak, src = measured_peaks()
+    per = []
+    shapes = [(32 + 16 * k, 16 + 8 * k) for k in range(7)] if not args.shapes else \
+        [tuple(int(v) for v in a.split("x")) for a in args.shapes.split(",")]
+    for (r, c) in shapes:
+        nb = args.class_blocks or args.mixed_blocks // 7
+        A = torch.empty(nb * r * c, dtype=torch.float64, device="cuda")
+        check(L.qrk_synth_fill(vp(A), SEED_A, 0, nb, r, c, 0.5, 5.0, stream))
+        b = torch.empty(nb * r, dtype=torch.float64, device="cuda")
+        check(L.qrk_synth_fill(vp(b), SEED_A + 5, 0, nb * r, 1, 0, -1.0, 1.0, stream))
+        x = torch.empty(nb * c, dtype=torch.float64, device="cuda")
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting = 0, nb, r, c, 0
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_set_stream(h, stream), h)
+        ms = time_steps(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), args.steps, args.warmup)
+        L.qrk_destroy(h)
+        alg = nb * (16.0 * r * c + 8 * r + 16 * c)
+        fl = nb * (2.0 * r * c * c - (2.0 / 3.0) * c ** 3 + 4 * r * c + c * c)
+        per.append({"block": [r, c], "blocks": nb, "ms": round(ms, 4), "us_per_block_per_sm": round(ms * 1e3 * 148 / nb, 3),
+                    "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "fp64_frac": round(fl / (ms * 1e-3) / 1e12 / 37.0, 4)})
+    print(json.dumps({"workload": "config 5 per size class (uniform blocks, fused QR+solve, unpivoted)", "classes": per,
+                      "total_ms": sum(p["ms"] for p in per), "peak_source": src}), flush=True)
+
+
 def bench_two_call(args, L, stream):
     nb, r, c = 1_000_000, 8, 4
     A = torch.empty(nb * r * c, dtype=torch.float64, device="cuda")
@@ -174,6 +202,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--mixed-blocks", type=int, default=100_000)
+    ap.add_argument("--class-blocks", type=int, default=0)
+    ap.add_argument("--shapes", default="")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: qrkit_b200 has no CPU fallback")
@@ -183,7 +213,7 @@ def main():
     stream = C.c_void_p(s.cuda_stream)
     L = capi.lib()
     for w in args.workload.split(","):
-        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call}[w](args, L, stream)
+        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call, "classes": bench_classes}[w](args, L, stream)
 
 
 if __name__ == "__main__":

@@ -124,12 +124,16 @@ double orc_bd_compact_uniform(int64_t nb, int r, int c, double* values, const do
   for (int64_t i = 0; i < nb; i++) {
     double* A = values + (size_t)i * r * c;
     double* ta = tau + (size_t)i * c;
-    int p[64];
+    int pstack[64];
+    std::vector<int> pheap(c > 64 ? c : 0);
+    int* p = c > 64 ? pheap.data() : pstack;
     if (colpiv) colpiv_householder_qr(A, r, c, ta, p);
     else { householder_qr(A, r, c, ta); for (int j = 0; j < c; j++) p[j] = j; }
     if (perm) for (int j = 0; j < c; j++) perm[(size_t)i * c + j] = (int)(i * c + p[j]);
     if (b) {
-      double bb[256];
+      double bstack[256];
+      std::vector<double> bheap(r > 256 ? r : 0);
+      double* bb = r > 256 ? bheap.data() : bstack;
       for (int k = 0; k < r; k++) bb[k] = b[(size_t)i * r + k];
       apply_qt_inplace(A, r, c, ta, bb, r, 1);
       for (int j = c - 1; j >= 0; --j) {

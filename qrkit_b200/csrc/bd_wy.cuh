@@ -1,0 +1,355 @@
+// bd_wy.cuh — blocked (compact-WY) FP64 Householder QR of medium diagonal blocks, one CTA per block, the
+// trailing update on the FP64 tensor cores (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4).
+//
+// Reference path: BlockDiagonalSparseQR::factorize for dynamically sized blocks
+// (src/QRKit/BlockDiagonalSparseQR.h:432-526 with BlockQRSolver = HouseholderQR<MatrixXd>), and the panel /
+// compact-WY machinery of BlockedThinQRBase (src/QRKit/BlockedThinQRBase.h:308-333: Y, T and the trailing update
+// A[:,j] += Y (T^T (Y^T A[:,j])), which the reference performs one column at a time as GEMVs).  Here the same
+// update is three small GEMMs per 8-column tile, A2^T -= ((A2^T V) T) V^T, issued as DMMA.  BASELINE config 5.
+//
+// Layout.  The block lives in shared memory column-major with leading dimension ld = rp + 4 (rp = rows padded
+// to a multiple of 8, so ld = 4 mod 8): the two access patterns of the DMMA fragments,
+//   (row + q, col + g) and (row + g', col + q)   with q = lane & 3, g = lane >> 2,
+// then hit 16 distinct 8-byte banks per half-warp.  Inside an 8-row tile the K/N slots of the fragments are
+// permuted (kappa below) so that the SAME two registers of a thread are the A operand of the first GEMM and the
+// accumulator of the last one: a tile of A2 is read once and written once per panel, and V is read in place.
+//
+// Schedule.  Panels of 8 columns.  One warp factors a panel in registers (rows across lanes, ONE batched
+// warp-shuffle all-reduce per column: tail dot products of the pivot column with itself and with the columns to
+// its right), writes the packed columns back, forms S = V^T V with DMMA and the 8x8 T by the dlarft recurrence
+// (one lane per row of T).  In phase p every warp applies panel p to its 8-column tiles; the owner of the next
+// panel takes tile p+1 first and factors it at once (look-ahead) while the others finish the phase.
+// The right-hand side rides along as one more (virtual) tile, then R x = (Q^T b)[0:c] is solved by warp 0.
+#pragma once
+#include "bd_generic.cuh"
+
+namespace qrk {
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+struct WyGeom {
+  int rp, cp, ld;
+  __host__ __device__ WyGeom(int r, int c) {
+    cp = (c + 7) & ~7;
+    const int r8 = (r + 7) & ~7;
+    rp = r8 > cp ? r8 : cp;
+    ld = rp + 4;
+  }
+};
+constexpr int kWyPB = 96;   // diagonal tile of V (unit lower triangular 8x8), column stride 12 (= 12 mod 16)
+
+__host__ __device__ inline size_t wy_smem_bytes(int r, int c) {
+  const WyGeom g(r, c);
+  const size_t d = (size_t)g.cp * g.ld + g.ld + 2 * kWyPB + 2 * 64 + 64 + 2 * (size_t)g.cp;
+  return d * 8 + 16;
+}
+// rows per lane of the panel warp (template parameter MR): 1, 2 or 4; 0 = block too tall for this kernel
+__host__ __device__ inline int wy_mr(int r, int c) {
+  const WyGeom g(r, c);
+  return g.rp <= 32 ? 1 : g.rp <= 64 ? 2 : g.rp <= 128 ? 4 : 0;
+}
+__host__ __device__ inline int wy_warps(int r, int c) { return WyGeom(r, c).cp <= 16 ? 2 : 4; }
+
+// fragment slot -> row inside an 8-row tile: k-step h, slot q  (see header)
+__device__ __forceinline__ int wy_kappa(int q, int h) { return h ? 4 + ((q + 2) & 3) : q; }
+
+// ---- panel factorisation: columns p..p+7, rows p..rp-1, by ONE warp -------------------------------------------
+// One column step; K is a template parameter so that every register-array index is a compile-time constant.
+template <int MR, int K>
+__device__ __forceinline__ void wy_panel_step(double (&a)[MR][8], double (&tauv)[8], int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  // tail dot products t_j = sum_{rows > K} a_K a_j, j = K..7 (t_K = tailSqNorm), one batched all-reduce
+  double t[8];
+#pragma unroll
+  for (int j = K; j < 8; j++) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+      const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0;
+      s = fma(ak, a[m][j], s);
+    }
+    t[j] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = K; j < 8; j++) t[j] += __shfl_xor_sync(FULL, t[j], o);
+  double piv[8];
+#pragma unroll
+  for (int j = K; j < 8; j++) piv[j] = __shfl_sync(FULL, a[0][j], K);
+  // Eigen makeHouseholder: beta = -sign(x0) ||x||, ess = tail / (x0 - beta), tau = (beta - x0) / beta
+  const double c0 = piv[K];
+  const bool degenerate = t[K] <= DBL_MIN;
+  double norm;
+  const double rnorm = fast_rsqrt(fma(c0, c0, t[K]), norm);
+  double beta = (c0 >= 0.0) ? -norm : norm;
+  const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
+  double inv = fast_rcp(c0 - beta);
+  double tau = (beta - c0) * ib;
+  if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
+#pragma unroll
+  for (int j = K + 1; j < 8; j++) {
+    const double w = fma(t[j], inv, piv[j]);      // v^T a_j
+    const double s = tau * w;
+    const double sinv = s * inv;
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+      if (m == 0) {
+        if (lane == K) a[0][j] -= s;
+        else if (lane > K) a[0][j] = fma(-a[0][K], sinv, a[0][j]);
+      } else {
+        a[m][j] = fma(-a[m][K], sinv, a[m][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; m++) {
+    if (m == 0) {
+      if (lane == K) a[0][K] = beta;
+      else if (lane > K) a[0][K] *= inv;
+    } else {
+      a[m][K] *= inv;
+    }
+  }
+  tauv[K] = tau;
+}
+
+template <int MR>
+__device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int p, double* PB0, double* sT, double* sS,
+                                                double* sTau, int lane) {
+  const int nrow = rp - p;
+  double a[MR][8];
+#pragma unroll
+  for (int m = 0; m < MR; m++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[m][j] = (lane + 32 * m < nrow) ? sA[(size_t)(p + j) * ld + p + lane + 32 * m] : 0.0;
+  double tauv[8];
+  wy_panel_step<MR, 0>(a, tauv, lane);
+  wy_panel_step<MR, 1>(a, tauv, lane);
+  wy_panel_step<MR, 2>(a, tauv, lane);
+  wy_panel_step<MR, 3>(a, tauv, lane);
+  wy_panel_step<MR, 4>(a, tauv, lane);
+  wy_panel_step<MR, 5>(a, tauv, lane);
+  wy_panel_step<MR, 6>(a, tauv, lane);
+  wy_panel_step<MR, 7>(a, tauv, lane);
+  // packed columns back in place (R above / on the diagonal, essential parts below), unit-lower diagonal tile of V
+#pragma unroll
+  for (int m = 0; m < MR; m++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (lane + 32 * m < nrow) sA[(size_t)(p + j) * ld + p + lane + 32 * m] = a[m][j];
+  if (lane < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      PB0[j * 12 + lane] = (lane < j) ? 0.0 : (lane == j) ? 1.0 : a[0][j];
+      if (lane == j) sTau[p + j] = tauv[j];
+    }
+  }
+  __syncwarp();
+  // S = V^T V on the tensor cores: A and B fragments are the same registers
+  const int q = lane & 3, g = lane >> 2;
+  const int k0 = wy_kappa(q, 0), k1 = wy_kappa(q, 1);
+  const int nt = nrow >> 3;
+  const double* vcol = sA + (size_t)(p + g) * ld + p;
+  double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+  for (int t8 = 0; t8 < 4 * MR; t8++) {
+    if (t8 < nt) {
+      const double v0 = (t8 == 0) ? PB0[g * 12 + k0] : vcol[8 * t8 + k0];
+      const double v1 = (t8 == 0) ? PB0[g * 12 + k1] : vcol[8 * t8 + k1];
+      dmma884(s00, s01, v0, v0);
+      dmma884(s10, s11, v1, v1);
+    }
+  }
+  sS[g * 8 + 2 * q] = s00 + s10;
+  sS[g * 8 + 2 * q + 1] = s01 + s11;
+  __syncwarp();
+  // T (upper triangular, Q = I - V T V^T): T_kk = tau_k, T[0:k,k] = -tau_k T[0:k,0:k] S[0:k,k]   (LAPACK dlarft /
+  // Eigen make_block_householder_triangular_factor); lane i owns row i
+  if (lane < 8) {
+    double Tr[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < k; m++) sum = fma(Tr[m], sS[m * 8 + k], sum);
+      Tr[k] = (k < lane) ? 0.0 : (k == lane) ? tauv[k] : -tauv[k] * sum;
+      sT[lane * 8 + k] = Tr[k];
+    }
+  }
+  __syncwarp();
+}
+
+// ---- apply panel p to one 8-column tile (or to the right-hand side), by ONE warp ---------------------------------
+template <int MR>
+__device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld, int rp, int p, int jt, bool is_rhs,
+                                               const double* PB0, const double* sT, int lane) {
+  constexpr int NT = 4 * MR;
+  const int q = lane & 3, g = lane >> 2;
+  const int k0 = wy_kappa(q, 0), k1 = wy_kappa(q, 1);
+  const int rho = wy_kappa(g >> 1, g & 1);
+  const int nt = (rp - p) >> 3;
+  const bool valid = !is_rhs || g == 0;
+  double* col = (is_rhs ? sRhs : sA + (size_t)(8 * jt + g) * ld) + p;
+  double a0[NT], a1[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    const bool ld_ok = valid && t < nt;
+    a0[t] = ld_ok ? col[8 * t + k0] : 0.0;
+    a1[t] = ld_ok ? col[8 * t + k1] : 0.0;
+  }
+  // W^T = A2^T V   (8 columns x 8 reflectors)
+  const double* vcol = sA + (size_t)(p + g) * ld + p;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t < nt) {
+      const double v0 = (t == 0) ? PB0[g * 12 + k0] : vcol[8 * t + k0];
+      const double v1 = (t == 0) ? PB0[g * 12 + k1] : vcol[8 * t + k1];
+      dmma884(c00, c01, a0[t], v0);
+      dmma884(c10, c11, a1[t], v1);
+    }
+  }
+  const double w0 = c00 + c10, w1 = c01 + c11;
+  // W2^T = W^T T ; output slots 2q+e hold reflector q + 4e
+  const int pg = (g >> 1) + 4 * (g & 1);
+  double d0 = 0.0, d1 = 0.0;
+  dmma884(d0, d1, w0, sT[(2 * q) * 8 + pg]);
+  dmma884(d0, d1, w1, sT[(2 * q + 1) * 8 + pg]);
+  d0 = -d0; d1 = -d1;
+  // A2^T -= W2^T V^T
+  const double* vq0 = sA + (size_t)(p + q) * ld + p + rho;
+  const double* vq1 = sA + (size_t)(p + q + 4) * ld + p + rho;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t < nt) {
+      const double b0 = (t == 0) ? PB0[q * 12 + rho] : vq0[8 * t];
+      const double b1 = (t == 0) ? PB0[(q + 4) * 12 + rho] : vq1[8 * t];
+      dmma884(a0[t], a1[t], d0, b0);
+      dmma884(a0[t], a1[t], d1, b1);
+      if (valid) { col[8 * t + k0] = a0[t]; col[8 * t + k1] = a1[t]; }
+    }
+  }
+}
+
+// ---- kernel: grid.x = blocks of this size class -----------------------------------------------------------------
+template <int MR, int W, bool SOLVE>
+__global__ void __launch_bounds__(32 * W, (MR == 4 ? 12 : MR == 2 ? 16 : 16) / W)
+bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_in, double* packed,
+                    double* __restrict__ tau_out, const double* __restrict__ b, double* __restrict__ x) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long blk = ids ? ids[blockIdx.x] : blockIdx.x;
+  int r, c;
+  long long vo, ro, co;
+  bi.get(blk, r, c, vo, ro, co);
+  const WyGeom G(r, c);
+  const int rp = G.rp, cp = G.cp, ld = G.ld;
+  constexpr int T = 32 * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  double* sA = reinterpret_cast<double*>(smem_raw);
+  double* sRhs = sA + (size_t)cp * ld;
+  double* sPB = sRhs + ld;
+  double* sT = sPB + 2 * kWyPB;
+  double* sS = sT + 2 * 64;
+  double* sTau = sS + 64;
+  double* sRd = sTau + cp;
+
+  // ---- stage the block: contiguous column-major r x c in HBM -> padded columns in shared memory ----
+  const double* gA = A_in + vo;
+  const bool vec2 = ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(packed + vo) & 15) == 0);
+  if (vec2) {
+    const unsigned chunks = (unsigned)(r * c) >> 1;
+    for (unsigned e = tid; e < chunks; e += T) {
+      const unsigned j = (2 * e) / (unsigned)r, i = 2 * e - j * r;
+      cp_async16(sA + (size_t)j * ld + i, gA + 2 * e);
+    }
+    cp_async_commit();
+  } else {
+    for (unsigned e = tid; e < (unsigned)(r * c); e += T) {
+      const unsigned j = e / (unsigned)r, i = e - j * r;
+      sA[(size_t)j * ld + i] = gA[e];
+    }
+  }
+  {
+    const int padr = rp - r;                      // zero rows below the block: they stay zero under every reflector
+    for (int e = tid; e < padr * c; e += T) { const int j = e / padr, i = e - j * padr; sA[(size_t)j * ld + r + i] = 0.0; }
+    for (int e = tid; e < (cp - c) * rp; e += T) { const int j = e / rp, i = e - j * rp; sA[(size_t)(c + j) * ld + i] = 0.0; }
+    if (SOLVE) for (int i = tid; i < rp; i += T) sRhs[i] = (i < r) ? b[ro + i] : 0.0;
+  }
+  if (vec2) cp_async_wait<0>();
+  __syncthreads();
+
+  const int P = cp >> 3;
+  const int n_tiles = P + (SOLVE ? 1 : 0);
+  if (warp == 0) wy_factor_panel<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
+  __syncthreads();
+  for (int pi = 0; pi < P; pi++) {
+    const int p = 8 * pi, buf = pi & 1;
+    const bool has_next = pi + 1 < P;
+    const int onext = (pi + 1) % W;
+    for (int jt = pi + 1; jt < n_tiles; jt++) {
+      int wsel;
+      if (W == 1) wsel = 0;
+      else if (has_next) wsel = (jt == pi + 1) ? onext : (onext + 1 + (jt - pi - 2) % (W - 1)) % W;
+      else wsel = (jt - pi - 1) % W;
+      if (wsel != warp) continue;
+      wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
+      if (W > 1 && has_next && jt == pi + 1) {
+        __syncwarp();
+        wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+      }
+    }
+    if (W == 1 && has_next) {
+      __syncwarp();
+      wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: x = R^-1 (Q^T b)[0:c] (warp 0, y in registers), tau, packed factors ----
+  if (SOLVE) {
+    for (int j = tid; j < c; j += T) sRd[j] = 1.0 / sA[(size_t)j * ld + j];
+    __syncthreads();
+    if (warp == 0) {
+      double y[MR];
+#pragma unroll
+      for (int m = 0; m < MR; m++) y[m] = (lane + 32 * m < c) ? sRhs[lane + 32 * m] : 0.0;
+      for (int j = c - 1; j >= 0; --j) {
+        const int mj = j >> 5;
+        double ym = y[0];
+#pragma unroll
+        for (int m = 1; m < MR; m++) if (mj == m) ym = y[m];
+        const double yj = __shfl_sync(0xffffffffu, ym, j & 31) * sRd[j];
+        const double* cj = sA + (size_t)j * ld;
+#pragma unroll
+        for (int m = 0; m < MR; m++) {
+          const int i = lane + 32 * m;
+          if (i < j) y[m] = fma(-cj[i], yj, y[m]);
+          else if (i == j) y[m] = yj;
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MR; m++) if (lane + 32 * m < c) x[co + lane + 32 * m] = y[m];
+    }
+  }
+  for (int j = tid; j < c; j += T) tau_out[co + j] = sTau[j];
+  double* gP = packed + vo;
+  if (vec2) {
+    const unsigned chunks = (unsigned)(r * c) >> 1;
+    for (unsigned e = tid; e < chunks; e += T) {
+      const unsigned j = (2 * e) / (unsigned)r, i = 2 * e - j * r;
+      *reinterpret_cast<double2*>(gP + 2 * e) = *reinterpret_cast<const double2*>(sA + (size_t)j * ld + i);
+    }
+  } else {
+    for (unsigned e = tid; e < (unsigned)(r * c); e += T) {
+      const unsigned j = e / (unsigned)r, i = e - j * r;
+      gP[e] = sA[(size_t)j * ld + i];
+    }
+  }
+}
+
+}  // namespace qrk

@@ -5,10 +5,12 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <new>
 #include <numeric>
 
 #include "bd_generic.cuh"
+#include "bd_wy.cuh"
 #include "bd_small.cuh"
 #include "export.cuh"
 #include "solver.hpp"
@@ -175,6 +177,43 @@ cudaError_t launch_generic_factor(bool piv, bool solve, const BlockIndex& bi, co
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
+// ---- blocked compact-WY / DMMA kernel (bd_wy.cuh): unpivoted blocks wider than one panel -------------------------
+template <int MR, int W>
+cudaError_t launch_wy_factor_mw(bool solve, const BlockIndex& bi, const SizeClass& sc, const double* A, double* packed,
+                                double* tau, const double* b, double* x, cudaStream_t s) {
+#define LAUNCH(SOLVE)                                                                             \
+  {                                                                                               \
+    auto kernel = bd_wy_factor_kernel<MR, W, SOLVE>;                                              \
+    if (sc.smem > 48 * 1024) {                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.smem); \
+      if (e != cudaSuccess) return e;                                                             \
+    }                                                                                             \
+    kernel<<<(unsigned)sc.count, 32 * W, sc.smem, s>>>(bi, sc.d_ids, A, packed, tau, b, x);        \
+  }
+  if (solve) LAUNCH(true)
+  else LAUNCH(false)
+#undef LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wy_factor(bool solve, const BlockIndex& bi, const SizeClass& sc, const double* A, double* packed,
+                             double* tau, const double* b, double* x, cudaStream_t s) {
+  const int key = sc.wy_mr * 10 + sc.warps;
+  switch (key) {
+    case 12: return launch_wy_factor_mw<1, 2>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 14: return launch_wy_factor_mw<1, 4>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 22: return launch_wy_factor_mw<2, 2>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 24: return launch_wy_factor_mw<2, 4>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 42: return launch_wy_factor_mw<4, 2>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 44: return launch_wy_factor_mw<4, 4>(solve, bi, sc, A, packed, tau, b, x, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+bool wy_eligible(int r, int c, bool piv) {
+  return !piv && c > 8 && r >= c && wy_mr(r, c) != 0 && wy_smem_bytes(r, c) <= kMaxSmem;
+}
+
 int team_warps_for(int r, int c) {
   const long long e = (long long)r * c;
   if (e <= 1024) return 1;
@@ -235,8 +274,12 @@ int run_factor(qrk_solver* h, const double* A_in, const double* d_b, double* d_x
   } else {
     const BlockIndex bi = block_index(h);
     for (const auto& sc : h->classes) {
-      QRK_TRY_CUDA(h, launch_generic_factor(piv, solve, bi, sc, A_in, h->d_values, h->d_tau, h->d_perm, d_b, d_x,
-                                            h->stream));
+      if (sc.wy_mr) {
+        QRK_TRY_CUDA(h, launch_wy_factor(solve, bi, sc, A_in, h->d_values, h->d_tau, d_b, d_x, h->stream));
+      } else {
+        QRK_TRY_CUDA(h, launch_generic_factor(piv, solve, bi, sc, A_in, h->d_values, h->d_tau, h->d_perm, d_b, d_x,
+                                              h->stream));
+      }
       h->launches++;
     }
   }
@@ -573,24 +616,39 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   }
   if (!h->small_path && !banded && h->nb > 0 && h->info == QRK_INFO_SUCCESS) {
     // size classes of the generic kernel: (team warps, shared memory rounded up to 8 KB steps)
+    const bool piv_cfg = desc->pivoting == QRK_PIVOT_COLPIV;
     if (uniform) {
       SizeClass sc;
-      sc.warps = team_warps_for(h->ur, h->uc);
-      sc.smem = generic_smem_bytes(h->ur, h->uc);
+      if (wy_eligible(h->ur, h->uc, piv_cfg)) {
+        sc.wy_mr = wy_mr(h->ur, h->uc);
+        sc.warps = wy_warps(h->ur, h->uc);
+        sc.smem = wy_smem_bytes(h->ur, h->uc);
+      } else {
+        sc.warps = team_warps_for(h->ur, h->uc);
+        sc.smem = generic_smem_bytes(h->ur, h->uc);
+      }
       sc.count = h->nb;
       if (sc.smem > kMaxSmem) return fail(QRK_STATUS_UNSUPPORTED);
       h->classes.push_back(sc);
     } else {
-      std::map<std::pair<int, size_t>, std::vector<int>> bins;
+      // key: (shared memory class, kernel kind (0 generic / MR of the WY kernel), team warps)
+      std::map<std::tuple<size_t, int, int>, std::vector<int>> bins;
       for (long long i = 0; i < h->nb; i++) {
-        const size_t need = generic_smem_bytes(h->h_rows[i], h->h_cols[i]);
-        if (need > kMaxSmem) return fail(QRK_STATUS_UNSUPPORTED);
-        const size_t cls = std::min(kMaxSmem, (need + 8191) / 8192 * 8192);
-        bins[{team_warps_for(h->h_rows[i], h->h_cols[i]), cls}].push_back((int)i);
+        const int r = h->h_rows[i], c = h->h_cols[i];
+        if (wy_eligible(r, c, piv_cfg)) {
+          const size_t cls = std::min(kMaxSmem, (wy_smem_bytes(r, c) + 2047) / 2048 * 2048);
+          bins[{cls, wy_mr(r, c), wy_warps(r, c)}].push_back((int)i);
+        } else {
+          const size_t need = generic_smem_bytes(r, c);
+          if (need > kMaxSmem) return fail(QRK_STATUS_UNSUPPORTED);
+          const size_t cls = std::min(kMaxSmem, (need + 8191) / 8192 * 8192);
+          bins[{cls, 0, team_warps_for(r, c)}].push_back((int)i);
+        }
       }
       for (auto it = bins.rbegin(); it != bins.rend(); ++it) {   // largest first: long CTAs start early
         SizeClass sc;
-        sc.warps = it->first.first; sc.smem = it->first.second; sc.count = (long long)it->second.size();
+        sc.smem = std::get<0>(it->first); sc.wy_mr = std::get<1>(it->first); sc.warps = std::get<2>(it->first);
+        sc.count = (long long)it->second.size();
         if (up(sc.d_ids, it->second) != cudaSuccess) return fail(QRK_STATUS_ALLOC_FAILED);
         h->classes.push_back(sc);
       }

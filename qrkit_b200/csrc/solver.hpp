@@ -14,6 +14,7 @@ namespace qrk {
 
 struct SizeClass {          // one launch of the generic kernel: blocks with a similar shared-memory need
   int warps = 1;            // team size W
+  int wy_mr = 0;            // 0: bd_generic kernel; 1/2/4: bd_wy kernel with that many panel rows per lane
   size_t smem = 0;          // dynamic shared memory per CTA
   long long count = 0;
   int* d_ids = nullptr;     // block numbers of this class (nullptr: all blocks, identity order)

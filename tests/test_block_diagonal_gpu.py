@@ -15,6 +15,10 @@ TOL_R, TOL_QR, TOL_X = 1e-12, 1e-13, 1e-10
 
 SMALL_SHAPES = [(2, 1), (3, 1), (4, 2), (6, 3), (7, 2), (8, 2), (8, 4), (9, 2)]          # thread-per-block kernels
 GENERIC_SHAPES = [(5, 3), (4, 4), (1, 1), (16, 8), (33, 7), (32, 16), (64, 32), (128, 64), (60, 50)]   # team-per-block
+# unpivoted blocks wider than one 8-column panel take the blocked compact-WY / DMMA kernel (bd_wy.cuh): every row-per-lane
+# class (rp <= 32 / 64 / 128), ragged rows and columns (zero padding), square blocks, one- and two-warp tile schedules
+WY_SHAPES = [(48, 24), (80, 40), (96, 48), (112, 56), (20, 12), (40, 9), (127, 63), (100, 100), (17, 16), (24, 24),
+             (128, 16), (31, 30), (72, 64), (128, 128)]
 
 
 @pytest.fixture(scope="module")
@@ -86,6 +90,12 @@ def test_generic_uniform_blocks_vs_oracle(qk, oracle, r, c, piv):
     nb = 37 if r * c > 1000 else 301
     _check_uniform(qk, oracle, nb, r, c, piv)
     _check_uniform(qk, oracle, 3, r, c, piv, lo=-1.0, hi=1.0, seed=SEED_A + 3)
+
+
+@pytest.mark.parametrize("r,c", WY_SHAPES)
+def test_blocked_wy_blocks_vs_oracle(qk, oracle, r, c):
+    _check_uniform(qk, oracle, 41, r, c, 0)
+    _check_uniform(qk, oracle, 3, r, c, 0, lo=-1.0, hi=1.0, seed=SEED_A + 11)
 
 
 def _mixed_problem(nb, seed=SEED_A):
