@@ -25,6 +25,21 @@
 
 namespace qrk {
 
+// Optional cycle trace of CTA 0 (tools/wy_trace.cu compiles with -DQRK_WY_TRACE); compiled out of the library.
+#ifdef QRK_WY_TRACE
+__device__ long long g_wy_trace[4096];
+__device__ int g_wy_trace_n;
+#define WY_TRACE(tag)                                                                     \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                     \
+      const int slot = atomicAdd(&g_wy_trace_n, 1);                                       \
+      if (slot < 2048) { g_wy_trace[2 * slot] = (tag) * 16 + (threadIdx.x >> 5); g_wy_trace[2 * slot + 1] = clock64(); } \
+    }                                                                                     \
+  } while (0)
+#else
+#define WY_TRACE(tag) do { } while (0)
+#endif
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
@@ -50,10 +65,62 @@ __host__ __device__ inline int wy_mr(int r, int c) {
   const WyGeom g(r, c);
   return g.rp <= 32 ? 1 : g.rp <= 64 ? 2 : g.rp <= 128 ? 4 : 0;
 }
-__host__ __device__ inline int wy_warps(int r, int c) { return WyGeom(r, c).cp <= 16 ? 2 : 4; }
+// Team size.  The panel chain is serial (one warp), the other warps only apply finished panels, and the kernel is
+// latency bound: what counts is how many blocks are resident per SM.  Small blocks are limited by registers x threads,
+// so they get one or two warps; only blocks whose shared-memory footprint already caps residency get four.
+__host__ __device__ inline int wy_warps(int r, int c) {
+  const int cp = WyGeom(r, c).cp;
+  return cp <= 24 ? 1 : cp <= 48 ? 2 : 4;
+}
 
 // fragment slot -> row inside an 8-row tile: k-step h, slot q  (see header)
 __device__ __forceinline__ int wy_kappa(int q, int h) { return h ? 4 + ((q + 2) & 3) : q; }
+
+// All-reduce of N (<= 8) doubles per lane over the warp by recursive halving (reduce-scatter: each round a lane
+// keeps one half of its values and adds the partner's copy of that half) followed by an all-gather with indexed
+// shuffles: N = 8 costs 17 64-bit shuffles and 9 additions instead of the 40 + 40 of a butterfly per value.
+template <int N>
+__device__ __forceinline__ constexpr int wy_slot_lane(int j) {
+  int n = N, off = 16, src = 0;
+  while (n > 1) {
+    const int h = (n + 1) / 2;
+    if (j >= h) { src |= off; j -= h; }
+    n = h; off >>= 1;
+  }
+  return src;
+}
+template <int N, int OFF>
+__device__ __forceinline__ double wy_reduce_scatter(double (&v)[N], int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  if constexpr (N == 1) {
+    double x = v[0];
+#pragma unroll
+    for (int o = OFF; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+  } else {
+    constexpr int H = (N + 1) / 2;
+    const bool upper = (lane & OFF) != 0;
+    double w[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const double lo = v[i];
+      const double hi = (H + i < N) ? v[(H + i < N) ? H + i : 0] : 0.0;
+      const double recv = __shfl_xor_sync(FULL, upper ? lo : hi, OFF);
+      w[i] = (upper ? hi : lo) + recv;
+    }
+    return wy_reduce_scatter<H, OFF / 2>(w, lane);
+  }
+}
+template <int N>
+__device__ __forceinline__ void warp_allreduce_vec(double (&v)[N], int lane) {
+  const double mine = wy_reduce_scatter<N, 16>(v, lane);
+  if constexpr (N == 1) {
+    v[0] = mine;
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = __shfl_sync(0xffffffffu, mine, wy_slot_lane<N>(j));
+  }
+}
 
 // ---- panel factorisation: columns p..p+7, rows p..rp-1, by ONE warp -------------------------------------------
 // One column step; K is a template parameter so that every register-array index is a compile-time constant.
@@ -62,20 +129,22 @@ __device__ __forceinline__ void wy_panel_step(double (&a)[MR][8], double (&tauv)
   constexpr unsigned FULL = 0xffffffffu;
   // tail dot products t_j = sum_{rows > K} a_K a_j, j = K..7 (t_K = tailSqNorm), one batched all-reduce
   double t[8];
+  {
+    double part[8 - K];
 #pragma unroll
-  for (int j = K; j < 8; j++) {
-    double s = 0.0;
+    for (int j = K; j < 8; j++) {
+      double s = 0.0;
 #pragma unroll
-    for (int m = 0; m < MR; m++) {
-      const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0;
-      s = fma(ak, a[m][j], s);
+      for (int m = 0; m < MR; m++) {
+        const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0;
+        s = fma(ak, a[m][j], s);
+      }
+      part[j - K] = s;
     }
-    t[j] = s;
+    warp_allreduce_vec<8 - K>(part, lane);
+#pragma unroll
+    for (int j = K; j < 8; j++) t[j] = part[j - K];
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int j = K; j < 8; j++) t[j] += __shfl_xor_sync(FULL, t[j], o);
   double piv[8];
 #pragma unroll
   for (int j = K; j < 8; j++) piv[j] = __shfl_sync(FULL, a[0][j], K);
@@ -120,12 +189,14 @@ template <int MR>
 __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int p, double* PB0, double* sT, double* sS,
                                                 double* sTau, int lane) {
   const int nrow = rp - p;
+  WY_TRACE(0);
   double a[MR][8];
 #pragma unroll
   for (int m = 0; m < MR; m++)
 #pragma unroll
     for (int j = 0; j < 8; j++) a[m][j] = (lane + 32 * m < nrow) ? sA[(size_t)(p + j) * ld + p + lane + 32 * m] : 0.0;
   double tauv[8];
+  WY_TRACE(1);
   wy_panel_step<MR, 0>(a, tauv, lane);
   wy_panel_step<MR, 1>(a, tauv, lane);
   wy_panel_step<MR, 2>(a, tauv, lane);
@@ -134,6 +205,7 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
   wy_panel_step<MR, 5>(a, tauv, lane);
   wy_panel_step<MR, 6>(a, tauv, lane);
   wy_panel_step<MR, 7>(a, tauv, lane);
+  WY_TRACE(2);
   // packed columns back in place (R above / on the diagonal, essential parts below), unit-lower diagonal tile of V
 #pragma unroll
   for (int m = 0; m < MR; m++)
@@ -148,6 +220,7 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
     }
   }
   __syncwarp();
+  WY_TRACE(3);
   // S = V^T V on the tensor cores: A and B fragments are the same registers
   const int q = lane & 3, g = lane >> 2;
   const int k0 = wy_kappa(q, 0), k1 = wy_kappa(q, 1);
@@ -166,6 +239,7 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
   sS[g * 8 + 2 * q] = s00 + s10;
   sS[g * 8 + 2 * q + 1] = s01 + s11;
   __syncwarp();
+  WY_TRACE(4);
   // T (upper triangular, Q = I - V T V^T): T_kk = tau_k, T[0:k,k] = -tau_k T[0:k,0:k] S[0:k,k]   (LAPACK dlarft /
   // Eigen make_block_householder_triangular_factor); lane i owns row i
   if (lane < 8) {
@@ -180,6 +254,7 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
     }
   }
   __syncwarp();
+  WY_TRACE(5);
 }
 
 // ---- apply panel p to one 8-column tile (or to the right-hand side), by ONE warp ---------------------------------
@@ -236,7 +311,7 @@ __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld,
 
 // ---- kernel: grid.x = blocks of this size class -----------------------------------------------------------------
 template <int MR, int W, bool SOLVE>
-__global__ void __launch_bounds__(32 * W, (MR == 4 ? 12 : MR == 2 ? 16 : 16) / W)
+__global__ void __launch_bounds__(32 * W)
 bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_in, double* packed,
                     double* __restrict__ tau_out, const double* __restrict__ b, double* __restrict__ x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -262,16 +337,20 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   const bool vec2 = ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(packed + vo) & 15) == 0);
   if (vec2) {
-    const unsigned chunks = (unsigned)(r * c) >> 1;
-    for (unsigned e = tid; e < chunks; e += T) {
-      const unsigned j = (2 * e) / (unsigned)r, i = 2 * e - j * r;
-      cp_async16(sA + (size_t)j * ld + i, gA + 2 * e);
+    const int rc = r >> 1;                         // 16-byte chunks per column
+    int j = tid / rc, i = tid - j * rc;
+    while (j < c) {
+      cp_async16(sA + (size_t)j * ld + 2 * i, gA + (size_t)j * r + 2 * i);
+      i += T;
+      while (i >= rc) { i -= rc; j++; }
     }
     cp_async_commit();
   } else {
-    for (unsigned e = tid; e < (unsigned)(r * c); e += T) {
-      const unsigned j = e / (unsigned)r, i = e - j * r;
-      sA[(size_t)j * ld + i] = gA[e];
+    int j = tid / r, i = tid - j * r;
+    while (j < c) {
+      sA[(size_t)j * ld + i] = gA[(size_t)j * r + i];
+      i += T;
+      while (i >= r) { i -= r; j++; }
     }
   }
   {
@@ -283,21 +362,27 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   if (vec2) cp_async_wait<0>();
   __syncthreads();
 
+  WY_TRACE(11);
   const int P = cp >> 3;
   const int n_tiles = P + (SOLVE ? 1 : 0);
-  if (warp == 0) wy_factor_panel<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
+  // panel pi is factored by warp (pi + rot) % W: CTAs resident on one SM start in lock step, the rotation keeps
+  // their (serial, FP64-heavy) panel warps on different SM sub-partitions
+  const int rot = blockIdx.x % W;
+  if (warp == rot) wy_factor_panel<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
     const int p = 8 * pi, buf = pi & 1;
     const bool has_next = pi + 1 < P;
-    const int onext = (pi + 1) % W;
+    const int onext = (pi + 1 + rot) % W;
     for (int jt = pi + 1; jt < n_tiles; jt++) {
       int wsel;
       if (W == 1) wsel = 0;
       else if (has_next) wsel = (jt == pi + 1) ? onext : (onext + 1 + (jt - pi - 2) % (W - 1)) % W;
-      else wsel = (jt - pi - 1) % W;
+      else wsel = (jt - pi - 1 + rot) % W;
       if (wsel != warp) continue;
+      WY_TRACE(6);
       wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
+      WY_TRACE(7);
       if (W > 1 && has_next && jt == pi + 1) {
         __syncwarp();
         wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
@@ -307,7 +392,9 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
       __syncwarp();
       wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
     }
+    WY_TRACE(8);
     __syncthreads();
+    WY_TRACE(9);
   }
 
   // ---- epilogue: x = R^-1 (Q^T b)[0:c] (warp 0, y in registers), tau, packed factors ----
@@ -336,18 +423,23 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
       for (int m = 0; m < MR; m++) if (lane + 32 * m < c) x[co + lane + 32 * m] = y[m];
     }
   }
+  WY_TRACE(10);
   for (int j = tid; j < c; j += T) tau_out[co + j] = sTau[j];
   double* gP = packed + vo;
   if (vec2) {
-    const unsigned chunks = (unsigned)(r * c) >> 1;
-    for (unsigned e = tid; e < chunks; e += T) {
-      const unsigned j = (2 * e) / (unsigned)r, i = 2 * e - j * r;
-      *reinterpret_cast<double2*>(gP + 2 * e) = *reinterpret_cast<const double2*>(sA + (size_t)j * ld + i);
+    const int rc = r >> 1;
+    int j = tid / rc, i = tid - j * rc;
+    while (j < c) {
+      *reinterpret_cast<double2*>(gP + (size_t)j * r + 2 * i) = *reinterpret_cast<const double2*>(sA + (size_t)j * ld + 2 * i);
+      i += T;
+      while (i >= rc) { i -= rc; j++; }
     }
   } else {
-    for (unsigned e = tid; e < (unsigned)(r * c); e += T) {
-      const unsigned j = e / (unsigned)r, i = e - j * r;
-      gP[e] = sA[(size_t)j * ld + i];
+    int j = tid / r, i = tid - j * r;
+    while (j < c) {
+      gP[(size_t)j * r + i] = sA[(size_t)j * ld + i];
+      i += T;
+      while (i >= r) { i -= r; j++; }
     }
   }
 }

@@ -200,6 +200,9 @@ cudaError_t launch_wy_factor(bool solve, const BlockIndex& bi, const SizeClass& 
                              double* tau, const double* b, double* x, cudaStream_t s) {
   const int key = sc.wy_mr * 10 + sc.warps;
   switch (key) {
+    case 11: return launch_wy_factor_mw<1, 1>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 21: return launch_wy_factor_mw<2, 1>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 41: return launch_wy_factor_mw<4, 1>(solve, bi, sc, A, packed, tau, b, x, s);
     case 12: return launch_wy_factor_mw<1, 2>(solve, bi, sc, A, packed, tau, b, x, s);
     case 14: return launch_wy_factor_mw<1, 4>(solve, bi, sc, A, packed, tau, b, x, s);
     case 22: return launch_wy_factor_mw<2, 2>(solve, bi, sc, A, packed, tau, b, x, s);
