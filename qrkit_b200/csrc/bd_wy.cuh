@@ -36,9 +36,20 @@ __device__ int g_wy_trace_n;
       if (slot < 2048) { g_wy_trace[2 * slot] = (tag) * 16 + (threadIdx.x >> 5); g_wy_trace[2 * slot + 1] = clock64(); } \
     }                                                                                     \
   } while (0)
+#define WY_CLK(i) do { const long long now_ = clock64(); wy_acc[i] += now_ - wy_last; wy_last = now_; } while (0)
+#define WY_TRACE_VAL(tag, val)                                                            \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                     \
+      const int slot = atomicAdd(&g_wy_trace_n, 1);                                       \
+      if (slot < 2048) { g_wy_trace[2 * slot] = (tag) * 16 + (threadIdx.x >> 5); g_wy_trace[2 * slot + 1] = (val); } \
+    }                                                                                     \
+  } while (0)
 #else
 #define WY_TRACE(tag) do { } while (0)
+#define WY_CLK(i) do { } while (0)
 #endif
+
+__device__ unsigned g_wy_sm_ticket[256];   // see bd_wy_factor_kernel: spreads panel warps over the SM sub-partitions
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -76,19 +87,9 @@ __host__ __device__ inline int wy_warps(int r, int c) {
 // fragment slot -> row inside an 8-row tile: k-step h, slot q  (see header)
 __device__ __forceinline__ int wy_kappa(int q, int h) { return h ? 4 + ((q + 2) & 3) : q; }
 
-// All-reduce of N (<= 8) doubles per lane over the warp by recursive halving (reduce-scatter: each round a lane
-// keeps one half of its values and adds the partner's copy of that half) followed by an all-gather with indexed
-// shuffles: N = 8 costs 17 64-bit shuffles and 9 additions instead of the 40 + 40 of a butterfly per value.
-template <int N>
-__device__ __forceinline__ constexpr int wy_slot_lane(int j) {
-  int n = N, off = 16, src = 0;
-  while (n > 1) {
-    const int h = (n + 1) / 2;
-    if (j >= h) { src |= off; j -= h; }
-    n = h; off >>= 1;
-  }
-  return src;
-}
+// Reduce-scatter of N (<= 8) doubles per lane over the warp by recursive halving: each round a lane keeps one half
+// of its values and adds the partner's copy of that half; for N = 8 every lane ends with the total of value
+// (lane >> 2), at 9 64-bit shuffles and 9 additions instead of the 40 + 40 of a butterfly per value.
 template <int N, int OFF>
 __device__ __forceinline__ double wy_reduce_scatter(double (&v)[N], int lane) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -111,78 +112,107 @@ __device__ __forceinline__ double wy_reduce_scatter(double (&v)[N], int lane) {
     return wy_reduce_scatter<H, OFF / 2>(w, lane);
   }
 }
-template <int N>
-__device__ __forceinline__ void warp_allreduce_vec(double (&v)[N], int lane) {
-  const double mine = wy_reduce_scatter<N, 16>(v, lane);
-  if constexpr (N == 1) {
-    v[0] = mine;
-  } else {
-#pragma unroll
-    for (int j = 0; j < N; j++) v[j] = __shfl_sync(0xffffffffu, mine, wy_slot_lane<N>(j));
-  }
-}
-
 // ---- panel factorisation: columns p..p+7, rows p..rp-1, by ONE warp -------------------------------------------
 // One column step; K is a template parameter so that every register-array index is a compile-time constant.
+//
+// The step needs ONE warp all-reduce: d_j = sum_{rows > K} a_K a_j for ALL eight columns of the panel.  For j >= K
+// these are Eigen's tail quantities (d_K = tailSqNorm, d_j -> v^T a_j); for j < K column j already holds the
+// essential part of v_j, so d_j is the cross term of S = V^T V that the T factor needs: T comes out of the same
+// reduction and is finished when the last column is (no separate V^T V pass).  The sums are reduce-scattered with
+// shuffles (9 instead of 40), the eight totals and the pivot row travel through 32 doubles of shared memory.
+// Scalar chain (all lanes redundantly): 1/||x|| by MUFU.RSQ64H + 2 Newton steps; the reciprocal of x0 - beta is
+// seeded from the half-converged norm so that MUFU.RCP64H overlaps the second Newton step; tau v^T a_j is formed as
+// -(d a_Kj + t_j) / beta so that it does not wait for that reciprocal.
 template <int MR, int K>
-__device__ __forceinline__ void wy_panel_step(double (&a)[MR][8], double (&tauv)[8], int lane) {
-  constexpr unsigned FULL = 0xffffffffu;
-  // tail dot products t_j = sum_{rows > K} a_K a_j, j = K..7 (t_K = tailSqNorm), one batched all-reduce
-  double t[8];
-  {
-    double part[8 - K];
+__device__ __forceinline__ void wy_panel_step(double (&a)[MR][8], double* tau_out, double (&Trow)[8], double* scratch,
+                                              int lane
+#ifdef QRK_WY_TRACE
+                                              , long long (&wy_acc)[6], long long& wy_last
+#endif
+                                              ) {
+  double* gbuf = scratch + (K & 1) * 16;      // [0..8): reduced sums, [8..16): pivot row
+  double part[8];
 #pragma unroll
-    for (int j = K; j < 8; j++) {
-      double s = 0.0;
-#pragma unroll
-      for (int m = 0; m < MR; m++) {
-        const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0;
-        s = fma(ak, a[m][j], s);
-      }
-      part[j - K] = s;
-    }
-    warp_allreduce_vec<8 - K>(part, lane);
-#pragma unroll
-    for (int j = K; j < 8; j++) t[j] = part[j - K];
-  }
-  double piv[8];
-#pragma unroll
-  for (int j = K; j < 8; j++) piv[j] = __shfl_sync(FULL, a[0][j], K);
-  // Eigen makeHouseholder (SURVEY 8c): beta = -sign(x0) ||x||, ess = tail / (x0 - beta), tau = (beta - x0) / beta
-  const double c0 = piv[K];
-  const bool degenerate = t[K] <= DBL_MIN;
-  double norm;
-  const double rnorm = fast_rsqrt(fma(c0, c0, t[K]), norm);
-  double beta = (c0 >= 0.0) ? -norm : norm;
-  const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
-  double inv = fast_rcp(c0 - beta);
-  double tau = (beta - c0) * ib;
-  if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
-#pragma unroll
-  for (int j = K + 1; j < 8; j++) {
-    const double w = fma(t[j], inv, piv[j]);      // v^T a_j
-    const double s = tau * w;
-    const double sinv = s * inv;
+  for (int j = 0; j < 8; j++) {
+    double s = 0.0;
 #pragma unroll
     for (int m = 0; m < MR; m++) {
-      if (m == 0) {
-        if (lane == K) a[0][j] -= s;
-        else if (lane > K) a[0][j] = fma(-a[0][K], sinv, a[0][j]);
-      } else {
-        a[m][j] = fma(-a[m][K], sinv, a[m][j]);
-      }
+      const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0;
+      s = fma(ak, a[m][j], s);
     }
+    part[j] = s;
   }
+  WY_CLK(0);
+  const double mine = wy_reduce_scatter<8, 16>(part, lane);
+  WY_CLK(1);
+  if ((lane & 3) == 0) gbuf[lane >> 2] = mine;
+  __syncwarp();
+  double d[8], row[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const double2 u = *reinterpret_cast<const double2*>(gbuf + j);
+    const double2 w = *reinterpret_cast<const double2*>(gbuf + 8 + j);
+    d[j] = u.x; d[j + 1] = u.y; row[j] = w.x; row[j + 1] = w.y;
+  }
+  WY_CLK(2);
+  // Eigen makeHouseholder (SURVEY 8c): beta = -sign(x0) ||x||, ess = tail / (x0 - beta), tau = (beta - x0) / beta
+  const double c0 = row[K];
+  const bool degenerate = d[K] <= DBL_MIN;
+  const double nsq = fma(c0, c0, d[K]);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(nsq));
+  const double hx = 0.5 * nsq, ac0 = fabs(c0);
+  double y = y0;
+  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  double r0;
+  { const double n1 = nsq * y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(ac0 + n1)); }   // seed only
+  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  double norm = nsq * y;
+  norm = fma(fma(-norm, norm, nsq), 0.5 * y, norm);
+  const double dabs = ac0 + norm;              // |x0 - beta|
+  double rabs = r0;
+  { double e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); }
+  const bool pos = c0 >= 0.0;
+  double beta = pos ? -norm : norm;
+  double ib = pos ? -y : y;                    // 1 / beta
+  double dd = pos ? dabs : -dabs;              // x0 - beta
+  double inv = pos ? rabs : -rabs;             // 1 / (x0 - beta)
+  double tau = (beta - c0) * ib;
+  if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; ib = 0.0; dd = 0.0; }
+  WY_CLK(3);
+  // rows >= K of the columns to the right: a_j -= (tau v^T a_j) v, with v = [1; tail * inv] = mult * inv
+  double mult[MR];
+#pragma unroll
+  for (int m = 0; m < MR; m++) mult[m] = (m > 0 || lane > K) ? a[m][K] : (lane == K) ? dd : 0.0;
+#pragma unroll
+  for (int j = K + 1; j < 8; j++) {
+    const double sj = -fma(dd, row[j], d[j]) * ib;     // tau v^T a_j
+    const double sinv = sj * inv;
+#pragma unroll
+    for (int m = 0; m < MR; m++) a[m][j] = fma(-mult[m], sinv, a[m][j]);
+  }
+  // column K of T (lane i < 8 owns row i): S_iK = v_i[K] + inv d_i, T_iK = -tau sum_m T_im S_mK, T_KK = tau
+  {
+    double sum = 0.0;
+#pragma unroll
+    for (int m = 0; m < K; m++) sum = fma(Trow[m], fma(inv, d[m], row[m]), sum);
+    Trow[K] = (lane == K) ? tau : (lane < K) ? -tau * sum : 0.0;
+  }
+  // column K: beta on the diagonal, essential part below
 #pragma unroll
   for (int m = 0; m < MR; m++) {
-    if (m == 0) {
-      if (lane == K) a[0][K] = beta;
-      else if (lane > K) a[0][K] *= inv;
-    } else {
-      a[m][K] *= inv;
+    if (m == 0) a[0][K] = (lane > K) ? a[0][K] * inv : (lane == K) ? beta : a[0][K];
+    else a[m][K] *= inv;
+  }
+  if (lane == K) tau_out[K] = tau;
+  if (K < 7) {
+    if (lane == K + 1) {
+      double* nb = scratch + ((K + 1) & 1) * 16 + 8;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(nb + j) = make_double2(a[0][j], a[0][j + 1]);
     }
   }
-  tauv[K] = tau;
+  WY_CLK(4);
 }
 
 template <int MR>
@@ -191,66 +221,57 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
   const int nrow = rp - p;
   WY_TRACE(0);
   double a[MR][8];
+  {
+    const double* base = sA + p * ld + p + lane;
 #pragma unroll
-  for (int m = 0; m < MR; m++)
+    for (int m = 0; m < MR; m++) {
+      const bool ok = lane + 32 * m < nrow;
 #pragma unroll
-    for (int j = 0; j < 8; j++) a[m][j] = (lane + 32 * m < nrow) ? sA[(size_t)(p + j) * ld + p + lane + 32 * m] : 0.0;
-  double tauv[8];
+      for (int j = 0; j < 8; j++) a[m][j] = ok ? base[j * ld + 32 * m] : 0.0;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(sS + 8 + j) = make_double2(a[0][j], a[0][j + 1]);
+  }
+  double Trow[8];
+  double* tauv = sTau + p;
+#ifdef QRK_WY_TRACE
+  long long wy_acc[6] = {0, 0, 0, 0, 0, 0};
+  long long wy_last = clock64();
+#define WY_STEP(k) wy_panel_step<MR, k>(a, tauv, Trow, sS, lane, wy_acc, wy_last)
+#else
+#define WY_STEP(k) wy_panel_step<MR, k>(a, tauv, Trow, sS, lane)
+#endif
   WY_TRACE(1);
-  wy_panel_step<MR, 0>(a, tauv, lane);
-  wy_panel_step<MR, 1>(a, tauv, lane);
-  wy_panel_step<MR, 2>(a, tauv, lane);
-  wy_panel_step<MR, 3>(a, tauv, lane);
-  wy_panel_step<MR, 4>(a, tauv, lane);
-  wy_panel_step<MR, 5>(a, tauv, lane);
-  wy_panel_step<MR, 6>(a, tauv, lane);
-  wy_panel_step<MR, 7>(a, tauv, lane);
+  WY_STEP(0);
+  WY_STEP(1);
+  WY_STEP(2);
+  WY_STEP(3);
+  WY_STEP(4);
+  WY_STEP(5);
+  WY_STEP(6);
+  WY_STEP(7);
   WY_TRACE(2);
-  // packed columns back in place (R above / on the diagonal, essential parts below), unit-lower diagonal tile of V
+#ifdef QRK_WY_TRACE
+  for (int i = 0; i < 5; i++) WY_TRACE_VAL(12 + i, wy_acc[i]);
+#endif
+  // packed columns back in place (R above / on the diagonal, essential parts below), unit-lower diagonal tile of V, T
+  {
+    double* base = sA + p * ld + p + lane;
 #pragma unroll
-  for (int m = 0; m < MR; m++)
+    for (int m = 0; m < MR; m++) {
+      if (lane + 32 * m < nrow) {
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (lane + 32 * m < nrow) sA[(size_t)(p + j) * ld + p + lane + 32 * m] = a[m][j];
+        for (int j = 0; j < 8; j++) base[j * ld + 32 * m] = a[m][j];
+      }
+    }
+  }
   if (lane < 8) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       PB0[j * 12 + lane] = (lane < j) ? 0.0 : (lane == j) ? 1.0 : a[0][j];
-      if (lane == j) sTau[p + j] = tauv[j];
-    }
-  }
-  __syncwarp();
-  WY_TRACE(3);
-  // S = V^T V on the tensor cores: A and B fragments are the same registers
-  const int q = lane & 3, g = lane >> 2;
-  const int k0 = wy_kappa(q, 0), k1 = wy_kappa(q, 1);
-  const int nt = nrow >> 3;
-  const double* vcol = sA + (size_t)(p + g) * ld + p;
-  double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-  for (int t8 = 0; t8 < 4 * MR; t8++) {
-    if (t8 < nt) {
-      const double v0 = (t8 == 0) ? PB0[g * 12 + k0] : vcol[8 * t8 + k0];
-      const double v1 = (t8 == 0) ? PB0[g * 12 + k1] : vcol[8 * t8 + k1];
-      dmma884(s00, s01, v0, v0);
-      dmma884(s10, s11, v1, v1);
-    }
-  }
-  sS[g * 8 + 2 * q] = s00 + s10;
-  sS[g * 8 + 2 * q + 1] = s01 + s11;
-  __syncwarp();
-  WY_TRACE(4);
-  // T (upper triangular, Q = I - V T V^T): T_kk = tau_k, T[0:k,k] = -tau_k T[0:k,0:k] S[0:k,k]   (LAPACK dlarft /
-  // Eigen make_block_householder_triangular_factor); lane i owns row i
-  if (lane < 8) {
-    double Tr[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      double sum = 0.0;
-#pragma unroll
-      for (int m = 0; m < k; m++) sum = fma(Tr[m], sS[m * 8 + k], sum);
-      Tr[k] = (k < lane) ? 0.0 : (k == lane) ? tauv[k] : -tauv[k] * sum;
-      sT[lane * 8 + k] = Tr[k];
+      sT[lane * 8 + j] = Trow[j];
     }
   }
   __syncwarp();
@@ -310,8 +331,11 @@ __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld,
 }
 
 // ---- kernel: grid.x = blocks of this size class -----------------------------------------------------------------
+// resident CTAs per SM the register allocation must leave room for (shared memory allows about as many)
+__host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr == 4 ? 12 : mr == 2 ? 16 : 20) / w; }
+
 template <int MR, int W, bool SOLVE>
-__global__ void __launch_bounds__(32 * W)
+__global__ void __launch_bounds__(32 * W, wy_min_ctas(MR, W))
 bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_in, double* packed,
                     double* __restrict__ tau_out, const double* __restrict__ b, double* __restrict__ x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -332,6 +356,17 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   double* sTau = sS + 64;
   double* sRd = sTau + cp;
 
+  // panel pi is factored by warp (pi + rot) % W.  The CTAs resident on one SM run in lock step and the panel warp is
+  // serial and FP64-heavy: if they all used warp 0 the three or more panel chains would share ONE sub-partition's
+  // FP64 pipe.  A per-SM ticket gives consecutive CTAs of an SM consecutive rotations.
+  __shared__ int s_rot;
+  if (W > 1) {
+    if (tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_rot = (int)(atomicAdd(&g_wy_sm_ticket[smid & 255], 1u) % W);
+    }
+  }
   // ---- stage the block: contiguous column-major r x c in HBM -> padded columns in shared memory ----
   const double* gA = A_in + vo;
   const bool vec2 = ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0) &&
@@ -365,9 +400,7 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   WY_TRACE(11);
   const int P = cp >> 3;
   const int n_tiles = P + (SOLVE ? 1 : 0);
-  // panel pi is factored by warp (pi + rot) % W: CTAs resident on one SM start in lock step, the rotation keeps
-  // their (serial, FP64-heavy) panel warps on different SM sub-partitions
-  const int rot = blockIdx.x % W;
+  const int rot = (W > 1) ? s_rot : 0;
   if (warp == rot) wy_factor_panel<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
@@ -377,7 +410,7 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
     for (int jt = pi + 1; jt < n_tiles; jt++) {
       int wsel;
       if (W == 1) wsel = 0;
-      else if (has_next) wsel = (jt == pi + 1) ? onext : (onext + 1 + (jt - pi - 2) % (W - 1)) % W;
+      else if (has_next) wsel = (jt == pi + 1) ? onext : (onext + 1 + (jt - pi - 2) % (W > 1 ? W - 1 : 1)) % W;
       else wsel = (jt - pi - 1 + rot) % W;
       if (wsel != warp) continue;
       WY_TRACE(6);
