@@ -170,6 +170,33 @@ def bench_classes(args, L, stream):
                       "total_ms": sum(p["ms"] for p in per), "peak_source": src}), flush=True)
 
 
+def bench_banded(args, L, stream):
+    """BASELINE config 4: block-banded, nb block rows of 16x24, column step 8 (overlap 16), single GPU."""
+    nb, br, bc, ov = args.banded_blocks, 16, 24, 16
+    n_rows, n_cols = nb * br, (nb - 1) * (bc - ov) + bc
+    A = torch.empty(nb * br * bc, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(A), SEED_A, 0, nb, br, bc, 0.5, 5.0, stream))
+    b = torch.empty(n_rows, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(b), SEED_A + 5, 0, n_rows, 1, 0, -1.0, 1.0, stream))
+    x = torch.empty(n_cols, dtype=torch.float64, device="cuda")
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.block_rows, d.block_cols, d.block_overlap = capi.QRK_BANDED_BLOCKED, nb, br, bc, ov
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_stream(h, stream), h)
+    ms = time_steps(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), max(2, args.steps // 4), 1)
+    L.qrk_destroy(h)
+    peak, src = measured_peaks()
+    # SURVEY 8d: 8 (nnz A + nnz R + nnz V) + 8 (rows + 2 cols) bytes
+    alg = 8.0 * (nb * br * bc + n_cols * bc + nb * br * bc) + 8.0 * (n_rows + 2 * n_cols)
+    print(json.dumps({"workload": f"block-banded, {nb} block rows of {br}x{bc}, step {bc-ov} (BASELINE config 4), fused QR+solve, single GPU",
+                      "metric": "rows/s", "value": n_rows / (ms * 1e-3), "ms_per_step": ms, "rows": n_rows, "cols": n_cols,
+                      "us_per_window": ms * 1e3 / nb,
+                      "roofline": {"bound": "latency (sequential window chain); HBM fraction for the record", "achieved": alg / (ms * 1e-3) / 1e9,
+                                   "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src},
+                      "dtype": "f64"}), flush=True)
+
+
 def bench_two_call(args, L, stream):
     nb, r, c = 1_000_000, 8, 4
     A = torch.empty(nb * r * c, dtype=torch.float64, device="cuda")
@@ -197,12 +224,13 @@ def bench_two_call(args, L, stream):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="angular,mixed,two_call")
+    ap.add_argument("--workload", default="angular,mixed,banded,two_call")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--mixed-blocks", type=int, default=100_000)
     ap.add_argument("--class-blocks", type=int, default=0)
+    ap.add_argument("--banded-blocks", type=int, default=100_000)
     ap.add_argument("--shapes", default="")
     args = ap.parse_args()
     if not torch.cuda.is_available():
@@ -213,7 +241,7 @@ def main():
     stream = C.c_void_p(s.cuda_stream)
     L = capi.lib()
     for w in args.workload.split(","):
-        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call, "classes": bench_classes}[w](args, L, stream)
+        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call, "classes": bench_classes, "banded": bench_banded}[w](args, L, stream)
 
 
 if __name__ == "__main__":
