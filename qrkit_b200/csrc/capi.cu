@@ -11,6 +11,7 @@
 
 #include "bd_generic.cuh"
 #include "bd_wy.cuh"
+#include "dense_border.cuh"
 #include "bd_small.cuh"
 #include "export.cuh"
 #include "solver.hpp"
@@ -177,6 +178,8 @@ cudaError_t launch_generic_factor(bool piv, bool solve, const BlockIndex& bi, co
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
+inline bool ang(const qrk_solver* h) { return h->avt != nullptr || h->wide; }   // kind == QRK_BLOCK_ANGULAR
+
 // ---- blocked compact-WY / DMMA kernel (bd_wy.cuh): unpivoted blocks wider than one panel -------------------------
 template <int MR, int W>
 cudaError_t launch_wy_factor_mw(bool solve, const BlockIndex& bi, const SizeClass& sc, const double* A, double* packed,
@@ -239,6 +242,7 @@ void free_dev(qrk_solver* h) {
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin);
+  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wperm); F(h->d_wiscal);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
@@ -294,7 +298,7 @@ int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X,
   const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
   const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
   const bool in_full_layout = (op == OP_APPLY_Q) && full_q;
-  const long long q_nstart = h->avt ? h->sum_cols : h->n_cols;   // N_start = mat.cols() of the block-diagonal matrix (:430)
+  const long long q_nstart = ang(h) ? h->sum_cols : h->n_cols;   // N_start = mat.cols() of the block-diagonal matrix (:430)
   const bool vec_ok = aligned16(d_B) && aligned16(d_X) && (ldb % 2 == 0) && (ldx % 2 == 0) &&
                       (!(in_full_layout || (op == OP_APPLY_QT && full_q)) || (q_nstart % 2 == 0));
   if (h->small_path && vec_ok) {
@@ -346,7 +350,7 @@ __global__ void synth_fill_kernel(double* out, uint64_t seed, long long block0, 
 
 // ---- block angular ---------------------------------------------------------------------------------
 // border columns of R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:296-305)
-__global__ void export_angular_border_kernel(const double* __restrict__ atop, const double* __restrict__ root,
+__global__ void export_angular_border_kernel(const double* __restrict__ atop, long long ld_atop, const double* __restrict__ root,
                                              const int* __restrict__ root_i, long long m1, int m2, long long base,
                                              int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals) {
   const long long per_col_max = m1 + m2;
@@ -358,7 +362,7 @@ __global__ void export_angular_border_kernel(const double* __restrict__ atop, co
     if (r == 0) outer[m1 + c] = (int)start;
     if (r < m1) {
       inner[start + r] = (int)r;
-      vals[start + r] = atop[(long long)root_i[c] * m1 + r];
+      vals[start + r] = atop[(long long)root_i[c] * ld_atop + r];
     } else if (r - m1 <= c) {
       inner[start + r] = (int)r;
       vals[start + r] = root[(long long)c * m2 + (r - m1)];
@@ -408,9 +412,88 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
   return QRK_STATUS_OK;
 }
 
+// ---- block angular, dense right block in global memory (dense_border.cuh) ------------------------------------------
+int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X, long long ldx, int nrhs);
+
+DenseBorder wide_desc(qrk_solver* h, int nrhs) {
+  DenseBorder d;
+  d.A = h->d_wx + h->sum_cols;            // rows [m1, n) of Q1^T [J2 | b]
+  d.ld = h->n_rows; d.N = h->n_rows - h->sum_cols; d.M = h->m2; d.nrhs = nrhs;
+  d.upd = h->d_wupd; d.dir = h->d_wdir; d.tau = h->d_wtau2; d.perm = h->d_wperm; d.scal = h->d_wscal; d.iscal = h->d_wiscal;
+  return d;
+}
+
+// rank / root record / P_c tail, then (with a right-hand side) y2, x2, x1 = P1 R1^-1 (ytop - Atop x2)
+int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
+  const DenseBorder d = wide_desc(h, have_rhs ? 1 : 0);
+  const long long n = h->n_rows, m1 = h->sum_cols;
+  const int M = h->m2;
+  double* rhs_col = h->d_wx + (long long)M * n;
+  dense_finish_kernel<256><<<1, 256, (size_t)M * sizeof(double), h->stream>>>(d, have_rhs ? rhs_col + m1 : nullptr, h->d_root, h->d_root_i,
+                                                                        h->d_perm + m1, (int)m1, have_rhs ? d_x + m1 : nullptr);
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  h->launches++;
+  h->root_done = true;
+  if (have_rhs && m1 > 0) {
+    dense_top_kernel<<<(unsigned)((m1 + 255) / 256), 256, (size_t)M * sizeof(double), h->stream>>>(h->d_wx, n, m1, M, h->d_root + (size_t)M * M + 2 * M,
+                                                                                         rhs_col);
+    QRK_TRY_CUDA(h, cudaGetLastError());
+    const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
+    bd_rsolve_kernel<4><<<(unsigned)((h->nb + 3) / 4), 128, (size_t)4 * h->max_c * sizeof(double), h->stream>>>(
+        block_index(h), h->nb, h->d_values, piv ? h->d_perm : nullptr, rhs_col, d_x, h->max_c);
+    QRK_TRY_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+  }
+  return QRK_STATUS_OK;
+}
+
+int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
+  const long long n = h->n_rows;
+  const int M = h->m2;
+  int st = run_factor(h, A_in, nullptr, nullptr);                       // m_leftSolver.compute (BlockAngularSparseQR.h:472)
+  if (st != QRK_STATUS_OK) return st;
+  st = run_op(h, OP_APPLY_QT, h->d_border, h->ld_border, h->d_wx, n, M);   // Q1^T J2 (:365)
+  if (st != QRK_STATUS_OK) return st;
+  if (d_b) {
+    st = run_op(h, OP_APPLY_QT, d_b, n, h->d_wx + (long long)M * n, n, 1);
+    if (st != QRK_STATUS_OK) return st;
+  }
+  const DenseBorder d = wide_desc(h, d_b ? 1 : 0);
+  if (d.N > 0) {
+    dense_norms_kernel<<<M, 256, 0, h->stream>>>(d);
+    dense_prep_kernel<<<1, 256, 0, h->stream>>>(d);
+    h->launches += 2;
+    const int size = (int)std::min<long long>(d.N, M);
+    for (int k = 0; k < size; k++) {                                     // rightSolver.compute(J2.bottomRows(...)) (:368)
+      dense_piv_kernel<1024><<<1, 1024, 0, h->stream>>>(d, k);
+      const int ncols = M - k - 1 + d.nrhs;
+      if (ncols > 0) dense_upd_kernel<128><<<ncols, 128, 0, h->stream>>>(d, k);
+      h->launches += ncols > 0 ? 2 : 1;
+    }
+    QRK_TRY_CUDA(h, cudaGetLastError());
+  }
+  return wide_back(h, d_b != nullptr, d_x);
+}
+
+int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
+  const long long n = h->n_rows;
+  const int M = h->m2;
+  double* rhs_col = h->d_wx + (long long)M * n;
+  int st = run_op(h, OP_APPLY_QT, d_b, n, rhs_col, n, 1);
+  if (st != QRK_STATUS_OK) return st;
+  const DenseBorder d = wide_desc(h, 1);
+  if (d.N > 0) {
+    dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(d, rhs_col + h->sum_cols);   // Q2^T on the bottom rows (:619-624)
+    QRK_TRY_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  return wide_back(h, true, d_x);
+}
+
 // compute (+ fused solve when d_b != nullptr).  keep_abot: store the residual panel for later solve(b) calls.
 int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x, bool keep_abot) {
   QRK_REQUIRE(h, h->d_border, "no border set: call qrk_set_border first (BlockMatrix1x2 right block)");
+  if (h->wide) return wide_run(h, A_in, d_b, d_x);
   AngularArgs a = angular_args(h);
   a.A_in = A_in;
   a.b = d_b;
@@ -426,6 +509,7 @@ int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_
 
 // solve(b) on a stored factorisation: Q1^T b, TSQR redone over [Abot | b_bot], root, back substitution
 int angular_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
+  if (h->wide) return wide_solve_stored(h, d_b, d_x);
   QRK_REQUIRE(h, h->have_abot, "solve() after a fused compute_solve(): the residual panel was not kept; call compute() first");
   AngularArgs a = angular_args(h);
   a.b = d_b;
@@ -592,7 +676,11 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     // left block: uniform small blocks covering all rows, FullQ; border: 1..8 dense columns
     h->m2 = desc->border_cols;
     h->avt = angular_vtable(h->m2);
-    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc) || desc->q_format != QRK_FULL_Q) return fail(QRK_STATUS_UNSUPPORTED);
+    if (desc->q_format != QRK_FULL_Q || h->m2 < 1 || h->m2 > 4096) return fail(QRK_STATUS_UNSUPPORTED);
+    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc)) {   // wide border / other left blocks: dense_border.cuh
+      h->avt = nullptr;
+      h->wide = true;
+    }
     if (h->n_rows != h->sum_rows || (desc->n_cols > 0 && desc->n_cols != h->sum_cols + h->m2)) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->n_cols = h->sum_cols + h->m2;     // cols() = m1 + m2
   }
@@ -669,7 +757,19 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         cudaMalloc(&h->d_ythin, (size_t)h->n_cols * sizeof(double)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);
   }
-  if (angular) {
+  if (angular && h->wide) {
+    const size_t M = (size_t)h->m2;
+    if (cudaMalloc(&h->d_wx, std::max<size_t>(1, (size_t)h->n_rows * (M + 1)) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_wupd, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wdir, M * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_wtau2, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wscal, 2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_root, (M * M + 3 * M) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_root_i, (M + 1) * sizeof(int)) != cudaSuccess)
+      return fail(QRK_STATUS_ALLOC_FAILED);
+    cudaMemsetAsync(h->d_root, 0, (M * M + 3 * M) * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_root_i, 0, (M + 1) * sizeof(int), h->stream);
+    cudaMemsetAsync(h->d_wtau2, 0, M * sizeof(double), h->stream);
+  } else if (angular) {
     const bool piv = desc->pivoting == QRK_PIVOT_COLPIV;
     if (h->avt->max_grid(h->ur, h->uc, piv, &h->a_grid) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);
     const size_t tri = (size_t)h->avt->tri_doubles;
@@ -763,7 +863,7 @@ int qrk_factorize(qrk_handle_t h) {
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;   // reported through info(), as the reference
   DeviceGuard g(h->device);
   int st = h->bvt ? banded_run(h, h->d_values, nullptr, nullptr)
-                  : (h->avt ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr));
+                  : (ang(h) ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -781,9 +881,9 @@ static int compute_from_device(qrk_solver* h, const double* values, const double
   h->factorized = false;
   if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
-  if (d_x && h->n_cols > h->sum_cols && !h->avt)
+  if (d_x && h->n_cols > h->sum_cols && !ang(h))
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  st = h->bvt ? banded_run(h, values, d_b, d_x) : (h->avt ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x));
+  st = h->bvt ? banded_run(h, values, d_b, d_x) : (ang(h) ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -818,9 +918,9 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   } else {
     QRK_REQUIRE(h, aligned16(b) && aligned16(x), "device b / x must be 16-byte aligned");
   }
-  if (h->n_cols > h->sum_cols && !h->avt)
+  if (h->n_cols > h->sum_cols && !ang(h))
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  int st = h->bvt ? banded_run(h, h->d_values, d_b, d_x) : (h->avt ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x));
+  int st = h->bvt ? banded_run(h, h->d_values, d_b, d_x) : (ang(h) ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   if (h->pending) {            // multi-GPU block angular: x is produced by qrk_angular_merge
@@ -853,7 +953,7 @@ int qrk_rank(qrk_handle_t h, int64_t* rank) {
   if (!h || !rank) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
   *rank = h->sum_cols;   // rank += blockSolver.cols() (BlockDiagonalSparseQR.h:440)
-  if (h->avt) {          // + rightSolver.rank() (BlockAngularSparseQR.h:510)
+  if (ang(h)) {          // + rightSolver.rank() (BlockAngularSparseQR.h:510)
     if (!h->root_done) return QRK_STATUS_NOT_FACTORIZED;
     DeviceGuard g(h->device);
     int r2 = 0;
@@ -867,7 +967,7 @@ int qrk_info(qrk_handle_t h, int32_t* info) { if (!h || !info) return QRK_STATUS
 
 int qrk_cols_permutation(qrk_handle_t h, int32_t* indices, int memspace) {
   if (!h || !indices) return QRK_STATUS_INVALID_ARGUMENT;
-  if (!h->factorized || (h->avt && !h->root_done)) return QRK_STATUS_NOT_FACTORIZED;
+  if (!h->factorized || (ang(h) && !h->root_done)) return QRK_STATUS_NOT_FACTORIZED;
   DeviceGuard g(h->device);
   QRK_TRY_CUDA(h, cudaMemcpyAsync(indices, h->d_perm, h->n_cols * sizeof(int),
                                   memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
@@ -906,7 +1006,7 @@ int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz) {
   long long n = 0;
   if (h->uniform) n = h->nb * ((long long)h->uc * (h->uc + 1) / 2);
   else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
-  if (h->avt) n += h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2;   // border columns (makeR :296-305)
+  if (ang(h)) n += h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2;   // border columns (makeR :296-305)
   if (h->bvt) n = banded_r_outer(h).back();
   *nnz = n;
   return QRK_STATUS_OK;
@@ -925,7 +1025,7 @@ int qrk_matrix_q_nnz(qrk_handle_t h, int64_t* nnz) {
 static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* inner, double* values, int memspace) {
   if (!h || !outer || !inner || !values) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
-  if (h->avt && !want_q && !h->root_done) return QRK_STATUS_NOT_FACTORIZED;
+  if (ang(h) && !want_q && !h->root_done) return QRK_STATUS_NOT_FACTORIZED;
   int64_t nnz = 0;
   if (want_q) qrk_matrix_q_nnz(h, &nnz); else qrk_matrix_r_nnz(h, &nnz);
   QRK_REQUIRE(h, nnz <= INT32_MAX, "matrix has more than 2^31-1 stored entries (StorageIndex = int)");
@@ -968,12 +1068,13 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
       e = cudaGetLastError();
       cudaStreamSynchronize(h->stream);     // ho must outlive the copy
     }
-  } else if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, h->avt ? h->sum_cols : h->n_cols, h->sum_rows,
+  } else if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, ang(h) ? h->sum_cols : h->n_cols, h->sum_rows,
                                   nnz - (h->n_rows - h->sum_rows), full_q, h->max_r, d_outer, d_inner, d_vals, h->stream);
-  else if (h->avt) {
+  else if (ang(h)) {
     const long long nnz_r1 = nnz - (h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2);
     e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->sum_cols, h->sum_cols, nnz_r1, 1, d_outer, d_inner, d_vals, h->stream);
-    export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->d_atop, h->d_root, h->d_root_i, h->sum_cols, h->m2, nnz_r1, d_outer,
+    export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->wide ? h->d_wx : h->d_atop, h->wide ? h->n_rows : h->sum_cols, h->d_root,
+                                                             h->d_root_i, h->sum_cols, h->m2, nnz_r1, d_outer,
                                                              d_inner, d_vals);
     if (e == cudaSuccess) e = cudaGetLastError();
     h->launches++;
@@ -1023,7 +1124,7 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     d_B = h->d_b; d_X = h->d_x;
   }
   if (op == OP_SOLVE) {
-    if (h->n_cols > h->sum_cols && !h->avt)   // y.bottomRows(...).setZero() (:272)
+    if (h->n_cols > h->sum_cols && !ang(h))   // y.bottomRows(...).setZero() (:272)
       QRK_TRY_CUDA(h, cudaMemset2DAsync(d_X + h->sum_cols, dldx * sizeof(double), 0, (h->n_cols - h->sum_cols) * sizeof(double),
                                         nrhs, h->stream));
   } else if (h->n_rows > h->sum_rows && !h->bvt) {
@@ -1049,7 +1150,7 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
       if (e == cudaSuccess && op == OP_SOLVE) { a.x = d_X + j * dldx; e = h->bvt->backsolve(a, h->stream); h->launches++; }
       if (e != cudaSuccess) { h->err = std::string("banded op: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
     }
-  } else if (h->avt && op == OP_SOLVE) {
+  } else if (ang(h) && op == OP_SOLVE) {
     QRK_REQUIRE(h, h->world == 1 || nrhs == 1, "multi-GPU block-angular solve takes one right-hand side per call");
     for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) st = angular_solve_stored(h, d_B + j * dldb, d_X + j * dldx);
     if (st == QRK_STATUS_OK && h->pending) {
@@ -1083,7 +1184,7 @@ int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, int64_t l
 // ---- block angular entry points --------------------------------------------------------------------
 int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
-  QRK_REQUIRE(h, h->avt, "qrk_set_border: the handle is not of kind QRK_BLOCK_ANGULAR");
+  QRK_REQUIRE(h, ang(h), "qrk_set_border: the handle is not of kind QRK_BLOCK_ANGULAR");
   QRK_REQUIRE(h, J2 && ld >= h->n_rows, "border is null or its leading dimension is smaller than the number of rows");
   DeviceGuard g(h->device);
   if (memspace == QRK_DEVICE) {

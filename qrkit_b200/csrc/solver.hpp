@@ -69,6 +69,12 @@ struct qrk_solver {
   int pending_space = 0;
   int pending_keep_rhs_only = 0;
 
+  // ---- block angular, wide border or a left block outside the TSQR kernels (dense_border.cuh) ----
+  bool wide = false;
+  double* d_wx = nullptr;              // n x (m2 + 1): Q1^T [J2 | b]; rows [m1, n) hold the right block's packed QR
+  double *d_wupd = nullptr, *d_wdir = nullptr, *d_wtau2 = nullptr, *d_wscal = nullptr;
+  int *d_wperm = nullptr, *d_wiscal = nullptr;
+
   // ---- banded blocked (kind == QRK_BANDED_BLOCKED): sequential window sweep on one SM ----
   const qrk::BandedVTable* bvt = nullptr;
   int b_ov = 0, b_step = 0;            // overlap, column step S = block_cols - overlap

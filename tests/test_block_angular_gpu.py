@@ -109,13 +109,47 @@ def test_multi_gpu_exchange_on_one_device(qk, oracle):
         assert np.array_equal(x2s[g], x2s[0]), "the redundantly computed shared parameters must be bit-identical on every rank"
 
 
-def test_unsupported_border_width_is_reported(qk):
+@pytest.mark.parametrize("r,c,m2,nb", [(2, 1, 9, 200), (7, 2, 24, 120), (8, 4, 5, 150), (7, 2, 96, 96), (16, 8, 40, 40)])
+@pytest.mark.parametrize("piv", [0, 1])
+def test_wide_border_vs_oracle(qk, oracle, r, c, m2, nb, piv):
+    """Borders wider than the in-SM TSQR path (m2 > 8) and left blocks outside its shape list take the dense right-block
+    solver (dense_border.cuh: Eigen's ColPivHouseholderQR on the residual rows): same checks, P2 and R2 included."""
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    b = vector(nb * r, seed=5)
+    _check(qk, oracle, vals, r, c, J2, b, piv=piv)
+
+
+def test_reference_test4_border_384(qk, oracle):
+    """The reference's block-angular test sizes (test/test-qrkit.cpp:388-391): 7168 rows, 2048 left columns as 1024 blocks
+    of 7x2, a fully dense border of 384 columns, right solver ColPivHouseholderQR<MatrixXd> (:46-48).  The test asserts what
+    the reference asserts (x recovered from a consistent system, :289) at 1e-10 instead of 1e-6, plus P2 and rank."""
+    nb, r, c, m2 = 1024, 7, 2, 384
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    A = np.hstack([blocks_to_dense(vals, np.full(nb, r), np.full(nb, c)), J2])
+    x_true = vector(nb * c + m2, seed=21)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    s = qk.BlockAngularSparseQR(mat, pivoting=1)
+    assert s.rank() == nb * c + m2 and s.info() == qk.QRK_INFO_SUCCESS
+    assert rel(s.solve(A @ x_true), x_true) <= 1e-10
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True, right_kind=0)
+    assert np.array_equal(s.colsPermutation(), ref.colsPermutation())
+    b = vector(nb * r, seed=22)
+    assert rel(s.solve(b), ref.solve(b)) <= 1e-10
+    s2 = qk.BlockAngularSparseQR(pivoting=1)
+    assert rel(s2.compute_solve(mat, b), ref.solve(b)) <= 1e-10
+
+
+def test_multi_gpu_exchange_needs_the_tsqr_path(qk):
     import ctypes as C
     from qrkit_b200 import capi
     d = capi.QrkDesc()
     d.kind, d.num_blocks, d.block_rows, d.block_cols, d.border_cols = capi.QRK_BLOCK_ANGULAR, 10, 2, 1, 9
     h = C.c_void_p()
-    assert capi.lib().qrk_create(C.byref(d), C.byref(h)) == capi.QRK_STATUS_UNSUPPORTED
+    assert capi.lib().qrk_create(C.byref(d), C.byref(h)) == capi.QRK_STATUS_OK
+    assert capi.lib().qrk_angular_set_world(h, 2) == capi.QRK_STATUS_INVALID_ARGUMENT     # wide borders: single GPU for now
+    capi.lib().qrk_destroy(h)
 
 
 def test_config3_full_size_properties(qk, oracle):
