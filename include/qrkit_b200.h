@@ -65,6 +65,13 @@ typedef enum {
   QRK_PIVOT_COLPIV = 1  /* Eigen::ColPivHouseholderQR (test/test-qrkit.cpp:49-51) */
 } qrk_pivoting;
 
+/* The dense right-block solver of BlockAngularSparseQR (template parameter RightSolver, BlockAngularSparseQR.h:79). */
+typedef enum {
+  QRK_RIGHT_COLPIV = 0,    /* Eigen::ColPivHouseholderQR<MatrixXd> (test/test-qrkit.cpp:46-48, examples/ellipse_fitting.cpp:35) */
+  QRK_RIGHT_UNPIVOTED = 1  /* BlockedThinDenseQR<MatrixXd, N> / Eigen::HouseholderQR: no column pivoting, P2 = identity,
+                              rank() = cols (BlockedThinDenseQR.h:132); R2 equals the reference's up to row signs */
+} qrk_right_solver;
+
 /* MatrixQFormat (BlockDiagonalSparseQR.h:59-62). */
 typedef enum { QRK_FULL_Q = 0, QRK_BLOCK_DIAGONAL_Q = 1 } qrk_qformat;
 
@@ -85,7 +92,8 @@ typedef struct {
   int32_t q_format;        /* qrk_qformat */
   int32_t border_cols;     /* block angular: m2 = columns of the dense right block (BlockAngularSparseQR.h:464); else 0 */
   int32_t block_overlap;   /* banded: column overlap of consecutive blocks (_BlockOverlap, BandedBlockedSparseQR.h:122); else 0 */
-  int32_t reserved[4];
+  int32_t right_solver;    /* block angular: qrk_right_solver, the RightSolver template argument (BlockAngularSparseQR.h:79) */
+  int32_t reserved[3];
 } qrk_desc_t;
 
 /* ---- library ------------------------------------------------------------------------------- */

@@ -22,6 +22,7 @@ QRK_STATUS_UNSUPPORTED = 6
 
 QRK_INFO_SUCCESS, QRK_INFO_NUMERICAL_ISSUE, QRK_INFO_NO_CONVERGENCE, QRK_INFO_INVALID_INPUT = 0, 1, 2, 3
 QRK_BLOCK_DIAGONAL, QRK_BLOCK_ANGULAR, QRK_BANDED_BLOCKED = 0, 1, 2
+QRK_RIGHT_COLPIV, QRK_RIGHT_UNPIVOTED = 0, 1
 QRK_PIVOT_NONE, QRK_PIVOT_COLPIV = 0, 1
 QRK_FULL_Q, QRK_BLOCK_DIAGONAL_Q = 0, 1
 QRK_HOST, QRK_DEVICE = 0, 1
@@ -35,7 +36,7 @@ class QrkDesc(C.Structure):
         ("n_rows", C.c_int64), ("n_cols", C.c_int64),
         ("pivoting", C.c_int32), ("q_format", C.c_int32),
         ("border_cols", C.c_int32), ("block_overlap", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("right_solver", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

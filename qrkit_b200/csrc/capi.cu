@@ -419,6 +419,7 @@ DenseBorder wide_desc(qrk_solver* h, int nrhs) {
   DenseBorder d;
   d.A = h->d_wx + h->sum_cols;            // rows [m1, n) of Q1^T [J2 | b]
   d.ld = h->n_rows; d.N = h->n_rows - h->sum_cols; d.M = h->m2; d.nrhs = nrhs;
+  d.pivot = h->desc.right_solver == QRK_RIGHT_UNPIVOTED ? 0 : 1;
   d.upd = h->d_wupd; d.dir = h->d_wdir; d.tau = h->d_wtau2; d.perm = h->d_wperm; d.scal = h->d_wscal; d.iscal = h->d_wiscal;
   return d;
 }
@@ -677,7 +678,8 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     h->m2 = desc->border_cols;
     h->avt = angular_vtable(h->m2);
     if (desc->q_format != QRK_FULL_Q || h->m2 < 1 || h->m2 > 4096) return fail(QRK_STATUS_UNSUPPORTED);
-    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc)) {   // wide border / other left blocks: dense_border.cuh
+    if (desc->right_solver != QRK_RIGHT_COLPIV && desc->right_solver != QRK_RIGHT_UNPIVOTED) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc) || desc->right_solver == QRK_RIGHT_UNPIVOTED) {   // dense_border.cuh
       h->avt = nullptr;
       h->wide = true;
     }

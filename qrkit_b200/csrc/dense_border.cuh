@@ -20,6 +20,7 @@ struct DenseBorder {
   double* A;         // N x (M + nrhs) column-major
   long long ld, N;
   int M, nrhs;
+  int pivot;         // 1: ColPivHouseholderQR (Eigen's pivot rule), 0: HouseholderQR / BlockedThinDenseQR (no pivoting)
   double *upd, *dir, *tau;
   int* perm;         // P2: perm[c] = original border column at position c
   double* scal;      // [0] threshold_helper, [1] maxpivot
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double bv = -1.0;
   int bj = 0x7fffffff;
-  for (int j = k + tid; j < d.M; j += TPB) {
+  if (!d.pivot) { bv = 0.0; bj = k; }
+  else for (int j = k + tid; j < d.M; j += TPB) {
     const double u = d.upd[j];
     if (u > bv) { bv = u; bj = j; }                    // strict '>': the first maximum wins inside a thread
   }
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
     for (int w = 1; w < TPB / 32; w++)
       if (sval[w] > bv || (sval[w] == bv && sidx[w] < bj)) { bv = sval[w]; bj = sidx[w]; }
     const int size = (int)(d.N < d.M ? d.N : d.M);
-    if (d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.N - k)) d.iscal[0] = k;
+    if (d.pivot && d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.N - k)) d.iscal[0] = k;
     if (bj != k) {
       double t = d.upd[k]; d.upd[k] = d.upd[bj]; d.upd[bj] = t;
       t = d.dir[k]; d.dir[k] = d.dir[bj]; d.dir[bj] = t;
@@ -200,7 +202,8 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
   if (tid == 0) {
     const double thresh = fabs(d.scal[1]) * (DBL_EPSILON * (double)size);
     int rank = 0;
-    for (int i = 0; i < d.iscal[0]; i++) rank += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
+    if (!d.pivot) rank = M;              // BlockedThinDenseQR: m_nonzeroPivots = m_R.cols() (BlockedThinDenseQR.h:132)
+    else for (int i = 0; i < d.iscal[0]; i++) rank += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
     s_rank = rank;
     root_i[M] = rank;
   }

@@ -266,15 +266,17 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
     """BlockAngularSparseQR<BlockDiagonalSparseQR<...>, ColPivHouseholderQR<MatrixXd>> (BlockAngularSparseQR.h:79-281):
     left block diagonal, dense border factored by a TSQR tree + Eigen's ColPiv rule at the root."""
 
-    def __init__(self, mat: BlockMatrix1x2 | None = None, *, pivoting=QRK_PIVOT_COLPIV, device=0, stream=None, world=1):
+    def __init__(self, mat: BlockMatrix1x2 | None = None, *, pivoting=QRK_PIVOT_COLPIV, device=0, stream=None, world=1,
+                 right_solver=0):
         self._world = world
+        self._right_solver = right_solver      # 0: ColPivHouseholderQR<MatrixXd>, 1: BlockedThinDenseQR / HouseholderQR (unpivoted)
         super().__init__(None, pivoting=pivoting, q_format=QRK_FULL_Q, device=device, stream=stream)
         if mat is not None:
             self.compute(mat)
 
     def _ensure_handle_angular(self, mat: BlockMatrix1x2):
         left, m2 = mat.left, mat.right.shape[1]
-        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2)
+        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2, self._right_solver)
         if self._h and key == self._shape_key:
             return
         self.close()
@@ -282,6 +284,7 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
         d.kind, d.device, d.num_blocks = capi.QRK_BLOCK_ANGULAR, self._device, left.num_blocks
         d.block_rows, d.block_cols = left.block_rows, left.block_cols
         d.pivoting, d.q_format, d.border_cols = self._pivoting, QRK_FULL_Q, m2
+        d.right_solver = self._right_solver
         h = C.c_void_p()
         check(lib().qrk_create(C.byref(d), C.byref(h)))
         self._h, self._shape_key = h, key

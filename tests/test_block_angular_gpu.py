@@ -141,6 +141,27 @@ def test_reference_test4_border_384(qk, oracle):
     assert rel(s2.compute_solve(mat, b), ref.solve(b)) <= 1e-10
 
 
+@pytest.mark.parametrize("r,c,m2,nb", [(7, 2, 5, 100), (7, 2, 48, 64), (4, 2, 9, 128)])
+def test_unpivoted_right_solver_vs_oracle(qk, oracle, r, c, m2, nb):
+    """RightSolver = BlockedThinDenseQR<MatrixXd, 2> (reference test 5, test/test-qrkit.cpp:53-56, 294-327): no column
+    pivoting in the right block, P2 = identity, rank = cols; R2 is unique up to row signs whatever the panel width."""
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    b = vector(nb * r, seed=6)
+    m1 = nb * c
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True, right_kind=1, panel=2)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    s = qk.BlockAngularSparseQR(mat, pivoting=1, right_solver=1)
+    assert s.rank() == ref.rank == m1 + m2
+    assert np.array_equal(s.colsPermutation(), ref.colsPermutation())
+    assert np.array_equal(s.colsPermutation()[m1:], m1 + np.arange(m2))
+    Rd, Rrd = s.matrixR().toarray(), ref.matrixR().toarray()
+    assert rel(Rd[:m1, :], Rrd[:m1, :]) <= TOL_R
+    assert rel(_sign_fix(Rd[m1:m1 + m2, m1:], Rrd[m1:m1 + m2, m1:]), Rrd[m1:m1 + m2, m1:]) <= TOL_R * 10
+    assert rel(s.solve(b), ref.solve(b)) <= TOL_X
+    assert rel(qk.BlockAngularSparseQR(pivoting=1, right_solver=1).compute_solve(mat, b), ref.solve(b)) <= TOL_X
+
+
 def test_multi_gpu_exchange_needs_the_tsqr_path(qk):
     import ctypes as C
     from qrkit_b200 import capi
