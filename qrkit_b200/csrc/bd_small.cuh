@@ -184,7 +184,8 @@ struct SmallSmem {
 template <int R, int C, bool PIV, bool SOLVE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
 bd_small_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out,
-                       int* __restrict__ perm_out, const double* __restrict__ b, double* __restrict__ x, long long nb) {
+                       int* __restrict__ perm_out, const double* __restrict__ b, double* __restrict__ x, long long nb,
+                       long long block0) {
   static_assert(R >= C, "portrait blocks only (BlockDiagonalSparseQR.h:509-516 rejects landscape blocks)");
   using L = SmallSmem<R, C, TPB>;
   extern __shared__ __align__(16) double smem[];
@@ -215,7 +216,7 @@ bd_small_factor_kernel(const double* A_in, double* packed, double* __restrict__ 
     store_group<R * C>(sA + t * L::SA, a);
     store_group<C>(sT + t * L::ST, tau);
     if (PIV) {
-      const int base_col = (int)((tile0 + t) * C);
+      const int base_col = (int)((block0 + tile0 + t) * C);   // block0: first block of this launch (chunked host pipeline)
 #pragma unroll
       for (int j = 0; j < C; j++) sP[t * L::SP + j] = base_col + perm[j];
     }

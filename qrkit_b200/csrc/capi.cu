@@ -83,14 +83,14 @@ cudaError_t ensure_smem(K kernel, size_t bytes, bool (&done)[64]) {
 
 template <int R, int C, bool PIV, bool SOLVE>
 cudaError_t launch_small_factor(const double* A, double* packed, double* tau, int* perm, const double* b, double* x,
-                                long long nb, cudaStream_t s) {
+                                long long nb, cudaStream_t s, long long block0) {
   auto kernel = bd_small_factor_kernel<R, C, PIV, SOLVE, kSmallTPB, kSmallMinBlocks>;
   constexpr size_t smem = SmallSmem<R, C, kSmallTPB>::bytes;
   static bool smem_opt_in[64] = {};
   cudaError_t attr = ensure_smem(kernel, smem, smem_opt_in);
   if (attr != cudaSuccess) return attr;
   const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
-  kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(A, packed, tau, perm, b, x, nb);
+  kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(A, packed, tau, perm, b, x, nb, block0);
   return cudaGetLastError();
 }
 
@@ -116,13 +116,13 @@ bool small_shape_available(int r, int c) {
 }
 
 cudaError_t launch_small_factor_dyn(int r, int c, bool piv, bool solve, const double* A, double* packed, double* tau,
-                                    int* perm, const double* b, double* x, long long nb, cudaStream_t s) {
+                                    int* perm, const double* b, double* x, long long nb, cudaStream_t s, long long block0 = 0) {
 #define X(R_, C_)                                                                                     \
   if (r == R_ && c == C_) {                                                                           \
-    if (piv) return solve ? launch_small_factor<R_, C_, true, true>(A, packed, tau, perm, b, x, nb, s) \
-                          : launch_small_factor<R_, C_, true, false>(A, packed, tau, perm, b, x, nb, s); \
-    return solve ? launch_small_factor<R_, C_, false, true>(A, packed, tau, perm, b, x, nb, s)        \
-                 : launch_small_factor<R_, C_, false, false>(A, packed, tau, perm, b, x, nb, s);      \
+    if (piv) return solve ? launch_small_factor<R_, C_, true, true>(A, packed, tau, perm, b, x, nb, s, block0) \
+                          : launch_small_factor<R_, C_, true, false>(A, packed, tau, perm, b, x, nb, s, block0); \
+    return solve ? launch_small_factor<R_, C_, false, true>(A, packed, tau, perm, b, x, nb, s, block0)        \
+                 : launch_small_factor<R_, C_, false, false>(A, packed, tau, perm, b, x, nb, s, block0);      \
   }
   QRK_SMALL_SHAPES(X)
 #undef X
@@ -246,6 +246,10 @@ void free_dev(qrk_solver* h) {
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
+  for (cudaEvent_t e : h->pipe_events) cudaEventDestroy(e);
+  h->pipe_events.clear();
+  if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
+  if (h->s_out) { cudaStreamDestroy(h->s_out); h->s_out = nullptr; }
 }
 
 int ensure_buffer(qrk_solver* h, double*& p, size_t& cap, size_t n) {
@@ -937,8 +941,64 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   return QRK_STATUS_OK;
 }
 
+// Host buffers, thread-per-block kernels: the blocks are independent, so the upload, the fused kernel and the download
+// of x are pipelined in chunks over three streams (H2D and D2H run concurrently on the two PCIe directions; the kernel
+// time disappears behind the copies).  With pageable host memory the copies serialise and this degrades gracefully.
+static int compute_solve_host_pipelined(qrk_solver* h, const double* values, const double* b, double* x) {
+  DeviceGuard g(h->device);
+  int st = ensure_own_values(h);
+  if (st != QRK_STATUS_OK) return st;
+  st = ensure_buffer(h, h->d_b, h->cap_b, (size_t)h->n_rows);
+  if (st != QRK_STATUS_OK) return st;
+  st = ensure_buffer(h, h->d_x, h->cap_x, (size_t)h->n_cols);
+  if (st != QRK_STATUS_OK) return st;
+  if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
+  const int r = h->ur, c = h->uc;
+  const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
+  const long long chunk = std::max<long long>(kSmallTPB, ((16LL << 20) / ((long long)r * c * 8)) / kSmallTPB * kSmallTPB);
+  const int nchunks = (int)((h->nb + chunk - 1) / chunk);
+  if (!h->s_in) {
+    QRK_TRY_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    QRK_TRY_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  }
+  while ((int)h->pipe_events.size() < 2 * nchunks + 1) {
+    cudaEvent_t e;
+    QRK_TRY_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->pipe_events.push_back(e);
+  }
+  cudaEvent_t ev0 = h->pipe_events[2 * nchunks];
+  QRK_TRY_CUDA(h, cudaEventRecord(ev0, h->stream));            // earlier work on the handle's stream comes first
+  QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_in, ev0, 0));
+  QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_out, ev0, 0));
+  for (int i = 0; i < nchunks; i++) {
+    const long long b0 = i * chunk, cnt = std::min(chunk, h->nb - b0);
+    cudaEvent_t ev_in = h->pipe_events[2 * i], ev_k = h->pipe_events[2 * i + 1];
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_values + b0 * r * c, values + b0 * r * c, (size_t)cnt * r * c * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->s_in));
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_b + b0 * r, b + b0 * r, (size_t)cnt * r * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    QRK_TRY_CUDA(h, cudaEventRecord(ev_in, h->s_in));
+    QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->stream, ev_in, 0));
+    QRK_TRY_CUDA(h, launch_small_factor_dyn(r, c, piv, true, h->d_values + b0 * r * c, h->d_values + b0 * r * c, h->d_tau + b0 * c,
+                                            h->d_perm + b0 * c, h->d_b + b0 * r, h->d_x + b0 * c, cnt, h->stream, b0));
+    h->launches++;
+    QRK_TRY_CUDA(h, cudaEventRecord(ev_k, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_k, 0));
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(x + b0 * c, h->d_x + b0 * c, (size_t)cnt * c * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+  }
+  if (h->n_cols > h->sum_cols) std::fill(x + h->sum_cols, x + h->n_cols, 0.0);     // y.bottomRows(...).setZero() (:272)
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->s_out));
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->has_blocks = true;
+  h->factorized = true;
+  return QRK_STATUS_OK;
+}
+
 int qrk_compute_solve(qrk_handle_t h, const double* values, const double* b, double* x, int memspace) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
+  if (memspace == QRK_HOST && h->small_path && !h->bvt && !ang(h) && h->info != QRK_INFO_INVALID_INPUT && h->nb >= 4 * kSmallTPB) {
+    QRK_REQUIRE(h, values && b && x, "values / b / x is null");
+    return compute_solve_host_pipelined(h, values, b, x);
+  }
   if (memspace == QRK_DEVICE) {
     QRK_REQUIRE(h, b && x, "b / x is null");
     QRK_REQUIRE(h, aligned16(b) && aligned16(x), "device b / x must be 16-byte aligned");

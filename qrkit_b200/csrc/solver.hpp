@@ -27,6 +27,8 @@ struct qrk_solver {
   int device = 0;
   cudaStream_t stream = nullptr;      // the stream work is enqueued on
   cudaStream_t own_stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the chunked host pipeline (qrk_compute_solve, QRK_HOST)
+  std::vector<cudaEvent_t> pipe_events;
   std::string err;
   long long launches = 0;
 
