@@ -42,6 +42,55 @@ def time_steps(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def _cpu(fn, rows, sample, cores=1):
+    """Time the CPU oracle (restatement of the reference's algorithm, oracle/) once on a bounded sample."""
+    import time
+    t0 = time.perf_counter()
+    fn()
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": "rows/s", "cores": cores, "kind": "port", "seconds": dt, "sample": sample}
+
+
+def cpu_angular(n):
+    from helpers import ellipse_problem
+    from oracle import oracle as orc
+    J1, J2, rhs = ellipse_problem(n)
+    def run():
+        ref = orc.BlockAngularOracle(J2, br=np.full(n, 2, dtype=np.int32), bc=np.full(n, 1, dtype=np.int32), values=J1, left_colpiv=True, right_kind=0)
+        ref.solve(rhs)
+    return _cpu(run, 2 * n, f"ellipse Jacobian at N={n} points, BlockAngular<BlockDiagonal 2x1 ColPiv, dense ColPiv> factorize + solve, reference-faithful (explicit sparse Q1, dense tall ColPiv QR), 1 thread")
+
+
+def cpu_mixed(nb):
+    from helpers import uniform_blocks, vector
+    from oracle import oracle as orc
+    br, bc = mixed_sizes(nb)
+    vals = np.concatenate([uniform_blocks(1, int(r), int(c), block0=i) for i, (r, c) in enumerate(zip(br, bc))])
+    b = vector(int(br.sum()), seed=17)
+    def run():
+        ref = orc.BlockDiagonalOracle(br, bc, vals, colpiv=False)
+        ref.solve(b)
+    return _cpu(run, int(br.sum()), f"{nb} mixed blocks 32x16..128x64, BlockDiagonalSparseQR<HouseholderQR> factorize + solve, reference-faithful (explicit Q_i, sparse Q/R assembly), 1 thread")
+
+
+def cpu_banded(nb):
+    import scipy.sparse as sp
+    from helpers import reference_style_windows, uniform_blocks, vector
+    from oracle import oracle as orc
+    br, bc, ov = 16, 24, 16
+    slabs = uniform_blocks(nb, br, bc).reshape(nb, bc, br)
+    jj, ii = np.meshgrid(np.arange(bc), np.arange(br), indexing="ij")
+    rows = (np.arange(nb)[:, None, None] * br + ii[None]).reshape(-1)
+    cols = (np.arange(nb)[:, None, None] * (bc - ov) + jj[None]).reshape(-1)
+    A = sp.csc_matrix((slabs.reshape(-1), (rows, cols)), shape=(nb * br, (nb - 1) * (bc - ov) + bc))
+    blocks = reference_style_windows(nb, br, bc, ov, 2)
+    b = vector(nb * br, seed=3)
+    def run():
+        ref = orc.BandedOracle(A, blocks)
+        ref.solve(b)
+    return _cpu(run, nb * br, f"{nb} block rows 16x24 step 8, BandedBlockedSparseQR with the reference's merged windows ({len(blocks)} of them) factorize + solve, 1 thread")
+
+
 def ellipse_device(n):
     """Ellipse-fit Jacobian at the initial LM iterate (bench/bench_sparse_qr_extra.cpp:79-114, 221-282) on the device."""
     a, b, x0, y0, r = 7.5, 2.0, 17.0, 23.0, 0.23
@@ -93,6 +142,8 @@ def bench_angular(args, L, stream):
                          "algorithmic_bytes_per_point": bytes_per_point, "peak_source": src},
             "colpiv_left": {"ms_per_step": out[1][0], "value": 2 * n / (out[1][0] * 1e-3)},
             "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_angular(min(n, 500_000))
     print(json.dumps(line), flush=True)
 
 
@@ -139,6 +190,8 @@ def bench_mixed(args, L, stream):
                                   "frac": flops / (ms * 1e-3) / 1e12 / 37.0},
                          "algorithmic_bytes": alg_bytes, "flops": flops, "peak_source": src},
             "colpiv": {"ms_per_step": res[1], "value": rows / (res[1] * 1e-3)}, "steps": args.steps, "dtype": "f64"}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_mixed(min(nb, 5000))
     print(json.dumps(line), flush=True)
 
 
@@ -189,12 +242,15 @@ def bench_banded(args, L, stream):
     peak, src = measured_peaks()
     # 8 (nnz A + nnz R + nnz V) + 8 (rows + 2 cols) bytes
     alg = 8.0 * (nb * br * bc + n_cols * bc + nb * br * bc) + 8.0 * (n_rows + 2 * n_cols)
-    print(json.dumps({"workload": f"block-banded, {nb} block rows of {br}x{bc}, step {bc-ov} (BASELINE config 4), fused QR+solve, single GPU",
-                      "metric": "rows/s", "value": n_rows / (ms * 1e-3), "ms_per_step": ms, "rows": n_rows, "cols": n_cols,
-                      "us_per_window": ms * 1e3 / nb,
-                      "roofline": {"bound": "latency (sequential window chain); HBM fraction for the record", "achieved": alg / (ms * 1e-3) / 1e9,
-                                   "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src},
-                      "dtype": "f64"}), flush=True)
+    line = {"workload": f"block-banded, {nb} block rows of {br}x{bc}, step {bc-ov} (BASELINE config 4), fused QR+solve, single GPU",
+            "metric": "rows/s", "value": n_rows / (ms * 1e-3), "ms_per_step": ms, "rows": n_rows, "cols": n_cols,
+            "us_per_window": ms * 1e3 / nb,
+            "roofline": {"bound": "latency (sequential window chain); HBM fraction for the record", "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src},
+            "dtype": "f64"}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_banded(min(nb, 50_000))
+    print(json.dumps(line), flush=True)
 
 
 def bench_angular_wide(args, L, stream):
@@ -259,6 +315,7 @@ def main():
     ap.add_argument("--class-blocks", type=int, default=0)
     ap.add_argument("--banded-blocks", type=int, default=100_000)
     ap.add_argument("--shapes", default="")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle timings (cpu_baseline)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: qrkit_b200 has no CPU fallback")

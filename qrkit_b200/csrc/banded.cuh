@@ -44,6 +44,7 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
   constexpr int S = G::S, M = G::M;
   const int lane = threadIdx.x;
   const bool is_col = lane < BC, is_rhs = (lane == BC) && (b != nullptr);
+  __shared__ __align__(16) double sv[2 * BR];
   double cw[OV > 0 ? OV : 1], bw[BR], nxt[BR], tau_mine = 0.0;
 #pragma unroll
   for (int i = 0; i < (OV > 0 ? OV : 1); i++) cw[i] = 0.0;
@@ -74,9 +75,10 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
       if (c >= ncols_w) continue;                  // columns beyond the matrix: no reflector
       const int P0 = (c < OV) ? 0 : c - OV + 1;   // first participating slab row (compile time after unrolling)
       // ---- reflector of column c, computed in lane c (every lane runs the arithmetic, lane c's result is used)
-      double tailSq = 0.0;
+      double tq[4] = {0.0, 0.0, 0.0, 0.0};          // four partial sums: the dependent FMA chain is BR/4 long, not BR
 #pragma unroll
-      for (int i = 0; i < BR; i++) if (i >= P0) tailSq = fma(bw[i], bw[i], tailSq);
+      for (int i = 0; i < BR; i++) if (i >= P0) tq[i & 3] = fma(bw[i], bw[i], tq[i & 3]);
+      const double tailSq = (tq[0] + tq[1]) + (tq[2] + tq[3]);
       const double c0 = QRK_WROW(c);
       const bool degenerate = (P0 >= BR) || (tailSq <= DBL_MIN);
       double norm;
@@ -90,15 +92,24 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
       // ---- broadcast v = [1; inv * tail] from lane c; dot product and rank-1 update are lane-local
       const bool upd = lane > c;                  // columns right of c and the right-hand side
       double pv = QRK_WROW(c);
-      double dot = pv;
       double v[BR];
+      // lane c publishes its scaled tail through shared memory (8 STS.128 + 8 broadcast LDS.128 instead of 2 BR shuffles
+      // through the one-per-clock SHFL pipe); the buffer alternates with the column parity, one __syncwarp per column
+      double* vb = sv + (c & 1) * BR;
+      if (lane == c) {
+#pragma unroll
+        for (int i = 0; i < BR; i++) if (i >= P0) vb[i] = bw[i] * inv;
+      }
+      __syncwarp();
+      double dq[4] = {pv, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int i = 0; i < BR; i++) {
         if (i >= P0) {
-          v[i] = __shfl_sync(0xffffffffu, bw[i] * inv, c);
-          dot = fma(v[i], bw[i], dot);
+          v[i] = vb[i];
+          dq[i & 3] = fma(v[i], bw[i], dq[i & 3]);
         }
       }
+      const double dot = (dq[0] + dq[1]) + (dq[2] + dq[3]);
       const double w = upd ? tau * dot : 0.0;
       pv -= w;
       if (lane == c) { pv = beta; tau_mine = tau; }
