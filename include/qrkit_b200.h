@@ -202,6 +202,34 @@ QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count,
  *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation
  * Supported (block_rows, block_cols, overlap): (16,24,16), (7,4,2), (7,2,0), (8,8,4), (12,8,4), (4,6,4). */
 
+/* ---- pattern analysis on the host (no GPU needed; qrkit_b200/csrc/structure.cpp) ---------------------- */
+/* SparseQROrdering::AsBandedAsPossible (SparseQROrdering.h:53-120): rows of a row-major (CSR) pattern stably sorted by
+ * their first stored column.  perm_indices[original row] = new row (PermutationMatrix::indices()); *has_permutation = 0
+ * when the rows already are in order (then perm_indices is the identity). */
+QRK_API int qrk_order_as_banded_as_possible(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner,
+                                            int32_t* perm_indices, int32_t* has_permutation);
+/* SparseQROrdering::ColumnDensity (SparseQROrdering.h:22-50): columns of a column-major (CSC) pattern stably sorted by
+ * their number of stored entries, ascending; perm_indices[original column] = new column. */
+QRK_API int qrk_order_column_density(int64_t cols, const int32_t* csc_outer, int32_t* perm_indices);
+/* BlockBandedMatrixInfo::operator() (SparseQRUtils.h:186-253) including mergeBlocks (:308-385), on a row-major pattern
+ * whose rows are already ordered.  blocks: 4 int32 per block {idxRow, idxCol, numRows, numCols} in blockOrder order;
+ * blocks == NULL only counts.  suggested_block_cols = the SuggestedBlockCols template argument (default 2). */
+QRK_API int qrk_detect_blocks(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner,
+                              int32_t suggested_block_cols, int32_t* blocks, int64_t capacity, int64_t* num_blocks,
+                              int64_t* nonzero_q_estimate);
+/* fromBlockDiagonalPattern (SparseQRUtils.h:255-272) and fromBlockBandedPattern (:274-302, merge included). */
+QRK_API int qrk_block_diagonal_pattern(int64_t rows, int64_t cols, int32_t block_rows, int32_t block_cols, int32_t* blocks,
+                                       int64_t capacity, int64_t* num_blocks);
+QRK_API int qrk_block_banded_pattern(int64_t rows, int64_t cols, int32_t block_rows, int32_t block_cols, int32_t block_overlap,
+                                     int32_t suggested_block_cols, int32_t* blocks, int64_t capacity, int64_t* num_blocks);
+/* The mat.block(idxRow, idxCol, numRows, numCols) loop of SparseBlockDiagonal::fromSparseMatrix (SparseBlockDiagonal.h:
+ * 123-128): dense blocks of P*A in the block-COO layout (column-major, back to back), P given as row_perm[original row]
+ * = new row (NULL = identity).  Note: the reference slices the UNPERMUTED matrix there (:127) although the blocks were
+ * detected on the permuted one; pass row_perm = NULL to reproduce that. */
+QRK_API int qrk_extract_blocks(int64_t rows, int64_t cols, const int32_t* csc_outer, const int32_t* csc_inner,
+                               const double* csc_values, const int32_t* row_perm, const int32_t* blocks, int64_t num_blocks,
+                               double* values_out);
+
 /* ---- measurement hooks ---------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 QRK_API int qrk_launch_count(qrk_handle_t h, int64_t* launches);

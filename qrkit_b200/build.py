@@ -44,7 +44,8 @@ ANGULAR_M2 = range(1, 9)      # border widths instantiated for the block-angular
 
 def translation_units():
     """(object name, source, extra flags): capi.cu once, angular_inst.cu once per border width."""
-    tus = [("capi.o", os.path.join(CSRC, "capi.cu"), []), ("banded.o", os.path.join(CSRC, "banded_inst.cu"), [])]
+    tus = [("capi.o", os.path.join(CSRC, "capi.cu"), []), ("banded.o", os.path.join(CSRC, "banded_inst.cu"), []),
+           ("structure.o", os.path.join(CSRC, "structure.cpp"), [])]
     tus += [(f"angular_m{k}.o", os.path.join(CSRC, "angular_inst.cu"), [f"-DQRK_M2={k}"]) for k in ANGULAR_M2]
     return tus
 

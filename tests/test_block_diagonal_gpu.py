@@ -174,6 +174,30 @@ def test_reference_test0_properties(qk, oracle, qformat):
         assert rel(X[:, 1], 2 * x_true) <= TOL_X
 
 
+def test_general_sparse_matrix_through_structure_detection(qk):
+    """SparseBlockDiagonal::fromSparseMatrix (SparseBlockDiagonal.h:96-130) in front of the solver: a row-shuffled
+    block-diagonal sparse matrix is reordered (AsBandedAsPossible), its blocks detected and extracted on the host, then
+    factored on the GPU; the caller applies rowsPermutation() to b as in test/test-qrkit.cpp:235."""
+    import scipy.sparse as sp
+    from qrkit_b200 import structure
+    nb, r, c = 300, 7, 2
+    vals0 = uniform_blocks(nb, r, c)
+    A0 = sp.csr_matrix(blocks_to_dense(vals0, np.full(nb, r), np.full(nb, c)))
+    shuffle = np.random.default_rng(3).permutation(nb * r)
+    A = A0[shuffle, :]
+    vals, br, bc, blocks, perm, has = structure.from_sparse_matrix(A)
+    assert has and len(br) == nb and np.all(br == r) and np.all(bc == c)
+    x_true = vector(nb * c, seed=31)
+    b = A @ x_true
+    pb = np.empty_like(b)
+    pb[perm] = b                                          # (P b)[perm[i]] = b[i]
+    solver = qk.BlockDiagonalSparseQR(qk.SparseBlockDiagonal(vals, rows=br, cols=bc), pivoting=1)
+    assert rel(solver.solve(pb), x_true) <= TOL_X
+    b2 = vector(nb * r, seed=32)
+    pb2 = np.empty_like(b2); pb2[perm] = b2
+    assert rel(solver.solve(pb2), np.linalg.lstsq(A.toarray(), b2, rcond=None)[0]) <= TOL_X
+
+
 def test_zero_block_tail_rows(qk, oracle):
     """Rows below the last block get Q(i,i)=1 (BlockDiagonalSparseQR.h:530-533)."""
     nb, r, c = 10, 7, 2
