@@ -177,9 +177,22 @@ def bench_mixed(args, L, stream):
             check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h)
         res[piv] = time_steps(step, args.steps, args.warmup)
         L.qrk_destroy(h)
+    # the two-call path on the stored factors: solve(b) and matrixQ().transpose() * b (bd_generic_op_kernel)
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.pivoting = 0, nb, 0
+    d.rows = br.ctypes.data_as(C.POINTER(C.c_int32)); d.cols = bc.ctypes.data_as(C.POINTER(C.c_int32))
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_stream(h, stream), h)
+    ms_f = time_steps(lambda: check(L.qrk_compute(h, vp(A), QRK_DEVICE), h), args.steps, args.warmup)
+    ms_s = time_steps(lambda: check(L.qrk_solve(h, vp(b), rows, vp(x), cols, 1, QRK_DEVICE), h), args.steps, args.warmup)
+    y = torch.empty_like(b)
+    ms_q = time_steps(lambda: check(L.qrk_apply_qt(h, vp(b), rows, vp(y), rows, 1, QRK_DEVICE), h), args.steps, args.warmup)
+    L.qrk_destroy(h)
     peak, src = measured_peaks()
     r64, c64 = br.astype(np.float64), bc.astype(np.float64)
     alg_bytes = float((16 * r64 * c64 + 8 * r64 + 16 * c64).sum())
+    op_bytes = float((8 * r64 * c64 + 16 * r64 + 8 * c64).sum())
     flops = float((2 * r64 * c64 * c64 - (2.0 / 3.0) * c64 ** 3 + 4 * r64 * c64 + c64 * c64).sum())
     ms = res[0]
     line = {"workload": f"mixed block-diagonal, {nb} blocks 32x16..128x64 (BASELINE config 5), fused QR+solve",
@@ -189,7 +202,11 @@ def bench_mixed(args, L, stream):
                          "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": 37.0, "unit": "TFLOP/s (nominal FP64 vector peak)",
                                   "frac": flops / (ms * 1e-3) / 1e12 / 37.0},
                          "algorithmic_bytes": alg_bytes, "flops": flops, "peak_source": src},
-            "colpiv": {"ms_per_step": res[1], "value": rows / (res[1] * 1e-3)}, "steps": args.steps, "dtype": "f64"}
+            "colpiv": {"ms_per_step": res[1], "value": rows / (res[1] * 1e-3)},
+            "two_call": {"compute_ms": ms_f, "solve_ms": ms_s, "solve_hbm_frac": op_bytes / (ms_s * 1e-3) / 1e9 / peak,
+                         "apply_qt_ms": ms_q, "apply_qt_hbm_frac": op_bytes / (ms_q * 1e-3) / 1e9 / peak,
+                         "note": "solve / Q^T b on stored factors read packed V (8rc) + tau + the vector once"},
+            "steps": args.steps, "dtype": "f64"}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_mixed(min(nb, 5000))
     print(json.dumps(line), flush=True)
