@@ -2,6 +2,7 @@
 // interface: same class names, method names, argument meaning and error behaviour as
 //   BlockDiagonalSparseQR  (reference src/QRKit/BlockDiagonalSparseQR.h:37-335)
 //   BlockAngularSparseQR   (reference src/QRKit/BlockAngularSparseQR.h:79-281)
+//   BandedBlockedSparseQR  (reference src/QRKit/BandedBlockedSparseQR.h:122-344), fixed block-banded pattern
 //   SparseBlockDiagonal    (reference src/QRKit/SparseBlockDiagonal.h:44-163)
 //   BlockMatrix1x2         (reference src/QRKit/BlockMatrix1x2.h:31-67)
 // so that code written against QRKit's Eigen-style API (compute(), matrixQ().transpose() * b, matrixR(),
@@ -95,6 +96,9 @@ struct PermutationMatrix {
 // per-block dense solver tags (template parameter _BlockQRSolver of the reference)
 template <typename BlockMatrix> struct HouseholderQR { using MatrixType = BlockMatrix; static constexpr int pivoting = QRK_PIVOT_NONE; };
 template <typename BlockMatrix> struct ColPivHouseholderQR { using MatrixType = BlockMatrix; static constexpr int pivoting = QRK_PIVOT_COLPIV; };
+// dense right-block solver of BlockAngularSparseQR without column pivoting (reference src/QRKit/BlockedThinDenseQR.h:62;
+// test/test-qrkit.cpp:53-56): P2 = identity, rank() = cols; the panel width does not change R
+template <typename DenseMatrix, int SuggestedBlockCols = 2> struct BlockedThinDenseQR { using MatrixType = DenseMatrix; static constexpr int pivoting = QRK_PIVOT_NONE; };
 
 // ---- SparseBlockDiagonal (SparseBlockDiagonal.h:44-163) ------------------------------------------------
 template <typename BlockMatrixType>
@@ -310,8 +314,10 @@ class BlockMatrix1x2 {
   const RightBlock& m_right;
 };
 
-// ---- BlockAngularSparseQR (BlockAngularSparseQR.h:79-281), Left = BlockDiagonalSparseQR<...>, Right = dense ColPiv ---------
-template <typename BlockQRSolverLeftTag>
+// ---- BlockAngularSparseQR (BlockAngularSparseQR.h:79-281), Left = BlockDiagonalSparseQR<...>, Right = dense ColPiv (default)
+// or BlockedThinDenseQR / HouseholderQR (unpivoted).  Any border width: up to 8 columns with a ColPiv right solver take the fused
+// TSQR kernels, everything else the dense right-block kernels.
+template <typename BlockQRSolverLeftTag, typename RightSolverTag = ColPivHouseholderQR<MatrixXd>>
 class BlockAngularSparseQR {
  public:
   using LeftBlockMatrixType = SparseBlockDiagonal<typename BlockQRSolverLeftTag::MatrixType>;
@@ -392,6 +398,7 @@ class BlockAngularSparseQR {
     qrk_desc_t d{};
     d.kind = QRK_BLOCK_ANGULAR; d.num_blocks = L.size(); d.block_rows = Blk::RowsAtCompileTime; d.block_cols = Blk::ColsAtCompileTime;
     d.pivoting = BlockQRSolverLeftTag::pivoting; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2;
+    d.right_solver = RightSolverTag::pivoting == QRK_PIVOT_COLPIV ? QRK_RIGHT_COLPIV : QRK_RIGHT_UNPIVOTED;
     const int st = qrk_create(&d, &m_h);
     m_nb = L.size(); m_m2 = m2; m_rows = mat.rows(); m_cols = mat.cols();
     if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
@@ -403,6 +410,84 @@ class BlockAngularSparseQR {
   mutable bool m_haveR = false;
   mutable MatrixRType m_R;
   mutable PermutationType m_outputPerm_c, m_rowPerm;
+  std::string m_lastError;
+};
+
+// ---- BandedBlockedSparseQR (BandedBlockedSparseQR.h:122-344) for the fixed block-banded pattern of fromBlockBandedPattern
+// (SparseQRUtils.h:274-302): num_blocks dense BlockRows x BlockCols slabs, slab k at rows [k*BlockRows, ...), columns
+// [k*(BlockCols-BlockOverlap), ...).  The input is the block-COO array of the slabs (column-major, back to back).
+// Single GPU, sequential window chain.  matrixQ() is available as its transpose-apply, like the reference uses it (:299).
+template <int BlockRows, int BlockCols, int BlockOverlap>
+class BandedBlockedSparseQR {
+ public:
+  using MatrixRType = SparseMatrix<ColMajor>;
+  using PermutationType = PermutationMatrix;
+  BandedBlockedSparseQR() {}
+  ~BandedBlockedSparseQR() { qrk_destroy(m_h); }
+  BandedBlockedSparseQR(const BandedBlockedSparseQR&) = delete;
+  BandedBlockedSparseQR& operator=(const BandedBlockedSparseQR&) = delete;
+
+  void compute(const std::vector<double>& slabs, Index numBlocks) {                                           // :170-178
+    ensureHandle(numBlocks);
+    if (!m_h) return;
+    detail::throw_if(qrk_compute(m_h, slabs.data(), QRK_HOST), m_h, "compute");
+    m_haveR = false; m_isInitialized = true;
+  }
+  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const VectorXd& b) {
+    ensureHandle(numBlocks);
+    VectorXd x((size_t)m_cols);
+    if (!m_h) return x;
+    detail::throw_if(qrk_compute_solve(m_h, slabs.data(), b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
+    m_haveR = false; m_isInitialized = true;
+    return x;
+  }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index rank() const { int64_t r = 0; qrk_rank(m_h, &r); return r; }                                         // :514
+  ComputationInfo info() const { if (!m_h) return InvalidInput; int32_t i = 0; qrk_info(m_h, &i); return (ComputationInfo)i; }
+  std::string lastErrorMessage() const { return m_h ? qrk_last_error(m_h) : m_lastError; }
+  const MatrixRType& matrixR() const {                                                                        // :484-491, explicit zeros included
+    if (!m_haveR) {
+      int64_t nnz = 0;
+      detail::throw_if(qrk_matrix_r_nnz(m_h, &nnz), m_h, "matrixR");
+      m_R.m_rows = m_rows; m_R.m_cols = m_cols;
+      m_R.outer.resize((size_t)m_cols + 1); m_R.inner.resize((size_t)nnz); m_R.values.resize((size_t)nnz);
+      detail::throw_if(qrk_matrix_r(m_h, m_R.outer.data(), m_R.inner.data(), m_R.values.data(), QRK_HOST), m_h, "matrixR");
+      m_haveR = true;
+    }
+    return m_R;
+  }
+  VectorXd applyQt(const VectorXd& v) const {                                                                 // matrixQ().transpose() * v (:655-670)
+    VectorXd y((size_t)m_rows);
+    detail::throw_if(qrk_apply_qt(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ().transpose() * v");
+    return y;
+  }
+  VectorXd solve(const VectorXd& B) const {                                                                   // :287-307
+    assert(m_isInitialized && "The factorization should be called first, use compute()");
+    VectorXd x((size_t)m_cols);
+    detail::throw_if(qrk_solve(m_h, B.data(), m_rows, x.data(), m_cols, 1, QRK_HOST), m_h, "solve");
+    return x;
+  }
+ private:
+  void ensureHandle(Index numBlocks) {
+    if (m_h && m_nb == numBlocks) return;
+    qrk_destroy(m_h);
+    m_h = nullptr;
+    qrk_desc_t d{};
+    d.kind = QRK_BANDED_BLOCKED; d.num_blocks = numBlocks; d.block_rows = BlockRows; d.block_cols = BlockCols; d.block_overlap = BlockOverlap;
+    const int st = qrk_create(&d, &m_h);
+    m_nb = numBlocks;
+    if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
+    detail::throw_if(st, nullptr, "BandedBlockedSparseQR");
+    int64_t r = 0, c = 0;
+    qrk_rows(m_h, &r); qrk_cols(m_h, &c);
+    m_rows = r; m_cols = c;
+  }
+  qrk_handle_t m_h = nullptr;
+  Index m_nb = -1, m_rows = 0, m_cols = 0;
+  bool m_isInitialized = false;
+  mutable bool m_haveR = false;
+  mutable MatrixRType m_R;
   std::string m_lastError;
 };
 

@@ -96,6 +96,54 @@ int main() {
   CHECK(rel(ang.solve(ba), xa) <= 1e-10, "block angular: solve(b) recovers x  (1e-10)");
   const auto& Ra = ang.matrixR();
   CHECK(Ra.nonZeros() == n + 5 * n + 15, "block angular: nnz(R) = nnz(R1) + m1*m2 + m2(m2+1)/2");
+
+  // block angular with a wide border (m2 = 24) and the unpivoted right solver (test/test-qrkit.cpp:53-56, 294-327)
+  {
+    const Index nw = 200, m2 = 24;
+    SparseBlockDiagonal<Block7x2> L1(nw * 7, nw * 2);
+    MatrixXd B2(nw * 7, m2);
+    for (Index i = 0; i < nw; i++) {
+      Block7x2 blk;
+      for (int j = 0; j < 2; j++) for (int k = 0; k < 7; k++) blk(k, j) = synth(21, i, k, j);
+      L1.insertBack(blk);
+    }
+    for (Index j = 0; j < m2; j++) for (Index i = 0; i < nw * 7; i++) B2(i, j) = synth(23, 1, i, j);
+    BlockMatrix1x2<SparseBlockDiagonal<Block7x2>, MatrixXd> Jw(L1, B2);
+    VectorXd xw(nw * 2 + m2), bw(nw * 7, 0.0);
+    for (size_t j = 0; j < xw.size(); j++) xw[j] = synth(27, j, 0, 0, -1.0, 1.0);
+    for (Index i = 0; i < nw; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 7; k++) bw[i * 7 + k] += L1[i](k, j) * xw[i * 2 + j];
+    for (Index j = 0; j < m2; j++) for (Index i = 0; i < nw * 7; i++) bw[i] += B2(i, j) * xw[nw * 2 + j];
+    BlockAngularSparseQR<ColPivHouseholderQR<Block7x2>> wide(Jw);
+    CHECK(wide.info() == Success && wide.rank() == nw * 2 + m2, "wide border (24 columns): info / rank");
+    CHECK(rel(wide.solve(bw), xw) <= 1e-10, "wide border: solve(b) recovers x  (1e-10)");
+    BlockAngularSparseQR<ColPivHouseholderQR<Block7x2>, BlockedThinDenseQR<MatrixXd, 2>> thin(Jw);
+    CHECK(thin.rank() == nw * 2 + m2, "BlockedThinDenseQR right solver: rank = cols");
+    bool ident = true;
+    const auto& Pw = thin.colsPermutation();
+    for (Index j = 0; j < m2; j++) ident = ident && Pw.indices()[nw * 2 + j] == nw * 2 + j;
+    CHECK(ident, "BlockedThinDenseQR right solver: P2 = identity");
+    CHECK(rel(thin.solve(bw), xw) <= 1e-10, "BlockedThinDenseQR right solver: solve(b) recovers x  (1e-10)");
+  }
+
+  // block banded: the overlapping 7x4 / overlap 2 pattern of test/test-qrkit.cpp:63-96 (dense slabs), x recovered (:255)
+  {
+    const Index nbb = 128;
+    std::vector<double> slabs((size_t)nbb * 7 * 4);
+    for (Index k = 0; k < nbb; k++) for (int j = 0; j < 4; j++) for (int i = 0; i < 7; i++) slabs[(size_t)(k * 4 + j) * 7 + i] = synth(31, k, i, j);
+    BandedBlockedSparseQR<7, 4, 2> band;
+    band.compute(slabs, nbb);
+    CHECK(band.info() == Success && band.rows() == nbb * 7 && band.cols() == (nbb - 1) * 2 + 4 && band.rank() == band.cols(), "banded: info / rows / cols / rank");
+    VectorXd xb((size_t)band.cols()), bb((size_t)band.rows(), 0.0);
+    for (size_t j = 0; j < xb.size(); j++) xb[j] = synth(33, j, 0, 0, -1.0, 1.0);
+    for (Index k = 0; k < nbb; k++) for (int j = 0; j < 4; j++) for (int i = 0; i < 7; i++) bb[k * 7 + i] += slabs[(size_t)(k * 4 + j) * 7 + i] * xb[k * 2 + j];
+    CHECK(rel(band.solve(bb), xb) <= 1e-10, "banded: solve(b) recovers x  (1e-10)");
+    BandedBlockedSparseQR<7, 4, 2> band2;
+    CHECK(rel(band2.computeAndSolve(slabs, nbb, bb), xb) <= 1e-10, "banded: computeAndSolve recovers x  (1e-10)");
+    const auto& Rb = band.matrixR();
+    bool upper = true;
+    for (Index j = 0; j < band.cols(); j++) for (int p = Rb.outer[j]; p < Rb.outer[j + 1]; p++) upper = upper && (Rb.inner[p] <= j || Rb.values[p] == 0.0);
+    CHECK(upper, "banded: matrixR() is upper triangular");
+  }
   std::printf(failures ? "FAILED (%d)\n" : "All passed.\n", failures);
   return failures ? 1 : 0;
 }
