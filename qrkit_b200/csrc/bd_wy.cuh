@@ -64,11 +64,12 @@ struct WyGeom {
     ld = rp + 4;
   }
 };
+constexpr int kWyScratch = 160;   // panel warp scratch: 2 x 16 step buffers, 8x8 Gram, 8x8 S = V^T V
 constexpr int kWyPB = 96;   // diagonal tile of V (unit lower triangular 8x8), column stride 12 (= 12 mod 16)
 
 __host__ __device__ inline size_t wy_smem_bytes(int r, int c) {
   const WyGeom g(r, c);
-  const size_t d = (size_t)g.cp * g.ld + g.ld + 2 * kWyPB + 2 * 64 + 64 + 2 * (size_t)g.cp;
+  const size_t d = (size_t)g.cp * g.ld + g.ld + 2 * kWyPB + 2 * 64 + kWyScratch + 2 * (size_t)g.cp;
   return d * 8 + 16;
 }
 // rows per lane of the panel warp (template parameter MR): 1, 2 or 4; 0 = block too tall for this kernel
@@ -278,6 +279,232 @@ __device__ __forceinline__ void wy_factor_panel(double* sA, int ld, int rp, int 
   WY_TRACE(5);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gram-downdated panel (experimental, -DQRK_WY_GRAM).  The per-column all-reduce above is the longest link of the serial chain.  Here the
+// warp reduces ONCE per panel: G = P^T P over the panel rows (36 sums).  Reflections are orthogonal on rows >= k, so the
+// Gram of the current columns over rows >= k+1 is G_k+1 = G_k - R_k R_k^T with R_k the finished row k: every later
+// tail quantity follows from scalars,  t_j = G_k[k][j] - a_kk a_kj,  tailSq = G_k[k][k] - a_kk^2,
+// and a column step shrinks to [row k through shared memory -> scalar chain -> lane-local rank-1 update].
+// Accuracy: t_j carries an absolute error eps ||a_k|| ||a_j||, the same order as the rounding of v^T a_j itself;
+// tailSq is a difference and loses digits when the tail is short against the head, so whenever tailSq <= 2^-10 G_kk
+// (or is not positive) it is re-summed directly from the registers (one butterfly): the norm, hence beta, tau and the
+// essential part, keep full relative accuracy.  The Gram lives distributed over the lanes (two entries each).
+// S = V^T V for the T factor is one more batched reduction after the last column.
+// ---------------------------------------------------------------------------------------------------------------
+struct WyRefl { double beta, tau, inv, dd, ib; };
+
+// Eigen makeHouseholder from x0 and tailSqNorm: beta = -sign(x0) ||x||, ess = tail / (x0 - beta), tau = (beta - x0) / beta
+__device__ __forceinline__ WyRefl wy_reflector(double c0, double tailSq) {
+  const bool degenerate = tailSq <= DBL_MIN;
+  const double nsq = fma(c0, c0, tailSq);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(nsq));
+  const double hx = 0.5 * nsq, ac0 = fabs(c0);
+  double y = y0;
+  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  double r0;
+  { const double n1 = nsq * y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(ac0 + n1)); }   // seed only
+  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  double norm = nsq * y;
+  norm = fma(fma(-norm, norm, nsq), 0.5 * y, norm);
+  const double dabs = ac0 + norm;              // |x0 - beta|
+  double rabs = r0;
+  { double e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); }
+  const bool pos = c0 >= 0.0;
+  WyRefl h;
+  h.beta = pos ? -norm : norm;
+  h.ib = pos ? -y : y;                         // 1 / beta
+  h.dd = pos ? dabs : -dabs;                   // x0 - beta
+  h.inv = pos ? rabs : -rabs;                  // 1 / (x0 - beta)
+  h.tau = (h.beta - c0) * h.ib;
+  if (degenerate) { h.inv = 0.0; h.tau = 0.0; h.beta = c0; h.ib = 0.0; h.dd = 0.0; }
+  return h;
+}
+
+// slot whose total a lane holds after wy_reduce_scatter<n, 16> (-1: padding)
+__device__ __forceinline__ int wy_slot_of_lane(int n, int lane) {
+  int base = 0;
+  for (int off = 16; off > 0 && n > 1; off >>= 1) {
+    const int h = (n + 1) >> 1;
+    if (lane & off) { base += h; n -= h; } else n = h;
+  }
+  return n >= 1 ? base : -1;
+}
+// strictly-upper pair (i < j) number e = j(j-1)/2 + i  ->  (i, j)
+__device__ __forceinline__ void wy_pair(int e, int& i, int& j) {
+  j = 1;
+  while ((j * (j + 1)) / 2 <= e) j++;
+  i = e - (j * (j - 1)) / 2;
+}
+
+template <int MR, int K>
+__device__ __forceinline__ void wy_gram_step(double (&a)[MR][8], double* tau_out, double& g0, double& g1, double* scratch, int lane) {
+  const double* buf = scratch + (K & 1) * 16;   // [0..8): row K of the downdated Gram, [8..16): panel row K
+  __syncwarp();
+  double gd[8], row[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const double2 u = *reinterpret_cast<const double2*>(buf + j);
+    const double2 w = *reinterpret_cast<const double2*>(buf + 8 + j);
+    gd[j] = u.x; gd[j + 1] = u.y; row[j] = w.x; row[j + 1] = w.y;
+  }
+  const int i0 = lane >> 3, i1 = 4 + (lane >> 3), j0 = lane & 7;      // this lane owns G[i0][j0] and G[i1][j0]
+  const double gx0 = buf[i0], gx1 = buf[i1], gxj = buf[j0], rx0 = buf[8 + i0], rx1 = buf[8 + i1], rxj = buf[8 + j0];
+  const double c0 = row[K], gkk = gd[K];
+  double tailSq = fma(-c0, c0, gkk);
+  if (!(tailSq > 0x1p-10 * gkk)) {             // warp-uniform: cancellation, a (numerically) zero column, or no rows left
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < MR; m++) { const double ak = (m > 0 || lane > K) ? a[m][K] : 0.0; s = fma(ak, ak, s); }
+    tailSq = warp_sum(s);
+  }
+  const WyRefl h = wy_reflector(c0, tailSq);
+  double mult[MR];
+#pragma unroll
+  for (int m = 0; m < MR; m++) mult[m] = (m > 0 || lane > K) ? a[m][K] : (lane == K) ? h.dd : 0.0;
+#pragma unroll
+  for (int j = K + 1; j < 8; j++) {
+    const double tj = fma(-c0, row[j], gd[j]);               // sum_{rows > K} a_K a_j
+    const double sj = -fma(h.dd, row[j], tj) * h.ib;         // tau v^T a_j
+    const double sinv = sj * h.inv;
+#pragma unroll
+    for (int m = 0; m < MR; m++) a[m][j] = fma(-mult[m], sinv, a[m][j]);
+  }
+#pragma unroll
+  for (int m = 0; m < MR; m++) {
+    if (m == 0) a[0][K] = (lane > K) ? a[0][K] * h.inv : (lane == K) ? h.beta : a[0][K];
+    else a[m][K] *= h.inv;
+  }
+  if (lane == K) tau_out[K] = h.tau;
+  // downdate the entries this lane owns with the finished row: R_Kx = a_Kx - tau v^T a_x
+  auto rk = [&](double rx, double gx) { const double tx = fma(-c0, rx, gx); return fma(fma(h.dd, rx, tx), h.ib, rx); };
+  const double Rj = rk(rxj, gxj);
+  g0 = fma(-rk(rx0, gx0), Rj, g0);
+  g1 = fma(-rk(rx1, gx1), Rj, g1);
+  if (K < 7) {
+    double* nb = scratch + ((K + 1) & 1) * 16;
+    if (K + 1 < 4) { if (i0 == K + 1) nb[j0] = g0; }
+    else { if (i1 == K + 1) nb[j0] = g1; }
+    if (lane == K + 1) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(nb + 8 + j) = make_double2(a[0][j], a[0][j + 1]);
+    }
+  }
+}
+
+template <int MR>
+__device__ __forceinline__ void wy_factor_panel_gram(double* sA, int ld, int rp, int p, double* PB0, double* sT, double* scratch,
+                                                     double* sTau, int lane) {
+  const int nrow = rp - p;
+  WY_TRACE(0);
+  double a[MR][8];
+  {
+    const double* base = sA + p * ld + p + lane;
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+      const bool ok = lane + 32 * m < nrow;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[m][j] = ok ? base[j * ld + 32 * m] : 0.0;
+    }
+  }
+  double* Gfull = scratch + 32;       // 8x8, symmetric
+  double* sS = scratch + 96;          // 8x8, strictly upper part used
+  // ---- G = P^T P: 28 off-diagonal + 4 diagonal sums in one 32-wide reduce-scatter (lane e ends with entry e), 4 more diagonals
+  double g0, g1;
+  {
+    double v32[32], v4[4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int i = 0; i <= j; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < MR; m++) s = fma(a[m][i], a[m][j], s);
+        if (i < j) v32[(j * (j - 1)) / 2 + i] = s;
+        else if (j < 4) v32[28 + j] = s;
+        else v4[j - 4] = s;
+      }
+    }
+    const double t32 = wy_reduce_scatter<32, 16>(v32, lane);
+    const double t4 = wy_reduce_scatter<4, 16>(v4, lane);
+    __syncwarp();                                  // the scratch of an earlier panel is no longer read
+    if (lane < 28) { int i, j; wy_pair(lane, i, j); Gfull[i * 8 + j] = t32; Gfull[j * 8 + i] = t32; }
+    else Gfull[(lane - 28) * 9] = t32;
+    if ((lane & 7) == 0) Gfull[(4 + (lane >> 3)) * 9] = t4;
+    __syncwarp();
+    const int i0 = lane >> 3, j0 = lane & 7;
+    g0 = Gfull[i0 * 8 + j0];
+    g1 = Gfull[(4 + i0) * 8 + j0];
+    if (i0 == 0) scratch[j0] = g0;                 // step 0 reads row 0 of G and panel row 0
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(scratch + 8 + j) = make_double2(a[0][j], a[0][j + 1]);
+    }
+  }
+  double* tauv = sTau + p;
+  WY_TRACE(1);
+  wy_gram_step<MR, 0>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 1>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 2>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 3>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 4>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 5>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 6>(a, tauv, g0, g1, scratch, lane);
+  wy_gram_step<MR, 7>(a, tauv, g0, g1, scratch, lane);
+  WY_TRACE(2);
+  // packed columns back in place, unit-lower diagonal tile of V
+  {
+    double* base = sA + p * ld + p + lane;
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+      if (lane + 32 * m < nrow) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) base[j * ld + 32 * m] = a[m][j];
+      }
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) PB0[j * 12 + lane] = (lane < j) ? 0.0 : (lane == j) ? 1.0 : a[0][j];
+  }
+  WY_TRACE(3);
+  // ---- S = V^T V (strictly upper part): one 28-wide reduce-scatter over the rows in registers
+  {
+    double sv[28];
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+#pragma unroll
+      for (int i = 0; i < j; i++) {
+        double s = (lane < j) ? 0.0 : (lane == j) ? a[0][i] : a[0][i] * a[0][j];     // rows 0..31: v_j = [0; 1; essential]
+#pragma unroll
+        for (int m = 1; m < MR; m++) s = fma(a[m][i], a[m][j], s);
+        sv[(j * (j - 1)) / 2 + i] = s;
+      }
+    }
+    const double ts = wy_reduce_scatter<28, 16>(sv, lane);
+    const int slot = wy_slot_of_lane(28, lane);
+    if (slot >= 0) { int i, j; wy_pair(slot, i, j); sS[i * 8 + j] = ts; }
+  }
+  __syncwarp();
+  WY_TRACE(4);
+  // T (upper triangular, Q = I - V T V^T): T_kk = tau_k, T[0:k,k] = -tau_k T[0:k,0:k] S[0:k,k]   (LAPACK dlarft /
+  // Eigen make_block_householder_triangular_factor); lane i owns row i
+  if (lane < 8) {
+    double Tr[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < k; m++) sum = fma(Tr[m], sS[m * 8 + k], sum);
+      const double tk = tauv[k];
+      Tr[k] = (k < lane) ? 0.0 : (k == lane) ? tk : -tk * sum;
+      sT[lane * 8 + k] = Tr[k];
+    }
+  }
+  __syncwarp();
+  WY_TRACE(5);
+}
+
 // ---- apply panel p to one 8-column tile (or to the right-hand side), by ONE warp ---------------------------------
 template <int MR>
 __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld, int rp, int p, int jt, bool is_rhs,
@@ -331,6 +558,15 @@ __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld,
 }
 
 // ---- kernel: grid.x = blocks of this size class -----------------------------------------------------------------
+// Measured on B200 (profiles/r01_wy_gram_panel_experiment.txt): the Gram-downdated panel shortens a column step from
+// ~1100 to ~830 cycles but its two wide reductions (G: 36 sums, S: 28 sums) cost 2.2-3.1 k cycles each, so config 5 runs
+// at 7.3 ms instead of 6.6 ms: the per-column all-reduce stays the default; -DQRK_WY_GRAM selects the other variant.
+#ifdef QRK_WY_GRAM
+#define WY_FACTOR_PANEL wy_factor_panel_gram   // one Gram reduction per panel
+#else
+#define WY_FACTOR_PANEL wy_factor_panel        // one all-reduce per column
+#endif
+
 // resident CTAs per SM the register allocation must leave room for (shared memory allows about as many)
 __host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr == 4 ? 12 : mr == 2 ? 16 : 20) / w; }
 
@@ -353,7 +589,7 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   double* sPB = sRhs + ld;
   double* sT = sPB + 2 * kWyPB;
   double* sS = sT + 2 * 64;
-  double* sTau = sS + 64;
+  double* sTau = sS + kWyScratch;
   double* sRd = sTau + cp;
 
   // panel pi is factored by warp (pi + rot) % W.  The CTAs resident on one SM run in lock step and the panel warp is
@@ -401,7 +637,7 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   const int P = cp >> 3;
   const int n_tiles = P + (SOLVE ? 1 : 0);
   const int rot = (W > 1) ? s_rot : 0;
-  if (warp == rot) wy_factor_panel<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
+  if (warp == rot) WY_FACTOR_PANEL<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
     const int p = 8 * pi, buf = pi & 1;
@@ -418,12 +654,12 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
       WY_TRACE(7);
       if (W > 1 && has_next && jt == pi + 1) {
         __syncwarp();
-        wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+        WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
       }
     }
     if (W == 1 && has_next) {
       __syncwarp();
-      wy_factor_panel<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+      WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
     }
     WY_TRACE(8);
     __syncthreads();
