@@ -322,6 +322,115 @@ def bench_two_call(args, L, stream):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-GPU (one process per GPU under torchrun).  The NAMED shape is sharded over the ranks ("strong"), or
+# every rank gets the named shape ("weak", --scaling weak).  Timing: barrier + CUDA events per rank, max over ranks.
+# ------------------------------------------------------------------------------------------------------------------
+def _dist_time(fn, steps, warmup):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    return float(t.item())
+
+
+def bench_angular_dist(args, L, stream):
+    """Config 3 on G GPUs: contiguous point ranges, per-GPU TSQR triangle, ONE NCCL all-gather of G x 20 doubles, redundant
+    root on every rank, local back substitution (x1 stays sharded, x2 replicated)."""
+    import torch.distributed as dist
+    from qrkit_b200.distributed import block_range
+    G, rank = dist.get_world_size(), dist.get_rank()
+    n_total = args.points * (G if args.scaling == "weak" else 1)
+    lo, hi = block_range(n_total, G, rank)
+    n = hi - lo
+    J1f, J2f, rhsf = ellipse_device(n_total)            # every rank builds the same global problem, then keeps its slice
+    J1 = J1f[2 * lo:2 * hi].contiguous()
+    J2 = J2f[:, 2 * lo:2 * hi].contiguous()
+    rhs = rhsf[2 * lo:2 * hi].contiguous()
+    del J1f, J2f, rhsf
+    x = torch.empty(n + 5, dtype=torch.float64, device="cuda")
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, n, 2, 1, 0, 5
+    d.device = torch.cuda.current_device()
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_stream(h, stream), h)
+    check(L.qrk_angular_set_world(h, max(G, 2)), h)      # G = 1 still goes through the exchange API (one triangle)
+    check(L.qrk_set_border(h, vp(J2), 2 * n, QRK_DEVICE), h)
+    tsz = C.c_int64(); check(L.qrk_angular_triangle_size(h, C.byref(tsz)), h)
+    tri = torch.empty(tsz.value, dtype=torch.float64, device="cuda")
+    tris = torch.empty(G * tsz.value, dtype=torch.float64, device="cuda")
+
+    def step():
+        check(L.qrk_compute_solve(h, vp(J1), vp(rhs), vp(x), QRK_DEVICE), h)
+        check(L.qrk_angular_local_triangle(h, vp(tri), QRK_DEVICE), h)
+        dist.all_gather_into_tensor(tris, tri)            # NCCL on torch's current stream == the handle's stream
+        check(L.qrk_angular_merge(h, vp(tris), G, QRK_DEVICE), h)
+    ms = _dist_time(step, args.steps, args.warmup)
+    # x2 must be bit-identical on every rank (redundant root on identical gathered triangles)
+    x2 = x[n:].clone()
+    x2all = torch.empty(G * 5, dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(x2all, x2)
+    same = bool((x2all.view(G, 5) == x2all.view(G, 5)[0]).all().item())
+    L.qrk_destroy(h)
+    if rank == 0:
+        peak, src = measured_peaks()
+        ach = 248.0 * n_total / (ms * 1e-3) / 1e9
+        print(json.dumps({"workload": f"block-angular ellipse Jacobian, N={n_total} points over {G} GPU(s) (BASELINE config 3), fused compute+solve with NCCL all-gather of the per-GPU triangles",
+                          "metric": "rows/s", "value": 2 * n_total / (ms * 1e-3), "ms_per_step": ms, "n_gpus": G, "scaling": args.scaling,
+                          "collective": {"op": "all_gather", "bytes_per_rank": tsz.value * 8, "backend": "nccl"},
+                          "x2_identical_on_all_ranks": same,
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * G, "unit": "GB/s", "frac": ach / (peak * G), "peak_source": src},
+                          "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}), flush=True)
+
+
+def bench_mixed_dist(args, L, stream):
+    """Config 5 on G GPUs: contiguous block ranges balanced by bytes (not count), no collective."""
+    import torch.distributed as dist
+    from qrkit_b200.distributed import byte_balanced_ranges
+    G, rank = dist.get_world_size(), dist.get_rank()
+    nb_total = args.mixed_blocks * (G if args.scaling == "weak" else 1)
+    br_all, bc_all = mixed_sizes(nb_total)
+    lo, hi = byte_balanced_ranges(br_all, bc_all, G)[rank]
+    br, bc = np.ascontiguousarray(br_all[lo:hi]), np.ascontiguousarray(bc_all[lo:hi])
+    nb = hi - lo
+    total = int((br.astype(np.int64) * bc).sum())
+    rows, cols = int(br.sum()), int(bc.sum())
+    A = torch.empty(total, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(A), SEED_A + rank, 0, total, 1, 0, 0.5, 5.0, stream))
+    b = torch.empty(rows, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(b), SEED_A + 5 + rank, 0, rows, 1, 0, -1.0, 1.0, stream))
+    x = torch.empty(cols, dtype=torch.float64, device="cuda")
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.pivoting = 0, nb, 0
+    d.device = torch.cuda.current_device()
+    d.rows = br.ctypes.data_as(C.POINTER(C.c_int32)); d.cols = bc.ctypes.data_as(C.POINTER(C.c_int32))
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_stream(h, stream), h)
+    ms = _dist_time(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), args.steps, args.warmup)
+    L.qrk_destroy(h)
+    if rank == 0:
+        peak, src = measured_peaks()
+        r64, c64 = br_all.astype(np.float64), bc_all.astype(np.float64)
+        alg = float((16 * r64 * c64 + 8 * r64 + 16 * c64).sum())
+        fl = float((2 * r64 * c64 * c64 - (2.0 / 3.0) * c64 ** 3 + 4 * r64 * c64 + c64 * c64).sum())
+        rows_total = int(br_all.sum())
+        print(json.dumps({"workload": f"mixed block-diagonal, {nb_total} blocks 32x16..128x64 over {G} GPU(s) (BASELINE config 5), byte-balanced contiguous ranges, no collective",
+                          "metric": "rows/s", "value": rows_total / (ms * 1e-3), "ms_per_step": ms, "n_gpus": G, "scaling": args.scaling,
+                          "roofline": {"hbm_frac": alg / (ms * 1e-3) / 1e9 / (peak * G), "fp64_frac_nominal_37TF": fl / (ms * 1e-3) / 1e12 / (37.0 * G), "peak_source": src},
+                          "steps": args.steps, "dtype": "f64"}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="angular,angular_wide,mixed,banded,two_call")
@@ -333,9 +442,32 @@ def main():
     ap.add_argument("--banded-blocks", type=int, default=100_000)
     ap.add_argument("--shapes", default="")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle timings (cpu_baseline)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="multi-GPU runs (torchrun): shard the named shape, or one named shape per GPU")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: qrkit_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or os.environ.get("QRK_BENCH_DIST"):
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        s = torch.cuda.Stream()
+        torch.cuda.set_stream(s)
+        stream = C.c_void_p(s.cuda_stream)
+        L = capi.lib()
+        for w in args.workload.split(","):
+            fn = {"angular": bench_angular_dist, "mixed": bench_mixed_dist}.get(w)
+            if fn is None:
+                if dist.get_rank() == 0:
+                    print(json.dumps({"workload": w, "skipped": "single-GPU workload (banded: sequential window chain, replicas only)"}), flush=True)
+                continue
+            fn(args, L, stream)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     torch.cuda.set_device(0)
     s = torch.cuda.Stream()
     torch.cuda.set_stream(s)

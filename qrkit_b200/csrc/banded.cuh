@@ -70,57 +70,56 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
     if (k + 1 < nb) load_slab(k + 1, nxt);       // in flight while this window is factored
     const int ncols_w = (k == nb - 1) ? last_cols : BC;   // the last slab may be narrower (fromBlockBandedPattern, SparseQRUtils.h:284)
 
+    // One column step = ONE dependent chain: [own norm^2 | raw dot with the published tail] -> scalars -> 2 broadcasts ->
+    // update.  Lane c publishes its RAW tail t (no scaling), so every other lane's dot product t^T a_j runs concurrently
+    // with lane c's rsqrt / reciprocal chain instead of behind it:  v = [1; inv t],  tau v^T a_j = tau (a_cj + inv t^T a_j)
+    // = w_j,  a_j -= (w_j inv) t.  Lane c keeps its raw tail and its inv; the essential parts are scaled once per window.
+    double inv_mine = 1.0;
 #pragma unroll
     for (int c = 0; c < BC; c++) {
       if (c >= ncols_w) continue;                  // columns beyond the matrix: no reflector
       const int P0 = (c < OV) ? 0 : c - OV + 1;   // first participating slab row (compile time after unrolling)
-      // ---- reflector of column c, computed in lane c (every lane runs the arithmetic, lane c's result is used)
+      double* vb = sv + (c & 1) * BR;              // the buffer alternates with the column parity, one __syncwarp per column
+      if (lane == c) {
+#pragma unroll
+        for (int i = 0; i < BR; i++) if (i >= P0) vb[i] = bw[i];
+      }
+      // ---- reflector scalars of the lane's own column (every lane runs the arithmetic, lane c's result is used)
       double tq[4] = {0.0, 0.0, 0.0, 0.0};          // four partial sums: the dependent FMA chain is BR/4 long, not BR
 #pragma unroll
       for (int i = 0; i < BR; i++) if (i >= P0) tq[i & 3] = fma(bw[i], bw[i], tq[i & 3]);
       const double tailSq = (tq[0] + tq[1]) + (tq[2] + tq[3]);
-      const double c0 = QRK_WROW(c);
-      const bool degenerate = (P0 >= BR) || (tailSq <= DBL_MIN);
-      double norm;
-      const double rnorm = fast_rsqrt(fma(c0, c0, tailSq), norm);
-      double beta = (c0 >= 0.0) ? -norm : norm;
-      const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
-      double inv = fast_rcp(c0 - beta);
-      double tau = (beta - c0) * ib;
-      if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
-      tau = __shfl_sync(0xffffffffu, tau, c);
-      // ---- broadcast v = [1; inv * tail] from lane c; dot product and rank-1 update are lane-local
-      const bool upd = lane > c;                  // columns right of c and the right-hand side
       double pv = QRK_WROW(c);
-      double v[BR];
-      // lane c publishes its scaled tail through shared memory (8 STS.128 + 8 broadcast LDS.128 instead of 2 BR shuffles
-      // through the one-per-clock SHFL pipe); the buffer alternates with the column parity, one __syncwarp per column
-      double* vb = sv + (c & 1) * BR;
-      if (lane == c) {
-#pragma unroll
-        for (int i = 0; i < BR; i++) if (i >= P0) vb[i] = bw[i] * inv;
-      }
+      double beta, inv, tau;
+      householder_scalars(pv, tailSq, P0 >= BR, beta, inv, tau);
       __syncwarp();
-      double dq[4] = {pv, 0.0, 0.0, 0.0};
+      // ---- raw dot product with the published tail (independent of the scalar chain above)
+      double t[BR];
+      double dq[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int i = 0; i < BR; i++) {
         if (i >= P0) {
-          v[i] = vb[i];
-          dq[i & 3] = fma(v[i], bw[i], dq[i & 3]);
+          t[i] = vb[i];
+          dq[i & 3] = fma(t[i], bw[i], dq[i & 3]);
         }
       }
       const double dot = (dq[0] + dq[1]) + (dq[2] + dq[3]);
-      const double w = upd ? tau * dot : 0.0;
+      const double tau_c = __shfl_sync(0xffffffffu, tau, c);
+      const double inv_c = __shfl_sync(0xffffffffu, inv, c);
+      const bool upd = lane > c;                  // columns right of c and the right-hand side
+      const double w = upd ? tau_c * fma(inv_c, dot, pv) : 0.0;
+      const double z = w * inv_c;
       pv -= w;
-      if (lane == c) { pv = beta; tau_mine = tau; }
+      if (lane == c) { pv = beta; tau_mine = tau; inv_mine = inv; }
       if (c < OV) cw[c < OV ? c : 0] = pv; else bw[c >= OV ? c - OV : 0] = pv;
 #pragma unroll
-      for (int i = 0; i < BR; i++) {
-        if (i >= P0) {
-          if (lane == c) bw[i] = v[i];            // store the essential part in place (LAPACK packing)
-          else bw[i] = fma(-v[i], w, bw[i]);
-        }
-      }
+      for (int i = 0; i < BR; i++) if (i >= P0) bw[i] = fma(-z, t[i], bw[i]);   // lane c: z = 0, keeps its raw tail
+    }
+    // essential parts (LAPACK packing): lane's own column below its pivot, scaled by its 1/(x0 - beta)
+    {
+      const int p0_lane = (lane < OV) ? 0 : lane - OV + 1;
+#pragma unroll
+      for (int i = 0; i < BR; i++) if (i >= p0_lane) bw[i] *= inv_mine;
     }
 
     // ---- outputs of this window
@@ -223,33 +222,77 @@ banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Back substitution with the band R, window by window from the bottom (R.topLeftCorner(rank, rank)
-// .triangularView<Upper>().solve, BandedBlockedSparseQR.h:299-304).  Lane j owns x[w*S + j].
+// Back substitution with the band R, from the bottom (R.topLeftCorner(rank, rank).triangularView<Upper>().solve,
+// BandedBlockedSparseQR.h:299-304).  One warp, 32 rows per chunk, lane l owns row g = 32 q + l.  Column-oriented: as soon as
+// x_t is known every lane subtracts its R(g, t) x_t, so the dependent chain per row is ONE FMA and ONE broadcast shuffle
+// (the rows are pre-scaled by 1/R(g,g)); the coefficients sit in registers indexed by the COLUMN (compile time after
+// unrolling), fetched from a cp.async ring of band rows that runs three chunks ahead of the chain.
+// Band row g holds columns [w(g) S, w(g) S + BC), w(g) = min(g / S, nb - 1)  (banded_factor_kernel's rband layout).
 // ---------------------------------------------------------------------------------------------
 template <int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
 banded_backsolve_kernel(const double* __restrict__ rband, const double* __restrict__ y, double* __restrict__ x, long long nb,
                         int last_cols) {
-  constexpr int S = BC - OV;
+  constexpr int S = BC - OV, CH = 32, NST = 4, NA = BC - 1;
+  static_assert(BC % 2 == 0, "16-byte cp.async of whole band rows");
+  __shared__ __align__(16) double ring[NST][CH * BC];
+  __shared__ double yring[NST][CH];
   const int lane = threadIdx.x;
-  double xj = 0.0;                                // x of window column `lane`
-  for (long long w = nb - 1; w >= 0; --w) {
-    const int nrows = (w == nb - 1) ? last_cols : S;
-    if (w != nb - 1) {
-      const double up = __shfl_up_sync(0xffffffffu, xj, S);   // column (w+1)*S + j  ==  w*S + (j + S)
-      xj = (lane >= S) ? up : 0.0;
+  const long long n_cols = (nb - 1) * S + last_cols;
+  const long long nchunks = (n_cols + CH - 1) / CH;
+
+  auto prefetch = [&](long long q) {
+    if (q >= 0) {
+      const int st = (int)(q % NST);
+      const long long r0 = q * CH;
+      const int valid = (int)((n_cols - r0 < CH) ? (n_cols - r0) : CH);
+      const double* src = rband + r0 * BC;
+      for (int i = lane; i < valid * BC / 2; i += 32) cp_async16(&ring[st][2 * i], src + 2 * i);
+      if (lane < valid) cp_async8(&yring[st][lane], y + r0 + lane);
     }
-    for (int r = nrows - 1; r >= 0; --r) {
-      const long long g = w * S + r;
-      const double rv = (lane < BC) ? rband[g * BC + lane] : 0.0;
-      double part = (lane > r && lane < BC) ? rv * xj : 0.0;
+    cp_async_commit();
+  };
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const double diag = __shfl_sync(0xffffffffu, rv, r);
-      const double xr = (y[g] - part) / diag;
-      if (lane == r) xj = xr;
+  for (int i = 0; i < NST - 1; i++) prefetch(nchunks - 1 - i);
+
+  double xprev = 0.0;                             // x of the chunk below (columns 32 (q+1) + lane)
+  for (long long q = nchunks - 1; q >= 0; --q) {
+    prefetch(q - (NST - 1));
+    cp_async_wait<NST - 1>();
+    __syncwarp();
+    const int st = (int)(q % NST);
+    const long long g = q * CH + lane;
+    const bool valid = g < n_cols;
+    const long long w = (g / S < nb - 1) ? g / S : nb - 1;
+    const int shift = (int)(q * CH - w * S);      // band offset of column 32 q + t is t + shift
+    const int ncw = (w == nb - 1) ? last_cols : BC;
+    const double* row = &ring[st][lane * BC];
+    const double diag = valid ? row[lane + shift] : 1.0;
+    const double dinv = valid ? 1.0 / diag : 0.0;
+    double c[CH], a[NA > 0 ? NA : 1];
+#pragma unroll
+    for (int t = 0; t < CH; t++) {
+      const int off = t + shift;
+      const bool use = valid && (t > lane) && (off < ncw);
+      c[t] = use ? row[use ? off : 0] * dinv : 0.0;
     }
-    if (lane < nrows) x[w * S + lane] = xj;
+#pragma unroll
+    for (int u = 0; u < NA; u++) {
+      const int off = CH + u + shift;
+      const bool use = valid && (off < ncw);
+      a[u] = use ? row[use ? off : 0] * dinv : 0.0;
+    }
+    double s = valid ? yring[st][lane] * dinv : 0.0;
+#pragma unroll
+    for (int u = 0; u < NA; u++) s = fma(-a[u], __shfl_sync(0xffffffffu, xprev, u), s);
+#pragma unroll
+    for (int t = CH - 1; t >= 0; --t) {
+      const double xt = __shfl_sync(0xffffffffu, s, t);    // lane t's row is complete: s = x_t
+      s = fma(-c[t], xt, s);                                // c[t] = 0 for lanes >= t
+    }
+    if (valid) x[g] = s;
+    xprev = s;
+    __syncwarp();                                  // the stage is refilled by the next iteration's prefetch
   }
 }
 

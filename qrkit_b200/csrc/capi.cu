@@ -58,7 +58,9 @@ namespace {
 
 struct DeviceGuard {
   int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  // Also clears a stale non-sticky error another library left in this thread (NCCL's lazy communicator set-up leaves
+  // cudaErrorInvalidValue behind): every launch here is checked with cudaGetLastError and must only see its own.
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; (void)cudaGetLastError(); }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
@@ -401,6 +403,7 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
     h->pending = true;
     h->pending_keep_rhs_only = keep_rhs_only;
     h->pending_x = have_rhs ? d_x : nullptr;
+    h->pending_space = QRK_DEVICE;     // d_x is a device pointer here; the host-buffer entry points override both
     return QRK_STATUS_OK;
   }
   a.root_mode = 1;

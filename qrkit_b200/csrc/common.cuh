@@ -148,6 +148,43 @@ __device__ __forceinline__ double fast_rsqrt(double x, double& sqrt_out) {
   return special ? y0 : y;
 }
 
+// Scalars of one Householder reflector (Eigen's makeHouseholder, [Eigen] Householder.h): x0 = pivot entry, tailSq =
+// squared norm of the entries below.  beta = -sign(x0) sqrt(x0^2 + tailSq), inv = 1/(x0 - beta) (essential part = tail * inv),
+// tau = (beta - x0)/beta; tailSq <= DBL_MIN (or `no_tail`) gives the identity: tau = 0, inv = 0, beta = x0.
+// One dependent chain: the reciprocal's MUFU seed is taken from the 20-bit square root while the Newton steps of the
+// rsqrt still run, so only the reciprocal's two Newton steps follow the accurate norm.
+__device__ __forceinline__ void householder_scalars(double x0, double tailSq, bool no_tail, double& beta, double& inv, double& tau) {
+  const double s = fma(x0, x0, tailSq);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+  const double ax = fabs(x0);
+  double r0;
+  {
+    const double d0 = fma(s, y0, ax);            // |x0| + norm to ~20 bits
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d0));
+  }
+  const double h = 0.5 * s;
+  double y = y0;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double t = y * y;
+    const double e = fma(-h, t, 0.5);
+    y = fma(y, e, y);
+  }
+  double nrm = s * y;
+  nrm = fma(fma(-nrm, nrm, s), 0.5 * y, nrm);   // one Heron correction of the square root
+  const double d = ax + nrm;                     // |x0 - beta|
+  double e = fma(-d, r0, 1.0);
+  double r = fma(r0, e, r0);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  const bool neg = x0 < 0.0;
+  const bool degenerate = no_tail || (tailSq <= DBL_MIN) || !(s < __longlong_as_double(0x7ff0000000000000LL));
+  beta = degenerate ? x0 : (neg ? nrm : -nrm);
+  inv = degenerate ? 0.0 : (neg ? -r : r);       // x0 - beta = sign(x0) (|x0| + norm), sign(0) = +
+  tau = degenerate ? 0.0 : d * y;                // (beta - x0)/beta = (|x0| + norm)/norm
+}
+
 // splitmix64 counter-based generator shared with the test-suite (tests/helpers.py)
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -109,6 +109,53 @@ def test_multi_gpu_exchange_on_one_device(qk, oracle):
         assert np.array_equal(x2s[g], x2s[0]), "the redundantly computed shared parameters must be bit-identical on every rank"
 
 
+@pytest.mark.parametrize("piv", [0, 1])
+def test_multi_gpu_exchange_with_device_pointers(qk, oracle, piv):
+    """The exchange as bench_extra.py / an NCCL caller runs it: every buffer (blocks, border, rhs, x, the local triangle
+    and the gathered triangles) is a DEVICE pointer; two emulated ranks on one device."""
+    import ctypes as C
+    import torch
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
+    L = capi.lib()
+    n, world = 3000, 2
+    J1, J2, rhs = ellipse_problem(n)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(n, 2), bc=np.full(n, 1), values=J1, left_colpiv=bool(piv), right_kind=0)
+    x_ref = ref.solve(rhs)
+    per = n // world
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    hs, bufs, tris = [], [], []
+    for g in range(world):
+        rows = slice(2 * g * per, 2 * (g + 1) * per)
+        dJ1, dJ2, db = dev(J1[rows]), dev(J2[rows, :].T), dev(rhs[rows])     # border column-major 2*per x 5
+        dx = torch.zeros(per + 5, dtype=torch.float64, device="cuda")
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, per, 2, 1, piv, 5
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_angular_set_world(h, world), h)
+        check(L.qrk_set_border(h, vp(dJ2), 2 * per, QRK_DEVICE), h)
+        check(L.qrk_compute_solve(h, vp(dJ1), vp(db), vp(dx), QRK_DEVICE), h)
+        tsz = C.c_int64()
+        check(L.qrk_angular_triangle_size(h, C.byref(tsz)), h)
+        tri = torch.empty(tsz.value, dtype=torch.float64, device="cuda")
+        check(L.qrk_angular_local_triangle(h, vp(tri), QRK_DEVICE), h)
+        check(L.qrk_synchronize(h), h)
+        hs.append(h); bufs.append((dJ1, dJ2, db, dx)); tris.append(tri)
+    gathered = torch.cat(tris)
+    x2s = []
+    for g, h in enumerate(hs):
+        check(L.qrk_angular_merge(h, vp(gathered), world, QRK_DEVICE), h)
+        check(L.qrk_synchronize(h), h)
+        xg = bufs[g][3].cpu().numpy()
+        assert rel(xg[:per], x_ref[g * per:(g + 1) * per]) <= 1e-9
+        assert rel(xg[per:], x_ref[n:]) <= 1e-9
+        x2s.append(xg[per:].copy())
+        L.qrk_destroy(h)
+    assert np.array_equal(x2s[0], x2s[1])
+
+
 @pytest.mark.parametrize("r,c,m2,nb", [(2, 1, 9, 200), (7, 2, 24, 120), (8, 4, 5, 150), (7, 2, 96, 96), (16, 8, 40, 40)])
 @pytest.mark.parametrize("piv", [0, 1])
 def test_wide_border_vs_oracle(qk, oracle, r, c, m2, nb, piv):
