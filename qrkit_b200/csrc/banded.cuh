@@ -1,24 +1,25 @@
-// banded.cuh — block-banded QR (BandedBlockedSparseQR, reference src/QRKit/BandedBlockedSparseQR.h:443-519):
-// a strictly sequential sliding-window Householder recurrence (window recurrence :494-507), hence ONE GPU,
-// one SM, and a latency-bound kernel by construction (SURVEY §7 hard part 5).
+// banded.cuh — block-banded QR (BandedBlockedSparseQR, reference src/QRKit/BandedBlockedSparseQR.h:443-519).
 //
 // Input: nb block rows; block row k is a dense BR x BC slab at rows [k*BR, (k+1)*BR), columns
 // [k*S, k*S + BC), S = BC - OV (fromBlockBandedPattern(rows, cols, BR, BC, OV), SparseQRUtils.h:274-302),
 // stored as block-COO slabs (column-major BR x BC, back to back).
 //
-// Window k = [carry (OV rows, upper triangular, left over from window k-1) ; slab k] is (OV+BR) x BC.
-// A full Householder QR of the window makes its first S rows final rows of R (rows k*S .. k*S+S-1, BC
-// entries each), annihilates OV+BR-BC rows, and leaves rows S..BC-1 as the next carry — the same
-// recurrence as the reference (which first merges block rows into larger windows; R is unique up to row
-// signs for a fixed column order, so the blocking is free).
-//
-// One warp, the whole window in registers, COLUMNS ACROSS LANES: lane j owns column j of the window (lane
-// BC owns the right-hand side), so every v^T a_j dot product and every rank-1 update is lane-local with no
-// reduction; the only cross-lane traffic is the broadcast of each reflector (<= BR values) from its lane.
-// Because the carry is upper triangular, reflector c < OV touches only the pivot entry and the BR slab
-// rows.  The next slab is prefetched into registers while the current window is factored.
-// Outputs: band R (n_cols x BC, row g holds columns [w(g)*S, w(g)*S+BC)), y = (Q^T b) thin part, the
-// packed windows (reflectors below the diagonal, in place over the slabs) and tau for later Q^T applications.
+// The reference's window recurrence (:494-507) is a chain of nb dependent window QRs: window k = [carry (OV rows, upper
+// triangular, left over from window k-1) ; slab k] is (OV+BR) x BC, its QR makes S rows of R final and leaves the next
+// carry.  R is unique up to row signs for a fixed column order, so the rows may be eliminated in any order.
+// Two phases:
+//   1. banded_factor_kernel, PARALLEL over groups of G consecutive slabs: the same window recurrence, started from a zero
+//      carry in every group, one warp per group.  Group g ends with its own band triangle R_g of W = (G-1) S + BC rows
+//      (the last OV of them overlap the next group's first OV columns).  All the O(rows) elimination work is here.
+//   2. banded_chase_kernel, ONE warp, sequential: the OV-row triangle handed over by group g-1 is merged into R_g by chasing
+//      it down the band — one Householder reflector per column with a tail of only OV entries — which finalises S rows of R
+//      per window with S column steps instead of BC, and hands the last OV rows on to group g+1.  This is the only
+//      sequential part: n_cols + (groups-1) OV short steps instead of nb BC long ones.
+// In both kernels a lane owns one COLUMN of the window (lane BC owns the right-hand side), so every dot product and every
+// rank-1 update is lane-local; the only cross-lane traffic per column step is the broadcast of the reflector through shared
+// memory and two scalars by shuffle.
+// Outputs: band R (n_cols x BC, row g holds columns [w(g)*S, w(g)*S+BC)), y = (Q^T b) thin part; for later Q^T / Q
+// applications the packed windows + tau of phase 1 and the chase reflectors (OV essentials + tau per step) of phase 2.
 #pragma once
 #include "common.cuh"
 
@@ -38,11 +39,19 @@ struct BandedCfg {
 
 template <int BR, int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
-banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, double* __restrict__ rband,
-                     const double* __restrict__ b, double* __restrict__ y, double* __restrict__ ycomp, long long nb, int last_cols) {
+banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, double* __restrict__ gband,
+                     const double* __restrict__ b, double* __restrict__ gy, long long nb_total, int last_cols, int group) {
   using G = BandedCfg<BR, BC, OV>;
-  constexpr int S = G::S, M = G::M;
+  constexpr int S = G::S;
   const int lane = threadIdx.x;
+  // this warp's group of slabs [k0, k0 + nb) and its slice of the group-band buffers (W rows per group)
+  const long long k0 = (long long)blockIdx.x * group;
+  const long long nb = (nb_total - k0 < group) ? (nb_total - k0) : group;
+  const long long W = (long long)(group - 1) * S + BC;
+  A_in += k0 * BC * (long long)BR; packed += k0 * BC * (long long)BR; tau_out += k0 * BC;
+  double* __restrict__ rband = gband + (long long)blockIdx.x * W * BC;
+  double* __restrict__ y = gy + (long long)blockIdx.x * W;
+  if (b) b += k0 * BR;
   const bool is_col = lane < BC, is_rhs = (lane == BC) && (b != nullptr);
   __shared__ __align__(16) double sv[2 * BR];
   double cw[OV > 0 ? OV : 1], bw[BR], nxt[BR], tau_mine = 0.0;
@@ -68,7 +77,7 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
 #pragma unroll
     for (int i = 0; i < BR; i++) bw[i] = nxt[i];
     if (k + 1 < nb) load_slab(k + 1, nxt);       // in flight while this window is factored
-    const int ncols_w = (k == nb - 1) ? last_cols : BC;   // the last slab may be narrower (fromBlockBandedPattern, SparseQRUtils.h:284)
+    const int ncols_w = (k0 + k == nb_total - 1) ? last_cols : BC;   // the last slab may be narrower (fromBlockBandedPattern, SparseQRUtils.h:284)
 
     // One column step = ONE dependent chain: [own norm^2 | raw dot with the published tail] -> scalars -> 2 broadcasts ->
     // update.  Lane c publishes its RAW tail t (no scaling), so every other lane's dot product t^T a_j runs concurrently
@@ -132,16 +141,12 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
     }
 #pragma unroll
     for (int r = 0; r < BC; r++) {
-      if (last ? (r < last_cols) : (r < S)) {
+      if (last ? (r < ncols_w) : (r < S)) {      // the group's last window hands over all its rows (R_g's tail triangle)
         const double val = QRK_WROW(r);
         const long long g = k * S + r;
         if (is_col) rband[g * BC + lane] = (lane >= r) ? val : 0.0;
         else if (is_rhs) y[g] = val;
       }
-    }
-    if (is_rhs && ycomp) {
-#pragma unroll
-      for (int r = BC; r < M; r++) ycomp[k * (M - BC) + (r - BC)] = QRK_WROW(r);
     }
     // ---- next carry: window rows S..BC-1, columns shifted left by S (the right-hand side lane keeps its own)
     if (OV > 0) {
@@ -159,17 +164,129 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
 }
 
 // ---------------------------------------------------------------------------------------------
-// Q^T applied to a new right-hand side on a stored factorisation (packed windows + tau): the same window
-// sweep with only the vector; lane i owns slab row i, the OV carried entries are replicated in every lane.
+// Phase 2: chase the OV-row bulge through the group triangles.  Lane l owns column l of the current window of the band
+// (lane BC the right-hand side): Bg[i] = bulge row i, P[c] = this lane's entry of pivot row c (band row w S + c of the
+// group triangle, prefetched one window ahead).  Column step c: reflector on [P[c] at lane c ; Bg[0..OV) of lane c]; the
+// updated pivot row is a final row of R (or, for the last OV rows of a group, the bulge handed to the next group).
+// Step q = group * W + local row; cvec[q*OV ..] / ctau[q] keep the reflector for later Q^T / Q applications.
+// ---------------------------------------------------------------------------------------------
+template <int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__ gy, double* __restrict__ rband,
+                    double* __restrict__ y, double* __restrict__ cvec, double* __restrict__ ctau, long long nb, int last_cols,
+                    int group, int have_rhs) {
+  constexpr int S = BC - OV, NO = OV > 0 ? OV : 1;
+  const int lane = threadIdx.x;
+  const bool is_col = lane < BC, is_rhs = (lane == BC) && have_rhs;
+  __shared__ __align__(16) double sv[2 * NO];
+  const long long W = (long long)(group - 1) * S + BC;
+  const long long ngroups = (nb + group - 1) / group;
+  double Bg[NO], P[BC], Pn[S];
+#pragma unroll
+  for (int i = 0; i < NO; i++) Bg[i] = 0.0;
+
+  auto load_rows = [&](long long q0, int c_lo, int c_hi, double* dst) {   // pivot rows q0 + c, c in [c_lo, c_hi)
+#pragma unroll
+    for (int c = 0; c < BC; c++) {
+      if (c >= c_lo && c < c_hi)
+        dst[c - c_lo] = is_col ? gband[(q0 + c) * BC + lane] : (is_rhs ? gy[q0 + c] : 0.0);
+    }
+  };
+  load_rows(0, 0, S, Pn);
+
+  long long gi = 0, lw = 0;                                    // group, window inside the group
+  long long n_g = (nb < group) ? nb : group;
+  for (long long kk = 0; kk < nb; kk++) {
+    const bool lastw = (lw == n_g - 1), lastgroup = (gi == ngroups - 1);
+    const long long q0 = gi * W + lw * S;                      // step index of this window's first pivot row
+    const long long g0 = (gi * group + lw) * S;                // its global row in R
+#pragma unroll
+    for (int c = 0; c < S; c++) P[c] = Pn[c];
+    if (kk + 1 < nb) load_rows(lastw ? (gi + 1) * W : q0 + S, 0, S, Pn);    // in flight while this window is chased
+    int nsteps = S;
+    if (lastw) {                                               // the group's tail triangle: all BC rows of its last window
+      nsteps = lastgroup ? last_cols : BC;
+      load_rows(q0, S, BC, P + S);
+    }
+    double cw[NO];                                             // rows handed to the next group
+#pragma unroll
+    for (int i = 0; i < NO; i++) cw[i] = 0.0;
+
+#pragma unroll
+    for (int c = 0; c < BC; c++) {
+      if (c >= nsteps) continue;
+      double* vb = sv + (c & 1) * NO;
+      if (lane == c) {
+#pragma unroll
+        for (int i = 0; i < OV; i++) vb[i] = Bg[i];
+      }
+      double tq[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < OV; i++) tq[i & 3] = fma(Bg[i], Bg[i], tq[i & 3]);
+      const double tailSq = (tq[0] + tq[1]) + (tq[2] + tq[3]);
+      double pv = P[c];
+      double beta, inv, tau;
+      householder_scalars(pv, tailSq, OV == 0, beta, inv, tau);
+      __syncwarp();
+      double t[NO];
+      double dq[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < OV; i++) {
+        t[i] = vb[i];
+        dq[i & 3] = fma(t[i], Bg[i], dq[i & 3]);
+      }
+      const double dot = (dq[0] + dq[1]) + (dq[2] + dq[3]);
+      const double tau_c = __shfl_sync(0xffffffffu, tau, c);
+      const double inv_c = __shfl_sync(0xffffffffu, inv, c);
+      const double w = (lane > c) ? tau_c * fma(inv_c, dot, pv) : 0.0;
+      const double z = (lane == c) ? 1.0 : w * inv_c;          // lane c: Bg - 1 * t = 0 exactly, its column is annihilated
+      pv -= w;
+      if (lane == c) pv = beta;
+#pragma unroll
+      for (int i = 0; i < OV; i++) Bg[i] = fma(-z, t[i], Bg[i]);
+      // the reflector, for later applications: essential part = raw tail * inv
+      if (lane < OV) cvec[(q0 + c) * OV + lane] = vb[lane] * inv_c;
+      if (lane == 0) ctau[q0 + c] = tau_c;
+      // the updated pivot row
+      const double outv = (lane >= c) ? pv : 0.0;
+      if (c < S || lastgroup) {
+        if (is_col) rband[(g0 + c) * BC + lane] = outv;
+        else if (is_rhs) y[g0 + c] = pv;
+      } else {
+        cw[c >= S ? c - S : 0] = outv;
+      }
+    }
+
+    // ---- next window: the bulge moves S columns to the right; at a group boundary it is replaced by the handed-over rows
+#pragma unroll
+    for (int i = 0; i < OV; i++) {
+      const double src = (lastw && !lastgroup) ? cw[i] : Bg[i];
+      const double shifted = __shfl_down_sync(0xffffffffu, src, S);
+      Bg[i] = (lane == BC) ? src : ((lane < BC - S) ? shifted : 0.0);
+    }
+    if (lastw) { gi++; lw = 0; n_g = (nb - gi * group < group) ? (nb - gi * group) : group; }
+    else lw++;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q^T applied to a new right-hand side on a stored factorisation, phase 1 (parallel over the groups): the window sweep of
+// banded_factor_kernel with only the vector; lane i owns slab row i, the OV carried entries are replicated in every lane.
+// Output: gy, the group's pivot-row values (W per group), input of banded_chase_apply_kernel.
 // ---------------------------------------------------------------------------------------------
 template <int BR, int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
 banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
-                       double* __restrict__ y, double* __restrict__ ycomp, long long nb, int last_cols) {
+                       double* __restrict__ gy, long long nb_total, int last_cols, int group) {
   using G = BandedCfg<BR, BC, OV>;
-  constexpr int S = G::S, M = G::M;
+  constexpr int S = G::S;
   static_assert(BR <= 32, "one lane per slab row");
   const int lane = threadIdx.x;
+  const long long k0 = (long long)blockIdx.x * group;
+  const long long nb = (nb_total - k0 < group) ? (nb_total - k0) : group;
+  const long long W = (long long)(group - 1) * S + BC;
+  packed += k0 * BC * (long long)BR; tau_in += k0 * BC; b += k0 * BR;
+  double* __restrict__ y = gy + (long long)blockIdx.x * W;
   double cy[OV > 0 ? OV : 1];
 #pragma unroll
   for (int i = 0; i < (OV > 0 ? OV : 1); i++) cy[i] = 0.0;
@@ -181,7 +298,7 @@ banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restri
       vv[c] = (lane < BR) ? packed[(k * BC + c) * (long long)BR + lane] : 0.0;
       tt[c] = tau_in[k * BC + c];
     }
-    const int ncols_w = (k == nb - 1) ? last_cols : BC;
+    const int ncols_w = (k0 + k == nb_total - 1) ? last_cols : BC;
 #pragma unroll
     for (int c = 0; c < BC; c++) {
       if (c >= ncols_w) continue;
@@ -198,16 +315,9 @@ banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restri
     const bool last = (k == nb - 1);
 #pragma unroll
     for (int r = 0; r < BC; r++) {
-      if (last ? (r < last_cols) : (r < S)) {
+      if (last ? (r < ncols_w) : (r < S)) {
         const double val = (r < OV) ? cy[r < OV ? r : 0] : __shfl_sync(0xffffffffu, bi, r >= OV ? r - OV : 0);
         if (lane == 0) y[k * S + r] = val;
-      }
-    }
-    if (ycomp) {
-#pragma unroll
-      for (int r = BC; r < M; r++) {
-        const double val = __shfl_sync(0xffffffffu, bi, r - OV);
-        if (lane == 0) ycomp[k * (M - BC) + (r - BC)] = val;
       }
     }
     if (OV > 0) {
@@ -218,6 +328,194 @@ banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restri
 #pragma unroll
       for (int i = 0; i < OV; i++) cy[i] = ncy[i];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q applied on a stored factorisation, phase 1 run BACKWARDS (parallel over the groups; it follows the backward chase):
+// gy holds the group's pivot-row values, the annihilated rows are zero (zero complement), the windows are undone from the
+// group's last to its first and every reflector of a window from the last to the first (H is symmetric).  Output: the
+// slab rows, x = Q1 y.  The virtual zero rows above a group's first slab come out as ~0 and are dropped.
+// ---------------------------------------------------------------------------------------------
+template <int BR, int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_apply_q_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ gy,
+                      double* __restrict__ x, long long nb_total, int last_cols, int group) {
+  using G = BandedCfg<BR, BC, OV>;
+  constexpr int S = G::S, NO = OV > 0 ? OV : 1;
+  static_assert(BR <= 32, "one lane per slab row");
+  const int lane = threadIdx.x;
+  const long long k0 = (long long)blockIdx.x * group;
+  const long long nb = (nb_total - k0 < group) ? (nb_total - k0) : group;
+  const long long W = (long long)(group - 1) * S + BC;
+  packed += k0 * BC * (long long)BR; tau_in += k0 * BC; x += k0 * BR;
+  const double* __restrict__ y = gy + (long long)blockIdx.x * W;
+  double cin[NO];                                  // window rows S..BC-1 as left by the window to the right
+#pragma unroll
+  for (int i = 0; i < NO; i++) cin[i] = 0.0;
+  for (long long k = nb - 1; k >= 0; --k) {
+    const bool last = (k == nb - 1);
+    const int ncols_w = (k0 + k == nb_total - 1) ? last_cols : BC;
+    double vv[BC], tt[BC];
+#pragma unroll
+    for (int c = 0; c < BC; c++) {
+      vv[c] = (lane < BR) ? packed[(k * BC + c) * (long long)BR + lane] : 0.0;
+      tt[c] = tau_in[k * BC + c];
+    }
+    // window rows: r < S pivot rows of this window; S <= r < BC from the right (or the group's tail rows); r >= BC zero
+    double cy[NO];
+#pragma unroll
+    for (int r = 0; r < OV; r++) {
+      if (r < S) cy[r] = y[k * S + r];
+      else cy[r] = last ? ((r < ncols_w) ? y[k * S + r] : 0.0) : cin[r >= S ? r - S : 0];
+    }
+    double bi = 0.0;
+    {
+      const int r = OV + lane;
+      if (lane < BR && r < BC) {
+        if (r < S || last) bi = (r < (last ? ncols_w : S)) ? y[k * S + r] : 0.0;
+        else {
+#pragma unroll
+          for (int j = 0; j < OV; j++) if (r - S == j) bi = cin[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = BC - 1; c >= 0; --c) {
+      if (c >= ncols_w) continue;
+      const int P0 = (c < OV) ? 0 : c - OV + 1;
+      double part = (lane >= P0 && lane < BR) ? vv[c] * bi : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const double pivot = (c < OV) ? cy[c < OV ? c : 0] : __shfl_sync(0xffffffffu, bi, c >= OV ? c - OV : 0);
+      const double w = tt[c] * (pivot + part);
+      if (c < OV) cy[c < OV ? c : 0] -= w;
+      else if (lane == c - OV) bi -= w;
+      if (lane >= P0 && lane < BR) bi = fma(-vv[c], w, bi);
+    }
+    if (lane < BR) x[k * BR + lane] = bi;
+#pragma unroll
+    for (int i = 0; i < OV; i++) cin[i] = cy[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q^T (forward) or Q (backward) of the chase reflectors applied to a vector of pivot-row values, phase 2 of an application
+// on stored factors.  One warp, sequential over the steps q (banded_chase_kernel's order, reversed for Q); the OV bulge
+// entries u live in registers (replicated in every lane), the reflectors stream through a cp.async ring.
+//   forward : p = gy[q];  w = tau (p + v.u);  p -= w;  u -= w v;   p -> y[global row]  (or -> next group's u for the last
+//             OV rows of a group)
+//   backward: the same reflector (H is symmetric) in reverse order; a group starts from u = 0 (zero complement), its
+//             last OV pivot rows take the u left by the group to the right;  p -> gy[q]
+// ---------------------------------------------------------------------------------------------
+template <int BC, int OV, bool BACKWARD>
+__global__ void __launch_bounds__(32, 1)
+banded_chase_apply_kernel(const double* __restrict__ cvec, const double* __restrict__ ctau, const double* __restrict__ in,
+                          double* __restrict__ out, long long nb, int last_cols, int group) {
+  constexpr int S = BC - OV, NO = OV > 0 ? OV : 1, CH = 32, NST = 4;
+  __shared__ __align__(16) double rv[NST][CH * NO];
+  __shared__ double rt[NST][CH], rp[NST][CH];
+  __shared__ double hand[NO];                          // the OV values that cross a group boundary
+  const int lane = threadIdx.x;
+  const long long W = (long long)(group - 1) * S + BC;
+  const long long ngroups = (nb + group - 1) / group;
+  const long long n_last = nb - (ngroups - 1) * group;           // slabs of the last group
+  const long long W_last = (n_last - 1) * S + last_cols;         // its pivot rows
+  const long long Q = (ngroups - 1) * W + W_last;                // steps in total
+  const long long nchunks = (Q + CH - 1) / CH;
+  const long long GS = (long long)group * S;                     // final rows per (full) group
+
+  // global row of step q (for the vector that is NOT indexed by q): final rows only
+  auto chunk_of = [&](long long i) { return BACKWARD ? nchunks - 1 - i : i; };
+  auto prefetch = [&](long long i) {
+    if (i < nchunks) {
+      const long long ck = chunk_of(i);
+      const int st = (int)(i % NST);
+      const long long q0 = ck * CH;
+      const int valid = (int)((Q - q0 < CH) ? (Q - q0) : CH);
+      if (OV > 0) {
+        const double* src = cvec + q0 * OV;
+        for (int j = lane; j < valid * OV / 2; j += 32) cp_async16(&rv[st][2 * j], src + 2 * j);
+        if ((valid * OV) & 1) { if (lane == 0) cp_async8(&rv[st][valid * OV - 1], src + valid * OV - 1); }
+      }
+      if (lane < valid) {
+        const long long q = q0 + lane;
+        cp_async8(&rt[st][lane], ctau + q);
+        const long long gi = q / W, r = q - gi * W;
+        const bool handed = (gi < ngroups - 1) && (r >= GS);      // pivot row that belongs to the next group's bulge
+        if (BACKWARD) { if (!handed) cp_async8(&rp[st][lane], in + gi * GS + r); }
+        else cp_async8(&rp[st][lane], in + q);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < NST - 1; i++) prefetch(i);
+
+  double u[NO];
+#pragma unroll
+  for (int i = 0; i < NO; i++) u[i] = 0.0;
+  if (lane < NO) hand[lane] = 0.0;
+  __syncwarp();
+
+  for (long long i = 0; i < nchunks; i++) {
+    prefetch(i + NST - 1);
+    cp_async_wait<NST - 1>();
+    __syncwarp();
+    const int st = (int)(i % NST);
+    const long long q0 = chunk_of(i) * CH;
+    const int valid = (int)((Q - q0 < CH) ? (Q - q0) : CH);
+    double keep = 0.0;                                   // lane j keeps the result of the chunk's step j
+    long long gi = (q0 + (BACKWARD ? valid - 1 : 0)) / W;          // one division per chunk, then incremental
+    long long r = q0 + (BACKWARD ? valid - 1 : 0) - gi * W;
+    for (int jj = 0; jj < valid; jj++) {
+      const int j = BACKWARD ? valid - 1 - jj : jj;
+      const long long W_g = (gi == ngroups - 1) ? W_last : W;
+      const bool handed = (gi < ngroups - 1) && (r >= GS);
+      if (BACKWARD && r == W_g - 1) {                    // entering a group from its end: zero complement
+#pragma unroll
+        for (int k = 0; k < NO; k++) u[k] = 0.0;
+      }
+      double p = (BACKWARD && handed) ? hand[r - GS] : rp[st][j];
+      const double* v = &rv[st][j * NO];
+      double dq[4] = {0.0, 0.0, 0.0, 0.0};
+      double vr[NO];
+#pragma unroll
+      for (int k = 0; k < OV; k++) { vr[k] = v[k]; dq[k & 3] = fma(vr[k], u[k], dq[k & 3]); }
+      const double w = rt[st][j] * (p + ((dq[0] + dq[1]) + (dq[2] + dq[3])));
+      p -= w;
+#pragma unroll
+      for (int k = 0; k < OV; k++) u[k] = fma(-w, vr[k], u[k]);
+      if (lane == j) keep = p;
+      if (!BACKWARD) {
+        if (handed) { if (lane == 0) hand[r - GS] = p; }
+        if (r == W_g - 1 && gi < ngroups - 1) {          // leaving a group: its last OV pivot rows are the next bulge
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < OV; k++) u[k] = hand[k];
+        }
+      } else if (r == 0) {                               // left end of a group: u is what the group to the left handed over
+        __syncwarp();
+        if (lane < OV) {
+          double mine = 0.0;
+#pragma unroll
+          for (int k = 0; k < OV; k++) if (lane == k) mine = u[k];
+          hand[lane] = mine;
+        }
+        __syncwarp();
+      }
+      if (BACKWARD) { if (--r < 0) { gi--; r = W - 1; } }
+      else if (++r == W_g) { gi++; r = 0; }
+    }
+    // coalesced store of the chunk's results
+    if (lane < valid) {
+      const long long q = q0 + lane;
+      const long long gi = q / W, r = q - gi * W;
+      const bool handed = (gi < ngroups - 1) && (r >= GS);
+      if (BACKWARD) out[q] = keep;
+      else if (!handed) out[gi * GS + r] = keep;
+    }
+    __syncwarp();
   }
 }
 

@@ -14,17 +14,24 @@ struct BandedArgs {
   double* rband = nullptr;
   const double* b = nullptr;
   double* y = nullptr;        // thin part of Q^T b (n_cols)
-  double* ycomp = nullptr;    // annihilated rows' part of Q^T b (n_rows - n_cols), optional
   double* x = nullptr;
+  // two-phase factorisation (banded.cuh): groups of `group` slabs are reduced in parallel, then chased sequentially
+  int group = 1;              // slabs per group
+  double* gband = nullptr;    // group triangles: groups x W x block_cols, W = (group-1) S + block_cols
+  double* gy = nullptr;       // groups x W: pivot-row values of the right-hand side between the two phases
+  double* cvec = nullptr;     // chase reflectors: groups x W x overlap essentials
+  double* ctau = nullptr;     // groups x W
 };
 
 struct BandedVTable {
   int br, bc, ov;
   cudaError_t (*factor)(const BandedArgs&, cudaStream_t);
-  cudaError_t (*apply_qt)(const BandedArgs&, cudaStream_t);
+  cudaError_t (*apply_qt)(const BandedArgs&, cudaStream_t);   // b (n_rows) -> y (thin part, n_cols)
+  cudaError_t (*apply_q)(const BandedArgs&, cudaStream_t);    // y (thin part, n_cols; zero complement) -> x = Q1 y (n_rows)
   cudaError_t (*backsolve)(const BandedArgs&, cudaStream_t);
 };
 
-const BandedVTable* banded_vtable(int br, int bc, int ov);   // nullptr when the shape is not instantiated
+const BandedVTable* banded_vtable(int br, int bc, int ov);
+int banded_launches_per_call();   // kernels per factor / apply call (for the launch counter)   // nullptr when the shape is not instantiated
 
 }  // namespace qrk

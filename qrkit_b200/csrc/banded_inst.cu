@@ -9,14 +9,30 @@ namespace {
 // (test/test-qrkit.cpp:63-96) and the non-overlapping 7x2 pattern (:101-131); a few more for coverage.
 #define QRK_BANDED_SHAPES(X) X(16, 24, 16) X(7, 4, 2) X(7, 2, 0) X(8, 8, 4) X(12, 8, 4) X(4, 6, 4)
 
+inline unsigned groups_of(const BandedArgs& a) { return (unsigned)((a.nb + a.group - 1) / a.group); }
+
 template <int BR, int BC, int OV>
 cudaError_t factor_t(const BandedArgs& a, cudaStream_t s) {
-  banded_factor_kernel<BR, BC, OV><<<1, 32, 0, s>>>(a.A_in, a.packed, a.tau, a.rband, a.b, a.y, a.ycomp, a.nb, a.last_cols);
+  banded_factor_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.A_in, a.packed, a.tau, a.gband, a.b, a.gy, a.nb, a.last_cols, a.group);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  banded_chase_kernel<BC, OV><<<1, 32, 0, s>>>(a.gband, a.gy, a.rband, a.y, a.cvec, a.ctau, a.nb, a.last_cols, a.group, a.b != nullptr);
   return cudaGetLastError();
 }
 template <int BR, int BC, int OV>
 cudaError_t apply_qt_t(const BandedArgs& a, cudaStream_t s) {
-  banded_apply_qt_kernel<BR, BC, OV><<<1, 32, 0, s>>>(a.packed, a.tau, a.b, a.y, a.ycomp, a.nb, a.last_cols);
+  banded_apply_qt_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  banded_chase_apply_kernel<BC, OV, false><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.gy, a.y, a.nb, a.last_cols, a.group);
+  return cudaGetLastError();
+}
+template <int BR, int BC, int OV>
+cudaError_t apply_q_t(const BandedArgs& a, cudaStream_t s) {
+  banded_chase_apply_kernel<BC, OV, true><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.y, a.gy, a.nb, a.last_cols, a.group);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  banded_apply_q_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.gy, a.x, a.nb, a.last_cols, a.group);
   return cudaGetLastError();
 }
 template <int BR, int BC, int OV>
@@ -25,7 +41,7 @@ cudaError_t backsolve_t(const BandedArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-#define X(BR, BC, OV) const BandedVTable kT_##BR##_##BC##_##OV = {BR, BC, OV, factor_t<BR, BC, OV>, apply_qt_t<BR, BC, OV>, backsolve_t<BR, BC, OV>};
+#define X(BR, BC, OV) const BandedVTable kT_##BR##_##BC##_##OV = {BR, BC, OV, factor_t<BR, BC, OV>, apply_qt_t<BR, BC, OV>, apply_q_t<BR, BC, OV>, backsolve_t<BR, BC, OV>};
 QRK_BANDED_SHAPES(X)
 #undef X
 
@@ -37,5 +53,7 @@ const BandedVTable* banded_vtable(int br, int bc, int ov) {
 #undef X
   return nullptr;
 }
+
+int banded_launches_per_call() { return 2; }
 
 }  // namespace qrk

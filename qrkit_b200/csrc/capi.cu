@@ -243,7 +243,7 @@ void free_dev(qrk_solver* h) {
   if (h->own_values) F(h->d_values);
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
-  F(h->d_rband); F(h->d_btau); F(h->d_ythin);
+  F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
   F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wperm); F(h->d_wiscal);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
@@ -533,6 +533,7 @@ BandedArgs banded_args(qrk_solver* h) {
   BandedArgs a;
   a.nb = h->nb; a.packed = h->d_values; a.tau = h->d_btau; a.rband = h->d_rband; a.y = h->d_ythin;
   a.last_cols = (int)(h->n_cols - (h->nb - 1) * (long long)h->b_step);
+  a.group = h->b_group; a.gband = h->d_gband; a.gy = h->d_gy; a.cvec = h->d_cvec; a.ctau = h->d_ctau;
   return a;
 }
 
@@ -541,7 +542,7 @@ int banded_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x
   BandedArgs a = banded_args(h);
   a.A_in = A_in; a.b = d_b;
   QRK_TRY_CUDA(h, h->bvt->factor(a, h->stream));
-  h->launches++;
+  h->launches += banded_launches_per_call();
   if (d_b) {
     a.x = d_x;
     QRK_TRY_CUDA(h, h->bvt->backsolve(a, h->stream));
@@ -761,9 +762,19 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   iota_kernel<<<256, 256, 0, h->stream>>>(h->d_perm, h->n_cols);   // m_outputPerm_c.setIdentity (:417)
   h->launches++;
   if (banded) {
+    // slabs per parallel group (banded.cuh): enough groups to fill the GPU with one warp each, few enough that the
+    // overlap rows the chase re-eliminates at every group boundary stay a small fraction (OV per group * S columns)
+    h->b_group = (int)std::max<long long>(8, std::min<long long>(64, h->nb / 2048));
+    if (const char* env = std::getenv("QRK_BANDED_GROUP")) h->b_group = std::max(1, std::atoi(env));
+    const size_t groups = (size_t)((h->nb + h->b_group - 1) / h->b_group);
+    const size_t gw = groups * ((size_t)(h->b_group - 1) * h->b_step + h->uc);
     if (cudaMalloc(&h->d_rband, (size_t)h->n_cols * h->uc * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_btau, (size_t)h->nb * h->uc * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_ythin, (size_t)h->n_cols * sizeof(double)) != cudaSuccess)
+        cudaMalloc(&h->d_ythin, (size_t)h->n_cols * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_gband, gw * h->uc * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_gy, gw * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_cvec, std::max<size_t>(1, gw * h->b_ov) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_ctau, gw * sizeof(double)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);
   }
   if (angular && h->wide) {
@@ -1200,19 +1211,26 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
   if (h->bvt) {
     // Q^T b by the window sweep over the stored reflectors (BandedBlockedSparseQR.h:655-670 applies the YTY blocks in
     // the same order), then the banded back substitution (:299-304).  Q^T b: thin part [0, n_cols), zeros after it.
-    // matrixQ() * v is not provided yet.
-    if (op == OP_APPLY_Q) { h->err = "banded matrixQ() * v is not implemented"; return QRK_STATUS_UNSUPPORTED; }
+    // matrixQ() * v: Q1 * v[0:n_cols] (zero complement), the reflectors in reverse order.
     for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) {
       BandedArgs a = banded_args(h);
-      a.b = d_B + j * dldb;
-      if (op == OP_APPLY_QT) {
-        a.y = d_X + j * dldx;      // thin part; the window sweep works on [0 (overlap rows); A], whose annihilated-row
-        a.ycomp = nullptr;         // components do not map one-to-one onto the n_rows - n_cols complement: left zero
-        if (h->n_rows > h->n_cols) cudaMemsetAsync(d_X + j * dldx + h->n_cols, 0, (h->n_rows - h->n_cols) * sizeof(double), h->stream);
+      cudaError_t e;
+      if (op == OP_APPLY_Q) {
+        a.y = const_cast<double*>(d_B + j * dldb);   // read only: the thin part of the input
+        a.x = d_X + j * dldx;
+        e = h->bvt->apply_q(a, h->stream);
+        h->launches += banded_launches_per_call();
+      } else {
+        a.b = d_B + j * dldb;
+        if (op == OP_APPLY_QT) {
+          a.y = d_X + j * dldx;      // thin part; the window sweep works on [0 (overlap rows); A], whose annihilated-row
+                                     // components do not map one-to-one onto the n_rows - n_cols complement: left zero
+          if (h->n_rows > h->n_cols) cudaMemsetAsync(d_X + j * dldx + h->n_cols, 0, (h->n_rows - h->n_cols) * sizeof(double), h->stream);
+        }
+        e = h->bvt->apply_qt(a, h->stream);
+        h->launches += banded_launches_per_call();
+        if (e == cudaSuccess && op == OP_SOLVE) { a.x = d_X + j * dldx; e = h->bvt->backsolve(a, h->stream); h->launches++; }
       }
-      cudaError_t e = h->bvt->apply_qt(a, h->stream);
-      h->launches++;
-      if (e == cudaSuccess && op == OP_SOLVE) { a.x = d_X + j * dldx; e = h->bvt->backsolve(a, h->stream); h->launches++; }
       if (e != cudaSuccess) { h->err = std::string("banded op: ") + cudaGetErrorString(e); st = QRK_STATUS_CUDA_ERROR; }
     }
   } else if (ang(h) && op == OP_SOLVE) {

@@ -83,6 +83,8 @@ struct qrk_solver {
   double *d_rband = nullptr;           // band R: n_cols x block_cols
   double *d_btau = nullptr;            // tau: num_blocks x block_cols
   double *d_ythin = nullptr;           // (Q^T b)[0:n_cols]
+  int b_group = 1;                     // slabs per parallel group of the two-phase banded factorisation (banded.cuh)
+  double *d_gband = nullptr, *d_gy = nullptr, *d_cvec = nullptr, *d_ctau = nullptr;   // group triangles / chase reflectors
 
   // ---- staging buffers for host-memspace calls ----
   double *d_b = nullptr, *d_x = nullptr;

@@ -67,12 +67,26 @@ def _check(qk, oracle, nb, br, bc, ov, suggested=2, lo=0.5, hi=5.0):
     assert rel(np.linalg.solve(R, y[:n_cols]), x_ref) <= 1e-9
     assert abs(np.linalg.norm(y[:n_cols]) ** 2 + np.linalg.norm(Ad @ x_ref - b) ** 2 - np.linalg.norm(b) ** 2) <= 1e-11 * np.linalg.norm(b) ** 2
     assert np.array_equal(s2.colsPermutation(), np.arange(n_cols, dtype=np.int32))
+    # matrixQ() * v on the thin part (zero complement): Q1 (R x) = A x, and Q1 Q1^T b = A x_ls (projection on range(A))
+    v = np.zeros(n_rows)
+    v[:n_cols] = R @ x_true
+    assert rel(s2.applyQ(v), Ad @ x_true) <= 1e-11
+    assert rel(s2.applyQ(y), Ad @ x_ref) <= 1e-9
 
 
 @pytest.mark.parametrize("br,bc,ov", [(16, 24, 16), (7, 4, 2), (7, 2, 0), (8, 8, 4), (12, 8, 4), (4, 6, 4)])
 @pytest.mark.parametrize("nb", [1, 2, 3, 40])
 def test_banded_vs_oracle(qk, oracle, br, bc, ov, nb):
     _check(qk, oracle, nb, br, bc, ov)
+
+
+@pytest.mark.parametrize("group", [1, 3, 5])
+@pytest.mark.parametrize("br,bc,ov", [(16, 24, 16), (7, 4, 2), (12, 8, 4)])
+def test_banded_group_sizes(qk, oracle, monkeypatch, br, bc, ov, group):
+    """The two-phase schedule (parallel groups of slabs, then the sequential chase across the group boundaries) must not
+    depend on the group size: 1 (a hand-over after every slab), 3 and 5 (ragged last group) on 11 block rows."""
+    monkeypatch.setenv("QRK_BANDED_GROUP", str(group))
+    _check(qk, oracle, 11, br, bc, ov)
 
 
 def test_banded_signed_inputs(qk, oracle):
