@@ -165,107 +165,131 @@ banded_factor_kernel(const double* A_in, double* packed, double* __restrict__ ta
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2: chase the OV-row bulge through the group triangles.  Lane l owns column l of the current window of the band
-// (lane BC the right-hand side): Bg[i] = bulge row i, P[c] = this lane's entry of pivot row c (band row w S + c of the
-// group triangle, prefetched one window ahead).  Column step c: reflector on [P[c] at lane c ; Bg[0..OV) of lane c]; the
-// updated pivot row is a final row of R (or, for the last OV rows of a group, the bulge handed to the next group).
-// Step q = group * W + local row; cvec[q*OV ..] / ctau[q] keep the reflector for later Q^T / Q applications.
+// (lane BC the right-hand side): Bg[i] = bulge row i of that column.  Step q (= group * W + local row; the steps of all
+// groups are contiguous) takes pivot row q of the group triangles: reflector on [pivot entry of lane c ; Bg[0..OV) of lane
+// c], c = the row's column inside its window; the updated pivot row is a final row of R — or, for the last OV rows of a
+// group, part of the bulge handed to the next group.
+// ONE rolled loop over q: a single warp cannot hide instruction fetch, so the body must stay inside the instruction
+// cache (the unrolled-by-column form of this loop spent 15 % of its cycles waiting for instructions).  Pivot rows stream
+// through a cp.async ring D steps ahead of the chain; all stores are branch-free (pointer selects).
+// craw[q*OV ..] (raw tail), cs[2q] = tau, cs[2q+1] = inv keep the reflector v = [1; inv * raw] for later applications.
 // ---------------------------------------------------------------------------------------------
 template <int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
 banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__ gy, double* __restrict__ rband,
-                    double* __restrict__ y, double* __restrict__ cvec, double* __restrict__ ctau, long long nb, int last_cols,
+                    double* __restrict__ y, double* __restrict__ craw, double* __restrict__ cs, long long nb, int last_cols,
                     int group, int have_rhs) {
-  constexpr int S = BC - OV, NO = OV > 0 ? OV : 1;
+  constexpr int S = BC - OV, NO = OV > 0 ? OV : 1, RING = 32, PW = BC + 2;
+  static_assert(BC % 2 == 0 && BC + 1 <= 32, "16-byte cp.async of whole band rows; one lane per column plus the rhs");
+  __shared__ __align__(16) double prow[RING][PW];       // pivot rows: BC entries + the right-hand side value
+  __shared__ __align__(16) double sv[2][NO];            // published raw tail (double buffered by step parity)
+  __shared__ __align__(16) double trash[NO];
+  __shared__ double hand[NO][33];                       // rows handed to the next group
   const int lane = threadIdx.x;
   const bool is_col = lane < BC, is_rhs = (lane == BC) && have_rhs;
-  __shared__ __align__(16) double sv[2 * NO];
   const long long W = (long long)(group - 1) * S + BC;
   const long long ngroups = (nb + group - 1) / group;
-  double Bg[NO], P[BC], Pn[S];
+  const long long n_last = nb - (ngroups - 1) * group;
+  const long long Q = (ngroups - 1) * W + (n_last - 1) * S + last_cols;      // steps in total
+
+  // pivot rows are fetched 8 at a time, two batches (16 rows) ahead of the chain: one cp.async group per 8 steps
+  auto prefetch8 = [&](long long q8) {                   // rows [q8, q8 + 8)
+    const int slot = (int)(q8 % RING);
+#pragma unroll
+    for (int j = lane; j < 8 * (BC / 2); j += 32) {
+      const int rr = j / (BC / 2), cc = j - rr * (BC / 2);
+      if (q8 + rr < Q) cp_async16(&prow[slot + rr][2 * cc], gband + (q8 + rr) * BC + 2 * cc);
+    }
+    if (lane < 8 && have_rhs && q8 + lane < Q) cp_async8(&prow[slot + lane][BC], gy + q8 + lane);
+    cp_async_commit();
+  };
+  prefetch8(0);
+  prefetch8(8);
+  cp_async_wait<0>();
+  __syncwarp();
+
+  double Bg[NO];
 #pragma unroll
   for (int i = 0; i < NO; i++) Bg[i] = 0.0;
+  double pv = (is_col || is_rhs) ? prow[0][lane] : 0.0;
 
-  auto load_rows = [&](long long q0, int c_lo, int c_hi, double* dst) {   // pivot rows q0 + c, c in [c_lo, c_hi)
-#pragma unroll
-    for (int c = 0; c < BC; c++) {
-      if (c >= c_lo && c < c_hi)
-        dst[c - c_lo] = is_col ? gband[(q0 + c) * BC + lane] : (is_rhs ? gy[q0 + c] : 0.0);
-    }
-  };
-  load_rows(0, 0, S, Pn);
-
-  long long gi = 0, lw = 0;                                    // group, window inside the group
+  long long gi = 0;                         // group
   long long n_g = (nb < group) ? nb : group;
-  for (long long kk = 0; kk < nb; kk++) {
-    const bool lastw = (lw == n_g - 1), lastgroup = (gi == ngroups - 1);
-    const long long q0 = gi * W + lw * S;                      // step index of this window's first pivot row
-    const long long g0 = (gi * group + lw) * S;                // its global row in R
+  double* p_raw = craw + (lane < OV ? lane : 0);
+  double* p_cs = cs + (lane < 2 ? lane : 0);
+  double* p_out = is_col ? rband + lane : y;                    // next final row of R (this lane's entry) / of y
+  const int out_stride = is_col ? BC : 1;
+  long long lw = 0;                         // window inside the group
+  int c = 0;                                // column of the pivot row inside its window
+  bool lastgroup = (ngroups == 1);
+  for (long long q = 0; q < Q; q++) {
+    const bool lastw = (lw == n_g - 1);
+    // ---- publish lane c's raw tail (every lane stores: lane c to the buffer, the others to a dump slot -> no divergence)
+    double* dst = (lane == c) ? sv[q & 1] : trash;
 #pragma unroll
-    for (int c = 0; c < S; c++) P[c] = Pn[c];
-    if (kk + 1 < nb) load_rows(lastw ? (gi + 1) * W : q0 + S, 0, S, Pn);    // in flight while this window is chased
-    int nsteps = S;
-    if (lastw) {                                               // the group's tail triangle: all BC rows of its last window
-      nsteps = lastgroup ? last_cols : BC;
-      load_rows(q0, S, BC, P + S);
+    for (int i = 0; i < OV; i++) dst[i] = Bg[i];
+    double tq[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < OV; i++) tq[i & 3] = fma(Bg[i], Bg[i], tq[i & 3]);
+    const double tailSq = (tq[0] + tq[1]) + (tq[2] + tq[3]);
+    double beta, inv, tau;
+    householder_scalars(pv, tailSq, OV == 0, beta, inv, tau);
+    if ((q & 7) == 0) {
+      prefetch8(q + 16);
+      cp_async_wait<1>();                    // rows < q + 16 have landed
     }
-    double cw[NO];                                             // rows handed to the next group
-#pragma unroll
-    for (int i = 0; i < NO; i++) cw[i] = 0.0;
-
-#pragma unroll
-    for (int c = 0; c < BC; c++) {
-      if (c >= nsteps) continue;
-      double* vb = sv + (c & 1) * NO;
-      if (lane == c) {
-#pragma unroll
-        for (int i = 0; i < OV; i++) vb[i] = Bg[i];
-      }
-      double tq[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int i = 0; i < OV; i++) tq[i & 3] = fma(Bg[i], Bg[i], tq[i & 3]);
-      const double tailSq = (tq[0] + tq[1]) + (tq[2] + tq[3]);
-      double pv = P[c];
-      double beta, inv, tau;
-      householder_scalars(pv, tailSq, OV == 0, beta, inv, tau);
-      __syncwarp();
-      double t[NO];
-      double dq[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int i = 0; i < OV; i++) {
-        t[i] = vb[i];
-        dq[i & 3] = fma(t[i], Bg[i], dq[i & 3]);
-      }
-      const double dot = (dq[0] + dq[1]) + (dq[2] + dq[3]);
-      const double tau_c = __shfl_sync(0xffffffffu, tau, c);
-      const double inv_c = __shfl_sync(0xffffffffu, inv, c);
-      const double w = (lane > c) ? tau_c * fma(inv_c, dot, pv) : 0.0;
-      const double z = (lane == c) ? 1.0 : w * inv_c;          // lane c: Bg - 1 * t = 0 exactly, its column is annihilated
-      pv -= w;
-      if (lane == c) pv = beta;
-#pragma unroll
-      for (int i = 0; i < OV; i++) Bg[i] = fma(-z, t[i], Bg[i]);
-      // the reflector, for later applications: essential part = raw tail * inv
-      if (lane < OV) cvec[(q0 + c) * OV + lane] = vb[lane] * inv_c;
-      if (lane == 0) ctau[q0 + c] = tau_c;
-      // the updated pivot row
-      const double outv = (lane >= c) ? pv : 0.0;
-      if (c < S || lastgroup) {
-        if (is_col) rband[(g0 + c) * BC + lane] = outv;
-        else if (is_rhs) y[g0 + c] = pv;
-      } else {
-        cw[c >= S ? c - S : 0] = outv;
-      }
-    }
-
-    // ---- next window: the bulge moves S columns to the right; at a group boundary it is replaced by the handed-over rows
+    __syncwarp();
+    const double pv_next = (is_col || is_rhs) ? prow[(q + 1) % RING][lane] : 0.0;
+    double t[NO];
+    double dq[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < OV; i++) {
-      const double src = (lastw && !lastgroup) ? cw[i] : Bg[i];
-      const double shifted = __shfl_down_sync(0xffffffffu, src, S);
-      Bg[i] = (lane == BC) ? src : ((lane < BC - S) ? shifted : 0.0);
+      t[i] = sv[q & 1][i];
+      dq[i & 3] = fma(t[i], Bg[i], dq[i & 3]);
     }
-    if (lastw) { gi++; lw = 0; n_g = (nb - gi * group < group) ? (nb - gi * group) : group; }
-    else lw++;
+    const double mine = (lane < OV) ? sv[q & 1][lane < OV ? lane : 0] : 0.0;
+    const double dot = (dq[0] + dq[1]) + (dq[2] + dq[3]);
+    const double tau_c = __shfl_sync(0xffffffffu, tau, c);
+    const double inv_c = __shfl_sync(0xffffffffu, inv, c);
+    const double w = (lane > c) ? tau_c * fma(inv_c, dot, pv) : 0.0;
+    const double z = (lane == c) ? 1.0 : w * inv_c;            // lane c: Bg - 1 * t = 0 exactly, its column is annihilated
+    pv -= w;
+    if (lane == c) pv = beta;
+#pragma unroll
+    for (int i = 0; i < OV; i++) Bg[i] = fma(-z, t[i], Bg[i]);
+    // ---- the reflector, for later applications (running per-lane pointers: no 64-bit index arithmetic in the loop)
+    if (lane < OV) *p_raw = mine;
+    if (lane < 2) *p_cs = lane ? inv_c : tau_c;
+    p_raw += OV; p_cs += 2;
+    // ---- the updated pivot row: final row of R, or handed to the next group
+    const double outv = (lane >= c) ? pv : 0.0;
+    if (!(lastw && !lastgroup && c >= S)) {
+      if (is_col || is_rhs) *p_out = outv;
+      p_out += out_stride;
+    } else {
+      hand[c - S][lane] = outv;
+    }
+    // ---- position of the next step
+    pv = pv_next;
+    c++;
+    if (!lastw) {
+      if (c == S) {                          // next window: the bulge moves S columns to the right
+        c = 0; lw++;
+#pragma unroll
+        for (int i = 0; i < OV; i++) {
+          const double shifted = __shfl_down_sync(0xffffffffu, Bg[i], S);
+          Bg[i] = (lane == BC) ? Bg[i] : ((lane < BC - S) ? shifted : 0.0);
+        }
+      }
+    } else if (!lastgroup && c == BC) {      // next group: the handed-over rows are the new bulge
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < OV; i++)
+        Bg[i] = (lane == BC) ? hand[i][BC] : ((lane < BC - S) ? hand[i][lane + S] : 0.0);
+      gi++; lw = 0; c = 0;
+      n_g = (nb - gi * group < group) ? (nb - gi * group) : group;
+      lastgroup = (gi == ngroups - 1);
+    }
   }
 }
 
@@ -403,18 +427,19 @@ banded_apply_q_kernel(const double* __restrict__ packed, const double* __restric
 // Q^T (forward) or Q (backward) of the chase reflectors applied to a vector of pivot-row values, phase 2 of an application
 // on stored factors.  One warp, sequential over the steps q (banded_chase_kernel's order, reversed for Q); the OV bulge
 // entries u live in registers (replicated in every lane), the reflectors stream through a cp.async ring.
-//   forward : p = gy[q];  w = tau (p + v.u);  p -= w;  u -= w v;   p -> y[global row]  (or -> next group's u for the last
+//   forward : p = gy[q];  w = tau (p + v.u);  p -= w;  u -= w v   (v = inv * raw tail);   p -> y[global row]  (or -> next group's u for the last
 //             OV rows of a group)
 //   backward: the same reflector (H is symmetric) in reverse order; a group starts from u = 0 (zero complement), its
 //             last OV pivot rows take the u left by the group to the right;  p -> gy[q]
 // ---------------------------------------------------------------------------------------------
 template <int BC, int OV, bool BACKWARD>
 __global__ void __launch_bounds__(32, 1)
-banded_chase_apply_kernel(const double* __restrict__ cvec, const double* __restrict__ ctau, const double* __restrict__ in,
+banded_chase_apply_kernel(const double* __restrict__ craw, const double* __restrict__ cs, const double* __restrict__ in,
                           double* __restrict__ out, long long nb, int last_cols, int group) {
   constexpr int S = BC - OV, NO = OV > 0 ? OV : 1, CH = 32, NST = 4;
   __shared__ __align__(16) double rv[NST][CH * NO];
-  __shared__ double rt[NST][CH], rp[NST][CH];
+  __shared__ __align__(16) double rt[NST][2 * CH];     // tau, inv per step
+  __shared__ double rp[NST][CH];
   __shared__ double hand[NO];                          // the OV values that cross a group boundary
   const int lane = threadIdx.x;
   const long long W = (long long)(group - 1) * S + BC;
@@ -434,13 +459,13 @@ banded_chase_apply_kernel(const double* __restrict__ cvec, const double* __restr
       const long long q0 = ck * CH;
       const int valid = (int)((Q - q0 < CH) ? (Q - q0) : CH);
       if (OV > 0) {
-        const double* src = cvec + q0 * OV;
+        const double* src = craw + q0 * OV;
         for (int j = lane; j < valid * OV / 2; j += 32) cp_async16(&rv[st][2 * j], src + 2 * j);
         if ((valid * OV) & 1) { if (lane == 0) cp_async8(&rv[st][valid * OV - 1], src + valid * OV - 1); }
       }
       if (lane < valid) {
         const long long q = q0 + lane;
-        cp_async8(&rt[st][lane], ctau + q);
+        cp_async16(&rt[st][2 * lane], cs + 2 * q);
         const long long gi = q / W, r = q - gi * W;
         const bool handed = (gi < ngroups - 1) && (r >= GS);      // pivot row that belongs to the next group's bulge
         if (BACKWARD) { if (!handed) cp_async8(&rp[st][lane], in + gi * GS + r); }
@@ -482,10 +507,12 @@ banded_chase_apply_kernel(const double* __restrict__ cvec, const double* __restr
       double vr[NO];
 #pragma unroll
       for (int k = 0; k < OV; k++) { vr[k] = v[k]; dq[k & 3] = fma(vr[k], u[k], dq[k & 3]); }
-      const double w = rt[st][j] * (p + ((dq[0] + dq[1]) + (dq[2] + dq[3])));
+      const double inv = rt[st][2 * j + 1];                  // v = [1; inv * raw]
+      const double w = rt[st][2 * j] * fma(inv, (dq[0] + dq[1]) + (dq[2] + dq[3]), p);
+      const double wz = w * inv;
       p -= w;
 #pragma unroll
-      for (int k = 0; k < OV; k++) u[k] = fma(-w, vr[k], u[k]);
+      for (int k = 0; k < OV; k++) u[k] = fma(-wz, vr[k], u[k]);
       if (lane == j) keep = p;
       if (!BACKWARD) {
         if (handed) { if (lane == 0) hand[r - GS] = p; }

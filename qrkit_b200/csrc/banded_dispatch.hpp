@@ -19,8 +19,8 @@ struct BandedArgs {
   int group = 1;              // slabs per group
   double* gband = nullptr;    // group triangles: groups x W x block_cols, W = (group-1) S + block_cols
   double* gy = nullptr;       // groups x W: pivot-row values of the right-hand side between the two phases
-  double* cvec = nullptr;     // chase reflectors: groups x W x overlap essentials
-  double* ctau = nullptr;     // groups x W
+  double* cvec = nullptr;     // chase reflectors: groups x W x overlap raw tails
+  double* ctau = nullptr;     // groups x W x {tau, inv}: v = [1; inv * raw tail]
 };
 
 struct BandedVTable {

@@ -774,7 +774,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         cudaMalloc(&h->d_gband, gw * h->uc * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_gy, gw * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_cvec, std::max<size_t>(1, gw * h->b_ov) * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_ctau, gw * sizeof(double)) != cudaSuccess)
+        cudaMalloc(&h->d_ctau, 2 * gw * sizeof(double)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);
   }
   if (angular && h->wide) {
