@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <new>
@@ -12,6 +13,7 @@
 #include "bd_generic.cuh"
 #include "bd_wy.cuh"
 #include "dense_border.cuh"
+#include "dense_blocked.cuh"
 #include "bd_small.cuh"
 #include "export.cuh"
 #include "solver.hpp"
@@ -244,7 +246,7 @@ void free_dev(qrk_solver* h) {
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
-  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wperm); F(h->d_wiscal);
+  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wperm); F(h->d_wiscal);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
@@ -425,19 +427,29 @@ int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X,
 DenseBorder wide_desc(qrk_solver* h, int nrhs) {
   DenseBorder d;
   d.A = h->d_wx + h->sum_cols;            // rows [m1, n) of Q1^T [J2 | b]
-  d.ld = h->n_rows; d.N = h->n_rows - h->sum_cols; d.M = h->m2; d.nrhs = nrhs;
+  d.ld = h->n_rows; d.N = h->n_rows - h->sum_cols; d.Nrule = d.N; d.M = h->m2; d.nrhs = nrhs;
   d.pivot = h->desc.right_solver == QRK_RIGHT_UNPIVOTED ? 0 : 1;
   d.upd = h->d_wupd; d.dir = h->d_wdir; d.tau = h->d_wtau2; d.perm = h->d_wperm; d.scal = h->d_wscal; d.iscal = h->d_wiscal;
   return d;
 }
 
+// The M x (M + nrhs) triangle left by the blocked first stage, as the matrix of the ColPiv second stage.
+DenseBorder wide_tri_desc(qrk_solver* h, int nrhs) {
+  DenseBorder d = wide_desc(h, nrhs);
+  d.Nrule = d.N;                          // Eigen's threshold / rank rules count the rows of the tall residual
+  d.A = h->d_wtri; d.ld = h->m2; d.N = h->m2;
+  return d;
+}
+
 // rank / root record / P_c tail, then (with a right-hand side) y2, x2, x1 = P1 R1^-1 (ytop - Atop x2)
 int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
-  const DenseBorder d = wide_desc(h, have_rhs ? 1 : 0);
+  const bool two_stage = h->wide_blocked && h->desc.right_solver != QRK_RIGHT_UNPIVOTED;
+  const DenseBorder d = two_stage ? wide_tri_desc(h, have_rhs ? 1 : 0) : wide_desc(h, have_rhs ? 1 : 0);
   const long long n = h->n_rows, m1 = h->sum_cols;
   const int M = h->m2;
   double* rhs_col = h->d_wx + (long long)M * n;
-  dense_finish_kernel<256><<<1, 256, (size_t)M * sizeof(double), h->stream>>>(d, have_rhs ? rhs_col + m1 : nullptr, h->d_root, h->d_root_i,
+  const double* z = two_stage ? h->d_wtri + (size_t)M * M : rhs_col + m1;
+  dense_finish_kernel<256><<<1, 256, (size_t)M * sizeof(double), h->stream>>>(d, have_rhs ? z : nullptr, h->d_root, h->d_root_i,
                                                                         h->d_perm + m1, (int)m1, have_rhs ? d_x + m1 : nullptr);
   QRK_TRY_CUDA(h, cudaGetLastError());
   h->launches++;
@@ -455,6 +467,50 @@ int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
   return QRK_STATUS_OK;
 }
 
+// Eigen's ColPivHouseholderQR (or, pivot = 0, HouseholderQR) column by column on d (dense_border.cuh)
+int wide_unblocked(qrk_solver* h, const DenseBorder& d) {
+  const int M = d.M;
+  dense_norms_kernel<<<M, 256, 0, h->stream>>>(d);
+  dense_prep_kernel<<<1, 256, 0, h->stream>>>(d);
+  h->launches += 2;
+  const int size = (int)std::min<long long>(d.N, M);
+  for (int k = 0; k < size; k++) {                                     // rightSolver.compute(J2.bottomRows(...)) (:368)
+    dense_piv_kernel<1024><<<1, 1024, 0, h->stream>>>(d, k);
+    const int ncols = M - k - 1 + d.nrhs;
+    if (ncols > 0) dense_upd_kernel<128><<<ncols, 128, 0, h->stream>>>(d, k);
+    h->launches += ncols > 0 ? 2 : 1;
+  }
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  return QRK_STATUS_OK;
+}
+
+// Blocked compact-WY QR of the tall residual (dense_blocked.cuh): one cluster launch per 8-column panel + one DMMA update
+// launch over the trailing columns (the right-hand side included).
+int wide_blocked_qr(qrk_solver* h, const DenseBorder& d) {
+  DenseBlocked b;
+  b.A = d.A; b.ld = d.ld; b.N = d.N; b.M = d.M; b.ncols = d.M + d.nrhs;
+  b.tau = d.pivot ? h->d_wtau1 : d.tau; b.T = h->d_wT;
+  for (int k0 = 0; k0 < d.M; k0 += 8) {
+    const int pw = std::min(8, d.M - k0);
+    const long long rows = d.N - k0;
+    const int rpt = (int)((rows + kDbCluster * kDbThreads - 1) / (kDbCluster * kDbThreads));
+    if (rpt <= 1) dense_panel_kernel<1><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
+    else if (rpt <= 2) dense_panel_kernel<2><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
+    else dense_panel_kernel<4><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
+    const int ntrail = b.ncols - (k0 + pw);
+    if (ntrail > 0) dense_wy_update_kernel<8><<<(ntrail + 7) / 8, 256, 0, h->stream>>>(b, k0, pw);
+    h->launches += ntrail > 0 ? 2 : 1;
+  }
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  return QRK_STATUS_OK;
+}
+
+// the blocked first stage needs a tall residual (N >= M) whose panel rows fit the cluster's registers
+bool wide_can_block(const DenseBorder& d) {
+  static const bool off = std::getenv("QRK_DENSE_UNBLOCKED") != nullptr;     // measurement switch: the BLAS-2 path
+  return !off && d.N >= d.M && d.N <= 4LL * kDbCluster * kDbThreads && d.M >= 16;
+}
+
 int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
   const long long n = h->n_rows;
   const int M = h->m2;
@@ -467,18 +523,35 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
     if (st != QRK_STATUS_OK) return st;
   }
   const DenseBorder d = wide_desc(h, d_b ? 1 : 0);
+  h->wide_blocked = false;
   if (d.N > 0) {
-    dense_norms_kernel<<<M, 256, 0, h->stream>>>(d);
-    dense_prep_kernel<<<1, 256, 0, h->stream>>>(d);
-    h->launches += 2;
-    const int size = (int)std::min<long long>(d.N, M);
-    for (int k = 0; k < size; k++) {                                     // rightSolver.compute(J2.bottomRows(...)) (:368)
-      dense_piv_kernel<1024><<<1, 1024, 0, h->stream>>>(d, k);
-      const int ncols = M - k - 1 + d.nrhs;
-      if (ncols > 0) dense_upd_kernel<128><<<ncols, 128, 0, h->stream>>>(d, k);
-      h->launches += ncols > 0 ? 2 : 1;
+    if (wide_can_block(d)) {
+      h->wide_blocked = true;
+      st = wide_blocked_qr(h, d);
+      if (st != QRK_STATUS_OK) return st;
+      if (d.pivot) {                      // ColPivHouseholderQR on the triangle: same P2, |R2|, rank and x as on the tall matrix
+        dense_extract_tri_kernel<<<148, 256, 0, h->stream>>>(d.A, d.ld, M, M + d.nrhs, h->d_wtri);
+        h->launches++;
+        const DenseBorder t = wide_tri_desc(h, d.nrhs);
+        const size_t smem = tri_colpiv_smem_bytes(M, d.nrhs);
+        constexpr size_t kTriMaxDyn = kMaxSmem - 1024;                     // the kernel's static shared memory comes on top
+        if (smem <= kTriMaxDyn) {         // the whole triangle fits the shared memory of one 8-CTA cluster: one launch
+          static bool opted[64] = {};
+          QRK_TRY_CUDA(h, ensure_smem(dense_tri_colpiv_kernel, kTriMaxDyn, opted));
+          dense_tri_colpiv_kernel<<<kDbCluster, kTriThreads, smem, h->stream>>>(t);
+          QRK_TRY_CUDA(h, cudaGetLastError());
+          h->launches++;
+        } else {
+          st = wide_unblocked(h, t);
+        }
+      } else {
+        dense_prep_kernel<<<1, 256, 0, h->stream>>>(d);                   // P2 = identity (reads the stale norm table only for
+        h->launches++;                                                    // the unused threshold)
+      }
+    } else {
+      st = wide_unblocked(h, d);
     }
-    QRK_TRY_CUDA(h, cudaGetLastError());
+    if (st != QRK_STATUS_OK) return st;
   }
   return wide_back(h, d_b != nullptr, d_x);
 }
@@ -489,16 +562,23 @@ int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
   double* rhs_col = h->d_wx + (long long)M * n;
   int st = run_op(h, OP_APPLY_QT, d_b, n, rhs_col, n, 1);
   if (st != QRK_STATUS_OK) return st;
-  const DenseBorder d = wide_desc(h, 1);
+  DenseBorder d = wide_desc(h, 1);
   if (d.N > 0) {
+    const bool two_stage = h->wide_blocked && d.pivot;
+    if (two_stage) d.tau = h->d_wtau1;
     dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(d, rhs_col + h->sum_cols);   // Q2^T on the bottom rows (:619-624)
-    QRK_TRY_CUDA(h, cudaGetLastError());
     h->launches++;
+    if (two_stage) {                      // second stage: the ColPiv reflectors of the triangle on the first M entries
+      QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_wtri + (size_t)M * M, rhs_col + h->sum_cols, M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      const DenseBorder t = wide_tri_desc(h, 1);
+      dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(t, h->d_wtri + (size_t)M * M);
+      h->launches++;
+    }
+    QRK_TRY_CUDA(h, cudaGetLastError());
   }
   return wide_back(h, true, d_x);
 }
 
-// compute (+ fused solve when d_b != nullptr).  keep_abot: store the residual panel for later solve(b) calls.
 int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x, bool keep_abot) {
   QRK_REQUIRE(h, h->d_border, "no border set: call qrk_set_border first (BlockMatrix1x2 right block)");
   if (h->wide) return wide_run(h, A_in, d_b, d_x);
@@ -783,6 +863,8 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         cudaMalloc(&h->d_wupd, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wdir, M * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wtau2, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wscal, 2 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_wtau1, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wT, 64 * ((M + 7) / 8) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_wtri, M * (M + 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_root, (M * M + 3 * M) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_root_i, (M + 1) * sizeof(int)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);

@@ -1,0 +1,492 @@
+// dense_blocked.cuh — blocked (compact-WY) unpivoted Householder QR of the tall dense border residual, trailing update on
+// the FP64 tensor cores (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4).
+//
+// Reference path: BlockedThinDenseQR (src/QRKit/BlockedThinDenseQR.h:104-176) factors the dense right block of
+// BlockAngularSparseQR panel by panel (panel width SuggestedBlockCols), builds Y / T per panel
+// (BlockedThinQRBase::computeBlockedRepresentation) and applies  A[:,j] += Y (T^T (Y^T A[:,j]))  ONE trailing column at a
+// time as GEMVs (BlockedThinQRBase.h:308-333, updateMat).  Here a panel is 8 columns and the same update is two small
+// GEMMs per 8-column block of the trailing matrix:  W = V^T A2  (8 x 8, contraction over the rows) and  A2 -= V (T^T W),
+// both issued as DMMA.  The right-hand side rides along as one more trailing column.
+//
+//   dense_panel_kernel<RPT>   ONE thread-block cluster of 8 CTAs x 512 threads, rows across threads (RPT rows each, the panel
+//                             in registers): 8 column steps, one fused cluster-wide reduction per step through distributed
+//                             shared memory (the column's squared tail norm and its dot products with the columns to its
+//                             right), then V^T V in one more reduction and the 8 x 8 triangular factor T
+//                             (H_0 ... H_7 = I - V T V^T)
+//   dense_wy_update_kernel    1 CTA per 8 trailing columns; every warp accumulates W over its row strips with DMMA, the
+//                             CTA reduces the warp partials, forms X = -T^T W, and applies A2 += V X strip by strip
+// The matrix lives in global memory; at the reference's sizes (5120 x 385 doubles = 15.8 MB) it is L2 resident.
+// With a ColPiv right solver this is the first stage: ColPivHouseholderQR then runs on the M x M triangle (same P2, |R2|
+// and x as on the tall matrix, the argument of the in-SM TSQR path) with dense_border.cuh's kernels.
+#pragma once
+#include <cooperative_groups.h>
+#include "bd_wy.cuh"
+
+namespace qrk {
+
+struct DenseBlocked {
+  double* A;          // N x ncols column-major: columns [0, M) the residual border, [M, ncols) right-hand sides
+  long long ld, N;
+  int M, ncols;
+  double* tau;        // M
+  double* T;          // 64 doubles per panel (column-major 8 x 8, upper triangular), panel p at T + 64 p
+};
+
+constexpr int kDbCluster = 8;      // CTAs per panel cluster (portable maximum)
+constexpr int kDbThreads = 512;    // threads per CTA: 4096 rows per pass, RPT passes in registers
+
+// Cluster-wide sum of nv <= 28 per-thread values (deterministic order: lanes, warps, CTA ranks — every CTA gets the
+// bit-identical total).  Also fetches rank 0's pivot-row entries.  par: double-buffer parity (one cluster.sync per call).
+template <int NV>
+__device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int par, double (*sred)[16][28], double (*stot)[28],
+                                                   double (*sfin)[36], const double (*spiv)[8]) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    if (j < nv) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+      if (lane == 0) sred[par][warp][j] = v[j];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      if (j < nv) {
+        double s = (lane < kDbThreads / 32) ? sred[par][lane][j] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) stot[par][j] = s;
+      }
+    }
+  }
+  cluster.sync();                                  // every CTA's stot[par] (and rank 0's spiv[par]) is visible
+  if (tid < nv) {
+    double s = 0.0;
+#pragma unroll
+    for (int rk = 0; rk < kDbCluster; rk++) s += cluster.map_shared_rank(&stot[par][0], rk)[tid];
+    sfin[par][tid] = s;
+  } else if (tid >= 28 && tid < 36) {
+    sfin[par][tid] = cluster.map_shared_rank(&spiv[par][0], 0)[tid - 28];
+  }
+  __syncthreads();
+}
+
+// Panel [k0, k0 + pw) of the matrix, rows [k0, N).  One cluster of 8 CTAs; thread t of CTA rank owns the rows
+// k0 + rank * 512 + t + 4096 i, i < RPT.
+template <int RPT>
+__global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads) dense_panel_kernel(DenseBlocked d, int k0, int pw) {
+  namespace cg = cooperative_groups;
+  __shared__ double sred[2][16][28];
+  __shared__ double stot[2][28];
+  __shared__ double sfin[2][36];
+  __shared__ double spiv[2][8];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int row0 = rank * kDbThreads + tid;      // row (relative to k0) of pass 0
+  constexpr int PASS = kDbCluster * kDbThreads;
+  double a[RPT][8];
+#pragma unroll
+  for (int i = 0; i < RPT; i++) {
+    const long long r = (long long)k0 + row0 + (long long)PASS * i;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[i][j] = (r < d.N && j < pw) ? d.A[(long long)(k0 + j) * d.ld + r] : 0.0;
+  }
+  double tau_r[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) tau_r[c] = 0.0;
+
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (c < pw) {                               // uniform
+      const int par = c & 1;
+      double part[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) part[j] = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        const bool below = (row0 + PASS * i) > c;
+        const double x = below ? a[i][c] : 0.0;
+#pragma unroll
+        for (int j = c; j < 8; j++) part[j - c] = fma(x, a[i][j], part[j - c]);
+      }
+      if (row0 == c) {                          // rank 0, thread c owns the pivot row
+#pragma unroll
+        for (int j = c; j < 8; j++) spiv[par][j] = a[0][j];
+      }
+      cluster_reduce_vec<8>(part, 8 - c, par, sred, stot, sfin, spiv);
+      const double tailSq = sfin[par][0], c0 = sfin[par][28 + c];
+      double beta, tau, inv;                    // Eigen makeHouseholder
+      if (tailSq <= DBL_MIN) { tau = 0.0; beta = c0; inv = 0.0; }
+      else {
+        beta = sqrt(fma(c0, c0, tailSq));
+        if (c0 >= 0.0) beta = -beta;
+        inv = 1.0 / (c0 - beta);
+        tau = (beta - c0) / beta;
+      }
+      tau_r[c] = tau;
+      double w[8];
+#pragma unroll
+      for (int j = c + 1; j < 8; j++) w[j] = tau * fma(inv, sfin[par][j - c], sfin[par][28 + j]);
+#pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        const int rel = row0 + PASS * i;
+        if (rel > c) {
+          const double vi = a[i][c] * inv;
+          a[i][c] = vi;
+#pragma unroll
+          for (int j = c + 1; j < 8; j++) a[i][j] = fma(-w[j], vi, a[i][j]);
+        } else if (rel == c) {
+          a[i][c] = beta;
+#pragma unroll
+          for (int j = c + 1; j < 8; j++) a[i][j] -= w[j];
+        }
+      }
+    }
+  }
+
+  // ---- G = V^T V (strictly upper part), V unit lower trapezoidal: G[c][j] = V[j][c] + sum_{r > j} V[r][c] V[r][j]
+  {
+    double g[28];
+#pragma unroll
+    for (int e = 0; e < 28; e++) g[e] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+      const int rel = row0 + PASS * i;
+      int e = 0;
+#pragma unroll
+      for (int j = 1; j < 8; j++) {
+        const double vj = (rel > j) ? a[i][j] : ((rel == j) ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < j; c++) { g[e] = fma(vj, a[i][c], g[e]); e++; }   // rel >= j > c: a[i][c] is V[rel][c]
+      }
+    }
+    cluster_reduce_vec<28>(g, 28, pw & 1, sred, stot, sfin, spiv);
+  }
+  if (rank == 0 && tid == 0) {                  // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j],  T[j][j] = tau_j
+    const double* G = sfin[pw & 1];
+    double T[8][8];
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) T[i][j] = 0.0;
+    for (int j = 0; j < 8; j++) {
+      if (j >= pw) break;
+      const double tj = tau_r[j];
+      T[j][j] = tj;
+      const int e0 = j * (j - 1) / 2;           // G[c][j] sits at G[e0 + c]
+      for (int i = 0; i < j; i++) {
+        double s = 0.0;
+        for (int l = i; l < j; l++) s = fma(T[i][l], G[e0 + l], s);
+        T[i][j] = -tj * s;
+      }
+    }
+    double* Tg = d.T + 64 * (k0 / 8);
+    for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) Tg[i + 8 * j] = T[i][j];
+    for (int j = 0; j < pw; j++) d.tau[k0 + j] = tau_r[j];
+  }
+#pragma unroll
+  for (int i = 0; i < RPT; i++) {
+    const long long r = (long long)k0 + row0 + (long long)PASS * i;
+    if (r < d.N) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (j < pw) d.A[(long long)(k0 + j) * d.ld + r] = a[i][j];
+    }
+  }
+  cluster.sync();                               // no CTA exits while its shared memory may still be read remotely
+}
+
+// entry (r, j) of the unit lower trapezoidal V of panel k0 (stored below the diagonal of the panel columns)
+__device__ __forceinline__ double wy_v(const DenseBlocked& d, int k0, int pw, long long r, int j) {
+  if (r >= d.N || j >= pw) return 0.0;
+  const long long rel = r - k0;
+  if (rel < j) return 0.0;
+  if (rel == j) return 1.0;
+  return d.A[(long long)(k0 + j) * d.ld + r];
+}
+
+// trailing columns [col0, col0 + 8) <- (I - V T^T V^T) columns, rows [k0, N)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) dense_wy_update_kernel(DenseBlocked d, int k0, int pw) {
+  __shared__ double sW[WARPS][64];
+  __shared__ double sT[64];
+  __shared__ double sX[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, g = lane >> 2;
+  const int col0 = k0 + pw + 8 * blockIdx.x;
+  const int ncb = (d.ncols - col0 < 8) ? (d.ncols - col0) : 8;
+  if (tid < 64) sT[tid] = d.T[64 * (k0 / 8) + tid];
+
+  // ---- W = V^T A2: D[m = reflector][n = column] += sum_k V[r0 + k][m] A2[r0 + k][n], 4 rows per DMMA
+  double w0 = 0.0, w1 = 0.0;
+  const double* colp = d.A + (long long)(col0 + (g < ncb ? g : 0)) * d.ld;
+  for (long long r0 = (long long)k0 + 4 * warp; r0 < d.N; r0 += 16 * WARPS) {
+    double va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long r = r0 + 4 * WARPS * u + q;
+      va[u] = wy_v(d, k0, pw, r, g);
+      vb[u] = (r < d.N && g < ncb) ? colp[r] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) dmma884(w0, w1, va[u], vb[u]);
+  }
+  sW[warp][g + 8 * (2 * q)] = w0;               // W[m + 8 n]
+  sW[warp][g + 8 * (2 * q + 1)] = w1;
+  __syncthreads();
+  if (tid < 64) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < WARPS; wv++) s += sW[wv][tid];
+    sW[0][tid] = s;
+  }
+  __syncthreads();
+  if (tid < 64) {                               // X = -T^T W:  X[k][n] = -sum_{m <= k} T[m][k] W[m][n]
+    const int k = tid & 7, n = tid >> 3;
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; m++) if (m <= k) s = fma(sT[m + 8 * k], sW[0][m + 8 * n], s);
+    sX[k + 8 * n] = -s;
+  }
+  __syncthreads();
+
+  // ---- A2 += V X, 8 rows per step: C[m = row][n = column], A = V (8 x 4, two k-steps), B = X
+  const double b0 = sX[q + 8 * g], b1 = sX[4 + q + 8 * g];
+  const int n0 = 2 * q, n1 = 2 * q + 1;
+  double* c0p = d.A + (long long)(col0 + (n0 < ncb ? n0 : 0)) * d.ld;
+  double* c1p = d.A + (long long)(col0 + (n1 < ncb ? n1 : 0)) * d.ld;
+  for (long long r0 = (long long)k0 + 8 * warp; r0 < d.N; r0 += 16 * WARPS) {
+    double v0[2], v1[2], c0[2], c1[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long r = r0 + 8 * WARPS * u + g;
+      v0[u] = wy_v(d, k0, pw, r, q);
+      v1[u] = wy_v(d, k0, pw, r, 4 + q);
+      c0[u] = (r < d.N && n0 < ncb) ? c0p[r] : 0.0;
+      c1[u] = (r < d.N && n1 < ncb) ? c1p[r] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long r = r0 + 8 * WARPS * u + g;
+      dmma884(c0[u], c1[u], v0[u], b0);
+      dmma884(c0[u], c1[u], v1[u], b1);
+      if (r < d.N) {
+        if (n0 < ncb) c0p[r] = c0[u];
+        if (n1 < ncb) c1p[r] = c1[u];
+      }
+    }
+  }
+}
+
+// upper triangle (and the right-hand side's first M entries) of the factored residual -> tri (M x (M + nrhs), ld = M)
+__global__ void __launch_bounds__(256) dense_extract_tri_kernel(const double* __restrict__ A, long long ld, int M, int ncols,
+                                                                double* __restrict__ tri) {
+  const long long total = (long long)M * ncols;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int c = (int)(e / M), r = (int)(e - (long long)c * M);
+    tri[e] = (c >= M || r <= c) ? A[(long long)c * ld + r] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Second stage with a ColPiv right solver: Eigen's ColPivHouseholderQR (first maximum of the LAWN-176 downdated norms,
+// recompute test, nonzero-pivot threshold — the rules of dense_border.cuh) on the M x (M + nrhs) triangle, in ONE launch.
+// One thread-block cluster of 8 CTAs keeps the whole matrix in shared memory, columns dealt round-robin (column j lives in
+// CTA j mod 8), so the work stays balanced as the factorisation advances.  Per column step: local pivot candidates ->
+// cluster.sync -> global first maximum; the owner of column k swaps it with the pivot column (through distributed shared
+// memory when that lives in another CTA), builds the reflector and publishes it -> cluster.sync -> every CTA copies v
+// over DSMEM and updates its own columns (one warp per column) and their norms.  Two hardware cluster barriers per step
+// instead of two kernel launches.
+// d: A = triangle (ld = N = M), Nrule = rows of the tall residual; needs (ceil((M+nrhs)/8) + 2) * M doubles of shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTriThreads = 512;
+
+__host__ __device__ inline size_t tri_colpiv_smem_bytes(int M, int nrhs) {
+  const size_t cpc = (size_t)(M + nrhs + kDbCluster - 1) / kDbCluster;
+  return (cpc * M + 2 * (size_t)M + 2 * cpc + 16) * sizeof(double) + (cpc + 8) * sizeof(int);
+}
+
+__global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads) dense_tri_colpiv_kernel(DenseBorder d) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double dyn[];
+  __shared__ double sred[kTriThreads / 32];
+  __shared__ double s_bigv;
+  __shared__ int s_big;
+  const int M = d.M, NC = M + d.nrhs, LDR = M;
+  const int CPC = (NC + kDbCluster - 1) / kDbCluster;
+  double* cols = dyn;                        // CPC columns of M rows: local column l is global column rank + 8 l
+  double* vloc = cols + (size_t)CPC * LDR;   // this step's reflector, local copy
+  double* vsh = vloc + M;                    // this CTA's published reflector (when it owns the pivot column)
+  double* upd = vsh + M;                     // m_colNormsUpdated of the local columns
+  double* dir = upd + CPC;                   // m_colNormsDirect
+  double* hdr = dir + CPC;                   // [0] tau [1] beta of the published reflector, [2..3] pivot candidate value (parity), [4] max norm
+  int* perm = reinterpret_cast<int*>(hdr + 16);
+  int* candj = perm + CPC;                   // [2] pivot candidate index (parity)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kTriThreads / 32;
+  const int rank = (int)cluster.block_rank();
+
+  // ---- load the local columns, their norms
+  for (int l = 0; l < CPC; l++) {
+    const int j = rank + kDbCluster * l;
+    for (int i = tid; i < M; i += kTriThreads) cols[(size_t)l * LDR + i] = (j < NC) ? d.A[(size_t)j * M + i] : 0.0;
+  }
+  __syncthreads();
+  double lmax = 0.0;
+  for (int l = warp; l < CPC; l += NW) {
+    const int j = rank + kDbCluster * l;
+    double s = 0.0;
+    for (int i = lane; i < M; i += 32) s = fma(cols[(size_t)l * LDR + i], cols[(size_t)l * LDR + i], s);
+    s = warp_sum(s);
+    const double nrm = sqrt(s);
+    if (lane == 0) { upd[l] = nrm; dir[l] = nrm; perm[l] = j; }
+    if (j < M) lmax = fmax(lmax, nrm);
+  }
+  if (lane == 0) sred[warp] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int w = 0; w < NW; w++) m = fmax(m, sred[w]);
+    hdr[4] = m;
+  }
+  cluster.sync();
+  double gmax = 0.0;
+  for (int rk = 0; rk < kDbCluster; rk++) gmax = fmax(gmax, cluster.map_shared_rank(hdr, rk)[4]);
+  const double me = gmax * DBL_EPSILON;
+  const double helper = me * me / (double)d.Nrule;               // threshold_helper
+  const int size = (int)(d.Nrule < M ? d.Nrule : M);
+  const int steps = size < M ? size : M;
+  int nonzero_pivots = size;
+  double maxpivot = 0.0;
+
+  for (int k = 0; k < steps; k++) {
+    const int par = k & 1;
+    // ---- (1) local pivot candidate: first maximum of upd over the local columns j >= k
+    if (warp == 0) {
+      double bv = -1.0;
+      int bj = 0x7fffffff;
+      for (int l = lane; l < CPC; l += 32) {
+        const int j = rank + kDbCluster * l;
+        if (j >= k && j < M) { const double u = upd[l]; if (u > bv) { bv = u; bj = j; } }   // j ascending: the first maximum stays
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      }
+      if (lane == 0) { hdr[2 + par] = bv; candj[par] = bj; }
+    }
+    cluster.sync();
+    // ---- (2) global first maximum
+    if (warp == 0) {
+      double bv = -1.0;
+      int bj = 0x7fffffff;
+      if (lane < kDbCluster) { bv = cluster.map_shared_rank(hdr, lane)[2 + par]; bj = cluster.map_shared_rank(candj, lane)[par]; }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      }
+      if (lane == 0) { s_bigv = bv; s_big = bj; }
+    }
+    __syncthreads();
+    const int big = s_big;
+    const double bigv = s_bigv;
+    if (nonzero_pivots == size && bigv * bigv < helper * (double)(d.Nrule - k)) nonzero_pivots = k;
+    // ---- (3) owner of column k: swap with the pivot column, reflector
+    const int owner = k & (kDbCluster - 1);
+    if (rank == owner) {
+      const int lk = k / kDbCluster;
+      double* ck = cols + (size_t)lk * LDR;
+      if (big != k) {
+        const int ob = big & (kDbCluster - 1), lb = big / kDbCluster;
+        double* cb = cluster.map_shared_rank(cols, ob) + (size_t)lb * LDR;
+        for (int i = tid; i < M; i += kTriThreads) { const double t = ck[i]; ck[i] = cb[i]; cb[i] = t; }
+        if (tid == 0) {
+          double* rupd = cluster.map_shared_rank(upd, ob);
+          double* rdir = cluster.map_shared_rank(dir, ob);
+          int* rperm = cluster.map_shared_rank(perm, ob);
+          double t = upd[lk]; upd[lk] = rupd[lb]; rupd[lb] = t;
+          t = dir[lk]; dir[lk] = rdir[lb]; rdir[lb] = t;
+          const int p = perm[lk]; perm[lk] = rperm[lb]; rperm[lb] = p;
+        }
+        __syncthreads();
+      }
+      double tailSq = 0.0;
+      for (int i = k + 1 + tid; i < M; i += kTriThreads) tailSq = fma(ck[i], ck[i], tailSq);
+      tailSq = warp_sum(tailSq);
+      if (lane == 0) sred[warp] = tailSq;
+      __syncthreads();
+      tailSq = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) tailSq += sred[w];
+      const double c0 = ck[k];
+      double beta, tau, inv;
+      if (tailSq <= DBL_MIN) { tau = 0.0; beta = c0; inv = 0.0; }
+      else {
+        beta = sqrt(fma(c0, c0, tailSq));
+        if (c0 >= 0.0) beta = -beta;
+        inv = 1.0 / (c0 - beta);
+        tau = (beta - c0) / beta;
+      }
+      __syncthreads();                                 // every thread has read ck[k] and sred
+      for (int i = k + 1 + tid; i < M; i += kTriThreads) { const double v = ck[i] * inv; ck[i] = v; vsh[i - k] = v; }
+      if (tid == 0) { ck[k] = beta; vsh[0] = 1.0; hdr[0] = tau; hdr[1] = beta; d.tau[k] = tau; }
+    }
+    cluster.sync();
+    // ---- (4) every CTA fetches the reflector
+    {
+      const double* rv = cluster.map_shared_rank(vsh, owner);
+      for (int i = tid; i < M - k; i += kTriThreads) vloc[i] = rv[i];
+    }
+    const double* rh = cluster.map_shared_rank(hdr, owner);
+    const double tau = rh[0], beta = rh[1];
+    if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+    __syncthreads();
+    // ---- (5) H_k on the local columns right of k (one warp per column), LAWN-176 downdate of their norms
+    for (int l = warp; l < CPC; l += NW) {
+      const int j = rank + kDbCluster * l;
+      if (j <= k || j >= NC) continue;
+      double* cj = cols + (size_t)l * LDR;
+      double dot = 0.0;
+      for (int i = k + lane; i < M; i += 32) dot = fma(vloc[i - k], cj[i], dot);
+      dot = warp_sum(dot);
+      const double w = tau * dot;
+      double nsq = 0.0, akj = 0.0;
+      for (int i = k + lane; i < M; i += 32) {
+        const double a = fma(-vloc[i - k], w, cj[i]);
+        cj[i] = a;
+        if (i > k) nsq = fma(a, a, nsq); else akj = a;
+      }
+      nsq = warp_sum(nsq);
+      akj = __shfl_sync(0xffffffffu, akj, 0);           // row k is lane 0's first element
+      if (lane == 0 && j < M) {
+        const double u = upd[l];
+        if (u != 0.0) {
+          double t = fabs(akj) / u;
+          t = (1.0 + t) * (1.0 - t);
+          t = t < 0.0 ? 0.0 : t;
+          const double qd = u / dir[l];
+          const double t2 = t * (qd * qd);
+          if (t2 <= 1.4901161193847656e-08) { const double nrm = sqrt(nsq); dir[l] = nrm; upd[l] = nrm; }   // sqrt(eps)
+          else upd[l] = u * sqrt(t);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back: packed factors, P2, rank bookkeeping
+  for (int l = 0; l < CPC; l++) {
+    const int j = rank + kDbCluster * l;
+    if (j < NC) for (int i = tid; i < M; i += kTriThreads) d.A[(size_t)j * M + i] = cols[(size_t)l * LDR + i];
+    if (j < M && tid == 0) d.perm[j] = perm[l];
+  }
+  if (rank == 0 && tid == 0) { d.scal[0] = helper; d.scal[1] = maxpivot; d.iscal[0] = nonzero_pivots; }
+  cluster.sync();                                      // shared memory stays alive while peers may still read it
+}
+
+}  // namespace qrk

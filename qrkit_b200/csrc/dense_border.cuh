@@ -19,6 +19,7 @@ namespace qrk {
 struct DenseBorder {
   double* A;         // N x (M + nrhs) column-major
   long long ld, N;
+  long long Nrule;   // rows of the matrix Eigen's rules refer to (= N, or the tall residual's rows when A is its M x M triangle)
   int M, nrhs;
   int pivot;         // 1: ColPivHouseholderQR (Eigen's pivot rule), 0: HouseholderQR / BlockedThinDenseQR (no pivoting)
   double *upd, *dir, *tau;
@@ -62,9 +63,9 @@ __global__ void __launch_bounds__(256) dense_prep_kernel(DenseBorder d) {
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; w++) m = fmax(m, sred[w]);
     const double me = m * DBL_EPSILON;
-    d.scal[0] = me * me / (double)d.N;
+    d.scal[0] = me * me / (double)d.Nrule;
     d.scal[1] = 0.0;
-    d.iscal[0] = (int)(d.N < d.M ? d.N : d.M);
+    d.iscal[0] = (int)(d.Nrule < d.M ? d.Nrule : d.M);
   }
 }
 
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
   if (tid == 0) {
     for (int w = 1; w < TPB / 32; w++)
       if (sval[w] > bv || (sval[w] == bv && sidx[w] < bj)) { bv = sval[w]; bj = sidx[w]; }
-    const int size = (int)(d.N < d.M ? d.N : d.M);
-    if (d.pivot && d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.N - k)) d.iscal[0] = k;
+    const int size = (int)(d.Nrule < d.M ? d.Nrule : d.M);
+    if (d.pivot && d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.Nrule - k)) d.iscal[0] = k;
     if (bj != k) {
       double t = d.upd[k]; d.upd[k] = d.upd[bj]; d.upd[bj] = t;
       t = d.dir[k]; d.dir[k] = d.dir[bj]; d.dir[bj] = t;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
   extern __shared__ double sy[];       // M doubles
   __shared__ int s_rank;
   const int tid = threadIdx.x, M = d.M;
-  const int size = (int)(d.N < M ? d.N : M);
+  const int size = (int)(d.Nrule < M ? d.Nrule : M);
   if (tid == 0) {
     const double thresh = fabs(d.scal[1]) * (DBL_EPSILON * (double)size);
     int rank = 0;

@@ -75,6 +75,10 @@ struct qrk_solver {
   bool wide = false;
   double* d_wx = nullptr;              // n x (m2 + 1): Q1^T [J2 | b]; rows [m1, n) hold the right block's packed QR
   double *d_wupd = nullptr, *d_wdir = nullptr, *d_wtau2 = nullptr, *d_wscal = nullptr;
+  // blocked first stage of the dense right block (dense_blocked.cuh): its tau, the per-panel T factors, and the
+  // M x (M + 1) triangle the ColPiv second stage works on; wide_blocked: the last compute() took that path
+  double *d_wtau1 = nullptr, *d_wT = nullptr, *d_wtri = nullptr;
+  bool wide_blocked = false;
   int *d_wperm = nullptr, *d_wiscal = nullptr;
 
   // ---- banded blocked (kind == QRK_BANDED_BLOCKED): sequential window sweep on one SM ----

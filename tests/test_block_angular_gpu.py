@@ -156,7 +156,7 @@ def test_multi_gpu_exchange_with_device_pointers(qk, oracle, piv):
     assert np.array_equal(x2s[0], x2s[1])
 
 
-@pytest.mark.parametrize("r,c,m2,nb", [(2, 1, 9, 200), (7, 2, 24, 120), (8, 4, 5, 150), (7, 2, 96, 96), (16, 8, 40, 40)])
+@pytest.mark.parametrize("r,c,m2,nb", [(2, 1, 9, 200), (7, 2, 24, 120), (8, 4, 5, 150), (7, 2, 96, 96), (16, 8, 40, 40), (7, 2, 21, 30), (7, 2, 19, 900)])
 @pytest.mark.parametrize("piv", [0, 1])
 def test_wide_border_vs_oracle(qk, oracle, r, c, m2, nb, piv):
     """Borders wider than the in-SM TSQR path (m2 > 8) and left blocks outside its shape list take the dense right-block
@@ -188,7 +188,7 @@ def test_reference_test4_border_384(qk, oracle):
     assert rel(s2.compute_solve(mat, b), ref.solve(b)) <= 1e-10
 
 
-@pytest.mark.parametrize("r,c,m2,nb", [(7, 2, 5, 100), (7, 2, 48, 64), (4, 2, 9, 128)])
+@pytest.mark.parametrize("r,c,m2,nb", [(7, 2, 5, 100), (7, 2, 48, 64), (4, 2, 9, 128), (7, 2, 20, 40), (7, 2, 35, 900)])
 def test_unpivoted_right_solver_vs_oracle(qk, oracle, r, c, m2, nb):
     """RightSolver = BlockedThinDenseQR<MatrixXd, 2> (reference test 5, test/test-qrkit.cpp:53-56, 294-327): no column
     pivoting in the right block, P2 = identity, rank = cols; R2 is unique up to row signs whatever the panel width."""
