@@ -293,7 +293,10 @@ bd_small_op_kernel(const double* __restrict__ packed, const double* __restrict__
 #pragma unroll
     for (int j = 0; j < C; j++) p[j] = PERM ? perm[(tile0 + t) * C + j] - (int)((tile0 + t) * C) : j;
   }
-  for (int rhs_i = 0; rhs_i < nrhs; rhs_i++) {
+  // many right-hand sides over few blocks (Q1^T J2 of a wide border): gridDim.y splits the rhs range
+  const int rhs_per = (nrhs + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int rhs_lo = (int)blockIdx.y * rhs_per, rhs_hi = (rhs_lo + rhs_per < nrhs) ? rhs_lo + rhs_per : nrhs;
+  for (int rhs_i = rhs_lo; rhs_i < rhs_hi; rhs_i++) {
     const double* Bc = B + (long long)rhs_i * ldb;
     double* Xc = X + (long long)rhs_i * ldx;
     __syncthreads();

@@ -108,7 +108,8 @@ cudaError_t launch_small_op_t(const double* packed, const double* tau, const int
   cudaError_t attr = ensure_smem(kernel, smem, smem_opt_in);
   if (attr != cudaSuccess) return attr;
   const long long grid = (nb + kSmallTPB - 1) / kSmallTPB;
-  kernel<<<(unsigned)grid, kSmallTPB, smem, s>>>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q);
+  const int gy = (int)std::max<long long>(1, std::min<long long>(nrhs, (2 * 148 + grid - 1) / grid));   // fill the GPU when blocks are few
+  kernel<<<dim3((unsigned)grid, (unsigned)gy), kSmallTPB, smem, s>>>(packed, tau, perm, B, ldb, X, ldx, nrhs, nb, n_cols, full_q);
   return cudaGetLastError();
 }
 
@@ -246,13 +247,16 @@ void free_dev(qrk_solver* h) {
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
-  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wperm); F(h->d_wiscal);
+  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wpart); F(h->d_wperm); F(h->d_wiscal);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
   for (cudaEvent_t e : h->pipe_events) cudaEventDestroy(e);
   h->pipe_events.clear();
   if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
+  for (cudaEvent_t e : h->aux_events) cudaEventDestroy(e);
+  h->aux_events.clear();
+  if (h->s_aux) { cudaStreamDestroy(h->s_aux); h->s_aux = nullptr; }
   if (h->s_out) { cudaStreamDestroy(h->s_out); h->s_out = nullptr; }
 }
 
@@ -449,7 +453,7 @@ int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
   const int M = h->m2;
   double* rhs_col = h->d_wx + (long long)M * n;
   const double* z = two_stage ? h->d_wtri + (size_t)M * M : rhs_col + m1;
-  dense_finish_kernel<256><<<1, 256, (size_t)M * sizeof(double), h->stream>>>(d, have_rhs ? z : nullptr, h->d_root, h->d_root_i,
+  dense_finish_kernel<1024><<<1, 1024, (size_t)M * sizeof(double), h->stream>>>(d, have_rhs ? z : nullptr, h->d_root, h->d_root_i,
                                                                         h->d_perm + m1, (int)m1, have_rhs ? d_x + m1 : nullptr);
   QRK_TRY_CUDA(h, cudaGetLastError());
   h->launches++;
@@ -484,23 +488,74 @@ int wide_unblocked(qrk_solver* h, const DenseBorder& d) {
   return QRK_STATUS_OK;
 }
 
-// Blocked compact-WY QR of the tall residual (dense_blocked.cuh): one cluster launch per 8-column panel + one DMMA update
-// launch over the trailing columns (the right-hand side included).
+// Blocked compact-WY QR of the tall residual (dense_blocked.cuh): one cluster launch per 8-column panel + DMMA update
+// launches over the trailing columns (the right-hand side included).  Look-ahead over two streams: the update of the NEXT
+// panel's 8 columns and that panel's factorisation run on the auxiliary stream beside the update of the remaining columns.
+constexpr int kWideRowSplit = 8;   // row ranges per column block of the trailing update
+
+cudaError_t launch_dense_panel(const DenseBlocked& b, int k0, int pw, cudaStream_t s) {
+  const long long rows = b.N - k0;
+  const int rpt = (int)((rows + kDbCluster * kDbThreads - 1) / (kDbCluster * kDbThreads));
+  static bool o1[64] = {}, o2[64] = {}, o4[64] = {};
+  cudaError_t e;
+  if (rpt <= 1) {
+    if ((e = ensure_smem(dense_panel_kernel<1>, kDbPanelSmem, o1)) != cudaSuccess) return e;
+    dense_panel_kernel<1><<<kDbCluster, kDbThreads, kDbPanelSmem, s>>>(b, k0, pw);
+  } else if (rpt <= 2) {
+    if ((e = ensure_smem(dense_panel_kernel<2>, kDbPanelSmem, o2)) != cudaSuccess) return e;
+    dense_panel_kernel<2><<<kDbCluster, kDbThreads, kDbPanelSmem, s>>>(b, k0, pw);
+  } else {
+    if ((e = ensure_smem(dense_panel_kernel<4>, kDbPanelSmem, o4)) != cudaSuccess) return e;
+    dense_panel_kernel<4><<<kDbCluster, kDbThreads, kDbPanelSmem, s>>>(b, k0, pw);
+  }
+  return cudaGetLastError();
+}
+
 int wide_blocked_qr(qrk_solver* h, const DenseBorder& d) {
   DenseBlocked b;
   b.A = d.A; b.ld = d.ld; b.N = d.N; b.M = d.M; b.ncols = d.M + d.nrhs;
   b.tau = d.pivot ? h->d_wtau1 : d.tau; b.T = h->d_wT;
-  for (int k0 = 0; k0 < d.M; k0 += 8) {
-    const int pw = std::min(8, d.M - k0);
-    const long long rows = d.N - k0;
-    const int rpt = (int)((rows + kDbCluster * kDbThreads - 1) / (kDbCluster * kDbThreads));
-    if (rpt <= 1) dense_panel_kernel<1><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
-    else if (rpt <= 2) dense_panel_kernel<2><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
-    else dense_panel_kernel<4><<<kDbCluster, kDbThreads, 0, h->stream>>>(b, k0, pw);
-    const int ntrail = b.ncols - (k0 + pw);
-    if (ntrail > 0) dense_wy_update_kernel<8><<<(ntrail + 7) / 8, 256, 0, h->stream>>>(b, k0, pw);
-    h->launches += ntrail > 0 ? 2 : 1;
+  const int P = (d.M + 7) / 8;
+  if (!h->s_aux) QRK_TRY_CUDA(h, cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+  while ((int)h->aux_events.size() < 2 * P + 2) {
+    cudaEvent_t e;
+    QRK_TRY_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->aux_events.push_back(e);
   }
+  cudaStream_t main = h->stream, aux = h->s_aux;
+  auto evP = [&](int p) { return h->aux_events[2 * p]; };       // panel p factored (recorded on aux)
+  auto evU = [&](int p) { return h->aux_events[2 * p + 1]; };   // update p of the far columns done (recorded on main)
+  cudaEvent_t fork = h->aux_events[2 * P], join = h->aux_events[2 * P + 1];
+  QRK_TRY_CUDA(h, cudaEventRecord(fork, main));
+  QRK_TRY_CUDA(h, cudaStreamWaitEvent(aux, fork, 0));
+  QRK_TRY_CUDA(h, launch_dense_panel(b, 0, std::min(8, d.M), aux));
+  QRK_TRY_CUDA(h, cudaEventRecord(evP(0), aux));
+  h->launches++;
+  for (int p = 0; p < P; p++) {
+    const int k0 = 8 * p, pw = std::min(8, d.M - k0);
+    const int ntrail = b.ncols - (k0 + pw);
+    const int nblocks = (ntrail + 7) / 8;
+    QRK_TRY_CUDA(h, cudaStreamWaitEvent(main, evP(p), 0));
+    if (nblocks > 0) {
+      if (p > 0) QRK_TRY_CUDA(h, cudaStreamWaitEvent(aux, evU(p - 1), 0));
+      dense_wy_w_kernel<<<dim3(1, kWideRowSplit), 32 * kWyWarps, 0, aux>>>(b, k0, pw, 0, h->d_wpart);        // the next panel's columns first
+      dense_wy_apply_kernel<<<dim3(1, kWideRowSplit), 32 * kWyWarps, 0, aux>>>(b, k0, pw, 0, h->d_wpart);
+      h->launches += 2;
+      if (p + 1 < P) {
+        QRK_TRY_CUDA(h, launch_dense_panel(b, k0 + 8, std::min(8, d.M - k0 - 8), aux));
+        QRK_TRY_CUDA(h, cudaEventRecord(evP(p + 1), aux));
+        h->launches++;
+      }
+      if (nblocks > 1) {
+        dense_wy_w_kernel<<<dim3(nblocks - 1, kWideRowSplit), 32 * kWyWarps, 0, main>>>(b, k0, pw, 1, h->d_wpart);
+        dense_wy_apply_kernel<<<dim3(nblocks - 1, kWideRowSplit), 32 * kWyWarps, 0, main>>>(b, k0, pw, 1, h->d_wpart);
+        h->launches += 2;
+      }
+      QRK_TRY_CUDA(h, cudaEventRecord(evU(p), main));
+    }
+  }
+  QRK_TRY_CUDA(h, cudaEventRecord(join, aux));
+  QRK_TRY_CUDA(h, cudaStreamWaitEvent(main, join, 0));
   QRK_TRY_CUDA(h, cudaGetLastError());
   return QRK_STATUS_OK;
 }
@@ -865,6 +920,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->d_wtau1, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wT, 64 * ((M + 7) / 8) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wtri, M * (M + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_wpart, ((M + 1 + 7) / 8 + 1) * (size_t)kWideRowSplit * 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_root, (M * M + 3 * M) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_root_i, (M + 1) * sizeof(int)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);

@@ -13,8 +13,8 @@
 //                             shared memory (the column's squared tail norm and its dot products with the columns to its
 //                             right), then V^T V in one more reduction and the 8 x 8 triangular factor T
 //                             (H_0 ... H_7 = I - V T V^T)
-//   dense_wy_update_kernel    1 CTA per 8 trailing columns; every warp accumulates W over its row strips with DMMA, the
-//                             CTA reduces the warp partials, forms X = -T^T W, and applies A2 += V X strip by strip
+//   dense_wy_w_kernel /       the trailing update as two launches over (8-column blocks) x (row ranges): partial W per row
+//   dense_wy_apply_kernel     range with DMMA, then X = -T^T (sum of the partials) and A2 += V X with DMMA
 // The matrix lives in global memory; at the reference's sizes (5120 x 385 doubles = 15.8 MB) it is L2 resident.
 // With a ColPiv right solver this is the first stage: ColPivHouseholderQR then runs on the M x M triangle (same P2, |R2|
 // and x as on the tall matrix, the argument of the in-SM TSQR path) with dense_border.cuh's kernels.
@@ -37,31 +37,28 @@ constexpr int kDbThreads = 512;    // threads per CTA: 4096 rows per pass, RPT p
 
 // Cluster-wide sum of nv <= 28 per-thread values (deterministic order: lanes, warps, CTA ranks — every CTA gets the
 // bit-identical total).  Also fetches rank 0's pivot-row entries.  par: double-buffer parity (one cluster.sync per call).
+constexpr size_t kDbPanelSmem = (size_t)28 * kDbThreads * sizeof(double);   // transposition buffer of the reductions
+
 template <int NV>
-__device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int par, double (*sred)[16][28], double (*stot)[28],
+__device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int par, double* buf, double (*stot)[28],
                                                    double (*sfin)[36], const double (*spiv)[8]) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // CTA level through shared memory (value j of thread t at buf[j][t], then one warp sums a row): a shuffle tree over
+  // nv values would cost 10 nv SHFL per warp, and the SHFL pipe issues one warp-instruction per clock per SM
 #pragma unroll
-  for (int j = 0; j < NV; j++) {
-    if (j < nv) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
-      if (lane == 0) sred[par][warp][j] = v[j];
-    }
-  }
+  for (int j = 0; j < NV; j++) if (j < nv) buf[j * kDbThreads + tid] = v[j];
   __syncthreads();
-  if (warp == 0) {
+  for (int j = warp; j < nv; j += kDbThreads / 32) {
+    const double* row = buf + j * kDbThreads + lane;
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
-      if (j < nv) {
-        double s = (lane < kDbThreads / 32) ? sred[par][lane][j] : 0.0;
+    for (int m = 0; m < kDbThreads / 32; m += 2) { s0 += row[32 * m]; s1 += row[32 * (m + 1)]; }
+    double s = s0 + s1;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) stot[par][j] = s;
-      }
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) stot[par][j] = s;
   }
   cluster.sync();                                  // every CTA's stot[par] (and rank 0's spiv[par]) is visible
   if (tid < nv) {
@@ -80,7 +77,7 @@ __device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int 
 template <int RPT>
 __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads) dense_panel_kernel(DenseBlocked d, int k0, int pw) {
   namespace cg = cooperative_groups;
-  __shared__ double sred[2][16][28];
+  extern __shared__ __align__(16) double sbuf[];      // kDbPanelSmem: 28 x 512 doubles
   __shared__ double stot[2][28];
   __shared__ double sfin[2][36];
   __shared__ double spiv[2][8];
@@ -118,7 +115,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
 #pragma unroll
         for (int j = c; j < 8; j++) spiv[par][j] = a[0][j];
       }
-      cluster_reduce_vec<8>(part, 8 - c, par, sred, stot, sfin, spiv);
+      cluster_reduce_vec<8>(part, 8 - c, par, sbuf, stot, sfin, spiv);
       const double tailSq = sfin[par][0], c0 = sfin[par][28 + c];
       double beta, tau, inv;                    // Eigen makeHouseholder
       if (tailSq <= DBL_MIN) { tau = 0.0; beta = c0; inv = 0.0; }
@@ -165,7 +162,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
         for (int c = 0; c < j; c++) { g[e] = fma(vj, a[i][c], g[e]); e++; }   // rel >= j > c: a[i][c] is V[rel][c]
       }
     }
-    cluster_reduce_vec<28>(g, 28, pw & 1, sred, stot, sfin, spiv);
+    cluster_reduce_vec<28>(g, 28, pw & 1, sbuf, stot, sfin, spiv);
   }
   if (rank == 0 && tid == 0) {                  // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j],  T[j][j] = tau_j
     const double* G = sfin[pw & 1];
@@ -206,30 +203,44 @@ __device__ __forceinline__ double wy_v(const DenseBlocked& d, int k0, int pw, lo
   return d.A[(long long)(k0 + j) * d.ld + r];
 }
 
-// trailing columns [col0, col0 + 8) <- (I - V T^T V^T) columns, rows [k0, N)
-template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) dense_wy_update_kernel(DenseBlocked d, int k0, int pw) {
-  __shared__ double sW[WARPS][64];
-  __shared__ double sT[64];
-  __shared__ double sX[64];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, g = lane >> 2;
-  const int col0 = k0 + pw + 8 * blockIdx.x;
-  const int ncb = (d.ncols - col0 < 8) ? (d.ncols - col0) : 8;
-  if (tid < 64) sT[tid] = d.T[64 * (k0 / 8) + tid];
+// Trailing update  A2 <- (I - V T^T V^T) A2  of the columns right of panel k0, rows [k0, N), as two launches so that BOTH
+// the column blocks and the rows are spread over the GPU (a CTA's time is its number of dependent L2 round trips: with the
+// rows split RS ways every CTA makes only a few):
+//   dense_wy_w_kernel      grid (column blocks, RS): partial W = V^T A2 over the CTA's row range, DMMA, 4 rows per step
+//   dense_wy_apply_kernel  grid (column blocks, RS): sums the RS partials in a fixed order, X = -T^T W, A2 += V X on its
+//                          row range, DMMA, 8 rows per step
+// first_block: column block offset (the look-ahead updates block 0 on its own stream).
+constexpr int kWyWarps = 8;
 
-  // ---- W = V^T A2: D[m = reflector][n = column] += sum_k V[r0 + k][m] A2[r0 + k][n], 4 rows per DMMA
+__device__ __forceinline__ void wy_row_range(const DenseBlocked& d, int k0, int rs, int nrs, long long& lo, long long& hi) {
+  const long long rows = d.N - k0;
+  const long long chunk = ((rows + nrs - 1) / nrs + 7) & ~7LL;       // multiple of 8 rows
+  lo = k0 + chunk * rs;
+  hi = lo + chunk < d.N ? lo + chunk : d.N;
+}
+
+__global__ void __launch_bounds__(32 * kWyWarps) dense_wy_w_kernel(DenseBlocked d, int k0, int pw, int first_block, double* __restrict__ wpart) {
+  __shared__ double sW[kWyWarps][64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, g = lane >> 2;
+  const int blk = first_block + (int)blockIdx.x;
+  const int col0 = k0 + pw + 8 * blk;
+  const int ncb = (d.ncols - col0 < 8) ? (d.ncols - col0) : 8;
+  long long lo, hi;
+  wy_row_range(d, k0, (int)blockIdx.y, (int)gridDim.y, lo, hi);
+  // D[m = reflector][n = column] += sum_k V[r0 + k][m] A2[r0 + k][n]
   double w0 = 0.0, w1 = 0.0;
   const double* colp = d.A + (long long)(col0 + (g < ncb ? g : 0)) * d.ld;
-  for (long long r0 = (long long)k0 + 4 * warp; r0 < d.N; r0 += 16 * WARPS) {
-    double va[4], vb[4];
+  for (long long r0 = lo + 4 * warp; r0 < hi; r0 += 32 * kWyWarps) {
+    double va[8], vb[8];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const long long r = r0 + 4 * WARPS * u + q;
-      va[u] = wy_v(d, k0, pw, r, g);
-      vb[u] = (r < d.N && g < ncb) ? colp[r] : 0.0;
+    for (int u = 0; u < 8; u++) {                // 16 independent loads in flight per lane
+      const long long r = r0 + 4 * kWyWarps * u + q;
+      const bool in = r < hi;
+      va[u] = in ? wy_v(d, k0, pw, r, g) : 0.0;
+      vb[u] = (in && g < ncb) ? colp[r] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) dmma884(w0, w1, va[u], vb[u]);
+    for (int u = 0; u < 8; u++) dmma884(w0, w1, va[u], vb[u]);
   }
   sW[warp][g + 8 * (2 * q)] = w0;               // W[m + 8 n]
   sW[warp][g + 8 * (2 * q + 1)] = w1;
@@ -237,40 +248,58 @@ __global__ void __launch_bounds__(32 * WARPS) dense_wy_update_kernel(DenseBlocke
   if (tid < 64) {
     double s = 0.0;
 #pragma unroll
-    for (int wv = 0; wv < WARPS; wv++) s += sW[wv][tid];
-    sW[0][tid] = s;
+    for (int wv = 0; wv < kWyWarps; wv++) s += sW[wv][tid];
+    wpart[((size_t)blk * gridDim.y + blockIdx.y) * 64 + tid] = s;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kWyWarps) dense_wy_apply_kernel(DenseBlocked d, int k0, int pw, int first_block, const double* __restrict__ wpart) {
+  __shared__ double sW[64];
+  __shared__ double sT[64];
+  __shared__ double sX[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, g = lane >> 2;
+  const int blk = first_block + (int)blockIdx.x;
+  const int col0 = k0 + pw + 8 * blk;
+  const int ncb = (d.ncols - col0 < 8) ? (d.ncols - col0) : 8;
+  long long lo, hi;
+  wy_row_range(d, k0, (int)blockIdx.y, (int)gridDim.y, lo, hi);
+  if (tid < 64) {
+    sT[tid] = d.T[64 * (k0 / 8) + tid];
+    double s = 0.0;
+    for (int rs = 0; rs < (int)gridDim.y; rs++) s += wpart[((size_t)blk * gridDim.y + rs) * 64 + tid];
+    sW[tid] = s;
   }
   __syncthreads();
   if (tid < 64) {                               // X = -T^T W:  X[k][n] = -sum_{m <= k} T[m][k] W[m][n]
     const int k = tid & 7, n = tid >> 3;
     double s = 0.0;
 #pragma unroll
-    for (int m = 0; m < 8; m++) if (m <= k) s = fma(sT[m + 8 * k], sW[0][m + 8 * n], s);
+    for (int m = 0; m < 8; m++) if (m <= k) s = fma(sT[m + 8 * k], sW[m + 8 * n], s);
     sX[k + 8 * n] = -s;
   }
   __syncthreads();
-
-  // ---- A2 += V X, 8 rows per step: C[m = row][n = column], A = V (8 x 4, two k-steps), B = X
+  // A2 += V X, 8 rows per step: C[m = row][n = column], A = V (8 x 4, two k-steps), B = X
   const double b0 = sX[q + 8 * g], b1 = sX[4 + q + 8 * g];
   const int n0 = 2 * q, n1 = 2 * q + 1;
   double* c0p = d.A + (long long)(col0 + (n0 < ncb ? n0 : 0)) * d.ld;
   double* c1p = d.A + (long long)(col0 + (n1 < ncb ? n1 : 0)) * d.ld;
-  for (long long r0 = (long long)k0 + 8 * warp; r0 < d.N; r0 += 16 * WARPS) {
-    double v0[2], v1[2], c0[2], c1[2];
+  for (long long r0 = lo + 8 * warp; r0 < hi; r0 += 32 * kWyWarps) {
+    double v0[4], v1[4], c0[4], c1[4];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const long long r = r0 + 8 * WARPS * u + g;
-      v0[u] = wy_v(d, k0, pw, r, q);
-      v1[u] = wy_v(d, k0, pw, r, 4 + q);
-      c0[u] = (r < d.N && n0 < ncb) ? c0p[r] : 0.0;
-      c1[u] = (r < d.N && n1 < ncb) ? c1p[r] : 0.0;
+    for (int u = 0; u < 4; u++) {
+      const long long r = r0 + 8 * kWyWarps * u + g;
+      const bool in = r < hi;
+      v0[u] = in ? wy_v(d, k0, pw, r, q) : 0.0;
+      v1[u] = in ? wy_v(d, k0, pw, r, 4 + q) : 0.0;
+      c0[u] = (in && n0 < ncb) ? c0p[r] : 0.0;
+      c1[u] = (in && n1 < ncb) ? c1p[r] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const long long r = r0 + 8 * WARPS * u + g;
+    for (int u = 0; u < 4; u++) {
+      const long long r = r0 + 8 * kWyWarps * u + g;
       dmma884(c0[u], c1[u], v0[u], b0);
       dmma884(c0[u], c1[u], v1[u], b1);
-      if (r < d.N) {
+      if (r < hi) {
         if (n0 < ncb) c0p[r] = c0[u];
         if (n1 < ncb) c1p[r] = c1[u];
       }
@@ -311,14 +340,11 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double dyn[];
   __shared__ double sred[kTriThreads / 32];
-  __shared__ double s_bigv;
-  __shared__ int s_big;
   const int M = d.M, NC = M + d.nrhs, LDR = M;
   const int CPC = (NC + kDbCluster - 1) / kDbCluster;
   double* cols = dyn;                        // CPC columns of M rows: local column l is global column rank + 8 l
   double* vloc = cols + (size_t)CPC * LDR;   // this step's reflector, local copy
-  double* vsh = vloc + M;                    // this CTA's published reflector (when it owns the pivot column)
-  double* upd = vsh + M;                     // m_colNormsUpdated of the local columns
+  double* upd = vloc + 2 * M;                // (M doubles after vloc are unused padding)                     // m_colNormsUpdated of the local columns
   double* dir = upd + CPC;                   // m_colNormsDirect
   double* hdr = dir + CPC;                   // [0] tau [1] beta of the published reflector, [2..3] pivot candidate value (parity), [4] max norm
   int* perm = reinterpret_cast<int*>(hdr + 16);
@@ -379,32 +405,30 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
       if (lane == 0) { hdr[2 + par] = bv; candj[par] = bj; }
     }
     cluster.sync();
-    // ---- (2) global first maximum
-    if (warp == 0) {
-      double bv = -1.0;
-      int bj = 0x7fffffff;
-      if (lane < kDbCluster) { bv = cluster.map_shared_rank(hdr, lane)[2 + par]; bj = cluster.map_shared_rank(candj, lane)[par]; }
+    // ---- (2) global first maximum: every thread reads the 8 candidates over DSMEM (no second intra-CTA stage)
+    int big = 0x7fffffff;
+    double bigv = -1.0;
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-        if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
-      }
-      if (lane == 0) { s_bigv = bv; s_big = bj; }
+    for (int rk = 0; rk < kDbCluster; rk++) {
+      const double ov = cluster.map_shared_rank(hdr, rk)[2 + par];
+      const int oj = cluster.map_shared_rank(candj, rk)[par];
+      if (ov > bigv || (ov == bigv && oj < big)) { bigv = ov; big = oj; }
     }
-    __syncthreads();
-    const int big = s_big;
-    const double bigv = s_bigv;
     if (nonzero_pivots == size && bigv * bigv < helper * (double)(d.Nrule - k)) nonzero_pivots = k;
-    // ---- (3) owner of column k: swap with the pivot column, reflector
+    // ---- (3) owner of column k: swap with the pivot column (fused with the tail norm), reflector, pushed to every CTA
     const int owner = k & (kDbCluster - 1);
     if (rank == owner) {
       const int lk = k / kDbCluster;
       double* ck = cols + (size_t)lk * LDR;
+      double tailSq = 0.0;
       if (big != k) {
         const int ob = big & (kDbCluster - 1), lb = big / kDbCluster;
         double* cb = cluster.map_shared_rank(cols, ob) + (size_t)lb * LDR;
-        for (int i = tid; i < M; i += kTriThreads) { const double t = ck[i]; ck[i] = cb[i]; cb[i] = t; }
+        for (int i = tid; i < M; i += kTriThreads) {
+          const double t = ck[i], x = cb[i];
+          ck[i] = x; cb[i] = t;
+          if (i > k) tailSq = fma(x, x, tailSq);
+        }
         if (tid == 0) {
           double* rupd = cluster.map_shared_rank(upd, ob);
           double* rdir = cluster.map_shared_rank(dir, ob);
@@ -413,10 +437,9 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
           t = dir[lk]; dir[lk] = rdir[lb]; rdir[lb] = t;
           const int p = perm[lk]; perm[lk] = rperm[lb]; rperm[lb] = p;
         }
-        __syncthreads();
+      } else {
+        for (int i = k + 1 + tid; i < M; i += kTriThreads) tailSq = fma(ck[i], ck[i], tailSq);
       }
-      double tailSq = 0.0;
-      for (int i = k + 1 + tid; i < M; i += kTriThreads) tailSq = fma(ck[i], ck[i], tailSq);
       tailSq = warp_sum(tailSq);
       if (lane == 0) sred[warp] = tailSq;
       __syncthreads();
@@ -433,46 +456,74 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
         tau = (beta - c0) / beta;
       }
       __syncthreads();                                 // every thread has read ck[k] and sred
-      for (int i = k + 1 + tid; i < M; i += kTriThreads) { const double v = ck[i] * inv; ck[i] = v; vsh[i - k] = v; }
-      if (tid == 0) { ck[k] = beta; vsh[0] = 1.0; hdr[0] = tau; hdr[1] = beta; d.tau[k] = tau; }
-    }
-    cluster.sync();
-    // ---- (4) every CTA fetches the reflector
-    {
-      const double* rv = cluster.map_shared_rank(vsh, owner);
-      for (int i = tid; i < M - k; i += kTriThreads) vloc[i] = rv[i];
-    }
-    const double* rh = cluster.map_shared_rank(hdr, owner);
-    const double tau = rh[0], beta = rh[1];
-    if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
-    __syncthreads();
-    // ---- (5) H_k on the local columns right of k (one warp per column), LAWN-176 downdate of their norms
-    for (int l = warp; l < CPC; l += NW) {
-      const int j = rank + kDbCluster * l;
-      if (j <= k || j >= NC) continue;
-      double* cj = cols + (size_t)l * LDR;
-      double dot = 0.0;
-      for (int i = k + lane; i < M; i += 32) dot = fma(vloc[i - k], cj[i], dot);
-      dot = warp_sum(dot);
-      const double w = tau * dot;
-      double nsq = 0.0, akj = 0.0;
-      for (int i = k + lane; i < M; i += 32) {
-        const double a = fma(-vloc[i - k], w, cj[i]);
-        cj[i] = a;
-        if (i > k) nsq = fma(a, a, nsq); else akj = a;
+      for (int i = k + 1 + tid; i < M; i += kTriThreads) {
+        const double v = ck[i] * inv;
+        ck[i] = v;
+#pragma unroll
+        for (int rk = 0; rk < kDbCluster; rk++) cluster.map_shared_rank(vloc, rk)[i - k] = v;
       }
-      nsq = warp_sum(nsq);
-      akj = __shfl_sync(0xffffffffu, akj, 0);           // row k is lane 0's first element
-      if (lane == 0 && j < M) {
-        const double u = upd[l];
-        if (u != 0.0) {
-          double t = fabs(akj) / u;
-          t = (1.0 + t) * (1.0 - t);
-          t = t < 0.0 ? 0.0 : t;
-          const double qd = u / dir[l];
-          const double t2 = t * (qd * qd);
-          if (t2 <= 1.4901161193847656e-08) { const double nrm = sqrt(nsq); dir[l] = nrm; upd[l] = nrm; }   // sqrt(eps)
-          else upd[l] = u * sqrt(t);
+      if (tid < kDbCluster) {
+        double* rv = cluster.map_shared_rank(vloc, tid);
+        double* rh = cluster.map_shared_rank(hdr, tid);
+        rv[0] = 1.0; rh[0] = tau; rh[1] = beta;
+      }
+      if (tid == 0) { ck[k] = beta; d.tau[k] = tau; }
+    }
+    cluster.sync();                                    // the reflector has landed in every CTA's vloc / hdr
+    const double tau = hdr[0], beta = hdr[1];
+    if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+    // ---- (5) H_k on the local columns right of k, LAWN-176 downdate of their norms.  A warp takes two local columns
+    // at a time through the same loops (two independent dependency chains).
+    for (int l0 = warp; l0 < CPC; l0 += 2 * NW) {
+      const int l1 = l0 + NW;
+      const int j0 = rank + kDbCluster * l0, j1 = rank + kDbCluster * l1;
+      const bool a0 = l0 < CPC && j0 > k && j0 < NC, a1 = l1 < CPC && j1 > k && j1 < NC;
+      if (a0 || a1) {
+        double* c0p = cols + (size_t)(a0 ? l0 : l1) * LDR;
+        double* c1p = cols + (size_t)(a1 ? l1 : l0) * LDR;     // a warp with one active column runs it twice (harmless)
+        double dot0 = 0.0, dot1 = 0.0;
+        for (int i = k + lane; i < M; i += 32) {
+          const double v = vloc[i - k];
+          dot0 = fma(v, c0p[i], dot0);
+          dot1 = fma(v, c1p[i], dot1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dot0 += __shfl_xor_sync(0xffffffffu, dot0, o);
+          dot1 += __shfl_xor_sync(0xffffffffu, dot1, o);
+        }
+        const double w0 = tau * dot0, w1 = tau * dot1;
+        const bool two = a0 && a1;
+        double nsq0 = 0.0, nsq1 = 0.0, ak0 = 0.0, ak1 = 0.0;
+        for (int i = k + lane; i < M; i += 32) {
+          const double v = vloc[i - k];
+          const double x0 = fma(-v, w0, c0p[i]);
+          const double x1 = fma(-v, w1, c1p[i]);
+          c0p[i] = x0;
+          if (two) c1p[i] = x1;
+          if (i > k) { nsq0 = fma(x0, x0, nsq0); nsq1 = fma(x1, x1, nsq1); } else { ak0 = x0; ak1 = x1; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          nsq0 += __shfl_xor_sync(0xffffffffu, nsq0, o);
+          nsq1 += __shfl_xor_sync(0xffffffffu, nsq1, o);
+        }
+        if (lane == 0) {                                        // row k is lane 0's first element
+          auto downdate = [&](int l, int j, double akj, double nsq) {
+            if (j >= M) return;                                  // a right-hand side: no norm
+            const double u = upd[l];
+            if (u != 0.0) {
+              double t = fabs(akj) / u;
+              t = (1.0 + t) * (1.0 - t);
+              t = t < 0.0 ? 0.0 : t;
+              const double qd = u / dir[l];
+              const double t2 = t * (qd * qd);
+              if (t2 <= 1.4901161193847656e-08) { const double nrm = sqrt(nsq); dir[l] = nrm; upd[l] = nrm; }   // sqrt(eps)
+              else upd[l] = u * sqrt(t);
+            }
+          };
+          if (a0) downdate(l0, j0, ak0, nsq0);
+          if (a1) downdate(l1, j1, two ? ak1 : ak0, two ? nsq1 : nsq0);
         }
       }
     }

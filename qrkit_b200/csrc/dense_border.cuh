@@ -200,13 +200,19 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
   __shared__ int s_rank;
   const int tid = threadIdx.x, M = d.M;
   const int size = (int)(d.Nrule < M ? d.Nrule : M);
-  if (tid == 0) {
+  {                                      // rank: |R_ii| > |maxpivot| eps size among the nonzero pivots, counted in parallel
     const double thresh = fabs(d.scal[1]) * (DBL_EPSILON * (double)size);
-    int rank = 0;
-    if (!d.pivot) rank = M;              // BlockedThinDenseQR: m_nonzeroPivots = m_R.cols() (BlockedThinDenseQR.h:132)
-    else for (int i = 0; i < d.iscal[0]; i++) rank += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
-    s_rank = rank;
-    root_i[M] = rank;
+    int cnt = 0;
+    if (d.pivot) for (int i = tid; i < d.iscal[0]; i += TPB) cnt += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
+    if (tid == 0) s_rank = 0;
+    __syncthreads();
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&s_rank, cnt);
+    __syncthreads();
+    if (tid == 0) {
+      if (!d.pivot) s_rank = M;            // BlockedThinDenseQR: m_nonzeroPivots = m_R.cols() (BlockedThinDenseQR.h:132)
+      root_i[M] = s_rank;
+    }
   }
   for (long long e = tid; e < (long long)M * M; e += TPB) {
     const int c = (int)(e / M), r = (int)(e - (long long)c * M);
@@ -221,12 +227,31 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
   double* rx = ry + M;
   for (int i = tid; i < M; i += TPB) { const double zi = (i < d.N) ? z[i] : 0.0; sy[i] = zi; rz[i] = zi; }
   __syncthreads();
-  for (int jj = rank - 1; jj >= 0; --jj) {
-    const double yj = sy[jj] / d.A[(long long)jj * d.ld + jj];
+  // back substitution in blocks of 32 columns from the bottom: warp 0 solves the 32 x 32 diagonal block in registers
+  // (lane i owns row j0 + i; one broadcast shuffle + one FMA per column), then every thread updates one row above it
+  for (int j0 = ((rank - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+    const int nbk = (rank - j0 < 32) ? (rank - j0) : 32;
+    if (tid < 32) {
+      const int lane = tid;
+      double rb[32];
+#pragma unroll
+      for (int c = 0; c < 32; c++) rb[c] = (lane < nbk && c < nbk && c > lane) ? d.A[(long long)(j0 + c) * d.ld + j0 + lane] : 0.0;
+      const double dg = (lane < nbk) ? d.A[(long long)(j0 + lane) * d.ld + j0 + lane] : 1.0;
+      double sv = (lane < nbk) ? sy[j0 + lane] : 0.0;
+#pragma unroll
+      for (int c = 31; c >= 0; --c) {
+        const double yc = __shfl_sync(0xffffffffu, sv / dg, c);      // row c is complete when the loop reaches it
+        sv = (lane == c) ? yc : fma(-rb[c], yc, sv);                 // rb[c] = 0 for lanes >= c
+      }
+      if (lane < nbk) sy[j0 + lane] = sv;
+    }
     __syncthreads();
-    const double* cj = d.A + (long long)jj * d.ld;
-    for (int i = tid; i < jj; i += TPB) sy[i] = fma(-cj[i], yj, sy[i]);
-    if (tid == 0) sy[jj] = yj;
+    for (int i = tid; i < j0; i += TPB) {
+      double acc = sy[i];
+#pragma unroll 8
+      for (int c = 0; c < nbk; c++) acc = fma(-d.A[(long long)(j0 + c) * d.ld + i], sy[j0 + c], acc);
+      sy[i] = acc;
+    }
     __syncthreads();
   }
   for (int c = tid; c < M; c += TPB) {

@@ -29,6 +29,8 @@ struct qrk_solver {
   cudaStream_t own_stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the chunked host pipeline (qrk_compute_solve, QRK_HOST)
   std::vector<cudaEvent_t> pipe_events;
+  cudaStream_t s_aux = nullptr;                     // look-ahead stream of the blocked dense border (panel p+1 beside update p)
+  std::vector<cudaEvent_t> aux_events;
   std::string err;
   long long launches = 0;
 
@@ -77,7 +79,7 @@ struct qrk_solver {
   double *d_wupd = nullptr, *d_wdir = nullptr, *d_wtau2 = nullptr, *d_wscal = nullptr;
   // blocked first stage of the dense right block (dense_blocked.cuh): its tau, the per-panel T factors, and the
   // M x (M + 1) triangle the ColPiv second stage works on; wide_blocked: the last compute() took that path
-  double *d_wtau1 = nullptr, *d_wT = nullptr, *d_wtri = nullptr;
+  double *d_wtau1 = nullptr, *d_wT = nullptr, *d_wtri = nullptr, *d_wpart = nullptr;   // d_wpart: partial W = V^T A2 per (column block, row range)
   bool wide_blocked = false;
   int *d_wperm = nullptr, *d_wiscal = nullptr;
 
