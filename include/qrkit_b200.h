@@ -172,7 +172,9 @@ QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, i
  *   qrk_compute_solve / qrk_factorize_solve / qrk_solve   _solve_impl (:203-227); b: n, x: m1 + m2
  *   qrk_matrix_r(_nnz), qrk_cols_permutation, qrk_rank (= rank1 + rank2, :510), qrk_rows, qrk_cols (= m1 + m2)
  * qrk_apply_qt / qrk_apply_q / qrk_matrix_q / qrk_packed_factors keep referring to the LEFT factor Q1.
- * Supported now: uniform left blocks of 2x1, 3x1, 4x2, 7x2 and 1 <= m2 <= 8 (else QRK_STATUS_UNSUPPORTED). */
+ * Uniform left blocks of 2x1, 3x1, 4x2, 7x2 with 1 <= m2 <= 8 and a ColPiv right solver take the fused in-SM TSQR path
+ * (and support the multi-GPU exchange below); every other left block / border width / right solver takes the dense
+ * right-block path (blocked compact-WY with DMMA, then ColPiv on the triangle), single GPU. */
 /* J2: n x m2 column-major with leading dimension ld (BlockMatrix1x2::rightBlock()).  Host: copied to the
  * device on the handle's stream; device: borrowed until the next compute returns. */
 QRK_API int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace);
@@ -190,13 +192,16 @@ QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count,
  * A handle of kind QRK_BANDED_BLOCKED describes num_blocks block rows of block_rows x block_cols; block row k sits at
  * rows [k*block_rows, ...) and columns [k*S, k*S + block_cols), S = block_cols - block_overlap
  * (fromBlockBandedPattern, SparseQRUtils.h:274-302).  values = the slabs, column-major, back to back.
- * Single GPU by construction (sequential window recurrence, BandedBlockedSparseQR.h:463-508).  Generic entry points:
+ * Single GPU by construction (R of a fixed column order is a left-to-right recurrence, BandedBlockedSparseQR.h:463-508;
+ * the device path reduces groups of block rows in parallel and keeps only a short chase sequential).  Generic entry points:
  *   qrk_compute / qrk_factorize / qrk_compute_solve / qrk_factorize_solve    factorize (:443-519) (+ fused solve)
  *   qrk_solve                         Q^T b by the window sweep (:655-670 / SparseBlockYTY.h:102-139), banded back
  *                                     substitution (:299-304)
  *   qrk_apply_qt                      matrixQ().transpose() * b: the thin part [0, n_cols) (what solve and LM use); rows
  *                                     beyond n_cols are returned as zero (the reference's complement depends on its own
  *                                     window blocking and is not unique)
+ *   qrk_apply_q                       matrixQ() * v for v = [thin part; 0]: Q1 * v[0:n_cols] (n_rows values), Q1 = A R^-1 the
+ *                                     thin factor (unique up to column signs); entries of v beyond n_cols are ignored
  *   qrk_matrix_r(_nnz)                R as CSC with its natural band pattern (values as the reference up to row signs;
  *                                     the reference additionally stores explicit zeros of its merged windows, :484-491)
  *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation
@@ -238,6 +243,21 @@ QRK_API int qrk_launch_count(qrk_handle_t h, int64_t* launches);
  * without a host copy. */
 QRK_API int qrk_synth_fill(double* device_out, uint64_t seed, int64_t block0, int64_t nb, int32_t r, int32_t c,
                            double lo, double hi, void* cuda_stream);
+
+/* ---- device-side assembly for the LM caller ------------------------------------------------
+ * The reference's published benchmark is a whole Levenberg-Marquardt ellipse fit (README.md:25-30); its functor builds the
+ * Jacobian on the host every iteration (examples/ellipse_fitting.cpp:85-113 = bench/bench_sparse_qr_extra.cpp:79-114) and
+ * the solver is constructed from it (:126-141).  With the factorisation at ~60 us, a host-built Jacobian (248 MB at 1M
+ * points over PCIe) would dominate; these two entry points keep the whole iteration on the device: the block-COO left
+ * block J1 (n blocks 2x1), the dense border J2 (2n x 5, column-major, ld = 2n) and the right-hand side are written straight
+ * into the buffers qrk_set_border / qrk_compute_solve(QRK_DEVICE) take.  All pointers are device pointers.
+ *   params: t[0..n) followed by {a, b, x0, y0, r}  (the functor's input vector, bench :68-76)
+ *   rhs   : -f(params)  (so that the least-squares solution is the Gauss-Newton step to ADD to params)
+ *   cost  : *cost += sum f^2  (optional; zero it first) */
+QRK_API int qrk_ellipse_points(double* px, double* py, int64_t n, double a, double b, double x0, double y0, double r,
+                               void* cuda_stream);   /* synthetic samples over 1.3 pi of the ellipse (bench :277-282) */
+QRK_API int qrk_ellipse_assemble(const double* px, const double* py, const double* params, int64_t n, double* J1, double* J2,
+                                 double* rhs, double* cost, void* cuda_stream);
 
 #ifdef __cplusplus
 }

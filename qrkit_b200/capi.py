@@ -90,6 +90,8 @@ def lib():
             "qrk_angular_merge": [vp, vp, i32, C.c_int],
             "qrk_synth_fill": [vp, C.c_uint64, i64, i64, i32, i32, C.c_double, C.c_double, vp],
             "qrk_device_count": [C.POINTER(C.c_int)],
+            "qrk_ellipse_points": [vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp],
+            "qrk_ellipse_assemble": [vp, vp, vp, i64, vp, vp, vp, vp, vp],
             "qrk_order_as_banded_as_possible": [i64, i64, vp, vp, vp, C.POINTER(i32)],
             "qrk_order_column_density": [i64, vp, vp],
             "qrk_detect_blocks": [i64, i64, vp, vp, i32, vp, i64, C.POINTER(i64), C.POINTER(i64)],

@@ -347,6 +347,55 @@ __global__ void iota_kernel(int* p, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = (int)i;
 }
 
+// ---- ellipse-fitting functor on the device (examples/ellipse_fitting.cpp:85-113; bench/bench_sparse_qr_extra.cpp:68-114)
+__global__ void ellipse_points_kernel(double* __restrict__ px, double* __restrict__ py, long long n, double a, double b, double x0,
+                                      double y0, double r) {
+  const double incr = 1.3 * 3.14159265358979323846 / (double)n, cr = cos(r), sr = sin(r);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double st, ct;
+    sincos((double)i * incr, &st, &ct);
+    px[i] = x0 + a * ct * cr - b * st * sr;
+    py[i] = y0 + a * ct * sr + b * st * cr;
+  }
+}
+
+// one thread per point: 2x1 block of J1, its two rows of the 5 border columns, -f, and the cost
+__global__ void __launch_bounds__(256) ellipse_assemble_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                                              const double* __restrict__ params, long long n, double* __restrict__ J1,
+                                                              double* __restrict__ J2, double* __restrict__ rhs, double* cost) {
+  const double a = params[n], b = params[n + 1], x0 = params[n + 2], y0 = params[n + 3], r = params[n + 4];
+  double sr, cr;
+  sincos(r, &sr, &cr);
+  double local = 0.0;
+  const long long ld = 2 * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double st, ct;
+    sincos(params[i], &st, &ct);
+    const double fx = px[i] - (a * ct * cr - b * st * sr + x0);
+    const double fy = py[i] - (a * ct * sr + b * st * cr + y0);
+    reinterpret_cast<double2*>(J1)[i] = make_double2(a * cr * st + b * sr * ct, a * sr * st - b * cr * ct);
+    reinterpret_cast<double2*>(J2)[i] = make_double2(-ct * cr, -ct * sr);
+    reinterpret_cast<double2*>(J2 + ld)[i] = make_double2(st * sr, -st * cr);
+    reinterpret_cast<double2*>(J2 + 2 * ld)[i] = make_double2(-1.0, 0.0);
+    reinterpret_cast<double2*>(J2 + 3 * ld)[i] = make_double2(0.0, -1.0);
+    reinterpret_cast<double2*>(J2 + 4 * ld)[i] = make_double2(a * ct * sr + b * st * cr, -a * ct * cr + b * st * sr);
+    reinterpret_cast<double2*>(rhs)[i] = make_double2(-fx, -fy);
+    local = fma(fx, fx, fma(fy, fy, local));
+  }
+  if (cost) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ double sred[8];
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; w++) s += sred[w];
+      atomicAdd(cost, s);
+    }
+  }
+}
+
 __global__ void synth_fill_kernel(double* out, uint64_t seed, long long block0, long long nb, int r, int c, double lo, double hi) {
   const long long per = (long long)r * (c > 0 ? c : 1);
   const long long total = nb * per;
@@ -1497,6 +1546,27 @@ int qrk_synth_fill(double* device_out, uint64_t seed, int64_t block0, int64_t nb
   if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
   if (nb == 0) return QRK_STATUS_OK;
   synth_fill_kernel<<<148 * 8, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(device_out, seed, block0, nb, r, c, lo, hi);
+  return cudaGetLastError() == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
+}
+
+int qrk_ellipse_points(double* px, double* py, int64_t n, double a, double b, double x0, double y0, double r, void* cuda_stream) {
+  if (!px || !py || n <= 0) return QRK_STATUS_INVALID_ARGUMENT;
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  ellipse_points_kernel<<<148 * 4, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(px, py, n, a, b, x0, y0, r);
+  return cudaGetLastError() == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
+}
+
+int qrk_ellipse_assemble(const double* px, const double* py, const double* params, int64_t n, double* J1, double* J2, double* rhs,
+                         double* cost, void* cuda_stream) {
+  if (!px || !py || !params || !J1 || !J2 || !rhs || n <= 0) return QRK_STATUS_INVALID_ARGUMENT;
+  if (!aligned16(J1) || !aligned16(J2) || !aligned16(rhs)) return QRK_STATUS_INVALID_ARGUMENT;
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 8);
+  ellipse_assemble_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(px, py, params, n, J1, J2, rhs, cost);
   return cudaGetLastError() == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
 }
 

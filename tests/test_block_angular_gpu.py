@@ -109,6 +109,53 @@ def test_multi_gpu_exchange_on_one_device(qk, oracle):
         assert np.array_equal(x2s[g], x2s[0]), "the redundantly computed shared parameters must be bit-identical on every rank"
 
 
+def test_device_side_ellipse_assembly_and_gauss_newton(qk):
+    """qrk_ellipse_assemble writes the functor's Jacobian (bench/bench_sparse_qr_extra.cpp:79-114) straight into
+    the device buffers of the block-angular solver; a Gauss-Newton loop that never leaves the device recovers the ellipse."""
+    import ctypes as C
+    import torch
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
+    L = capi.lib()
+    n = 20000
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    truth = np.array([7.5, 2.0, 17.0, 23.0, 0.23])
+    px = torch.empty(n, dtype=torch.float64, device="cuda"); py = torch.empty_like(px)
+    check(L.qrk_ellipse_points(vp(px), vp(py), n, *truth, None))
+    J1r, J2r, rhsr = ellipse_problem(n)
+    t0 = np.arange(n) * (1.3 * np.pi / n)
+    pxh, pyh = px.cpu().numpy(), py.cpu().numpy()
+    p0 = np.array([0.5 * (pxh.max() - pxh.min()), 0.5 * (pyh.max() - pyh.min()), 0.5 * (pxh.max() + pxh.min()), 0.5 * (pyh.max() + pyh.min()), 0.0])
+    params = torch.from_numpy(np.concatenate([t0, p0])).cuda()
+    J1 = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+    J2 = torch.empty(10 * n, dtype=torch.float64, device="cuda")
+    rhs = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+    cost = torch.zeros(8, dtype=torch.float64, device="cuda")
+    check(L.qrk_ellipse_assemble(vp(px), vp(py), vp(params), n, vp(J1), vp(J2), vp(rhs), vp(cost), None))
+    torch.cuda.synchronize()
+    assert rel(J1.cpu().numpy(), J1r) <= 1e-13                                   # same functor as the host generator
+    assert rel(J2.cpu().numpy().reshape(5, 2 * n).T, J2r) <= 1e-13
+    assert rel(-rhs.cpu().numpy(), rhsr) <= 1e-11
+    assert abs(cost[0].item() - float(rhsr @ rhsr)) <= 1e-10 * float(rhsr @ rhsr)
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, n, 2, 1, 1, 5
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    check(L.qrk_set_border(h, vp(J2), 2 * n, QRK_DEVICE), h)
+    step = torch.empty(n + 5, dtype=torch.float64, device="cuda")
+    for it in range(6):
+        check(L.qrk_ellipse_assemble(vp(px), vp(py), vp(params), n, vp(J1), vp(J2), vp(rhs), C.c_void_p(cost.data_ptr() + 8 * (it + 1)), None))
+        check(L.qrk_compute_solve(h, vp(J1), vp(rhs), vp(step), QRK_DEVICE), h)
+        check(L.qrk_synchronize(h), h)
+        params.add_(step)
+        torch.cuda.synchronize()
+    L.qrk_destroy(h)
+    c = cost.cpu().numpy()
+    assert c[6] < 1e-18 * c[1], c                                                # quadratic convergence to the exact fit
+    assert np.abs(params[n:].cpu().numpy() - truth).max() <= 1e-9
+    assert np.abs(params[:n].cpu().numpy() - t0).max() <= 1e-9
+
+
 @pytest.mark.parametrize("piv", [0, 1])
 def test_multi_gpu_exchange_with_device_pointers(qk, oracle, piv):
     """The exchange as bench_extra.py / an NCCL caller runs it: every buffer (blocks, border, rhs, x, the local triangle
