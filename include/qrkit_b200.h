@@ -187,6 +187,21 @@ QRK_API int qrk_angular_set_world(qrk_handle_t h, int32_t world_size);
 QRK_API int qrk_angular_triangle_size(qrk_handle_t h, int64_t* doubles);
 QRK_API int qrk_angular_local_triangle(qrk_handle_t h, double* tri, int memspace);
 QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int memspace);
+/* Fused exchange over NVLink peer memory (replaces the all-gather + qrk_angular_merge pair): after qrk_angular_p2p_attach the
+ * compute / solve calls of a world > 1 handle are complete again — the TSQR root kernel stores this GPU's triangle into every
+ * peer's exchange buffer, raises a flag, waits for the peers' flags (bounded spin) and merges the G triangles in rank order
+ * (bit-identical shared parameters on every rank), all inside one launch.  Every rank must issue the same sequence of calls.
+ *   qrk_angular_xchg_buffer   this handle's exchange buffer (a cudaMalloc allocation of *bytes bytes; call after set_world)
+ *   qrk_ipc_export / _import  cudaIpcGetMemHandle / cudaIpcOpenMemHandle (64-byte handles) for one-process-per-GPU callers;
+ *                             exchange the handles with any host-side collective (torch.distributed, MPI)
+ *   qrk_angular_p2p_attach    peer_buffers[g] = rank g's exchange buffer as mapped in THIS process (own buffer at [rank])
+ *   qrk_angular_p2p_status    *timed_out = 1 if a peer never arrived (the step then finished on incomplete data) */
+QRK_API int qrk_angular_xchg_buffer(qrk_handle_t h, void** device_ptr, int64_t* bytes);
+QRK_API int qrk_angular_p2p_attach(qrk_handle_t h, void* const* peer_buffers, int32_t world_size, int32_t rank);
+QRK_API int qrk_angular_p2p_status(qrk_handle_t h, int32_t* timed_out);
+QRK_API int qrk_ipc_export(const void* device_ptr, void* handle64);
+QRK_API int qrk_ipc_import(const void* handle64, void** device_ptr);
+QRK_API int qrk_ipc_close(void* device_ptr);
 
 /* ---- banded blocked (BandedBlockedSparseQR.h:122-344) ---------------------------------------------------------------
  * A handle of kind QRK_BANDED_BLOCKED describes num_blocks block rows of block_rows x block_cols; block row k sits at

@@ -88,6 +88,10 @@ def lib():
             "qrk_set_border": [vp, vp, i64, C.c_int], "qrk_angular_set_world": [vp, i32],
             "qrk_angular_triangle_size": [vp, C.POINTER(i64)], "qrk_angular_local_triangle": [vp, vp, C.c_int],
             "qrk_angular_merge": [vp, vp, i32, C.c_int],
+            "qrk_angular_xchg_buffer": [vp, C.POINTER(vp), C.POINTER(i64)],
+            "qrk_angular_p2p_attach": [vp, C.POINTER(vp), i32, i32],
+            "qrk_angular_p2p_status": [vp, C.POINTER(i32)],
+            "qrk_ipc_export": [vp, vp], "qrk_ipc_import": [vp, C.POINTER(vp)], "qrk_ipc_close": [vp],
             "qrk_synth_fill": [vp, C.c_uint64, i64, i64, i32, i32, C.c_double, C.c_double, vp],
             "qrk_device_count": [C.POINTER(C.c_int)],
             "qrk_ellipse_points": [vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp],

@@ -382,36 +382,96 @@ angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // K2: TSQR root.  mode 0: merge `count` triangles into out_tri (the per-GPU triangle; multi-GPU step 1).
 //     mode 1: merge, then ColPiv + rank + x2 (single GPU, or after the NCCL all-gather of G triangles).
+//     mode 2: merge, exchange the per-GPU triangles with the peers over NVLink inside this kernel, merge, root.
 //   root : [R2 (M2*M2 col-major) | z2 (M2) | y2 = R2^-1 z2 in pivoted order (M2) | x2 (M2, unpivoted)] doubles
 //   root_i: [P2 (M2) | rank2]
 // ---------------------------------------------------------------------------------------------
+// Peer exchange of the per-GPU triangles inside the root kernel (mode 2): the "all-gather" of SURVEY 8e as plain stores
+// into every peer's exchange buffer over NVLink (buffers mapped with cudaIpcOpenMemHandle), followed by a flag per
+// (step parity, source rank).  Buffer layout (identical on every rank): [2][G][Tri::N] doubles, then [2][G] uint64 flags.
+// A rank can run at most one step ahead of a peer (it waits for the peer's flag of the current step), so two parities
+// suffice.  The spin is bounded (~2 s): on a timeout *err is set and the step finishes with whatever arrived.
+struct AngularXchg {
+  double* const* peers = nullptr;   // device array of G pointers: peers[g] = rank g's exchange buffer as mapped here
+  int world = 0, rank = 0;
+  unsigned long long* seq = nullptr; // device-resident step counter (the kernel advances it: a captured launch replays correctly)
+  int* err = nullptr;
+};
+
 template <int M2, int TPB>
-__global__ void __launch_bounds__(TPB)
-angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
-                    double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only, int* __restrict__ perm_tail,
-                    int m1) {
-  using TR = Tri<M2>;
-  constexpr int N = TR::N;
-  __shared__ double scratch[(TPB / 32) * N];
-  double T[N];
+__device__ __forceinline__ void merge_triangle_list(const double* tris, int count, double (&T)[Tri<M2>::N], double* scratch,
+                                                    bool bypass_l1) {
+  constexpr int N = Tri<M2>::N;
 #pragma unroll
   for (int i = 0; i < N; i++) T[i] = 0.0;
   // every thread takes one triangle per round; a round is merged cooperatively (warp, then CTA)
   for (int q0 = 0; q0 < count; q0 += TPB) {
     const int q = q0 + threadIdx.x;
+    double S[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const double* src = tris + (long long)q * N + i;
+      S[i] = (q < count) ? (bypass_l1 ? __ldcv(src) : *src) : 0.0;
+    }
     if (q0 == 0) {
-      if (q < count) {
 #pragma unroll
-        for (int i = 0; i < N; i++) T[i] = tris[(long long)q * N + i];
-      }
+      for (int i = 0; i < N; i++) T[i] = S[i];
     } else {
-      double S[N];
-#pragma unroll
-      for (int i = 0; i < N; i++) S[i] = (q < count) ? tris[(long long)q * N + i] : 0.0;
       fold_tri<M2>(T, S);
     }
   }
   cta_merge_tri<M2, TPB / 32>(T, scratch);
+}
+
+template <int M2, int TPB>
+__global__ void __launch_bounds__(TPB)
+angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
+                    double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only, int* __restrict__ perm_tail,
+                    int m1, AngularXchg xc) {
+  using TR = Tri<M2>;
+  constexpr int N = TR::N;
+  __shared__ double scratch[(TPB / 32) * N];
+  double T[N];
+  merge_triangle_list<M2, TPB>(tris, count, T, scratch, false);
+  if (mode == 2) {
+    // ---- this GPU's triangle -> every rank's buffer (own included), then the flag; wait for all G flags
+    const unsigned long long seq = *xc.seq + 1;               // the same on every rank: every rank runs the same sequence of steps
+    const int G = xc.world, par = (int)(seq & 1ull);
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < G; g++) {
+        double* dst = xc.peers[g] + ((size_t)par * G + xc.rank) * N;
+#pragma unroll
+        for (int i = 0; i < N; i++) __stcg(dst + i, T[i]);
+      }
+      __threadfence_system();
+      for (int g = 0; g < G; g++) {
+        unsigned long long* flags = reinterpret_cast<unsigned long long*>(xc.peers[g] + (size_t)2 * G * N);
+        *reinterpret_cast<volatile unsigned long long*>(flags + (size_t)par * G + xc.rank) = seq;
+      }
+    }
+    if (threadIdx.x < G) {
+      const volatile unsigned long long* mine =
+          reinterpret_cast<const volatile unsigned long long*>(xc.peers[xc.rank] + (size_t)2 * G * N) + (size_t)par * G + threadIdx.x;
+      const long long t0 = clock64();
+      while (*mine != seq) {
+        if (clock64() - t0 > (1LL << 32)) { *xc.err = 1; break; }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *xc.seq = seq;
+    // ---- the G triangles in rank order: the same data, the same order, the same arithmetic on every rank
+    if (G <= 32) {                            // one triangle per lane of warp 0: a single cooperative warp merge
+      const double* src = xc.peers[xc.rank] + (size_t)par * G * N;
+      if (threadIdx.x < 32) {
+#pragma unroll
+        for (int i = 0; i < N; i++) T[i] = ((int)threadIdx.x < G) ? __ldcv(src + (size_t)threadIdx.x * N + i) : 0.0;
+        warp_merge_tri<M2>(T);
+      }
+    } else {
+      merge_triangle_list<M2, TPB>(xc.peers[xc.rank] + (size_t)par * G * N, G, T, scratch, true);
+    }
+  }
   if (threadIdx.x != 0) return;
   if (mode == 0) {
 #pragma unroll

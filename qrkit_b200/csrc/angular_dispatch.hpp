@@ -35,6 +35,11 @@ struct AngularArgs {
   int m1 = 0;
   // solution
   double* x = nullptr;
+  // fused peer exchange (root_mode 2)
+  double* const* xchg_peers = nullptr;
+  int xchg_world = 0, xchg_rank = 0;
+  unsigned long long* xchg_seq = nullptr;
+  int* xchg_err = nullptr;
 };
 
 struct AngularVTable {
@@ -47,6 +52,7 @@ struct AngularVTable {
   cudaError_t (*rhs)(const AngularArgs&, cudaStream_t);
   cudaError_t (*root)(const AngularArgs&, cudaStream_t);
   cudaError_t (*backsolve)(const AngularArgs&, cudaStream_t);
+  cudaError_t (*preload)(int r, int c, bool piv);                   // force the (lazily loaded) kernels of this shape into the context
 };
 
 constexpr int kAngularMaxM2 = 8;

@@ -122,12 +122,36 @@ cudaError_t backsolve(const AngularArgs& a, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 cudaError_t root(const AngularArgs& a, cudaStream_t s) {
+  AngularXchg xc;
+  xc.peers = a.xchg_peers; xc.world = a.xchg_world; xc.rank = a.xchg_rank; xc.seq = a.xchg_seq; xc.err = a.xchg_err;
   angular_root_kernel<M2, 512><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
-                                                 a.perm_tail, a.m1);
+                                                 a.perm_tail, a.m1, xc);
   return cudaGetLastError();
 }
 
-const AngularVTable kTable = {M2, Tri<M2>::N, shape_ok, max_grid, tile_blocks, factor, rhs, root, backsolve};
+// CUDA loads kernels lazily at their first launch, and loading can wait for running kernels: a root kernel that spins on a
+// peer (mode 2) must never be the reason the peer's kernels cannot be loaded (two ranks emulated in one process would
+// deadlock until the bounded spin gives up).  qrk_angular_p2p_attach therefore loads everything up front.
+template <int R, int C>
+cudaError_t preload_t(bool piv) {
+  using G = Cfg<R, C>;
+  cudaFuncAttributes fa;
+  cudaError_t e = piv ? cudaFuncGetAttributes(&fa, angular_factor_kernel<R, C, true, M2, TPB, G::U, G::NSTAGE, G::MINB>)
+                      : cudaFuncGetAttributes(&fa, angular_factor_kernel<R, C, false, M2, TPB, G::U, G::NSTAGE, G::MINB>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>);
+  if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, true, TPB>)
+                                : cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, false, TPB>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512>);
+  return e;
+}
+cudaError_t preload(int r, int c, bool piv) {
+#define X(R_, C_) if (r == R_ && c == C_) return preload_t<R_, C_>(piv);
+  QRK_ANGULAR_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+const AngularVTable kTable = {M2, Tri<M2>::N, shape_ok, max_grid, tile_blocks, factor, rhs, root, backsolve, preload};
 
 }  // namespace
 

@@ -247,7 +247,7 @@ void free_dev(qrk_solver* h) {
   h->d_values = nullptr;
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
-  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wpart); F(h->d_wperm); F(h->d_wiscal);
+  F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wpart); F(h->d_xchg); F(h->d_xchg_peers); F(h->d_xchg_err); F(h->d_xchg_seq); F(h->d_wperm); F(h->d_wiscal);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
@@ -448,9 +448,11 @@ AngularArgs angular_args(qrk_solver* h) {
   return a;
 }
 
-// TSQR root (+ back substitution when a right-hand side is present).  world > 1: stop at the per-GPU triangle.
+// TSQR root (+ back substitution when a right-hand side is present).  world > 1: either the triangles are exchanged with the
+// peers inside the root kernel (after qrk_angular_p2p_attach), or the call stops at the per-GPU triangle and
+// qrk_angular_merge finishes after the caller's all-gather.
 int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* d_x, int keep_rhs_only) {
-  if (h->world > 1) {
+  if (h->world > 1 && h->xchg_rank < 0) {
     a.root_mode = 0;
     QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
     h->launches++;
@@ -462,6 +464,11 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
     return QRK_STATUS_OK;
   }
   a.root_mode = 1;
+  if (h->world > 1) {
+    a.root_mode = 2;
+    a.xchg_peers = h->d_xchg_peers; a.xchg_world = h->world; a.xchg_rank = h->xchg_rank; a.xchg_err = h->d_xchg_err;
+    a.xchg_seq = h->d_xchg_seq;
+  }
   a.keep_rhs_only = keep_rhs_only;
   QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
   h->launches++;
@@ -1478,6 +1485,7 @@ int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace) {
 int qrk_angular_set_world(qrk_handle_t h, int32_t world_size) {
   if (!h || !h->avt || world_size < 1) return QRK_STATUS_INVALID_ARGUMENT;
   h->world = world_size;
+  h->xchg_rank = -1;                 // a new world needs a new qrk_angular_p2p_attach
   return QRK_STATUS_OK;
 }
 
@@ -1530,6 +1538,72 @@ int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int mem
   h->pending = false;
   h->pending_x = nullptr;
   return st;
+}
+
+int qrk_angular_xchg_buffer(qrk_handle_t h, void** device_ptr, int64_t* bytes) {
+  if (!h || !h->avt || !device_ptr || !bytes) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, h->world > 1 && !h->wide, "call qrk_angular_set_world(world > 1) first (fused TSQR path only)");
+  DeviceGuard g(h->device);
+  const size_t need = (size_t)2 * h->world * h->avt->tri_doubles * sizeof(double) + (size_t)2 * h->world * sizeof(unsigned long long);
+  if (h->d_xchg && h->xchg_bytes != need) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
+  if (!h->d_xchg) {
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg, need));          // a plain cudaMalloc allocation: exportable with cudaIpcGetMemHandle
+    QRK_TRY_CUDA(h, cudaMemset(h->d_xchg, 0, need));        // flags = 0 < every step number
+    h->xchg_bytes = need;
+  }
+  *device_ptr = h->d_xchg;
+  *bytes = (int64_t)need;
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_p2p_attach(qrk_handle_t h, void* const* peer_buffers, int32_t world_size, int32_t rank) {
+  if (!h || !h->avt || !peer_buffers) return QRK_STATUS_INVALID_ARGUMENT;
+  QRK_REQUIRE(h, world_size == h->world && world_size > 1 && rank >= 0 && rank < world_size, "world / rank do not match qrk_angular_set_world");
+  QRK_REQUIRE(h, h->d_xchg && peer_buffers[rank] == (void*)h->d_xchg, "peer_buffers[rank] must be this handle's qrk_angular_xchg_buffer");
+  for (int g = 0; g < world_size; g++) QRK_REQUIRE(h, peer_buffers[g] != nullptr, "null peer buffer");
+  DeviceGuard g(h->device);
+  if (!h->d_xchg_peers) QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg_peers, (size_t)world_size * sizeof(double*)));
+  if (!h->d_xchg_err) { QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg_err, sizeof(int))); QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_err, 0, sizeof(int))); }
+  QRK_TRY_CUDA(h, cudaMemcpy(h->d_xchg_peers, peer_buffers, (size_t)world_size * sizeof(double*), cudaMemcpyHostToDevice));
+  QRK_TRY_CUDA(h, h->avt->preload(h->ur, h->uc, h->desc.pivoting == QRK_PIVOT_COLPIV));   // no lazy load behind a spinning kernel
+  QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_err, 0, sizeof(int)));
+  if (!h->d_xchg_seq) QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg_seq, sizeof(unsigned long long)));
+  QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_seq, 0, sizeof(unsigned long long)));
+  QRK_TRY_CUDA(h, cudaMemset(h->d_xchg, 0, h->xchg_bytes));       // flags back to 0: attach restarts the step count on every rank
+  h->xchg_rank = rank;
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_p2p_status(qrk_handle_t h, int32_t* timed_out) {
+  if (!h || !timed_out) return QRK_STATUS_INVALID_ARGUMENT;
+  *timed_out = 0;
+  if (!h->d_xchg_err) return QRK_STATUS_OK;
+  DeviceGuard g(h->device);
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  QRK_TRY_CUDA(h, cudaMemcpy(timed_out, h->d_xchg_err, sizeof(int), cudaMemcpyDeviceToHost));
+  return QRK_STATUS_OK;
+}
+
+int qrk_ipc_export(const void* device_ptr, void* handle64) {
+  if (!device_ptr || !handle64) return QRK_STATUS_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI passes IPC handles as 64 bytes");
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, const_cast<void*>(device_ptr)) != cudaSuccess) { (void)cudaGetLastError(); return QRK_STATUS_CUDA_ERROR; }
+  std::memcpy(handle64, &hd, 64);
+  return QRK_STATUS_OK;
+}
+
+int qrk_ipc_import(const void* handle64, void** device_ptr) {
+  if (!device_ptr || !handle64) return QRK_STATUS_INVALID_ARGUMENT;
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle64, 64);
+  if (cudaIpcOpenMemHandle(device_ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); return QRK_STATUS_CUDA_ERROR; }
+  return QRK_STATUS_OK;
+}
+
+int qrk_ipc_close(void* device_ptr) {
+  if (!device_ptr) return QRK_STATUS_INVALID_ARGUMENT;
+  return cudaIpcCloseMemHandle(device_ptr) == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
 }
 
 int qrk_launch_count(qrk_handle_t h, int64_t* launches) {

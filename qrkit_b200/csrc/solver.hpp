@@ -69,6 +69,13 @@ struct qrk_solver {
   bool have_abot = false;              // the residual panel of the last compute() is resident (solve(b) possible)
   bool root_done = false;
   bool pending = false;                // a right-hand side waits for qrk_angular_merge
+  // fused peer exchange over NVLink (qrk_angular_p2p_attach): the triangles travel inside the root kernel
+  double* d_xchg = nullptr;            // this rank's exchange buffer: [2][world][Tri] doubles + [2][world] uint64 flags
+  size_t xchg_bytes = 0;
+  double** d_xchg_peers = nullptr;     // device array of world pointers (peer buffers as mapped in this process)
+  int* d_xchg_err = nullptr;
+  unsigned long long* d_xchg_seq = nullptr;   // step counter, advanced by the root kernel itself
+  int xchg_rank = -1;                  // >= 0 once attached
   double* pending_x = nullptr;
   int pending_space = 0;
   int pending_keep_rhs_only = 0;

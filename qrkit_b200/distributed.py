@@ -53,3 +53,40 @@ def angular_compute_solve(solver, mat_local, b_local, group=None):
     solver.compute_solve(mat_local, b_local)
     gathered = all_gather_triangles(solver.local_triangle(), group)
     return solver.merge(gathered.cpu().numpy())
+
+
+def attach_p2p(handle, group=None, device=None):
+    """Fused peer exchange for a block-angular handle (created with qrk_angular_set_world(world) already called): export this
+    rank's exchange buffer as a CUDA IPC handle, all-gather the 64-byte handles with torch.distributed, map the peers'
+    buffers and hand them to qrk_angular_p2p_attach.  Afterwards qrk_compute_solve / qrk_solve on this handle are complete
+    calls again: the triangles travel over NVLink inside the TSQR root kernel (no NCCL on the data path).
+    Returns the imported pointers (close them with qrk_ipc_close after destroying the handle)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from .capi import check, lib
+    L = lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf, nbytes = C.c_void_p(), C.c_int64()
+    check(L.qrk_angular_xchg_buffer(handle, C.byref(buf), C.byref(nbytes)), handle)
+    hd = (C.c_ubyte * 64)()
+    check(L.qrk_ipc_export(buf, hd))
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    mine = torch.tensor(list(hd), dtype=torch.uint8, device=dev)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    allh = allh.cpu().numpy().reshape(world, 64)
+    peers = (C.c_void_p * world)()
+    imported = []
+    for g in range(world):
+        if g == rank:
+            peers[g] = buf.value
+        else:
+            hb = (C.c_ubyte * 64)(*[int(v) for v in allh[g]])
+            p = C.c_void_p()
+            check(L.qrk_ipc_import(hb, C.byref(p)))
+            peers[g] = p.value
+            imported.append(p)
+    check(L.qrk_angular_p2p_attach(handle, peers, world, rank), handle)
+    dist.barrier(group)
+    return imported

@@ -126,10 +126,11 @@ def test_unsupported_shape_is_reported(qk):
     assert e.value.status == 6
 
 
-def test_config4_scaled_properties(qk):
-    """BASELINE config 4 pattern (16x24 slabs, step 8) at 20k block rows: size-independent checks — x recovered from a
-    consistent system, the normal equations of a least-squares rhs, |diag R| against the Cholesky-free identity on a window."""
-    nb, br, bc, ov = 20_000, 16, 24, 16
+@pytest.mark.parametrize("nb", [20_000, 100_000])
+def test_config4_properties(qk, nb):
+    """BASELINE config 4 pattern (16x24 slabs, step 8) at 20k block rows and at the full 100k (1.6M x 800,016): size-
+    independent checks — x recovered from a consistent system, the normal equations of a least-squares right-hand side."""
+    br, bc, ov = 16, 24, 16
     slabs = uniform_blocks(nb, br, bc)
     A = slabs_to_sparse(slabs, nb, br, bc, ov).tocsr()
     n_rows, n_cols = A.shape

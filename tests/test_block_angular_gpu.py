@@ -157,6 +157,61 @@ def test_device_side_ellipse_assembly_and_gauss_newton(qk):
 
 
 @pytest.mark.parametrize("piv", [0, 1])
+def test_fused_peer_exchange_two_ranks_on_one_device(qk, oracle, piv):
+    """qrk_angular_p2p_attach: the per-GPU triangles are exchanged inside the TSQR root kernel (stores into the peers'
+    exchange buffers + flags) instead of all-gather + qrk_angular_merge.  Two emulated ranks = two handles on two streams
+    of one device, their exchange buffers attached by plain pointer; three steps (both buffer parities) with different
+    right-hand sides; x2 bit-identical on both ranks."""
+    import ctypes as C
+    import torch
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
+    L = capi.lib()
+    n, world = 3000, 2
+    per = n // world
+    J1, J2, rhs0 = ellipse_problem(n)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(n, 2), bc=np.full(n, 1), values=J1, left_colpiv=bool(piv), right_kind=0)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    hs, bufs, xbufs = [], [], []
+    for g in range(world):
+        rows = slice(2 * g * per, 2 * (g + 1) * per)
+        dJ1, dJ2 = dev(J1[rows]), dev(J2[rows, :].T)
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, per, 2, 1, piv, 5
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_angular_set_world(h, world), h)
+        check(L.qrk_set_border(h, vp(dJ2), 2 * per, QRK_DEVICE), h)
+        check(L.qrk_set_blocks(h, vp(dJ1), QRK_DEVICE), h)          # allocations happen before any kernel spins
+        xb, nb_ = C.c_void_p(), C.c_int64()
+        check(L.qrk_angular_xchg_buffer(h, C.byref(xb), C.byref(nb_)), h)
+        hs.append(h); bufs.append((dJ1, dJ2)); xbufs.append(xb.value)
+    peers = (C.c_void_p * world)(*xbufs)
+    for g, h in enumerate(hs):
+        check(L.qrk_angular_p2p_attach(h, peers, world, g), h)
+    for step in range(3):
+        rhs = rhs0 if step == 0 else vector(2 * n, seed=100 + step)
+        x_ref = ref.solve(rhs)
+        dbs = [dev(rhs[2 * g * per:2 * (g + 1) * per]) for g in range(world)]
+        dxs = [torch.zeros(per + 5, dtype=torch.float64, device="cuda") for _ in range(world)]
+        for g, h in enumerate(hs):                                 # asynchronous: rank 0's root kernel waits for rank 1's
+            check(L.qrk_compute_solve(h, vp(bufs[g][0]), vp(dbs[g]), vp(dxs[g]), QRK_DEVICE), h)
+        x2s = []
+        for g, h in enumerate(hs):
+            to = C.c_int32(-1)
+            check(L.qrk_angular_p2p_status(h, C.byref(to)), h)
+            assert to.value == 0, "peer exchange timed out"
+            xg = dxs[g].cpu().numpy()
+            assert rel(xg[:per], x_ref[g * per:(g + 1) * per]) <= 1e-9
+            assert rel(xg[per:], x_ref[n:]) <= 1e-9
+            x2s.append(xg[per:].copy())
+        assert np.array_equal(x2s[0], x2s[1])
+    for h in hs:
+        L.qrk_destroy(h)
+
+
+@pytest.mark.parametrize("piv", [0, 1])
 def test_multi_gpu_exchange_with_device_pointers(qk, oracle, piv):
     """The exchange as bench_extra.py / an NCCL caller runs it: every buffer (blocks, border, rhs, x, the local triangle
     and the gathered triangles) is a DEVICE pointer; two emulated ranks on one device."""

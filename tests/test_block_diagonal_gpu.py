@@ -7,7 +7,7 @@ Shapes follow the reference's tests (test/test-qrkit.cpp:167-206: 256 blocks of 
 import numpy as np
 import pytest
 
-from helpers import SEED_A, blocks_to_dense, rel, synth, uniform_blocks, vector
+from helpers import SEED_A, blocks_to_dense, rel, splitmix64, synth, uniform_blocks, vector
 
 pytestmark = pytest.mark.gpu
 
@@ -293,3 +293,68 @@ def test_headline_config_full_size_properties(qk, oracle, piv):
     assert rel(pk[win], ref["packed"]) <= TOL_R
     assert np.array_equal(local[w0:w0 + 20_000].reshape(-1), ref["perm"] - np.repeat(np.arange(20_000) * c, c))
     assert rel(x[w0 * c:(w0 + 20_000) * c], ref["x"]) <= TOL_X
+
+
+def test_config5_full_size_properties(qk):
+    """BASELINE config 5 at full size: 100k mixed blocks 32x16 .. 128x64 (2.97 GB of values, generated on the device).
+    Size-independent checks through the C ABI with device pointers: x recovered from a consistent system, and the normal
+    equations A^T (A x - b) = 0 of a least-squares right-hand side, per size class with batched products."""
+    import ctypes as C
+    import torch
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
+    L = capi.lib()
+    nb = 100_000
+    hsh = splitmix64(np.arange(nb, dtype=np.uint64) ^ np.uint64(SEED_A))
+    br = (32 + 16 * (hsh % np.uint64(7)).astype(np.int64)).astype(np.int32)
+    bc = (br // 2).astype(np.int32)
+    sizes = br.astype(np.int64) * bc
+    voff = np.concatenate([[0], np.cumsum(sizes)])
+    roff = np.concatenate([[0], np.cumsum(br.astype(np.int64))])
+    coff = np.concatenate([[0], np.cumsum(bc.astype(np.int64))])
+    total, rows, cols = int(voff[-1]), int(roff[-1]), int(coff[-1])
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    A = torch.empty(total, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(A), SEED_A, 0, total, 1, 0, 0.5, 5.0, None))
+    x_true = torch.empty(cols, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(x_true), SEED_A + 1, 0, cols, 1, 0, -1.0, 1.0, None))
+    b_ls = torch.empty(rows, dtype=torch.float64, device="cuda")
+    check(L.qrk_synth_fill(vp(b_ls), SEED_A + 5, 0, rows, 1, 0, -1.0, 1.0, None))
+    torch.cuda.synchronize()
+
+    def per_class():
+        for r in sorted(set(br.tolist())):
+            c = r // 2
+            ids = np.nonzero(br == r)[0]
+            vo = torch.from_numpy(voff[ids]).cuda(); ro = torch.from_numpy(roff[ids]).cuda(); co = torch.from_numpy(coff[ids]).cuda()
+            blocks = A[vo[:, None] + torch.arange(r * c, device="cuda")[None, :]].reshape(len(ids), c, r).transpose(1, 2)   # nblk x r x c
+            yield blocks, ro[:, None] + torch.arange(r, device="cuda")[None, :], co[:, None] + torch.arange(c, device="cuda")[None, :]
+
+    def matvec(x):                                   # A x
+        out = torch.empty(rows, dtype=torch.float64, device="cuda")
+        for blocks, ri, ci in per_class():
+            out[ri] = torch.bmm(blocks, x[ci].unsqueeze(2)).squeeze(2)
+        return out
+
+    def rmatvec(v):                                  # A^T v
+        out = torch.empty(cols, dtype=torch.float64, device="cuda")
+        for blocks, ri, ci in per_class():
+            out[ci] = torch.bmm(blocks.transpose(1, 2), v[ri].unsqueeze(2)).squeeze(2)
+        return out
+
+    d = QrkDesc()
+    d.kind, d.num_blocks, d.pivoting = 0, nb, 0
+    d.rows = br.ctypes.data_as(C.POINTER(C.c_int32)); d.cols = bc.ctypes.data_as(C.POINTER(C.c_int32))
+    h = C.c_void_p()
+    check(L.qrk_create(C.byref(d), C.byref(h)))
+    x = torch.empty(cols, dtype=torch.float64, device="cuda")
+    b = matvec(x_true)
+    torch.cuda.synchronize()
+    check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h)
+    check(L.qrk_synchronize(h), h)
+    assert float(torch.linalg.norm(x - x_true) / torch.linalg.norm(x_true)) <= 1e-9
+    check(L.qrk_compute_solve(h, vp(A), vp(b_ls), vp(x), QRK_DEVICE), h)
+    check(L.qrk_synchronize(h), h)
+    g = rmatvec(matvec(x) - b_ls)
+    assert float(g.abs().max() / rmatvec(b_ls).abs().max()) <= 1e-11
+    L.qrk_destroy(h)
