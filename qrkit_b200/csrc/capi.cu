@@ -584,7 +584,7 @@ int wide_blocked_qr(qrk_solver* h, const DenseBorder& d) {
   cudaEvent_t fork = h->aux_events[2 * P], join = h->aux_events[2 * P + 1];
   QRK_TRY_CUDA(h, cudaEventRecord(fork, main));
   QRK_TRY_CUDA(h, cudaStreamWaitEvent(aux, fork, 0));
-  QRK_TRY_CUDA(h, launch_dense_panel(b, 0, std::min(8, d.M), aux));
+  if (launch_dense_panel(b, 0, std::min(8, d.M), aux) != cudaSuccess) return QRK_STATUS_UNSUPPORTED;   // no room for the cluster: nothing was modified yet
   QRK_TRY_CUDA(h, cudaEventRecord(evP(0), aux));
   h->launches++;
   for (int p = 0; p < P; p++) {
@@ -639,6 +639,12 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
     if (wide_can_block(d)) {
       h->wide_blocked = true;
       st = wide_blocked_qr(h, d);
+      if (st == QRK_STATUS_UNSUPPORTED) {   // the panel cluster could not be launched: the column-by-column path instead
+        h->wide_blocked = false;
+        st = wide_unblocked(h, d);
+        if (st != QRK_STATUS_OK) return st;
+        return wide_back(h, d_b != nullptr, d_x);
+      }
       if (st != QRK_STATUS_OK) return st;
       if (d.pivot) {                      // ColPivHouseholderQR on the triangle: same P2, |R2|, rank and x as on the tall matrix
         dense_extract_tri_kernel<<<148, 256, 0, h->stream>>>(d.A, d.ld, M, M + d.nrhs, h->d_wtri);
@@ -650,8 +656,8 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
           static bool opted[64] = {};
           QRK_TRY_CUDA(h, ensure_smem(dense_tri_colpiv_kernel, kTriMaxDyn, opted));
           dense_tri_colpiv_kernel<<<kDbCluster, kTriThreads, smem, h->stream>>>(t);
-          QRK_TRY_CUDA(h, cudaGetLastError());
-          h->launches++;
+          if (cudaGetLastError() == cudaSuccess) h->launches++;
+          else st = wide_unblocked(h, t);   // an 8-CTA cluster with this much shared memory could not be placed (partitioned / shared GPU)
         } else {
           st = wide_unblocked(h, t);
         }
