@@ -462,6 +462,11 @@ class BandedBlockedSparseQR {
     detail::throw_if(qrk_apply_qt(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ().transpose() * v");
     return y;
   }
+  VectorXd applyQ(const VectorXd& v) const {                                                                  // matrixQ() * v (:640-675) on the thin part:
+    VectorXd y((size_t)m_rows);                                                                              // Q1 * v[0:cols] (the complement is taken as zero)
+    detail::throw_if(qrk_apply_q(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ() * v");
+    return y;
+  }
   VectorXd solve(const VectorXd& B) const {                                                                   // :287-307
     assert(m_isInitialized && "The factorization should be called first, use compute()");
     VectorXd x((size_t)m_cols);

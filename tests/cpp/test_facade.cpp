@@ -143,6 +143,9 @@ int main() {
     bool upper = true;
     for (Index j = 0; j < band.cols(); j++) for (int p = Rb.outer[j]; p < Rb.outer[j + 1]; p++) upper = upper && (Rb.inner[p] <= j || Rb.values[p] == 0.0);
     CHECK(upper, "banded: matrixR() is upper triangular");
+    // matrixQ() * (matrixQ().transpose() * b) on the thin part = A x for a consistent b (Q1 Q1^T projects on range(A))
+    VectorXd qqt = band.applyQ(band.applyQt(bb));
+    CHECK(rel(qqt, bb) <= 1e-11, "banded: matrixQ() * (matrixQ().transpose() * b) = b for b in range(A)  (1e-11)");
   }
   std::printf(failures ? "FAILED (%d)\n" : "All passed.\n", failures);
   return failures ? 1 : 0;
