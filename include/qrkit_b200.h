@@ -72,6 +72,13 @@ typedef enum {
                               rank() = cols (BlockedThinDenseQR.h:132); R2 equals the reference's up to row signs */
 } qrk_right_solver;
 
+/* The left solver of BlockAngularSparseQR (template parameter LeftSolver, BlockAngularSparseQR.h:79). */
+typedef enum {
+  QRK_LEFT_BLOCK_DIAGONAL = 0,   /* BlockDiagonalSparseQR (examples/ellipse_fitting.cpp:36-37; the QRkitBD column of README.md:29) */
+  QRK_LEFT_BANDED_BLOCKED = 1    /* BandedBlockedSparseQR (test/test-qrkit.cpp:44-48; the QRkitBB column): J1 is given as num_blocks
+                                    slabs of block_rows x block_cols with block_overlap, as for kind QRK_BANDED_BLOCKED */
+} qrk_left_solver;
+
 /* MatrixQFormat (BlockDiagonalSparseQR.h:59-62). */
 typedef enum { QRK_FULL_Q = 0, QRK_BLOCK_DIAGONAL_Q = 1 } qrk_qformat;
 
@@ -93,7 +100,8 @@ typedef struct {
   int32_t border_cols;     /* block angular: m2 = columns of the dense right block (BlockAngularSparseQR.h:464); else 0 */
   int32_t block_overlap;   /* banded: column overlap of consecutive blocks (_BlockOverlap, BandedBlockedSparseQR.h:122); else 0 */
   int32_t right_solver;    /* block angular: qrk_right_solver, the RightSolver template argument (BlockAngularSparseQR.h:79) */
-  int32_t reserved[3];
+  int32_t left_solver;     /* block angular: qrk_left_solver, the LeftSolver template argument (BlockAngularSparseQR.h:79) */
+  int32_t reserved[2];
 } qrk_desc_t;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -174,7 +182,11 @@ QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, i
  * qrk_apply_qt / qrk_apply_q / qrk_matrix_q / qrk_packed_factors keep referring to the LEFT factor Q1.
  * Uniform left blocks of 2x1, 3x1, 4x2, 7x2 with 1 <= m2 <= 8 and a ColPiv right solver take the fused in-SM TSQR path
  * (and support the multi-GPU exchange below); every other left block / border width / right solver takes the dense
- * right-block path (blocked compact-WY with DMMA, then ColPiv on the triangle), single GPU. */
+ * right-block path (blocked compact-WY with DMMA, then ColPiv on the triangle), single GPU.
+ * left_solver = QRK_LEFT_BANDED_BLOCKED: J1 is block banded (values = the slabs, as for kind QRK_BANDED_BLOCKED); Q1^T [J2 | b] is
+ * the two-phase banded application INCLUDING its complement (the rows outside range(J1), which the dense right block is
+ * factored on), x1 = R1^-1 (y1 - Atop x2) the banded back substitution.  qrk_apply_qt / qrk_apply_q / qrk_packed_factors then
+ * refer to the banded left factor (thin part).  Dense right-block path, single GPU. */
 /* J2: n x m2 column-major with leading dimension ld (BlockMatrix1x2::rightBlock()).  Host: copied to the
  * device on the handle's stream; device: borrowed until the next compute returns. */
 QRK_API int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace);

@@ -36,7 +36,7 @@ class QrkDesc(C.Structure):
         ("n_rows", C.c_int64), ("n_cols", C.c_int64),
         ("pivoting", C.c_int32), ("q_format", C.c_int32),
         ("border_cols", C.c_int32), ("block_overlap", C.c_int32),
-        ("right_solver", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("right_solver", C.c_int32), ("left_solver", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

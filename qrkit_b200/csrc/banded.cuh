@@ -301,9 +301,9 @@ banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__
 template <int BR, int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
 banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
-                       double* __restrict__ gy, long long nb_total, int last_cols, int group) {
+                       double* __restrict__ gy, long long nb_total, int last_cols, int group, double* __restrict__ comp) {
   using G = BandedCfg<BR, BC, OV>;
-  constexpr int S = G::S;
+  constexpr int S = G::S, M = G::M;
   static_assert(BR <= 32, "one lane per slab row");
   const int lane = threadIdx.x;
   const long long k0 = (long long)blockIdx.x * group;
@@ -342,6 +342,25 @@ banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restri
       if (last ? (r < ncols_w) : (r < S)) {
         const double val = (r < OV) ? cy[r < OV ? r : 0] : __shfl_sync(0xffffffffu, bi, r >= OV ? r - OV : 0);
         if (lane == 0) y[k * S + r] = val;
+      }
+    }
+    // the annihilated rows of the window: the part of Q^T b outside range(A) (only kept when the caller wants the FULL
+    // orthogonal transform, e.g. the border of a block-angular matrix whose left block is banded).  Layout of comp:
+    // [nb_total * (M - BC) window rows | groups * OV bulge rows of the chase | BC - last_cols rows of the last window]
+    if (comp) {
+#pragma unroll
+      for (int r = BC; r < M; r++) {
+        const double val = (r < OV) ? cy[r < OV ? r : 0] : __shfl_sync(0xffffffffu, bi, r >= OV ? r - OV : 0);
+        if (lane == 0) comp[(k0 + k) * (long long)(M - BC) + (r - BC)] = val;
+      }
+      if (ncols_w < BC) {                       // the matrix's last slab is narrower: its rows [last_cols, BC) carry no pivot
+        const long long groups = (nb_total + group - 1) / group;
+        double* tail = comp + nb_total * (long long)(M - BC) + groups * OV;
+#pragma unroll
+        for (int r = 0; r < BC; r++) {
+          const double val = (r < OV) ? cy[r < OV ? r : 0] : __shfl_sync(0xffffffffu, bi, r >= OV ? r - OV : 0);
+          if (lane == 0 && r >= ncols_w) tail[r - ncols_w] = val;
+        }
       }
     }
     if (OV > 0) {
@@ -435,7 +454,7 @@ banded_apply_q_kernel(const double* __restrict__ packed, const double* __restric
 template <int BC, int OV, bool BACKWARD>
 __global__ void __launch_bounds__(32, 1)
 banded_chase_apply_kernel(const double* __restrict__ craw, const double* __restrict__ cs, const double* __restrict__ in,
-                          double* __restrict__ out, long long nb, int last_cols, int group) {
+                          double* __restrict__ out, long long nb, int last_cols, int group, double* __restrict__ ucomp) {
   constexpr int S = BC - OV, NO = OV > 0 ? OV : 1, CH = 32, NST = 4;
   __shared__ __align__(16) double rv[NST][CH * NO];
   __shared__ __align__(16) double rt[NST][2 * CH];     // tau, inv per step
@@ -516,6 +535,12 @@ banded_chase_apply_kernel(const double* __restrict__ craw, const double* __restr
       if (lane == j) keep = p;
       if (!BACKWARD) {
         if (handed) { if (lane == 0) hand[r - GS] = p; }
+        if (r == W_g - 1 && ucomp != nullptr && lane < OV) {   // the annihilated bulge rows of this group (forward only)
+          double mine = 0.0;
+#pragma unroll
+          for (int k = 0; k < OV; k++) if (lane == k) mine = u[k];
+          ucomp[gi * OV + lane] = mine;
+        }
         if (r == W_g - 1 && gi < ngroups - 1) {          // leaving a group: its last OV pivot rows are the next bulge
           __syncwarp();
 #pragma unroll

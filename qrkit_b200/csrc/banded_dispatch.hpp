@@ -21,6 +21,7 @@ struct BandedArgs {
   double* gy = nullptr;       // groups x W: pivot-row values of the right-hand side between the two phases
   double* cvec = nullptr;     // chase reflectors: groups x W x overlap raw tails
   double* ctau = nullptr;     // groups x W x {tau, inv}: v = [1; inv * raw tail]
+  double* comp = nullptr;     // apply_qt only, optional: the complement of Q^T b (banded.cuh, banded_apply_qt_kernel); see banded_comp_rows
 };
 
 struct BandedVTable {
@@ -32,6 +33,8 @@ struct BandedVTable {
 };
 
 const BandedVTable* banded_vtable(int br, int bc, int ov);
-int banded_launches_per_call();   // kernels per factor / apply call (for the launch counter)   // nullptr when the shape is not instantiated
+int banded_launches_per_call();
+// rows of the complement output of apply_qt: nb (OV + BR - BC) window rows + groups * OV chase rows + (BC - last_cols)
+long long banded_comp_rows(long long nb, int br, int bc, int ov, int group, int last_cols);   // kernels per factor / apply call (for the launch counter)   // nullptr when the shape is not instantiated
 
 }  // namespace qrk

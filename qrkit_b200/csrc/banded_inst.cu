@@ -21,15 +21,16 @@ cudaError_t factor_t(const BandedArgs& a, cudaStream_t s) {
 }
 template <int BR, int BC, int OV>
 cudaError_t apply_qt_t(const BandedArgs& a, cudaStream_t s) {
-  banded_apply_qt_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group);
+  banded_apply_qt_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group, a.comp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  banded_chase_apply_kernel<BC, OV, false><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.gy, a.y, a.nb, a.last_cols, a.group);
+  banded_chase_apply_kernel<BC, OV, false><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.gy, a.y, a.nb, a.last_cols, a.group,
+                                                         a.comp ? a.comp + a.nb * (long long)(OV + BR - BC) : nullptr);
   return cudaGetLastError();
 }
 template <int BR, int BC, int OV>
 cudaError_t apply_q_t(const BandedArgs& a, cudaStream_t s) {
-  banded_chase_apply_kernel<BC, OV, true><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.y, a.gy, a.nb, a.last_cols, a.group);
+  banded_chase_apply_kernel<BC, OV, true><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.y, a.gy, a.nb, a.last_cols, a.group, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   banded_apply_q_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.gy, a.x, a.nb, a.last_cols, a.group);
@@ -55,5 +56,10 @@ const BandedVTable* banded_vtable(int br, int bc, int ov) {
 }
 
 int banded_launches_per_call() { return 2; }
+
+long long banded_comp_rows(long long nb, int br, int bc, int ov, int group, int last_cols) {
+  const long long groups = (nb + group - 1) / group;
+  return nb * (long long)(ov + br - bc) + groups * ov + (bc - last_cols);
+}
 
 }  // namespace qrk

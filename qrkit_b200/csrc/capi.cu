@@ -483,11 +483,13 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
 
 // ---- block angular, dense right block in global memory (dense_border.cuh) ------------------------------------------
 int run_op(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X, long long ldx, int nrhs);
+BandedArgs banded_args(qrk_solver* h);
+int banded_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x);
 
 DenseBorder wide_desc(qrk_solver* h, int nrhs) {
   DenseBorder d;
-  d.A = h->d_wx + h->sum_cols;            // rows [m1, n) of Q1^T [J2 | b]
-  d.ld = h->n_rows; d.N = h->n_rows - h->sum_cols; d.Nrule = d.N; d.M = h->m2; d.nrhs = nrhs;
+  d.A = h->d_wx + h->sum_cols;            // the complement rows of Q1^T [J2 | b] (rows [m1, n) for a block-diagonal left block)
+  d.ld = h->w_ld; d.N = h->w_N; d.Nrule = h->n_rows - h->sum_cols; d.M = h->m2; d.nrhs = nrhs;
   d.pivot = h->desc.right_solver == QRK_RIGHT_UNPIVOTED ? 0 : 1;
   d.upd = h->d_wupd; d.dir = h->d_wdir; d.tau = h->d_wtau2; d.perm = h->d_wperm; d.scal = h->d_wscal; d.iscal = h->d_wiscal;
   return d;
@@ -505,7 +507,7 @@ DenseBorder wide_tri_desc(qrk_solver* h, int nrhs) {
 int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
   const bool two_stage = h->wide_blocked && h->desc.right_solver != QRK_RIGHT_UNPIVOTED;
   const DenseBorder d = two_stage ? wide_tri_desc(h, have_rhs ? 1 : 0) : wide_desc(h, have_rhs ? 1 : 0);
-  const long long n = h->n_rows, m1 = h->sum_cols;
+  const long long n = h->w_ld, m1 = h->sum_cols;
   const int M = h->m2;
   double* rhs_col = h->d_wx + (long long)M * n;
   const double* z = two_stage ? h->d_wtri + (size_t)M * M : rhs_col + m1;
@@ -518,10 +520,16 @@ int wide_back(qrk_solver* h, bool have_rhs, double* d_x) {
     dense_top_kernel<<<(unsigned)((m1 + 255) / 256), 256, (size_t)M * sizeof(double), h->stream>>>(h->d_wx, n, m1, M, h->d_root + (size_t)M * M + 2 * M,
                                                                                          rhs_col);
     QRK_TRY_CUDA(h, cudaGetLastError());
-    const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
-    bd_rsolve_kernel<4><<<(unsigned)((h->nb + 3) / 4), 128, (size_t)4 * h->max_c * sizeof(double), h->stream>>>(
-        block_index(h), h->nb, h->d_values, piv ? h->d_perm : nullptr, rhs_col, d_x, h->max_c);
-    QRK_TRY_CUDA(h, cudaGetLastError());
+    if (h->left_banded) {                 // x1 = R1^-1 ytop with the band R1 (BandedBlockedSparseQR.h:299-304)
+      BandedArgs a = banded_args(h);
+      a.y = rhs_col; a.x = d_x;
+      QRK_TRY_CUDA(h, h->bvt->backsolve(a, h->stream));
+    } else {
+      const bool piv = h->desc.pivoting == QRK_PIVOT_COLPIV;
+      bd_rsolve_kernel<4><<<(unsigned)((h->nb + 3) / 4), 128, (size_t)4 * h->max_c * sizeof(double), h->stream>>>(
+          block_index(h), h->nb, h->d_values, piv ? h->d_perm : nullptr, rhs_col, d_x, h->max_c);
+      QRK_TRY_CUDA(h, cudaGetLastError());
+    }
     h->launches += 2;
   }
   return QRK_STATUS_OK;
@@ -622,16 +630,44 @@ bool wide_can_block(const DenseBorder& d) {
   return !off && d.N >= d.M && d.N <= 4LL * kDbCluster * kDbThreads && d.M >= 16;
 }
 
+// Q1^T of a banded left block applied to ncols columns, INCLUDING the complement: column j of `src` (n_rows values, leading
+// dimension lds) -> column j of d_wx: thin part in rows [0, m1), complement in rows [m1, m1 + w_N)
+int banded_left_apply_qt(qrk_solver* h, const double* src, long long lds, double* dst, int ncols) {
+  for (int j = 0; j < ncols; j++) {
+    BandedArgs a = banded_args(h);
+    a.b = src + (long long)j * lds;
+    a.y = dst + (long long)j * h->w_ld;
+    a.comp = a.y + h->sum_cols;
+    QRK_TRY_CUDA(h, h->bvt->apply_qt(a, h->stream));
+    h->launches += banded_launches_per_call();
+  }
+  return QRK_STATUS_OK;
+}
+
 int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
-  const long long n = h->n_rows;
+  const long long n = h->w_ld;
   const int M = h->m2;
-  int st = run_factor(h, A_in, nullptr, nullptr);                       // m_leftSolver.compute (BlockAngularSparseQR.h:472)
-  if (st != QRK_STATUS_OK) return st;
-  st = run_op(h, OP_APPLY_QT, h->d_border, h->ld_border, h->d_wx, n, M);   // Q1^T J2 (:365)
-  if (st != QRK_STATUS_OK) return st;
-  if (d_b) {
-    st = run_op(h, OP_APPLY_QT, d_b, n, h->d_wx + (long long)M * n, n, 1);
+  int st;
+  if (h->left_banded) {
+    st = banded_run(h, A_in, nullptr, nullptr);                         // m_leftSolver.compute (BlockAngularSparseQR.h:472), left = BandedBlockedSparseQR
     if (st != QRK_STATUS_OK) return st;
+    if (h->w_ld > h->sum_cols + h->w_N)                                 // the padding row of the leading dimension
+      QRK_TRY_CUDA(h, cudaMemsetAsync(h->d_wx, 0, (size_t)h->w_ld * (M + 1) * sizeof(double), h->stream));
+    st = banded_left_apply_qt(h, h->d_border, h->ld_border, h->d_wx, M);   // Q1^T J2 (:365)
+    if (st != QRK_STATUS_OK) return st;
+    if (d_b) {
+      st = banded_left_apply_qt(h, d_b, h->n_rows, h->d_wx + (long long)M * n, 1);
+      if (st != QRK_STATUS_OK) return st;
+    }
+  } else {
+    st = run_factor(h, A_in, nullptr, nullptr);                         // m_leftSolver.compute (BlockAngularSparseQR.h:472)
+    if (st != QRK_STATUS_OK) return st;
+    st = run_op(h, OP_APPLY_QT, h->d_border, h->ld_border, h->d_wx, n, M);   // Q1^T J2 (:365)
+    if (st != QRK_STATUS_OK) return st;
+    if (d_b) {
+      st = run_op(h, OP_APPLY_QT, d_b, n, h->d_wx + (long long)M * n, n, 1);
+      if (st != QRK_STATUS_OK) return st;
+    }
   }
   const DenseBorder d = wide_desc(h, d_b ? 1 : 0);
   h->wide_blocked = false;
@@ -674,10 +710,10 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
 }
 
 int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
-  const long long n = h->n_rows;
+  const long long n = h->w_ld;
   const int M = h->m2;
   double* rhs_col = h->d_wx + (long long)M * n;
-  int st = run_op(h, OP_APPLY_QT, d_b, n, rhs_col, n, 1);
+  int st = h->left_banded ? banded_left_apply_qt(h, d_b, h->n_rows, rhs_col, 1) : run_op(h, OP_APPLY_QT, d_b, n, rhs_col, n, 1);
   if (st != QRK_STATUS_OK) return st;
   DenseBorder d = wide_desc(h, 1);
   if (d.N > 0) {
@@ -729,7 +765,7 @@ int angular_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
 BandedArgs banded_args(qrk_solver* h) {
   BandedArgs a;
   a.nb = h->nb; a.packed = h->d_values; a.tau = h->d_btau; a.rband = h->d_rband; a.y = h->d_ythin;
-  a.last_cols = (int)(h->n_cols - (h->nb - 1) * (long long)h->b_step);
+  a.last_cols = (int)(h->sum_cols - (h->nb - 1) * (long long)h->b_step);   // sum_cols = the banded columns (n_cols includes a border)
   a.group = h->b_group; a.gband = h->d_gband; a.gy = h->d_gy; a.cvec = h->d_cvec; a.ctau = h->d_ctau;
   return a;
 }
@@ -765,7 +801,7 @@ __global__ void export_banded_r_kernel(const double* __restrict__ rband, const i
 }
 
 std::vector<int> banded_r_outer(const qrk_solver* h) {
-  const long long n = h->n_cols, S = h->b_step, BC = h->uc, nb = h->nb;
+  const long long n = h->sum_cols, S = h->b_step, BC = h->uc, nb = h->nb;   // the banded columns (a border adds its own)
   std::vector<int> outer(n + 1, 0);
   long long acc = 0;
   for (long long j = 0; j < n; j++) {
@@ -814,8 +850,9 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   if (!desc || !out) return QRK_STATUS_INVALID_ARGUMENT;
   *out = nullptr;
   if (desc->kind != QRK_BLOCK_DIAGONAL && desc->kind != QRK_BLOCK_ANGULAR && desc->kind != QRK_BANDED_BLOCKED) return QRK_STATUS_UNSUPPORTED;
-  const bool banded = desc->kind == QRK_BANDED_BLOCKED;
   const bool angular = desc->kind == QRK_BLOCK_ANGULAR;
+  const bool left_banded = angular && desc->left_solver == QRK_LEFT_BANDED_BLOCKED;
+  const bool banded = desc->kind == QRK_BANDED_BLOCKED || left_banded;   // the slab layout / banded kernels of J (or J1)
   if (desc->num_blocks < 0) return QRK_STATUS_INVALID_ARGUMENT;
   const bool uniform = desc->block_rows > 0 && desc->block_cols > 0;
   if (!uniform && desc->num_blocks > 0 && (!desc->rows || !desc->cols)) return QRK_STATUS_INVALID_ARGUMENT;
@@ -871,7 +908,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     // n_cols defaults to the full width of the last slab; a narrower last slab (the reference's pattern gives the last
     // block block_cols - overlap columns, SparseQRUtils.h:284) is selected by passing n_cols explicitly
     const long long full = (h->nb - 1) * (long long)h->b_step + h->uc;
-    h->n_cols = desc->n_cols > 0 ? desc->n_cols : full;
+    h->n_cols = desc->n_cols > 0 ? desc->n_cols - (left_banded ? desc->border_cols : 0) : full;   // block angular: desc->n_cols = m1 + m2
     if (h->n_cols > full || h->n_cols <= (h->nb - 1) * (long long)h->b_step) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->sum_cols = h->n_cols;
     if (h->n_rows < h->n_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
@@ -884,12 +921,14 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     h->avt = angular_vtable(h->m2);
     if (desc->q_format != QRK_FULL_Q || h->m2 < 1 || h->m2 > 4096) return fail(QRK_STATUS_UNSUPPORTED);
     if (desc->right_solver != QRK_RIGHT_COLPIV && desc->right_solver != QRK_RIGHT_UNPIVOTED) return fail(QRK_STATUS_INVALID_ARGUMENT);
-    if (!uniform || !h->avt || !h->avt->shape_ok(h->ur, h->uc) || desc->right_solver == QRK_RIGHT_UNPIVOTED) {   // dense_border.cuh
+    h->left_banded = left_banded;
+    if (!uniform || !h->avt || left_banded || !h->avt->shape_ok(h->ur, h->uc) || desc->right_solver == QRK_RIGHT_UNPIVOTED) {   // dense_border.cuh
       h->avt = nullptr;
       h->wide = true;
     }
     if (h->n_rows != h->sum_rows || (desc->n_cols > 0 && desc->n_cols != h->sum_cols + h->m2)) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->n_cols = h->sum_cols + h->m2;     // cols() = m1 + m2
+    h->w_ld = h->n_rows; h->w_N = h->n_rows - h->sum_cols;
   }
   if (h->n_rows < h->sum_rows || h->n_cols < h->sum_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
   if (h->n_rows > INT32_MAX || h->n_cols > INT32_MAX) return fail(QRK_STATUS_UNSUPPORTED);  // StorageIndex = int
@@ -965,9 +1004,14 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     if (const char* env = std::getenv("QRK_BANDED_GROUP")) h->b_group = std::max(1, std::atoi(env));
     const size_t groups = (size_t)((h->nb + h->b_group - 1) / h->b_group);
     const size_t gw = groups * ((size_t)(h->b_group - 1) * h->b_step + h->uc);
-    if (cudaMalloc(&h->d_rband, (size_t)h->n_cols * h->uc * sizeof(double)) != cudaSuccess ||
+    if (left_banded) {
+      const int last_cols = (int)(h->sum_cols - (h->nb - 1) * (long long)h->b_step);
+      h->w_N = banded_comp_rows(h->nb, h->ur, h->uc, h->b_ov, h->b_group, last_cols);
+      h->w_ld = (h->sum_cols + h->w_N + 1) & ~1LL;
+    }
+    if (cudaMalloc(&h->d_rband, (size_t)h->sum_cols * h->uc * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_btau, (size_t)h->nb * h->uc * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_ythin, (size_t)h->n_cols * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_ythin, (size_t)h->sum_cols * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_gband, gw * h->uc * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_gy, gw * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_cvec, std::max<size_t>(1, gw * h->b_ov) * sizeof(double)) != cudaSuccess ||
@@ -976,7 +1020,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   }
   if (angular && h->wide) {
     const size_t M = (size_t)h->m2;
-    if (cudaMalloc(&h->d_wx, std::max<size_t>(1, (size_t)h->n_rows * (M + 1)) * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc(&h->d_wx, std::max<size_t>(1, (size_t)h->w_ld * (M + 1)) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wupd, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wdir, M * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wtau2, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wscal, 2 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, sizeof(int)) != cudaSuccess ||
@@ -1082,8 +1126,8 @@ int qrk_factorize(qrk_handle_t h) {
   if (!h->analyzed) qrk_analyze_pattern(h, nullptr);
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;   // reported through info(), as the reference
   DeviceGuard g(h->device);
-  int st = h->bvt ? banded_run(h, h->d_values, nullptr, nullptr)
-                  : (ang(h) ? angular_run(h, h->d_values, nullptr, nullptr, true) : run_factor(h, h->d_values, nullptr, nullptr));
+  int st = ang(h) ? angular_run(h, h->d_values, nullptr, nullptr, true)
+                  : (h->bvt ? banded_run(h, h->d_values, nullptr, nullptr) : run_factor(h, h->d_values, nullptr, nullptr));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -1103,7 +1147,7 @@ static int compute_from_device(qrk_solver* h, const double* values, const double
   if (h->info == QRK_INFO_INVALID_INPUT) return QRK_STATUS_OK;
   if (d_x && h->n_cols > h->sum_cols && !ang(h))
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  st = h->bvt ? banded_run(h, values, d_b, d_x) : (ang(h) ? angular_run(h, values, d_b, d_x, d_b == nullptr) : run_factor(h, values, d_b, d_x));
+  st = ang(h) ? angular_run(h, values, d_b, d_x, d_b == nullptr) : (h->bvt ? banded_run(h, values, d_b, d_x) : run_factor(h, values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   return QRK_STATUS_OK;
@@ -1140,7 +1184,7 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   }
   if (h->n_cols > h->sum_cols && !ang(h))
     QRK_TRY_CUDA(h, cudaMemsetAsync(d_x + h->sum_cols, 0, (h->n_cols - h->sum_cols) * sizeof(double), h->stream));
-  int st = h->bvt ? banded_run(h, h->d_values, d_b, d_x) : (ang(h) ? angular_run(h, h->d_values, d_b, d_x, false) : run_factor(h, h->d_values, d_b, d_x));
+  int st = ang(h) ? angular_run(h, h->d_values, d_b, d_x, false) : (h->bvt ? banded_run(h, h->d_values, d_b, d_x) : run_factor(h, h->d_values, d_b, d_x));
   if (st != QRK_STATUS_OK) return st;
   h->factorized = true;
   if (h->pending) {            // multi-GPU block angular: x is produced by qrk_angular_merge
@@ -1283,7 +1327,7 @@ int qrk_matrix_r_nnz(qrk_handle_t h, int64_t* nnz) {
   if (h->uniform) n = h->nb * ((long long)h->uc * (h->uc + 1) / 2);
   else for (long long i = 0; i < h->nb; i++) n += (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
   if (ang(h)) n += h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2;   // border columns (makeR :296-305)
-  if (h->bvt) n = banded_r_outer(h).back();
+  if (h->bvt) n = banded_r_outer(h).back() + (ang(h) ? h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2 : 0);
   *nnz = n;
   return QRK_STATUS_OK;
 }
@@ -1340,8 +1384,14 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
     else {
       const std::vector<int> ho = banded_r_outer(h);
       cudaMemcpyAsync(d_outer, ho.data(), ho.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-      export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->n_cols, h->nb, h->uc, h->b_step);
+      export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->sum_cols, h->nb, h->uc, h->b_step);
       e = cudaGetLastError();
+      if (ang(h) && e == cudaSuccess) {     // R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:285-308) with a banded R1
+        export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->d_wx, h->w_ld, h->d_root, h->d_root_i, h->sum_cols, h->m2, (long long)ho.back(),
+                                                                 d_outer, d_inner, d_vals);
+        e = cudaGetLastError();
+        h->launches++;
+      }
       cudaStreamSynchronize(h->stream);     // ho must outlive the copy
     }
   } else if (want_q) e = launch_export_q(bi, d_eoff, h->nb, h->d_values, h->d_tau, h->n_rows, ang(h) ? h->sum_cols : h->n_cols, h->sum_rows,
@@ -1349,7 +1399,7 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
   else if (ang(h)) {
     const long long nnz_r1 = nnz - (h->sum_cols * (long long)h->m2 + (long long)h->m2 * (h->m2 + 1) / 2);
     e = launch_export_r(bi, d_eoff, h->nb, h->d_values, h->sum_cols, h->sum_cols, nnz_r1, 1, d_outer, d_inner, d_vals, h->stream);
-    export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->wide ? h->d_wx : h->d_atop, h->wide ? h->n_rows : h->sum_cols, h->d_root,
+    export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->wide ? h->d_wx : h->d_atop, h->wide ? h->w_ld : h->sum_cols, h->d_root,
                                                              h->d_root_i, h->sum_cols, h->m2, nnz_r1, d_outer,
                                                              d_inner, d_vals);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1408,7 +1458,7 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     h->launches++;
   }
   int st = QRK_STATUS_OK;
-  if (h->bvt) {
+  if (h->bvt && !(ang(h) && op == OP_SOLVE)) {
     // Q^T b by the window sweep over the stored reflectors (BandedBlockedSparseQR.h:655-670 applies the YTY blocks in
     // the same order), then the banded back substitution (:299-304).  Q^T b: thin part [0, n_cols), zeros after it.
     // matrixQ() * v: Q1 * v[0:n_cols] (zero complement), the reflectors in reverse order.
@@ -1425,7 +1475,7 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
         if (op == OP_APPLY_QT) {
           a.y = d_X + j * dldx;      // thin part; the window sweep works on [0 (overlap rows); A], whose annihilated-row
                                      // components do not map one-to-one onto the n_rows - n_cols complement: left zero
-          if (h->n_rows > h->n_cols) cudaMemsetAsync(d_X + j * dldx + h->n_cols, 0, (h->n_rows - h->n_cols) * sizeof(double), h->stream);
+          if (h->n_rows > h->sum_cols) cudaMemsetAsync(d_X + j * dldx + h->sum_cols, 0, (h->n_rows - h->sum_cols) * sizeof(double), h->stream);
         }
         e = h->bvt->apply_qt(a, h->stream);
         h->launches += banded_launches_per_call();

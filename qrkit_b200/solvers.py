@@ -239,6 +239,23 @@ class BlockDiagonalSparseQR:
         return v.value
 
 
+class BandedSlabs:
+    """A block-banded left block as the device path takes it: num_blocks dense slabs of block_rows x block_cols (column-major,
+    back to back), slab k at rows [k*block_rows, ...), columns [k*(block_cols-overlap), ...) — the matrix of
+    fromBlockBandedPattern (SparseQRUtils.h:274-302).  n_cols: columns of the matrix when it ends inside the last slab."""
+
+    def __init__(self, values, *, num_blocks, block_rows, block_cols, overlap, n_cols=0):
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        self.num_blocks, self.block_rows, self.block_cols, self.overlap = num_blocks, block_rows, block_cols, overlap
+        self.n_cols = n_cols or (num_blocks - 1) * (block_cols - overlap) + block_cols
+
+    def rows(self):
+        return self.num_blocks * self.block_rows
+
+    def cols(self):
+        return self.n_cols
+
+
 class BlockMatrix1x2:
     """BlockMatrix1x2<Left, Right> (BlockMatrix1x2.h:31-67): references to a left block-diagonal matrix and a
     dense right block (n x m2, column-major) with the same number of rows."""
@@ -276,7 +293,9 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
 
     def _ensure_handle_angular(self, mat: BlockMatrix1x2):
         left, m2 = mat.left, mat.right.shape[1]
-        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2, self._right_solver)
+        banded = isinstance(left, BandedSlabs)      # LeftSolver = BandedBlockedSparseQR (test/test-qrkit.cpp:44-48)
+        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2, self._right_solver,
+               (left.overlap, left.n_cols) if banded else None)
         if self._h and key == self._shape_key:
             return
         self.close()
@@ -285,6 +304,8 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
         d.block_rows, d.block_cols = left.block_rows, left.block_cols
         d.pivoting, d.q_format, d.border_cols = self._pivoting, QRK_FULL_Q, m2
         d.right_solver = self._right_solver
+        if banded:
+            d.left_solver, d.block_overlap, d.n_cols, d.pivoting = 1, left.overlap, left.n_cols + m2, QRK_PIVOT_NONE
         h = C.c_void_p()
         check(lib().qrk_create(C.byref(d), C.byref(h)))
         self._h, self._shape_key = h, key

@@ -144,3 +144,14 @@ def reference_style_windows(nb, br, bc, ov, suggested=2):
         else:
             out.append([first * br, first * s, rows, cols])
     return np.array(out, dtype=np.int32)
+
+
+def slabs_to_sparse(slabs, nb, br, bc, ov):
+    """The block-banded matrix of fromBlockBandedPattern (SparseQRUtils.h:274-302) from its dense slabs (column-major,
+    back to back): slab k at rows [k*br, ...), columns [k*(bc-ov), ...)."""
+    s = bc - ov
+    S = np.asarray(slabs).reshape(nb, bc, br)
+    jj, ii = np.meshgrid(np.arange(bc), np.arange(br), indexing="ij")
+    rows = (np.arange(nb)[:, None, None] * br + ii[None]).reshape(-1)
+    cols = (np.arange(nb)[:, None, None] * s + jj[None]).reshape(-1)
+    return sp.csc_matrix((S.reshape(-1), (rows, cols)), shape=(nb * br, (nb - 1) * s + bc))

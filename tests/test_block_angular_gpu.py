@@ -109,6 +109,46 @@ def test_multi_gpu_exchange_on_one_device(qk, oracle):
         assert np.array_equal(x2s[g], x2s[0]), "the redundantly computed shared parameters must be bit-identical on every rank"
 
 
+@pytest.mark.parametrize("br,bc,ov,nb,m2", [(7, 4, 2, 60, 5), (7, 2, 0, 40, 9), (16, 24, 16, 30, 24), (12, 8, 4, 50, 3), (16, 24, 16, 70, 40)])
+@pytest.mark.parametrize("right", [0, 1])
+def test_banded_left_block_vs_lapack(qk, br, bc, ov, nb, m2, right):
+    """BlockAngularSparseQR<BandedBlockedSparseQR, RightSolver> — the solver combination of the reference's own block-angular
+    tests (test/test-qrkit.cpp:44-57) and of the QRkitBB benchmark column: J1 block banded, dense border.  Checked against
+    LAPACK on the assembled matrix: x (lstsq), (AP)^T AP = R^T R, P2 = dgeqp3's permutation of the residual rows
+    (Q1 complete from numpy), rank, and the left factor's Q^T through R1^T (Q1^T b) = J1^T b."""
+    import scipy.linalg as sla
+    from helpers import slabs_to_sparse
+    slabs = uniform_blocks(nb, br, bc)
+    A1 = slabs_to_sparse(slabs, nb, br, bc, ov).toarray()
+    n, m1 = A1.shape
+    J2 = dense_border(n, m2)
+    b = vector(n, seed=5)
+    A = np.hstack([A1, J2])
+    x_ls = np.linalg.lstsq(A, b, rcond=None)[0]
+    mat = qk.BlockMatrix1x2(qk.BandedSlabs(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov), J2)
+    s = qk.BlockAngularSparseQR(mat, right_solver=right)
+    assert s.rows() == n and s.cols() == m1 + m2 and s.rank() == m1 + m2 and s.info() == qk.QRK_INFO_SUCCESS
+    P = s.colsPermutation()
+    assert np.array_equal(P[:m1], np.arange(m1))
+    if right == 0:
+        Q1 = np.linalg.qr(A1, mode="complete")[0]
+        Abot = (Q1.T @ J2)[m1:, :]
+        assert np.array_equal(P[m1:] - m1, sla.qr(Abot, mode="r", pivoting=True)[1])
+    else:
+        assert np.array_equal(P[m1:], m1 + np.arange(m2))
+    R = s.matrixR().toarray()[:m1 + m2, :]
+    assert np.allclose(np.tril(R, -1), 0.0)
+    AP = A[:, P]
+    assert rel(R.T @ R, AP.T @ AP) <= 1e-12
+    assert rel(s.solve(b), x_ls) <= 1e-10
+    x_true = vector(m1 + m2, seed=77)
+    assert rel(s.solve(A @ x_true), x_true) <= 1e-10
+    s2 = qk.BlockAngularSparseQR(right_solver=right)
+    assert rel(s2.compute_solve(mat, b), x_ls) <= 1e-10
+    y = s.applyQt(b)                                            # the left factor's Q^T, thin part
+    assert rel(R[:m1, :m1].T @ y[:m1], A1.T @ b) <= 1e-11
+
+
 def test_device_side_ellipse_assembly_and_gauss_newton(qk):
     """qrk_ellipse_assemble writes the functor's Jacobian (bench/bench_sparse_qr_extra.cpp:79-114) straight into
     the device buffers of the block-angular solver; a Gauss-Newton loop that never leaves the device recovers the ellipse."""

@@ -18,3 +18,35 @@ s = qk.BlockAngularSparseQR(mat, pivoting=1)
 print("wide", float(np.abs(s.solve(b)).max()), s.rank())
 slabs = uniform_blocks(6, 16, 24)
 print("banded", float(np.abs(qk.BandedBlockedSparseQR(block_rows=16, block_cols=24, overlap=16).compute_solve(slabs, vector(96, seed=3), 6)).max()))
+# two-phase banded path: several groups (QRK_BANDED_GROUP), Q^T b and Q v on the stored factors
+os.environ["QRK_BANDED_GROUP"] = "3"
+for (br, bc, ov, nbk) in [(16, 24, 16, 11), (7, 4, 2, 9), (7, 2, 0, 5), (12, 8, 4, 10)]:
+    slabs = uniform_blocks(nbk, br, bc)
+    n_rows, n_cols = nbk * br, (nbk - 1) * (bc - ov) + bc
+    s = qk.BandedBlockedSparseQR(slabs, num_blocks=nbk, block_rows=br, block_cols=bc, overlap=ov)
+    bvec = vector(n_rows, seed=3)
+    y = s.applyQt(bvec)
+    print("banded2", br, bc, ov, float(np.abs(s.solve(bvec)).max()), float(np.abs(s.applyQ(y)).max()), s.matrixR().toarray().shape)
+del os.environ["QRK_BANDED_GROUP"]
+# dense border: blocked compact-WY first stage (cluster panel + DMMA update) and the cluster-resident ColPiv second stage,
+# ragged last panel (m2 = 21), unpivoted right solver, solve on the stored factors
+for (nb, r, c, m2, right) in [(30, 7, 2, 21, 0), (30, 7, 2, 24, 1), (120, 7, 2, 40, 0)]:
+    vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); b = vector(nb * r, seed=5)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    s = qk.BlockAngularSparseQR(mat, pivoting=1, right_solver=right)
+    print("wide blocked", m2, right, float(np.abs(s.solve(b)).max()), s.rank(),
+          float(np.abs(qk.BlockAngularSparseQR(pivoting=1, right_solver=right).compute_solve(mat, b)).max()))
+# device-side ellipse assembly
+import ctypes as C
+import torch
+from qrkit_b200 import capi
+L = capi.lib()
+n = 1000
+px = torch.empty(n, dtype=torch.float64, device="cuda"); py = torch.empty_like(px)
+capi.check(L.qrk_ellipse_points(px.data_ptr(), py.data_ptr(), n, 7.5, 2.0, 17.0, 23.0, 0.23, None))
+params = torch.cat([torch.arange(n, dtype=torch.float64, device="cuda") * (1.3 * np.pi / n), torch.tensor([7.0, 2.5, 17.0, 23.0, 0.0], dtype=torch.float64, device="cuda")])
+J1 = torch.empty(2 * n, dtype=torch.float64, device="cuda"); J2d = torch.empty(10 * n, dtype=torch.float64, device="cuda")
+rhs = torch.empty(2 * n, dtype=torch.float64, device="cuda"); cost = torch.zeros(1, dtype=torch.float64, device="cuda")
+capi.check(L.qrk_ellipse_assemble(px.data_ptr(), py.data_ptr(), params.data_ptr(), n, J1.data_ptr(), J2d.data_ptr(), rhs.data_ptr(), cost.data_ptr(), None))
+torch.cuda.synchronize()
+print("ellipse", float(cost.item()))
