@@ -301,11 +301,15 @@ banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__
 template <int BR, int BC, int OV>
 __global__ void __launch_bounds__(32, 1)
 banded_apply_qt_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
-                       double* __restrict__ gy, long long nb_total, int last_cols, int group, double* __restrict__ comp) {
+                       double* __restrict__ gy, long long nb_total, int last_cols, int group, double* __restrict__ comp,
+                       long long ldb, long long ldgy, long long ldcomp) {
   using G = BandedCfg<BR, BC, OV>;
   constexpr int S = G::S, M = G::M;
   static_assert(BR <= 32, "one lane per slab row");
   const int lane = threadIdx.x;
+  // several right-hand sides: blockIdx.y selects the column (leading dimensions ldb / ldgy / ldcomp)
+  b += (long long)blockIdx.y * ldb; gy += (long long)blockIdx.y * ldgy;
+  if (comp) comp += (long long)blockIdx.y * ldcomp;
   const long long k0 = (long long)blockIdx.x * group;
   const long long nb = (nb_total - k0 < group) ? (nb_total - k0) : group;
   const long long W = (long long)(group - 1) * S + BC;
@@ -566,6 +570,103 @@ banded_chase_apply_kernel(const double* __restrict__ craw, const double* __restr
       const bool handed = (gi < ngroups - 1) && (r >= GS);
       if (BACKWARD) out[q] = keep;
       else if (!handed) out[gi * GS + r] = keep;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward chase application on SEVERAL vectors at once (the border columns of a block-angular matrix whose left block is
+// banded): lane l of CTA c owns column 32 c + l — its OV bulge entries in registers, its hand-over slots in shared
+// memory — and all lanes share the reflector stream.  The steps are independent across the columns, so the sequential
+// sweep over the n_cols + groups OV steps is paid once per 32 columns.
+//   in : gy of column j at in + j ldin;  out: thin part at out + j ldout, bulge complement at ucomp + j lducomp
+// ---------------------------------------------------------------------------------------------
+template <int BC, int OV>
+__global__ void __launch_bounds__(32, 1)
+banded_chase_apply_multi_kernel(const double* __restrict__ craw, const double* __restrict__ cs, const double* __restrict__ in,
+                                long long ldin, double* __restrict__ out, long long ldout, double* __restrict__ ucomp,
+                                long long lducomp, int ncols, long long nb, int last_cols, int group) {
+  constexpr int S = BC - OV, NO = OV > 0 ? OV : 1, CH = 32, NST = 4;
+  __shared__ __align__(16) double rv[NST][CH * NO];
+  __shared__ __align__(16) double rt[NST][2 * CH];
+  __shared__ double hand[NO][33];
+  const int lane = threadIdx.x;
+  const int col = (int)blockIdx.x * 32 + lane;
+  const bool active = col < ncols;
+  const double* my_in = in + (long long)(active ? col : 0) * ldin;
+  double* my_out = out + (long long)(active ? col : 0) * ldout;
+  double* my_ucomp = ucomp ? ucomp + (long long)(active ? col : 0) * lducomp : nullptr;
+  const long long W = (long long)(group - 1) * S + BC;
+  const long long ngroups = (nb + group - 1) / group;
+  const long long n_last = nb - (ngroups - 1) * group;
+  const long long W_last = (n_last - 1) * S + last_cols;
+  const long long Q = (ngroups - 1) * W + W_last;
+  const long long nchunks = (Q + CH - 1) / CH;
+  const long long GS = (long long)group * S;
+
+  auto prefetch = [&](long long i) {
+    if (i < nchunks) {
+      const int st = (int)(i % NST);
+      const long long q0 = i * CH;
+      const int valid = (int)((Q - q0 < CH) ? (Q - q0) : CH);
+      if (OV > 0) {
+        const double* src = craw + q0 * OV;
+        for (int j = lane; j < valid * OV / 2; j += 32) cp_async16(&rv[st][2 * j], src + 2 * j);
+        if ((valid * OV) & 1) { if (lane == 0) cp_async8(&rv[st][valid * OV - 1], src + valid * OV - 1); }
+      }
+      if (lane < valid) cp_async16(&rt[st][2 * lane], cs + 2 * (q0 + lane));
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < NST - 1; i++) prefetch(i);
+
+  double u[NO];
+#pragma unroll
+  for (int i = 0; i < NO; i++) u[i] = 0.0;
+  long long gi = 0, r = 0;
+  for (long long i = 0; i < nchunks; i++) {
+    prefetch(i + NST - 1);
+    cp_async_wait<NST - 1>();
+    __syncwarp();
+    const int st = (int)(i % NST);
+    const long long q0 = i * CH;
+    const int valid = (int)((Q - q0 < CH) ? (Q - q0) : CH);
+    double pin[CH];                                     // this column's pivot-row values of the chunk (independent loads)
+#pragma unroll
+    for (int j = 0; j < CH; j++) pin[j] = (active && j < valid) ? my_in[q0 + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      if (j < valid) {                                  // uniform
+        const long long W_g = (gi == ngroups - 1) ? W_last : W;
+        const bool handed = (gi < ngroups - 1) && (r >= GS);
+        const double* v = &rv[st][j * NO];
+        double dq[4] = {0.0, 0.0, 0.0, 0.0};
+        double vr[NO];
+#pragma unroll
+        for (int k = 0; k < OV; k++) { vr[k] = v[k]; dq[k & 3] = fma(vr[k], u[k], dq[k & 3]); }
+        const double inv = rt[st][2 * j + 1];
+        double p = pin[j];
+        const double w = rt[st][2 * j] * fma(inv, (dq[0] + dq[1]) + (dq[2] + dq[3]), p);
+        const double wz = w * inv;
+        p -= w;
+#pragma unroll
+        for (int k = 0; k < OV; k++) u[k] = fma(-wz, vr[k], u[k]);
+        if (handed) hand[r - GS][lane] = p;             // own slot: no cross-lane traffic
+        else if (active) my_out[gi * GS + r] = p;
+        if (r == W_g - 1) {                              // end of the group: annihilated bulge out, handed rows in
+          if (my_ucomp && active) {
+#pragma unroll
+            for (int k = 0; k < OV; k++) my_ucomp[gi * OV + k] = u[k];
+          }
+          if (gi < ngroups - 1) {
+#pragma unroll
+            for (int k = 0; k < OV; k++) u[k] = hand[k][lane];
+          }
+        }
+        if (++r == W_g) { gi++; r = 0; }
+      }
     }
     __syncwarp();
   }

@@ -22,6 +22,9 @@ struct BandedArgs {
   double* cvec = nullptr;     // chase reflectors: groups x W x overlap raw tails
   double* ctau = nullptr;     // groups x W x {tau, inv}: v = [1; inv * raw tail]
   double* comp = nullptr;     // apply_qt only, optional: the complement of Q^T b (banded.cuh, banded_apply_qt_kernel); see banded_comp_rows
+  // apply_qt on several columns at once (ncols > 1): leading dimensions of b, y (thin part) and comp; gy must hold ncols * groups * W
+  int ncols = 1;
+  long long ldb = 0, ldy = 0, ldcomp = 0;
 };
 
 struct BandedVTable {

@@ -21,11 +21,18 @@ cudaError_t factor_t(const BandedArgs& a, cudaStream_t s) {
 }
 template <int BR, int BC, int OV>
 cudaError_t apply_qt_t(const BandedArgs& a, cudaStream_t s) {
-  banded_apply_qt_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group, a.comp);
+  constexpr int S = BC - OV;
+  const long long ldgy = (long long)groups_of(a) * ((long long)(a.group - 1) * S + BC);
+  banded_apply_qt_kernel<BR, BC, OV><<<dim3(groups_of(a), (unsigned)a.ncols), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group, a.comp,
+                                                                                   a.ldb, ldgy, a.ldcomp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  banded_chase_apply_kernel<BC, OV, false><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.gy, a.y, a.nb, a.last_cols, a.group,
-                                                         a.comp ? a.comp + a.nb * (long long)(OV + BR - BC) : nullptr);
+  double* ucomp = a.comp ? a.comp + a.nb * (long long)(OV + BR - BC) : nullptr;
+  if (a.ncols == 1)
+    banded_chase_apply_kernel<BC, OV, false><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.gy, a.y, a.nb, a.last_cols, a.group, ucomp);
+  else
+    banded_chase_apply_multi_kernel<BC, OV><<<(unsigned)((a.ncols + 31) / 32), 32, 0, s>>>(a.cvec, a.ctau, a.gy, ldgy, a.y, a.ldy, ucomp, a.ldcomp, a.ncols,
+                                                                                     a.nb, a.last_cols, a.group);
   return cudaGetLastError();
 }
 template <int BR, int BC, int OV>

@@ -633,14 +633,22 @@ bool wide_can_block(const DenseBorder& d) {
 // Q1^T of a banded left block applied to ncols columns, INCLUDING the complement: column j of `src` (n_rows values, leading
 // dimension lds) -> column j of d_wx: thin part in rows [0, m1), complement in rows [m1, m1 + w_N)
 int banded_left_apply_qt(qrk_solver* h, const double* src, long long lds, double* dst, int ncols) {
-  for (int j = 0; j < ncols; j++) {
-    BandedArgs a = banded_args(h);
-    a.b = src + (long long)j * lds;
-    a.y = dst + (long long)j * h->w_ld;
-    a.comp = a.y + h->sum_cols;
-    QRK_TRY_CUDA(h, h->bvt->apply_qt(a, h->stream));
-    h->launches += banded_launches_per_call();
+  // the buffer between the two phases holds one vector per column
+  const size_t groups = (size_t)((h->nb + h->b_group - 1) / h->b_group);
+  const size_t gw = groups * ((size_t)(h->b_group - 1) * h->b_step + h->uc);
+  if ((size_t)ncols * gw > h->cap_gy) {
+    if (h->d_gy) cudaFree(h->d_gy);
+    h->d_gy = nullptr; h->cap_gy = 0;
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_gy, (size_t)ncols * gw * sizeof(double)));
+    h->cap_gy = (size_t)ncols * gw;
   }
+  BandedArgs a = banded_args(h);
+  a.b = src; a.ldb = lds;
+  a.y = dst; a.ldy = h->w_ld;
+  a.comp = dst + h->sum_cols; a.ldcomp = h->w_ld;
+  a.ncols = ncols;
+  QRK_TRY_CUDA(h, h->bvt->apply_qt(a, h->stream));
+  h->launches += banded_launches_per_call();
   return QRK_STATUS_OK;
 }
 
@@ -1013,7 +1021,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
         cudaMalloc(&h->d_btau, (size_t)h->nb * h->uc * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_ythin, (size_t)h->sum_cols * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_gband, gw * h->uc * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_gy, gw * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_gy, gw * sizeof(double)) != cudaSuccess || (h->cap_gy = gw) == 0 ||
         cudaMalloc(&h->d_cvec, std::max<size_t>(1, gw * h->b_ov) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_ctau, 2 * gw * sizeof(double)) != cudaSuccess)
       return fail(QRK_STATUS_ALLOC_FAILED);

@@ -103,6 +103,7 @@ struct qrk_solver {
   double *d_ythin = nullptr;           // (Q^T b)[0:n_cols]
   int b_group = 1;                     // slabs per parallel group of the two-phase banded factorisation (banded.cuh)
   double *d_gband = nullptr, *d_gy = nullptr, *d_cvec = nullptr, *d_ctau = nullptr;   // group triangles / chase reflectors
+  size_t cap_gy = 0;                   // doubles in d_gy (one vector of groups x W per right-hand side column)
 
   // ---- staging buffers for host-memspace calls ----
   double *d_b = nullptr, *d_x = nullptr;

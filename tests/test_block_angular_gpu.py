@@ -149,6 +149,31 @@ def test_banded_left_block_vs_lapack(qk, br, bc, ov, nb, m2, right):
     assert rel(R[:m1, :m1].T @ y[:m1], A1.T @ b) <= 1e-11
 
 
+def test_reference_test4_with_its_banded_left_solver(qk):
+    """The reference's block-angular test at its own sizes AND with its own solver combination (test/test-qrkit.cpp:44-48,
+    388-391): 7168 rows, left block 1024 slabs of 7x2 (2048 columns) factored by BandedBlockedSparseQR, a fully dense border of
+    384 columns factored by ColPivHouseholderQR.  Asserts what the reference asserts (x recovered from a consistent system,
+    :289) at 1e-10, plus x of a least-squares right-hand side, rank and (AP)^T AP = R^T R."""
+    from helpers import slabs_to_sparse
+    nb, br, bc, ov, m2 = 1024, 7, 2, 0, 384
+    slabs = uniform_blocks(nb, br, bc)
+    A1 = slabs_to_sparse(slabs, nb, br, bc, ov).toarray()
+    n, m1 = A1.shape
+    J2 = dense_border(n, m2)
+    A = np.hstack([A1, J2])
+    mat = qk.BlockMatrix1x2(qk.BandedSlabs(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov), J2)
+    s = qk.BlockAngularSparseQR(mat)
+    assert s.rank() == m1 + m2 and s.info() == qk.QRK_INFO_SUCCESS
+    x_true = vector(m1 + m2, seed=21)
+    assert rel(s.solve(A @ x_true), x_true) <= 1e-10
+    b = vector(n, seed=22)
+    assert rel(s.solve(b), np.linalg.lstsq(A, b, rcond=None)[0]) <= 1e-10
+    P = s.colsPermutation()
+    R = s.matrixR().toarray()[:m1 + m2, :]
+    AP = A[:, P]
+    assert rel(R.T @ R, AP.T @ AP) <= 1e-12
+
+
 def test_device_side_ellipse_assembly_and_gauss_newton(qk):
     """qrk_ellipse_assemble writes the functor's Jacobian (bench/bench_sparse_qr_extra.cpp:79-114) straight into
     the device buffers of the block-angular solver; a Gauss-Newton loop that never leaves the device recovers the ellipse."""
