@@ -285,10 +285,12 @@ def bench_angular_wide(args, L, stream):
     flops = 2.0 * (n - nb * c) * m2 * m2 - (2.0 / 3.0) * m2 ** 3
     steps = max(2, args.steps // 4)
     res = {}
-    for name, right in (("colpiv", 0), ("unpivoted", 1)):
+    for name, right, left in (("colpiv", 0, 0), ("unpivoted", 1, 0), ("banded_left_colpiv", 0, 1)):
         d = QrkDesc()
         d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, nb, r, c, 1, m2
         d.right_solver = right
+        if left:            # LeftSolver = BandedBlockedSparseQR (test/test-qrkit.cpp:44-48): the same 7x2 blocks as slabs, overlap 0
+            d.left_solver, d.block_overlap, d.pivoting = 1, 0, 0
         h = C.c_void_p()
         check(L.qrk_create(C.byref(d), C.byref(h)))
         check(L.qrk_set_stream(h, stream), h)
