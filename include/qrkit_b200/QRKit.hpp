@@ -496,4 +496,87 @@ class BandedBlockedSparseQR {
   std::string m_lastError;
 };
 
+// ---- BlockAngularSparseQR<BandedBlockedSparseQR<..., BlockOverlap, ...>, RightSolver> (the solver pair of the reference's own
+// block-angular tests, test/test-qrkit.cpp:44-57, and of the QRkitBB benchmark column): the left block J1 is block banded and
+// given as its slabs (see BandedBlockedSparseQR above), the right block is dense (n x m2, column-major).
+template <int BlockRows, int BlockCols, int BlockOverlap, typename RightSolverTag = ColPivHouseholderQR<MatrixXd>>
+class BlockAngularBandedSparseQR {
+ public:
+  using MatrixRType = SparseMatrix<ColMajor>;
+  using PermutationType = PermutationMatrix;
+  BlockAngularBandedSparseQR() {}
+  ~BlockAngularBandedSparseQR() { qrk_destroy(m_h); }
+  BlockAngularBandedSparseQR(const BlockAngularBandedSparseQR&) = delete;
+  BlockAngularBandedSparseQR& operator=(const BlockAngularBandedSparseQR&) = delete;
+
+  void compute(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border) {                   // :134-138
+    ensureHandle(numBlocks, border);
+    if (!m_h) return;
+    detail::throw_if(qrk_set_border(m_h, border.data(), border.rows(), QRK_HOST), m_h, "compute/border");
+    detail::throw_if(qrk_compute(m_h, slabs.data(), QRK_HOST), m_h, "compute");
+    m_haveR = false; m_isInitialized = true;
+  }
+  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border, const VectorXd& b) {
+    ensureHandle(numBlocks, border);
+    VectorXd x((size_t)m_cols);
+    if (!m_h) return x;
+    detail::throw_if(qrk_set_border(m_h, border.data(), border.rows(), QRK_HOST), m_h, "border");
+    detail::throw_if(qrk_compute_solve(m_h, slabs.data(), b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
+    m_haveR = false; m_isInitialized = true;
+    return x;
+  }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index leftBlockCols() const { return m_cols - m_m2; }                                                       // :276-280
+  Index rank() const { int64_t r = 0; qrk_rank(m_h, &r); return r; }                                         // :510
+  ComputationInfo info() const { if (!m_h) return InvalidInput; int32_t i = 0; qrk_info(m_h, &i); return (ComputationInfo)i; }
+  std::string lastErrorMessage() const { return m_h ? qrk_last_error(m_h) : m_lastError; }
+  const PermutationType& colsPermutation() const {                                                            // [identity ; m1 + P2] (:498-503)
+    m_outputPerm_c.indices().resize((size_t)m_cols);
+    detail::throw_if(qrk_cols_permutation(m_h, m_outputPerm_c.indices().data(), QRK_HOST), m_h, "colsPermutation");
+    return m_outputPerm_c;
+  }
+  const MatrixRType& matrixR() const {                                                                        // [R1 band, Atop P2; 0, R2] (:285-308)
+    if (!m_haveR) {
+      int64_t nnz = 0;
+      detail::throw_if(qrk_matrix_r_nnz(m_h, &nnz), m_h, "matrixR");
+      m_R.m_rows = m_rows; m_R.m_cols = m_cols;
+      m_R.outer.resize((size_t)m_cols + 1); m_R.inner.resize((size_t)nnz); m_R.values.resize((size_t)nnz);
+      detail::throw_if(qrk_matrix_r(m_h, m_R.outer.data(), m_R.inner.data(), m_R.values.data(), QRK_HOST), m_h, "matrixR");
+      m_haveR = true;
+    }
+    return m_R;
+  }
+  VectorXd solve(const VectorXd& B) const {                                                                   // :203-227
+    assert(m_isInitialized && "The factorization should be called first, use compute()");
+    VectorXd x((size_t)m_cols);
+    detail::throw_if(qrk_solve(m_h, B.data(), m_rows, x.data(), m_cols, 1, QRK_HOST), m_h, "solve");
+    return x;
+  }
+ private:
+  void ensureHandle(Index numBlocks, const MatrixXd& border) {
+    const Index m2 = border.cols();
+    if (m_h && m_nb == numBlocks && m_m2 == m2) return;
+    qrk_destroy(m_h);
+    m_h = nullptr;
+    qrk_desc_t d{};
+    d.kind = QRK_BLOCK_ANGULAR; d.left_solver = QRK_LEFT_BANDED_BLOCKED; d.num_blocks = numBlocks;
+    d.block_rows = BlockRows; d.block_cols = BlockCols; d.block_overlap = BlockOverlap;
+    d.pivoting = QRK_PIVOT_NONE; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2;
+    d.right_solver = RightSolverTag::pivoting == QRK_PIVOT_COLPIV ? QRK_RIGHT_COLPIV : QRK_RIGHT_UNPIVOTED;
+    const int st = qrk_create(&d, &m_h);
+    m_nb = numBlocks; m_m2 = m2; m_rows = numBlocks * BlockRows;
+    m_cols = (numBlocks - 1) * (BlockCols - BlockOverlap) + BlockCols + m2;
+    if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
+    detail::throw_if(st, nullptr, "BlockAngularBandedSparseQR");
+  }
+  qrk_handle_t m_h = nullptr;
+  Index m_nb = -1, m_m2 = 0, m_rows = 0, m_cols = 0;
+  bool m_isInitialized = false;
+  mutable bool m_haveR = false;
+  mutable MatrixRType m_R;
+  mutable PermutationType m_outputPerm_c;
+  std::string m_lastError;
+};
+
 }  // namespace QRKit_b200

@@ -146,6 +146,21 @@ int main() {
     // matrixQ() * (matrixQ().transpose() * b) on the thin part = A x for a consistent b (Q1 Q1^T projects on range(A))
     VectorXd qqt = band.applyQ(band.applyQt(bb));
     CHECK(rel(qqt, bb) <= 1e-11, "banded: matrixQ() * (matrixQ().transpose() * b) = b for b in range(A)  (1e-11)");
+    // the same banded block as the LEFT block of a block-angular matrix (the solver pair of test/test-qrkit.cpp:44-48),
+    // dense border of 20 columns: x recovered from a consistent system (:289)
+    const int mb = 20;
+    MatrixXd Bb(band.rows(), mb);
+    for (Index i = 0; i < band.rows(); i++) for (int j = 0; j < mb; j++) Bb(i, j) = synth(37, i, j, 0);
+    VectorXd xa((size_t)(band.cols() + mb)), ba((size_t)band.rows(), 0.0);
+    for (size_t j = 0; j < xa.size(); j++) xa[j] = synth(39, j, 0, 0, -1.0, 1.0);
+    for (Index k = 0; k < nbb; k++) for (int j = 0; j < 4; j++) for (int i = 0; i < 7; i++) ba[k * 7 + i] += slabs[(size_t)(k * 4 + j) * 7 + i] * xa[k * 2 + j];
+    for (Index i = 0; i < band.rows(); i++) for (int j = 0; j < mb; j++) ba[i] += Bb(i, j) * xa[band.cols() + j];
+    BlockAngularBandedSparseQR<7, 4, 2> ab;
+    ab.compute(slabs, nbb, Bb);
+    CHECK(ab.info() == Success && ab.rows() == band.rows() && ab.cols() == band.cols() + mb && ab.rank() == ab.cols(), "banded-left angular: info / rows / cols / rank");
+    CHECK(rel(ab.solve(ba), xa) <= 1e-10, "banded-left angular: solve(b) recovers x  (1e-10)");
+    BlockAngularBandedSparseQR<7, 4, 2, BlockedThinDenseQR<MatrixXd, 2>> ab2;
+    CHECK(rel(ab2.computeAndSolve(slabs, nbb, Bb, ba), xa) <= 1e-10, "banded-left angular, unpivoted right solver: computeAndSolve recovers x  (1e-10)");
   }
   std::printf(failures ? "FAILED (%d)\n" : "All passed.\n", failures);
   return failures ? 1 : 0;
