@@ -423,7 +423,7 @@ __device__ __forceinline__ void merge_triangle_list(const double* tris, int coun
   cta_merge_tri<M2, TPB / 32>(T, scratch);
 }
 
-template <int M2, int TPB>
+template <int M2, int TPB, bool XCHG>
 __global__ void __launch_bounds__(TPB)
 angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
                     double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only, int* __restrict__ perm_tail,
@@ -432,8 +432,25 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   constexpr int N = TR::N;
   __shared__ double scratch[(TPB / 32) * N];
   double T[N];
-  merge_triangle_list<M2, TPB>(tris, count, T, scratch, false);
-  if (mode == 2) {
+#pragma unroll
+  for (int i = 0; i < N; i++) T[i] = 0.0;
+  // every thread takes one triangle per round; a round is merged cooperatively (warp, then CTA)
+  for (int q0 = 0; q0 < count; q0 += TPB) {
+    const int q = q0 + threadIdx.x;
+    if (q0 == 0) {
+      if (q < count) {
+#pragma unroll
+        for (int i = 0; i < N; i++) T[i] = tris[(long long)q * N + i];
+      }
+    } else {
+      double S[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) S[i] = (q < count) ? tris[(long long)q * N + i] : 0.0;
+      fold_tri<M2>(T, S);
+    }
+  }
+  cta_merge_tri<M2, TPB / 32>(T, scratch);
+  if constexpr (XCHG) {                          // mode 2 (a separate instantiation: the single-GPU root keeps its code)
     // ---- this GPU's triangle -> every rank's buffer (own included), then the flag; wait for all G flags
     const unsigned long long seq = *xc.seq + 1;               // the same on every rank: every rank runs the same sequence of steps
     const int G = xc.world, par = (int)(seq & 1ull);

@@ -124,8 +124,12 @@ cudaError_t backsolve(const AngularArgs& a, cudaStream_t s) {
 cudaError_t root(const AngularArgs& a, cudaStream_t s) {
   AngularXchg xc;
   xc.peers = a.xchg_peers; xc.world = a.xchg_world; xc.rank = a.xchg_rank; xc.seq = a.xchg_seq; xc.err = a.xchg_err;
-  angular_root_kernel<M2, 512><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
-                                                 a.perm_tail, a.m1, xc);
+  if (a.root_mode == 2)
+    angular_root_kernel<M2, 512, true><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
+                                                         a.perm_tail, a.m1, xc);
+  else
+    angular_root_kernel<M2, 512, false><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
+                                                          a.perm_tail, a.m1, xc);
   return cudaGetLastError();
 }
 
@@ -141,7 +145,8 @@ cudaError_t preload_t(bool piv) {
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>);
   if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, true, TPB>)
                                 : cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, false, TPB>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, true>);
   return e;
 }
 cudaError_t preload(int r, int c, bool piv) {
