@@ -120,40 +120,33 @@ __device__ __forceinline__ void warp_merge_tri(double (&T)[Tri<M2>::N]) {
   const bool lead = (threadIdx.x & 31) == 0;
 #pragma unroll
   for (int k = 0; k < M2; k++) {
-    double tail = 0.0;
+    // ONE reduction phase per column: the squared tail norm and the RAW dot products t^T a_j (t = the unscaled column
+    // entries of the lanes below the pivot) are summed together, before the reflector scalars exist:
+    //   v = [1; inv t],  tau v^T a_j = tau (pivot_j + inv t^T a_j) = w_j,  a_j -= (w_j inv) t
+    double red[M2 + 1];
 #pragma unroll
-    for (int p = 0; p <= k; p++) tail = fma(T[TR::idx(p, k)], T[TR::idx(p, k)], tail);
-    tail = lead ? 0.0 : tail;                     // lane 0 contributes only the pivot entry
-    const double tailSq = warp_sum_f64(tail);
-    const double c0 = __shfl_sync(0xffffffffu, T[TR::idx(k, k)], 0);
-    const bool degenerate = tailSq <= DBL_MIN;
-    double norm;
-    const double rnorm = fast_rsqrt(fma(c0, c0, tailSq), norm);
-    double beta = (c0 >= 0.0) ? -norm : norm;
-    const double ib = (c0 >= 0.0) ? -rnorm : rnorm;
-    double inv = fast_rcp(c0 - beta);
-    double tau = (beta - c0) * ib;
-    if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
-    double v[M2];
-#pragma unroll
-    for (int p = 0; p <= k; p++) v[p] = T[TR::idx(p, k)] * inv;
-    double dot[M2 + 1];
-#pragma unroll
-    for (int j = k + 1; j <= M2; j++) {
+    for (int j = k; j <= M2; j++) {
       double d = 0.0;
 #pragma unroll
-      for (int p = 0; p <= k; p++) d = fma(v[p], T[TR::idx(p, j)], d);
-      dot[j] = lead ? T[TR::idx(k, j)] : d;
+      for (int p = 0; p <= k; p++) d = fma(T[TR::idx(p, k)], T[TR::idx(p, j)], d);
+      red[j] = lead ? 0.0 : d;                    // lane 0 contributes only the pivot row
     }
+    double piv[M2 + 1];
 #pragma unroll
-    for (int j = k + 1; j <= M2; j++) dot[j] = warp_sum_f64(dot[j]) * tau;
+    for (int j = k; j <= M2; j++) piv[j] = __shfl_sync(0xffffffffu, T[TR::idx(k, j)], 0);
+#pragma unroll
+    for (int j = k; j <= M2; j++) red[j] = warp_sum_f64(red[j]);
+    double beta, inv, tau;
+    householder_scalars(piv[k], red[k], false, beta, inv, tau);
 #pragma unroll
     for (int j = k + 1; j <= M2; j++) {
+      const double w = tau * fma(inv, red[j], piv[j]);
       if (lead) {
-        T[TR::idx(k, j)] -= dot[j];
+        T[TR::idx(k, j)] -= w;
       } else {
+        const double z = w * inv;
 #pragma unroll
-        for (int p = 0; p <= k; p++) T[TR::idx(p, j)] = fma(-v[p], dot[j], T[TR::idx(p, j)]);
+        for (int p = 0; p <= k; p++) T[TR::idx(p, j)] = fma(-z, T[TR::idx(p, k)], T[TR::idx(p, j)]);
       }
     }
     if (lead) T[TR::idx(k, k)] = beta;
