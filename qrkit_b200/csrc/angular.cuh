@@ -424,6 +424,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   using TR = Tri<M2>;
   constexpr int N = TR::N;
   __shared__ double scratch[(TPB / 32) * N];
+  asm volatile("griddepcontrol.launch_dependents;");   // the back-substitution grid may be scheduled now (it waits for this grid)
   double T[N];
 #pragma unroll
   for (int i = 0; i < N; i++) T[i] = 0.0;
@@ -548,6 +549,9 @@ angular_backsolve_kernel(const double* __restrict__ packed, const int* __restric
   double* sA = smem;
   const int t = threadIdx.x;
   const long long m1 = nb * C;
+  // launched as a programmatic dependent of the root kernel (which triggers at its start): the launch latency of this grid
+  // overlaps the root; nothing is read before the root has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   double x2[M2];
 #pragma unroll
   for (int j = 0; j < M2; j++) x2[j] = root[M2 * M2 + 2 * M2 + j];

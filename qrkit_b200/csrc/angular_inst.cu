@@ -1,4 +1,5 @@
 // angular_inst.cu — instantiations of the block-angular kernels for ONE border width (-DQRK_M2=k).
+#include <cstdlib>
 #include "angular.cuh"
 #include "angular_dispatch.hpp"
 
@@ -76,11 +77,22 @@ cudaError_t rhs_t(const AngularArgs& a, cudaStream_t s) {
 
 template <int R, int C>
 cudaError_t backsolve_t(const AngularArgs& a, cudaStream_t s) {
-  const size_t smem = (size_t)TPB * Group<R * C>::stride * 8;
-  const unsigned grid = (unsigned)((a.nb + TPB - 1) / TPB);
-  if (a.piv) angular_backsolve_kernel<R, C, M2, true, TPB><<<grid, TPB, smem, s>>>(a.packed, a.perm, a.atop, a.y1, a.root, a.x, a.nb);
-  else angular_backsolve_kernel<R, C, M2, false, TPB><<<grid, TPB, smem, s>>>(a.packed, a.perm, a.atop, a.y1, a.root, a.x, a.nb);
-  return cudaGetLastError();
+  // programmatic dependent launch behind the root kernel: see angular_backsolve_kernel
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((a.nb + TPB - 1) / TPB));
+  cfg.blockDim = dim3(TPB);
+  cfg.dynamicSmemBytes = (size_t)TPB * Group<R * C>::stride * 8;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = std::getenv("QRK_NO_PDL") == nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const double* packed = a.packed; const int* perm = a.perm; const double* atop = a.atop; const double* y1 = a.y1; const double* root = a.root;
+  double* x = a.x; long long nb = a.nb;
+  if (a.piv) return cudaLaunchKernelEx(&cfg, angular_backsolve_kernel<R, C, M2, true, TPB>, packed, perm, atop, y1, root, x, nb);
+  return cudaLaunchKernelEx(&cfg, angular_backsolve_kernel<R, C, M2, false, TPB>, packed, perm, atop, y1, root, x, nb);
 }
 
 bool shape_ok(int r, int c) {
