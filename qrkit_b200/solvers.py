@@ -280,8 +280,10 @@ class BlockMatrix1x2:
 
 
 class BlockAngularSparseQR(BlockDiagonalSparseQR):
-    """BlockAngularSparseQR<BlockDiagonalSparseQR<...>, ColPivHouseholderQR<MatrixXd>> (BlockAngularSparseQR.h:79-281):
-    left block diagonal, dense border factored by a TSQR tree + Eigen's ColPiv rule at the root."""
+    """BlockAngularSparseQR<LeftSolver, RightSolver> (BlockAngularSparseQR.h:79-281).  mat.left is a SparseBlockDiagonal
+    (LeftSolver = BlockDiagonalSparseQR: narrow borders go through the fused TSQR kernels, Eigen's ColPiv rule at the root) or a
+    BandedSlabs (LeftSolver = BandedBlockedSparseQR, the pair of test/test-qrkit.cpp:44-48); right_solver: 0 =
+    ColPivHouseholderQR<MatrixXd>, 1 = BlockedThinDenseQR / HouseholderQR (unpivoted)."""
 
     def __init__(self, mat: BlockMatrix1x2 | None = None, *, pivoting=QRK_PIVOT_COLPIV, device=0, stream=None, world=1,
                  right_solver=0):
