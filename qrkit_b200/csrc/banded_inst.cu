@@ -11,8 +11,14 @@ namespace {
 
 inline unsigned groups_of(const BandedArgs& a) { return (unsigned)((a.nb + a.group - 1) / a.group); }
 
+// Without overlap (OV = 0) consecutive slabs share no column: the groups are independent, the group triangles ARE the rows
+// of R (the two buffers have the same layout) and there is nothing to chase — phase 2 is skipped in all three operations.
 template <int BR, int BC, int OV>
 cudaError_t factor_t(const BandedArgs& a, cudaStream_t s) {
+  if constexpr (OV == 0) {
+    banded_factor_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.A_in, a.packed, a.tau, a.rband, a.b, a.y, a.nb, a.last_cols, a.group);
+    return cudaGetLastError();
+  }
   banded_factor_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.A_in, a.packed, a.tau, a.gband, a.b, a.gy, a.nb, a.last_cols, a.group);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -23,6 +29,11 @@ template <int BR, int BC, int OV>
 cudaError_t apply_qt_t(const BandedArgs& a, cudaStream_t s) {
   constexpr int S = BC - OV;
   const long long ldgy = (long long)groups_of(a) * ((long long)(a.group - 1) * S + BC);
+  if constexpr (OV == 0) {                      // the pivot-row values of the groups are the thin part itself
+    banded_apply_qt_kernel<BR, BC, OV><<<dim3(groups_of(a), (unsigned)a.ncols), 32, 0, s>>>(a.packed, a.tau, a.b, a.y, a.nb, a.last_cols, a.group, a.comp,
+                                                                                     a.ldb, a.ldy, a.ldcomp);
+    return cudaGetLastError();
+  }
   banded_apply_qt_kernel<BR, BC, OV><<<dim3(groups_of(a), (unsigned)a.ncols), 32, 0, s>>>(a.packed, a.tau, a.b, a.gy, a.nb, a.last_cols, a.group, a.comp,
                                                                                    a.ldb, ldgy, a.ldcomp);
   cudaError_t e = cudaGetLastError();
@@ -37,6 +48,10 @@ cudaError_t apply_qt_t(const BandedArgs& a, cudaStream_t s) {
 }
 template <int BR, int BC, int OV>
 cudaError_t apply_q_t(const BandedArgs& a, cudaStream_t s) {
+  if constexpr (OV == 0) {
+    banded_apply_q_kernel<BR, BC, OV><<<groups_of(a), 32, 0, s>>>(a.packed, a.tau, a.y, a.x, a.nb, a.last_cols, a.group);
+    return cudaGetLastError();
+  }
   banded_chase_apply_kernel<BC, OV, true><<<1, 32, 0, s>>>(a.cvec, a.ctau, a.y, a.gy, a.nb, a.last_cols, a.group, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
