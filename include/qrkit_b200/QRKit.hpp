@@ -416,7 +416,8 @@ class BlockAngularSparseQR {
 // ---- BandedBlockedSparseQR (BandedBlockedSparseQR.h:122-344) for the fixed block-banded pattern of fromBlockBandedPattern
 // (SparseQRUtils.h:274-302): num_blocks dense BlockRows x BlockCols slabs, slab k at rows [k*BlockRows, ...), columns
 // [k*(BlockCols-BlockOverlap), ...).  The input is the block-COO array of the slabs (column-major, back to back).
-// Single GPU, sequential window chain.  matrixQ() is available as its transpose-apply, like the reference uses it (:299).
+// Single GPU (groups of slabs are reduced in parallel, a short chase across the group boundaries stays sequential).
+// matrixQ() is available in operator form on the thin part: applyQt (its transpose-apply, as the reference uses it, :299) and applyQ.
 template <int BlockRows, int BlockCols, int BlockOverlap>
 class BandedBlockedSparseQR {
  public:
