@@ -78,3 +78,23 @@ def test_product_does_not_touch_the_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read()
+
+
+def test_ctypes_descriptor_matches_the_c_struct(capi, tmp_path):
+    """qrk_desc_t as the Python binding declares it must be byte-compatible with the header (size and every field offset)."""
+    import ctypes as C
+    fields = [f[0] for f in capi.QrkDesc._fields_ if f[0] != "reserved"]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qrkit_b200.h"', 'int main(void){', '  printf("%zu\\n", sizeof(qrk_desc_t));']
+    for f in fields:
+        lines.append(f'  printf("{f} %zu\\n", offsetof(qrk_desc_t, {f}));')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.dirname(capi.HEADER), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert int(out[0]) == C.sizeof(capi.QrkDesc)
+    for ln in out[1:]:
+        if ln.strip():
+            name, off = ln.split()
+            assert getattr(capi.QrkDesc, name).offset == int(off), name
