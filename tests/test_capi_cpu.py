@@ -98,3 +98,22 @@ def test_ctypes_descriptor_matches_the_c_struct(capi, tmp_path):
         if ln.strip():
             name, off = ln.split()
             assert getattr(capi.QrkDesc, name).offset == int(off), name
+
+
+def test_new_entry_points_validate_arguments_and_refuse_without_a_device(capi):
+    """The multi-GPU exchange, IPC and device-side assembly entry points: null arguments are rejected, and nothing computes
+    without a CUDA device (no CPU fallback)."""
+    import ctypes as C
+    L = capi.lib()
+    null = C.c_void_p()
+    assert L.qrk_angular_xchg_buffer(null, None, None) == 1            # QRK_STATUS_INVALID_ARGUMENT
+    assert L.qrk_angular_p2p_attach(null, None, 2, 0) == 1
+    assert L.qrk_angular_p2p_status(null, None) == 1
+    assert L.qrk_ipc_export(null, null) == 1 and L.qrk_ipc_close(null) == 1
+    buf = (C.c_double * 16)()
+    p = C.cast(buf, C.c_void_p)
+    assert L.qrk_ellipse_points(null, null, 8, 1.0, 1.0, 0.0, 0.0, 0.0, None) == 1
+    assert L.qrk_ellipse_assemble(null, null, null, 8, null, null, null, null, None) == 1
+    if capi.device_count() == 0:
+        assert L.qrk_ellipse_points(p, p, 8, 1.0, 1.0, 0.0, 0.0, 0.0, None) == 4      # QRK_STATUS_NO_DEVICE
+        assert L.qrk_ellipse_assemble(p, p, p, 8, p, p, p, None, None) == 4
