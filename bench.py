@@ -107,6 +107,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_COMPACT_1T = None
+
+
 def cpu_reference_run(nb_sample, steps, warmup, piv):
     """The reference's own algorithm (explicit Q_i, sparse Q/R assembly, sparse Q^T b, sparse triangular solve —
     BlockDiagonalSparseQR.h:415-547, 258-280) restated in oracle/, single thread like the reference's serial loop."""
@@ -124,6 +127,9 @@ def cpu_reference_run(nb_sample, steps, warmup, piv):
     threads = os.cpu_count() or 1
     orc.bd_compact_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv), threads=threads)
     tc = min(orc.bd_compact_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv), threads=threads)["seconds"] for _ in range(3))
+    # SURVEY 8d variant B: the same compact algorithm on ONE thread
+    global _COMPACT_1T
+    _COMPACT_1T = min(orc.bd_compact_uniform(nb_sample, R, CC, vals, b, colpiv=bool(piv), threads=1)["seconds"] for _ in range(2))
     return sum(times) / len(times), tc, threads
 
 
@@ -143,7 +149,8 @@ def reference_arm(args):
                            "algorithm (oracle/), serial like the reference's block loop"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{nb_sample} of {NB} blocks per step (reference-faithful explicit-Q variant)",
-                         "compact_all_cores": {"value": nb_sample * R / tc, "cores": threads}},
+                         "compact_all_cores": {"value": nb_sample * R / tc, "cores": threads},
+                         "compact_one_core": {"value": nb_sample * R / _COMPACT_1T, "cores": 1}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -332,7 +339,9 @@ def main():
                "sample": f"{nb_sample} of {nb} blocks, 3 repetitions; reference-faithful variant (explicit Q_i, sparse Q/R assembly, "
                          "sparse Q^T b + triangular solve), serial like the reference's block loop",
                "compact_all_cores": {"value": nb_sample * R / tc, "cores": threads,
-                                     "note": "packed reflectors + fused solve with OpenMP over blocks (not what the reference does)"}}
+                                     "note": "packed reflectors + fused solve with OpenMP over blocks (not what the reference does)"},
+               "compact_one_core": {"value": nb_sample * R / _COMPACT_1T, "cores": 1,
+                                    "note": "the same compact algorithm on one thread (SURVEY 8d variant B)"}}
 
     line = {
         "metric": METRIC, "value": world * nb * R / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
