@@ -23,6 +23,8 @@ from qrkit_b200 import capi
 from qrkit_b200.capi import QRK_DEVICE, QrkDesc, check
 
 SEED_A = 0x51524B49
+# 64 FP64 FMA per clock per SM (DFMA and DMMA alike, measured: profiles/r01_fp64_pipes_b200.txt) x 148 SMs x 1.965 GHz max clock
+FP64_NOMINAL_TFLOPS = 2 * 64 * 148 * 1.965e9 / 1e12
 
 
 def vp(t):
@@ -71,6 +73,20 @@ def cpu_mixed(nb):
         ref = orc.BlockDiagonalOracle(br, bc, vals, colpiv=False)
         ref.solve(b)
     return _cpu(run, int(br.sum()), f"{nb} mixed blocks 32x16..128x64, BlockDiagonalSparseQR<HouseholderQR> factorize + solve, reference-faithful (explicit Q_i, sparse Q/R assembly), 1 thread")
+
+
+def cpu_angular_wide(nb, r, c, m2):
+    """Reference test 4 (test/test-qrkit.cpp:283-327): BlockAngular<BlockDiagonal 7x2 ColPiv, dense ColPiv>."""
+    from helpers import uniform_blocks, vector
+    from oracle import oracle as orc
+    n = nb * r
+    vals = uniform_blocks(nb, r, c)
+    J2 = np.asfortranarray(vector(m2 * n, SEED_A + 7, 0.5, 5.0).reshape(m2, n).T)
+    b = vector(n, seed=SEED_A + 5)
+    def run():
+        ref = orc.BlockAngularOracle(J2, br=np.full(nb, r, dtype=np.int32), bc=np.full(nb, c, dtype=np.int32), values=vals, left_colpiv=True, right_kind=0)
+        ref.solve(b)
+    return _cpu(run, n, f"reference test 4 at its own sizes ({nb} blocks {r}x{c} + dense {n}x{m2} border), the whole problem, reference-faithful (explicit sparse Q1, dense tall ColPiv QR), 1 thread")
 
 
 def cpu_banded(nb):
@@ -143,8 +159,8 @@ def bench_angular(args, L, stream):
             "colpiv_left": {"ms_per_step": out[1][0], "value": 2 * n / (out[1][0] * 1e-3)},
             "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_angular(min(n, 500_000))
-    print(json.dumps(line), flush=True)
+        line["cpu_baseline"] = cpu_angular(min(n, args.cpu_points))
+    return line
 
 
 def mixed_sizes(nb, seed=SEED_A):
@@ -199,8 +215,8 @@ def bench_mixed(args, L, stream):
             "metric": "rows/s", "value": rows / (ms * 1e-3), "ms_per_step": ms, "rows": rows,
             "roofline": {"hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak},
-                         "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": 37.0, "unit": "TFLOP/s (nominal FP64 vector peak)",
-                                  "frac": flops / (ms * 1e-3) / 1e12 / 37.0},
+                         "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s (nominal FP64: 64 FMA/clk/SM at 1.965 GHz)",
+                                  "frac": flops / (ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS},
                          "algorithmic_bytes": alg_bytes, "flops": flops, "peak_source": src},
             "colpiv": {"ms_per_step": res[1], "value": rows / (res[1] * 1e-3)},
             "two_call": {"compute_ms": ms_f, "solve_ms": ms_s, "solve_hbm_frac": op_bytes / (ms_s * 1e-3) / 1e9 / peak,
@@ -208,8 +224,8 @@ def bench_mixed(args, L, stream):
                          "note": "solve / Q^T b on stored factors read packed V (8rc) + tau + the vector once"},
             "steps": args.steps, "dtype": "f64"}
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_mixed(min(nb, 5000))
-    print(json.dumps(line), flush=True)
+        line["cpu_baseline"] = cpu_mixed(min(nb, args.cpu_mixed_blocks))
+    return line
 
 
 def bench_classes(args, L, stream):
@@ -235,9 +251,9 @@ def bench_classes(args, L, stream):
         alg = nb * (16.0 * r * c + 8 * r + 16 * c)
         fl = nb * (2.0 * r * c * c - (2.0 / 3.0) * c ** 3 + 4 * r * c + c * c)
         per.append({"block": [r, c], "blocks": nb, "ms": round(ms, 4), "us_per_block_per_sm": round(ms * 1e3 * 148 / nb, 3),
-                    "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "fp64_frac": round(fl / (ms * 1e-3) / 1e12 / 37.0, 4)})
-    print(json.dumps({"workload": "config 5 per size class (uniform blocks, fused QR+solve, unpivoted)", "classes": per,
-                      "total_ms": sum(p["ms"] for p in per), "peak_source": src}), flush=True)
+                    "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "fp64_frac": round(fl / (ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS, 4)})
+    return {"workload": "config 5 per size class (uniform blocks, fused QR+solve, unpivoted)", "classes": per,
+            "total_ms": sum(p["ms"] for p in per), "peak_source": src}
 
 
 def bench_banded(args, L, stream):
@@ -266,8 +282,8 @@ def bench_banded(args, L, stream):
                          "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": src},
             "dtype": "f64"}
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_banded(min(nb, 50_000))
-    print(json.dumps(line), flush=True)
+        line["cpu_baseline"] = cpu_banded(min(nb, args.cpu_banded_blocks))
+    return line
 
 
 def bench_angular_wide(args, L, stream):
@@ -301,9 +317,16 @@ def bench_angular_wide(args, L, stream):
         L.qrk_destroy(h)
         res[name] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "launches_per_step": (l1.value - l0.value) // (steps + 1),
                      "border_qr_gflops": flops / (ms * 1e-3) / 1e9}
-    print(json.dumps({"workload": f"block-angular, reference test 4/5 sizes: {nb} blocks {r}x{c} + dense {n}x{m2} border; blocked compact-WY (DMMA) first stage, ColPiv on the triangle in one cluster launch",
-                      "metric": "rows/s", "value": res["colpiv"]["value"], "ms_per_step": res["colpiv"]["ms_per_step"],
-                      "right_solver": res, "dtype": "f64"}), flush=True)
+    line = {"workload": f"block-angular, reference test 4/5 sizes: {nb} blocks {r}x{c} + dense {n}x{m2} border; blocked compact-WY (DMMA) first stage, ColPiv on the triangle in one cluster launch",
+            "metric": "rows/s", "value": res["colpiv"]["value"], "ms_per_step": res["colpiv"]["ms_per_step"],
+            "right_solver": res, "dtype": "f64",
+            "roofline": {"bound": "fp64", "achieved": res["colpiv"]["border_qr_gflops"] / 1e3, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                         "frac": res["colpiv"]["border_qr_gflops"] / 1e3 / FP64_NOMINAL_TFLOPS, "traffic": None,
+                         "peak_source": "nominal FP64 (64 FMA/clk/SM x 148 SMs x 1.965 GHz; DFMA = DMMA peak, profiles/r01_fp64_pipes_b200.txt)",
+                         "flops": flops}}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_angular_wide(nb, r, c, m2)
+    return line
 
 
 def bench_two_call(args, L, stream):
@@ -328,7 +351,7 @@ def bench_two_call(args, L, stream):
             "factor": {"ms": ms_f, "bytes_per_block": 544, "frac": 544 * nb / (ms_f * 1e-3) / 1e9 / peak},
             "solve": {"ms": ms_s, "bytes_per_block": 384, "frac": 384 * nb / (ms_s * 1e-3) / 1e9 / peak},
             "apply_qt": {"ms": ms_q, "bytes_per_block": 256 + 32 + 128, "frac": 416 * nb / (ms_q * 1e-3) / 1e9 / peak}}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -389,6 +412,8 @@ def bench_angular_dist(args, L, stream):
     # eager loop is bound by the host issuing ~8 calls per step, not by the device
     ms_graph = None
     try:
+        if not getattr(args, "graphs", True):
+            raise RuntimeError("graphs disabled")
         torch.cuda.synchronize(); dist.barrier()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
@@ -396,8 +421,8 @@ def bench_angular_dist(args, L, stream):
         ms_graph = _dist_time(g.replay, args.steps, args.warmup)
     except Exception as e:                                   # capture is an optimisation of the measurement, not of the product
         ms_graph = None
-        if rank == 0:
-            print(json.dumps({"graph_capture_failed": str(e)[:200]}), flush=True)
+        if rank == 0 and getattr(args, "graphs", True):
+            print(json.dumps({"graph_capture_failed": str(e)[:200]}), file=sys.stderr, flush=True)
     # fused peer exchange: the triangles travel over NVLink inside the TSQR root kernel (qrk_angular_p2p_attach); the step is
     # ONE library call again, no NCCL and no merge launch on the data path
     ms_fused = ms_fused_graph = None
@@ -412,6 +437,8 @@ def bench_angular_dist(args, L, stream):
         to = C.c_int32(-1); check(L.qrk_angular_p2p_status(h, C.byref(to)), h)
         fused_matches = bool(torch.equal(x, x_nccl)) and to.value == 0
         try:                                   # the step counter lives on the device, so a captured step replays correctly
+            if not getattr(args, "graphs", True):
+                raise RuntimeError("graphs disabled")
             torch.cuda.synchronize(); dist.barrier()
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, stream=torch.cuda.current_stream()):
@@ -421,18 +448,21 @@ def bench_angular_dist(args, L, stream):
             fused_matches = fused_matches and bool(torch.equal(x, x_nccl)) and to.value == 0
         except Exception as e:
             ms_fused_graph = None
-            if rank == 0:
-                print(json.dumps({"fused_graph_capture_failed": str(e)[:200]}), flush=True)
+            if rank == 0 and getattr(args, "graphs", True):
+                print(json.dumps({"fused_graph_capture_failed": str(e)[:200]}), file=sys.stderr, flush=True)
     # x2 must be bit-identical on every rank (redundant root on identical gathered triangles)
     x2 = x[n:].clone()
     x2all = torch.empty(G * 5, dtype=torch.float64, device="cuda")
     dist.all_gather_into_tensor(x2all, x2)
     same = bool((x2all.view(G, 5) == x2all.view(G, 5)[0]).all().item())
     L.qrk_destroy(h)
+    if G > 1:
+        for pimp in imported:
+            L.qrk_ipc_close(pimp)
     if rank == 0:
         peak, src = measured_peaks()
         ach = 248.0 * n_total / (ms * 1e-3) / 1e9
-        print(json.dumps({"workload": f"block-angular ellipse Jacobian, N={n_total} points over {G} GPU(s) (BASELINE config 3), fused compute+solve with NCCL all-gather of the per-GPU triangles",
+        return ({"workload": f"block-angular ellipse Jacobian, N={n_total} points over {G} GPU(s) (BASELINE config 3), fused compute+solve with NCCL all-gather of the per-GPU triangles",
                           "metric": "rows/s", "value": 2 * n_total / (ms * 1e-3), "ms_per_step": ms, "n_gpus": G, "scaling": args.scaling,
                           "cuda_graph_replay": None if ms_graph is None else {"ms_per_step": ms_graph, "value": 2 * n_total / (ms_graph * 1e-3)},
                           "fused_peer_exchange": None if ms_fused is None else {"ms_per_step": ms_fused, "value": 2 * n_total / (ms_fused * 1e-3), "x_identical_to_nccl_path": fused_matches,
@@ -441,7 +471,8 @@ def bench_angular_dist(args, L, stream):
                           "collective": {"op": "all_gather", "bytes_per_rank": tsz.value * 8, "backend": "nccl"},
                           "x2_identical_on_all_ranks": same,
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * G, "unit": "GB/s", "frac": ach / (peak * G), "peak_source": src},
-                          "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}), flush=True)
+                          "steps": args.steps, "warmup": args.warmup, "dtype": "f64"})
+    return None
 
 
 def bench_mixed_dist(args, L, stream):
@@ -476,10 +507,11 @@ def bench_mixed_dist(args, L, stream):
         alg = float((16 * r64 * c64 + 8 * r64 + 16 * c64).sum())
         fl = float((2 * r64 * c64 * c64 - (2.0 / 3.0) * c64 ** 3 + 4 * r64 * c64 + c64 * c64).sum())
         rows_total = int(br_all.sum())
-        print(json.dumps({"workload": f"mixed block-diagonal, {nb_total} blocks 32x16..128x64 over {G} GPU(s) (BASELINE config 5), byte-balanced contiguous ranges, no collective",
+        return ({"workload": f"mixed block-diagonal, {nb_total} blocks 32x16..128x64 over {G} GPU(s) (BASELINE config 5), byte-balanced contiguous ranges, no collective",
                           "metric": "rows/s", "value": rows_total / (ms * 1e-3), "ms_per_step": ms, "n_gpus": G, "scaling": args.scaling,
-                          "roofline": {"hbm_frac": alg / (ms * 1e-3) / 1e9 / (peak * G), "fp64_frac_nominal_37TF": fl / (ms * 1e-3) / 1e12 / (37.0 * G), "peak_source": src},
-                          "steps": args.steps, "dtype": "f64"}), flush=True)
+                          "roofline": {"hbm_frac": alg / (ms * 1e-3) / 1e9 / (peak * G), "fp64_frac_nominal": fl / (ms * 1e-3) / 1e12 / (FP64_NOMINAL_TFLOPS * G), "peak_source": src},
+                          "steps": args.steps, "dtype": "f64"})
+    return None
 
 
 def bench_lm(args, L, stream):
@@ -528,8 +560,8 @@ def bench_lm(args, L, stream):
                     "cost": [float(v) for v in cost.cpu().numpy()], "max_param_error": err})
     published = {"QRkitBD_total_seconds": {"500": 0.005, "2000": 0.017, "10000": 0.098, "100000": 1.036, "500000": 5.342},
                  "source": "imgs/benchmark_table.png via README.md:29 (whole LM fit, unstated CPU; Eigen LevenbergMarquardt, more iterations than Gauss-Newton needs)"}
-    print(json.dumps({"workload": "ellipse fit entirely on the device: Jacobian assembly + BlockAngularSparseQR compute+solve + update per iteration (Gauss-Newton from the reference's initialisation)",
-                      "fits": res, "reference_published": published, "dtype": "f64"}), flush=True)
+    return {"workload": "ellipse fit entirely on the device: Jacobian assembly + BlockAngularSparseQR compute+solve + update per iteration (Gauss-Newton from the reference's initialisation)",
+            "fits": res, "reference_published": published, "dtype": "f64"}
 
 
 def main():
@@ -545,6 +577,10 @@ def main():
     ap.add_argument("--lm-points", default="500,10000,100000,500000,1000000")
     ap.add_argument("--lm-iters", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle timings (cpu_baseline)")
+    ap.add_argument("--cpu-points", type=int, default=500_000, help="points of the CPU oracle sample of config 3")
+    ap.add_argument("--cpu-mixed-blocks", type=int, default=5000, help="blocks of the CPU oracle sample of config 5")
+    ap.add_argument("--cpu-banded-blocks", type=int, default=50_000, help="block rows of the CPU oracle sample of config 4")
+    ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="multi-GPU: skip the CUDA-graph replays")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="multi-GPU runs (torchrun): shard the named shape, or one named shape per GPU")
     args = ap.parse_args()
     if not torch.cuda.is_available():
@@ -567,7 +603,9 @@ def main():
                 if dist.get_rank() == 0:
                     print(json.dumps({"workload": w, "skipped": "single-GPU workload (banded: sequential window chain, replicas only)"}), flush=True)
                 continue
-            fn(args, L, stream)
+            line = fn(args, L, stream)
+            if line is not None:
+                print(json.dumps(line), flush=True)
         dist.barrier()
         dist.destroy_process_group()
         return
@@ -577,7 +615,8 @@ def main():
     stream = C.c_void_p(s.cuda_stream)
     L = capi.lib()
     for w in args.workload.split(","):
-        {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call, "classes": bench_classes, "banded": bench_banded, "angular_wide": bench_angular_wide, "lm": bench_lm}[w](args, L, stream)
+        line = {"angular": bench_angular, "mixed": bench_mixed, "two_call": bench_two_call, "classes": bench_classes, "banded": bench_banded, "angular_wide": bench_angular_wide, "lm": bench_lm}[w](args, L, stream)
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

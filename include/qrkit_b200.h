@@ -127,6 +127,17 @@ QRK_API int qrk_set_blocks(qrk_handle_t h, const double* values, int memspace);
 QRK_API int qrk_adopt_blocks(qrk_handle_t h, double* device_values);
 QRK_API int qrk_total_values(qrk_handle_t h, int64_t* n);
 
+/* Host side of the upload (the reference keeps the blocks in a std::vector<Block> on the host, SparseBlockDiagonal.h:46,159).
+ * Host-memspace calls run at PCIe speed only from PINNED memory that is NUMA-local to the GPU; with one process per GPU on a
+ * two-socket host, buffers that all land on one socket cap the aggregate upload (measured: 1/2/4/8 ranks 59/57/30/22 GB/s each).
+ *   qrk_bind_host_thread_to_device  pins the CALLING thread to the CPUs of the GPU's PCIe root complex (sysfs local_cpulist of
+ *                                   its bus id) and makes that NUMA node the preferred one for the thread's allocations;
+ *                                   *numa_node = -1 and *cpus_bound = 0 when the platform does not expose the topology
+ *   qrk_host_alloc / qrk_host_free  page-locked host memory (cudaHostAlloc), allocated and first-touched under that binding */
+QRK_API int qrk_bind_host_thread_to_device(int32_t device, int32_t* numa_node, int32_t* cpus_bound);
+QRK_API int qrk_host_alloc(void** ptr, int64_t bytes, int32_t device);
+QRK_API int qrk_host_free(void* ptr);
+
 /* ---- compute / factorize (BlockDiagonalSparseQR.h:94-104, 415-547) ----------------------------- */
 /* row_perm: optional int32[n_rows] host array, the rowPerm argument of compute()/analyzePattern()
  * (:94,:392-400); NULL => identity.  It is stored and returned by rowsPermutation() only — as in

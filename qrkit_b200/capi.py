@@ -92,6 +92,8 @@ def lib():
             "qrk_angular_p2p_attach": [vp, C.POINTER(vp), i32, i32],
             "qrk_angular_p2p_status": [vp, C.POINTER(i32)],
             "qrk_ipc_export": [vp, vp], "qrk_ipc_import": [vp, C.POINTER(vp)], "qrk_ipc_close": [vp],
+            "qrk_bind_host_thread_to_device": [i32, C.POINTER(i32), C.POINTER(i32)],
+            "qrk_host_alloc": [C.POINTER(vp), i64, i32], "qrk_host_free": [vp],
             "qrk_synth_fill": [vp, C.c_uint64, i64, i64, i32, i32, C.c_double, C.c_double, vp],
             "qrk_device_count": [C.POINTER(C.c_int)],
             "qrk_ellipse_points": [vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp],

@@ -1,7 +1,12 @@
 // capi.cu — the C ABI of qrkit_b200 (include/qrkit_b200.h): handle management, block-COO upload,
 // kernel dispatch.  Host logic only; every floating-point operation of the hot path runs in the
 // CUDA kernels of bd_small.cuh / bd_generic.cuh.  There is deliberately no CPU fallback.
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -1089,6 +1094,79 @@ int qrk_total_values(qrk_handle_t h, int64_t* n) {
   if (!h || !n) return QRK_STATUS_INVALID_ARGUMENT;
   *n = h->total_values;
   return QRK_STATUS_OK;
+}
+
+// ---- NUMA-local pinned host memory (Linux; silently a no-op where sysfs / the syscalls are unavailable) ----------------
+static int parse_cpulist(const char* s, cpu_set_t* set) {
+  CPU_ZERO(set);
+  int count = 0;
+  while (*s) {
+    char* end = nullptr;
+    long a = std::strtol(s, &end, 10);
+    if (end == s) break;
+    long b = a;
+    s = end;
+    if (*s == '-') { b = std::strtol(s + 1, &end, 10); s = end; }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); count++; }
+    if (*s == ',') s++; else break;
+  }
+  return count;
+}
+
+int qrk_bind_host_thread_to_device(int32_t device, int32_t* numa_node, int32_t* cpus_bound) {
+  if (numa_node) *numa_node = -1;
+  if (cpus_bound) *cpus_bound = 0;
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  if (device < 0 || device >= ndev) return QRK_STATUS_INVALID_ARGUMENT;
+  char bus[64] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus) - 1, device) != cudaSuccess) { (void)cudaGetLastError(); return QRK_STATUS_OK; }
+  for (char* p = bus; *p; ++p) *p = (char)std::tolower((unsigned char)*p);
+  char path[160];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  int node = -1;
+  if (FILE* f = std::fopen(path, "r")) { if (std::fscanf(f, "%d", &node) != 1) node = -1; std::fclose(f); }
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  char list[4096] = {0};
+  if (FILE* f = std::fopen(path, "r")) { if (!std::fgets(list, sizeof(list) - 1, f)) list[0] = 0; std::fclose(f); }
+  cpu_set_t want, allowed, both;
+  const int n_local = parse_cpulist(list, &want);
+  int bound = 0;
+  if (n_local > 0 && sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+    CPU_AND(&both, &want, &allowed);                       // never leave the cpuset the container grants
+    bound = CPU_COUNT(&both);
+    if (bound > 0 && sched_setaffinity(0, sizeof(both), &both) != 0) bound = 0;
+  }
+  if (node >= 0 && node < 1024) {                          // MPOL_PREFERRED: allocations of this thread prefer the GPU's node
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+    (void)syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(8 * sizeof(mask)));
+  }
+  if (numa_node) *numa_node = node;
+  if (cpus_bound) *cpus_bound = bound;
+  return QRK_STATUS_OK;
+}
+
+int qrk_host_alloc(void** ptr, int64_t bytes, int32_t device) {
+  if (!ptr || bytes <= 0) return QRK_STATUS_INVALID_ARGUMENT;
+  *ptr = nullptr;
+  int st = qrk_bind_host_thread_to_device(device, nullptr, nullptr);
+  if (st != QRK_STATUS_OK) return st;
+  DeviceGuard g(device);
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return QRK_STATUS_ALLOC_FAILED; }
+  // pages are pinned at allocation; touching them here keeps the placement decision inside this (bound) thread even
+  // on drivers that populate lazily
+  volatile char* c = static_cast<volatile char*>(p);
+  for (int64_t i = 0; i < bytes; i += 4096) c[i] = 0;
+  *ptr = p;
+  return QRK_STATUS_OK;
+}
+
+int qrk_host_free(void* ptr) {
+  if (!ptr) return QRK_STATUS_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
 }
 
 int qrk_set_blocks(qrk_handle_t h, const double* values, int memspace) {
