@@ -46,7 +46,8 @@ typedef enum {
   QRK_STATUS_CUDA_ERROR = 3,
   QRK_STATUS_NO_DEVICE = 4,
   QRK_STATUS_ALLOC_FAILED = 5,
-  QRK_STATUS_UNSUPPORTED = 6
+  QRK_STATUS_UNSUPPORTED = 6,
+  QRK_STATUS_PEER_TIMEOUT = 7      /* fused peer exchange: a peer GPU never delivered its triangle; results are NaN-poisoned */
 } qrk_status;
 
 /* Eigen::ComputationInfo values, as returned by info() (BlockDiagonalSparseQR.h:309-313). */
@@ -177,6 +178,11 @@ QRK_API int qrk_packed_factors(qrk_handle_t h, double* packed, double* tau, int 
  * layout of the reference's Q format (FullQ: thin part first, complement after n_cols, :455-470). */
 QRK_API int qrk_apply_qt(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace);
 QRK_API int qrk_apply_q(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace);
+/* The thin factor Q1 = (A P) R^-1, n_rows x n_cols — the part of matrixQ() that _solve_impl (:266-267, topRows(rank)) and the
+ * LM caller read: Y = Q1^T B (B: n_rows x nrhs, Y: n_cols x nrhs) and X = Q1 Y.  Defined for every solver kind (block
+ * diagonal: FullQ layout only); for banded factors it is the only Q product there is (see below). */
+QRK_API int qrk_apply_qt_thin(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace);
+QRK_API int qrk_apply_q_thin(qrk_handle_t h, const double* Y, int64_t ldy, double* X, int64_t ldx, int32_t nrhs, int memspace);
 
 /* ---- solve (_solve_impl :258-280, solve :287-299) ------------------------------------------------ */
 /* X = P * R^-1 * (Q^T B)[0:rank]; B: n_rows x nrhs (ldb), X: n_cols x nrhs (ldx). */
@@ -190,14 +196,20 @@ QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, i
  *                                    R = [R1, Atop P2; 0, R2] (:285-308), P_c = [P1; m1 + P2] (:498-503)
  *   qrk_compute_solve / qrk_factorize_solve / qrk_solve   _solve_impl (:203-227); b: n, x: m1 + m2
  *   qrk_matrix_r(_nnz), qrk_cols_permutation, qrk_rank (= rank1 + rank2, :510), qrk_rows, qrk_cols (= m1 + m2)
- * qrk_apply_qt / qrk_apply_q / qrk_matrix_q / qrk_packed_factors keep referring to the LEFT factor Q1.
+ *   qrk_apply_qt / qrk_apply_q       matrixQ().transpose() * v = [I 0; 0 Q2^T] Q1^T v and matrixQ() * v = Q1 [I 0; 0 Q2] v on all
+ *                                    n rows (_QProduct::evalTo, :598-644): the left factor in its FullQ layout, then the right
+ *                                    solver's Q2 on the complement rows [m1, n).  On the fused TSQR path Q2 is built on demand
+ *                                    from the residual panel kept by qrk_compute (not by the fused qrk_compute_solve:
+ *                                    INVALID_ARGUMENT then), as the Householder QR of Abot P2 with its row signs aligned to R2
+ * qrk_matrix_q / qrk_packed_factors keep referring to the LEFT factor Q1 (the reference's matrixQ() is an expression, not a matrix).
  * Uniform left blocks of 2x1, 3x1, 4x2, 7x2 with 1 <= m2 <= 8 and a ColPiv right solver take the fused in-SM TSQR path
  * (and support the multi-GPU exchange below); every other left block / border width / right solver takes the dense
  * right-block path (blocked compact-WY with DMMA, then ColPiv on the triangle), single GPU.
  * left_solver = QRK_LEFT_BANDED_BLOCKED: J1 is block banded (values = the slabs, as for kind QRK_BANDED_BLOCKED); Q1^T [J2 | b] is
- * the two-phase banded application INCLUDING its complement (the rows outside range(J1), which the dense right block is
- * factored on), x1 = R1^-1 (y1 - Atop x2) the banded back substitution.  qrk_apply_qt / qrk_apply_q / qrk_packed_factors then
- * refer to the banded left factor (thin part).  Dense right-block path, single GPU. */
+ * the two-phase banded application INCLUDING its (extended) complement (the rows outside range(J1), which the dense right block
+ * is factored on), x1 = R1^-1 (y1 - Atop x2) the banded back substitution.  qrk_apply_qt_thin gives [Q1thin^T b; z2] (the
+ * vector _solve_impl back-substitutes); the n x n products qrk_apply_qt / qrk_apply_q return QRK_STATUS_UNSUPPORTED (banded
+ * factors have no n x n Q here, see below).  Dense right-block path, single GPU. */
 /* J2: n x m2 column-major with leading dimension ld (BlockMatrix1x2::rightBlock()).  Host: copied to the
  * device on the handle's stream; device: borrowed until the next compute returns. */
 QRK_API int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace);
@@ -218,9 +230,16 @@ QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count,
  *   qrk_ipc_export / _import  cudaIpcGetMemHandle / cudaIpcOpenMemHandle (64-byte handles) for one-process-per-GPU callers;
  *                             exchange the handles with any host-side collective (torch.distributed, MPI)
  *   qrk_angular_p2p_attach    peer_buffers[g] = rank g's exchange buffer as mapped in THIS process (own buffer at [rank])
- *   qrk_angular_p2p_status    *timed_out = 1 if a peer never arrived (the step then finished on incomplete data) */
+ *                             — every rank must have returned from attach (host barrier) before any rank starts a step
+ *   qrk_angular_p2p_set_timeout  bound of the in-kernel wait for the peers' flags, in seconds (default 10); ranks must launch
+ *                             their steps within this window of each other
+ *   qrk_angular_p2p_status    *timed_out = 1 if a peer never arrived.  The condition is sticky until the next attach; the
+ *                             merged triangle of that and every later step is poisoned with NaN (x, R2, the root record are
+ *                             NaN, never a plausible wrong answer) and qrk_synchronize / qrk_rank / host-memspace solves
+ *                             return QRK_STATUS_PEER_TIMEOUT */
 QRK_API int qrk_angular_xchg_buffer(qrk_handle_t h, void** device_ptr, int64_t* bytes);
 QRK_API int qrk_angular_p2p_attach(qrk_handle_t h, void* const* peer_buffers, int32_t world_size, int32_t rank);
+QRK_API int qrk_angular_p2p_set_timeout(qrk_handle_t h, double seconds);
 QRK_API int qrk_angular_p2p_status(qrk_handle_t h, int32_t* timed_out);
 QRK_API int qrk_ipc_export(const void* device_ptr, void* handle64);
 QRK_API int qrk_ipc_import(const void* handle64, void** device_ptr);
@@ -235,11 +254,12 @@ QRK_API int qrk_ipc_close(void* device_ptr);
  *   qrk_compute / qrk_factorize / qrk_compute_solve / qrk_factorize_solve    factorize (:443-519) (+ fused solve)
  *   qrk_solve                         Q^T b by the window sweep (:655-670 / SparseBlockYTY.h:102-139), banded back
  *                                     substitution (:299-304)
- *   qrk_apply_qt                      matrixQ().transpose() * b: the thin part [0, n_cols) (what solve and LM use); rows
- *                                     beyond n_cols are returned as zero (the reference's complement depends on its own
- *                                     window blocking and is not unique)
- *   qrk_apply_q                       matrixQ() * v for v = [thin part; 0]: Q1 * v[0:n_cols] (n_rows values), Q1 = A R^-1 the
- *                                     thin factor (unique up to column signs); entries of v beyond n_cols are ignored
+ *   qrk_apply_qt_thin / _q_thin       Q1^T b (n_cols values) and Q1 y (n_rows values), Q1 = A R^-1 the thin factor (unique up
+ *                                     to column signs): what solve and the LM caller use of matrixQ()
+ *   qrk_apply_qt / qrk_apply_q        QRK_STATUS_UNSUPPORTED: the two-phase factorisation represents Q as an isometry into an
+ *                                     EXTENDED complement (every group's overlap rows enter as virtual zero rows), so there
+ *                                     is no n x n orthogonal matrix to multiply with (the reference's complement depends on
+ *                                     its own window blocking and is not unique either)
  *   qrk_matrix_r(_nnz)                R as CSC with its natural band pattern (values as the reference up to row signs;
  *                                     the reference additionally stores explicit zeros of its merged windows, :484-491)
  *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation

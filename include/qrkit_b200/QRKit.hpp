@@ -133,9 +133,14 @@ class SparseBlockDiagonal {
 };
 
 namespace detail {
+// Every failing status throws, QRK_STATUS_NO_DEVICE included: there is no CPU fallback, so a compute()/solve() that cannot
+// run must not return as if it had (the handle-creating helpers probe for a device on their own and record it in info()).
 inline void throw_if(int status, qrk_handle_t h, const char* what) {
-  if (status != QRK_STATUS_OK && status != QRK_STATUS_NO_DEVICE)
+  if (status != QRK_STATUS_OK)
     throw std::runtime_error(std::string(what) + ": " + qrk_status_string(status) + (h ? std::string(" — ") + qrk_last_error(h) : ""));
+}
+inline void require(bool ok, const char* what) {
+  if (!ok) throw std::invalid_argument(what);
 }
 }  // namespace detail
 
@@ -170,7 +175,7 @@ class BlockDiagonalSparseQR {
   }
   void factorize(const MatrixType& mat) {                                                                     // :415-547
     ensureHandle(mat);
-    if (!m_h) return;
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "factorize");
     static_assert(sizeof(BlockMatrixType) == sizeof(double) * BlockMatrixType::RowsAtCompileTime * BlockMatrixType::ColsAtCompileTime,
                   "fixed-size blocks are stored back to back: the std::vector of blocks IS the block-COO value array");
     const double* values = mat.size() ? mat[0].data() : nullptr;
@@ -261,7 +266,7 @@ class BlockDiagonalSparseQR {
   VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {
     ensureHandle(mat);
     VectorXd x((size_t)m_cols);
-    if (!m_h) return x;
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "computeAndSolve");
     detail::throw_if(qrk_compute_solve(m_h, mat.size() ? mat[0].data() : nullptr, b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
     m_haveR = false; m_isInitialized = true;
     return x;
@@ -334,7 +339,7 @@ class BlockAngularSparseQR {
 
   void compute(const MatrixType& mat) {                                                                       // :134-138
     ensureHandle(mat);
-    if (!m_h) return;
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "compute");
     const auto& L = mat.leftBlock();
     detail::throw_if(qrk_set_border(m_h, mat.rightBlock().data(), mat.rightBlock().rows(), QRK_HOST), m_h, "compute/border");
     detail::throw_if(qrk_compute(m_h, L.size() ? L[0].data() : nullptr, QRK_HOST), m_h, "compute");
@@ -343,7 +348,7 @@ class BlockAngularSparseQR {
   VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {
     ensureHandle(mat);
     VectorXd x((size_t)mat.cols());
-    if (!m_h) return x;
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "computeAndSolve");
     const auto& L = mat.leftBlock();
     detail::throw_if(qrk_set_border(m_h, mat.rightBlock().data(), mat.rightBlock().rows(), QRK_HOST), m_h, "border");
     detail::throw_if(qrk_compute_solve(m_h, L.size() ? L[0].data() : nullptr, b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
@@ -405,7 +410,7 @@ class BlockAngularSparseQR {
     detail::throw_if(st, nullptr, "BlockAngularSparseQR");
   }
   qrk_handle_t m_h = nullptr;
-  Index m_nb = -1, m_m2 = 0, m_rows = 0, m_cols = 0;
+  Index m_nb = -1, m_m2 = 0, m_matCols = 0, m_rows = 0, m_cols = 0;
   bool m_isInitialized = false;
   mutable bool m_haveR = false;
   mutable MatrixRType m_R;
@@ -428,17 +433,20 @@ class BandedBlockedSparseQR {
   BandedBlockedSparseQR(const BandedBlockedSparseQR&) = delete;
   BandedBlockedSparseQR& operator=(const BandedBlockedSparseQR&) = delete;
 
-  void compute(const std::vector<double>& slabs, Index numBlocks) {                                           // :170-178
-    ensureHandle(numBlocks);
-    if (!m_h) return;
-    detail::throw_if(qrk_compute(m_h, slabs.data(), QRK_HOST), m_h, "compute");
+  // matCols: columns of the matrix when its last slab is narrower than BlockCols — the reference's pattern gives the last
+  // block BlockCols - BlockOverlap columns (SparseQRUtils.h:284, test/test-qrkit.cpp:63-96); 0 = a full last slab
+  void compute(const std::vector<double>& slabs, Index numBlocks, Index matCols = 0) {                        // :170-178
+    ensureHandle(numBlocks, matCols);
+    detail::require((Index)slabs.size() >= numBlocks * BlockRows * BlockCols, "BandedBlockedSparseQR::compute: slabs holds fewer than numBlocks * BlockRows * BlockCols values");
+    detail::throw_if(m_h ? qrk_compute(m_h, slabs.data(), QRK_HOST) : (int)QRK_STATUS_NO_DEVICE, m_h, "compute");
     m_haveR = false; m_isInitialized = true;
   }
-  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const VectorXd& b) {
-    ensureHandle(numBlocks);
+  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const VectorXd& b, Index matCols = 0) {
+    ensureHandle(numBlocks, matCols);
+    detail::require((Index)slabs.size() >= numBlocks * BlockRows * BlockCols, "BandedBlockedSparseQR::computeAndSolve: slabs holds fewer than numBlocks * BlockRows * BlockCols values");
+    detail::require((Index)b.size() == m_rows, "BandedBlockedSparseQR::computeAndSolve: b.size() != rows()");
     VectorXd x((size_t)m_cols);
-    if (!m_h) return x;
-    detail::throw_if(qrk_compute_solve(m_h, slabs.data(), b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
+    detail::throw_if(m_h ? qrk_compute_solve(m_h, slabs.data(), b.data(), x.data(), QRK_HOST) : (int)QRK_STATUS_NO_DEVICE, m_h, "computeAndSolve");
     m_haveR = false; m_isInitialized = true;
     return x;
   }
@@ -458,31 +466,37 @@ class BandedBlockedSparseQR {
     }
     return m_R;
   }
-  VectorXd applyQt(const VectorXd& v) const {                                                                 // matrixQ().transpose() * v (:655-670)
-    VectorXd y((size_t)m_rows);
-    detail::throw_if(qrk_apply_qt(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ().transpose() * v");
+  // The thin factor Q1 = A R^-1 (rows() x cols()): what solve() and the LM caller read of matrixQ() (:299, topRows(rank)).
+  // The two-phase factorisation has no n x n Q (banded.cuh), so these are the Q products of this solver.
+  VectorXd applyQt(const VectorXd& v) const {                                                                 // (matrixQ().transpose() * v).topRows(cols()) (:655-670)
+    detail::require((Index)v.size() == m_rows, "applyQt: v.size() != rows()");
+    VectorXd y((size_t)m_cols);
+    detail::throw_if(qrk_apply_qt_thin(m_h, v.data(), m_rows, y.data(), m_cols, 1, QRK_HOST), m_h, "matrixQ().transpose() * v");
     return y;
   }
-  VectorXd applyQ(const VectorXd& v) const {                                                                  // matrixQ() * v (:640-675) on the thin part:
-    VectorXd y((size_t)m_rows);                                                                              // Q1 * v[0:cols] (the complement is taken as zero)
-    detail::throw_if(qrk_apply_q(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ() * v");
-    return y;
+  VectorXd applyQ(const VectorXd& y) const {                                                                  // matrixQ() * [y; 0] (:640-675)
+    detail::require((Index)y.size() == m_cols, "applyQ: y.size() != cols()");
+    VectorXd x((size_t)m_rows);
+    detail::throw_if(qrk_apply_q_thin(m_h, y.data(), m_cols, x.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ() * y");
+    return x;
   }
   VectorXd solve(const VectorXd& B) const {                                                                   // :287-307
     assert(m_isInitialized && "The factorization should be called first, use compute()");
+    detail::require((Index)B.size() == m_rows, "solve: B.size() != rows()");
     VectorXd x((size_t)m_cols);
     detail::throw_if(qrk_solve(m_h, B.data(), m_rows, x.data(), m_cols, 1, QRK_HOST), m_h, "solve");
     return x;
   }
  private:
-  void ensureHandle(Index numBlocks) {
-    if (m_h && m_nb == numBlocks) return;
+  void ensureHandle(Index numBlocks, Index matCols) {
+    if (m_h && m_nb == numBlocks && m_matCols == matCols) return;
     qrk_destroy(m_h);
     m_h = nullptr;
     qrk_desc_t d{};
     d.kind = QRK_BANDED_BLOCKED; d.num_blocks = numBlocks; d.block_rows = BlockRows; d.block_cols = BlockCols; d.block_overlap = BlockOverlap;
+    d.n_cols = matCols;
     const int st = qrk_create(&d, &m_h);
-    m_nb = numBlocks;
+    m_nb = numBlocks; m_matCols = matCols;
     if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
     detail::throw_if(st, nullptr, "BandedBlockedSparseQR");
     int64_t r = 0, c = 0;
@@ -490,7 +504,7 @@ class BandedBlockedSparseQR {
     m_rows = r; m_cols = c;
   }
   qrk_handle_t m_h = nullptr;
-  Index m_nb = -1, m_rows = 0, m_cols = 0;
+  Index m_nb = -1, m_matCols = 0, m_rows = 0, m_cols = 0;
   bool m_isInitialized = false;
   mutable bool m_haveR = false;
   mutable MatrixRType m_R;
@@ -510,17 +524,22 @@ class BlockAngularBandedSparseQR {
   BlockAngularBandedSparseQR(const BlockAngularBandedSparseQR&) = delete;
   BlockAngularBandedSparseQR& operator=(const BlockAngularBandedSparseQR&) = delete;
 
-  void compute(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border) {                   // :134-138
-    ensureHandle(numBlocks, border);
-    if (!m_h) return;
+  // matCols: columns of the whole matrix [J1 | J2] when the last slab of J1 is narrower than BlockCols (see BandedBlockedSparseQR)
+  void compute(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border, Index matCols = 0) {   // :134-138
+    ensureHandle(numBlocks, border, matCols);
+    detail::require((Index)slabs.size() >= numBlocks * BlockRows * BlockCols, "BlockAngularBandedSparseQR::compute: slabs holds fewer than numBlocks * BlockRows * BlockCols values");
+    detail::require(border.rows() == m_rows, "BlockAngularBandedSparseQR::compute: border.rows() != rows()");
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "compute");
     detail::throw_if(qrk_set_border(m_h, border.data(), border.rows(), QRK_HOST), m_h, "compute/border");
     detail::throw_if(qrk_compute(m_h, slabs.data(), QRK_HOST), m_h, "compute");
     m_haveR = false; m_isInitialized = true;
   }
-  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border, const VectorXd& b) {
-    ensureHandle(numBlocks, border);
+  VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const MatrixXd& border, const VectorXd& b, Index matCols = 0) {
+    ensureHandle(numBlocks, border, matCols);
+    detail::require((Index)slabs.size() >= numBlocks * BlockRows * BlockCols, "BlockAngularBandedSparseQR::computeAndSolve: slabs holds fewer than numBlocks * BlockRows * BlockCols values");
+    detail::require(border.rows() == m_rows && (Index)b.size() == m_rows, "BlockAngularBandedSparseQR::computeAndSolve: border.rows() / b.size() != rows()");
     VectorXd x((size_t)m_cols);
-    if (!m_h) return x;
+    if (!m_h) detail::throw_if(QRK_STATUS_NO_DEVICE, nullptr, "computeAndSolve");
     detail::throw_if(qrk_set_border(m_h, border.data(), border.rows(), QRK_HOST), m_h, "border");
     detail::throw_if(qrk_compute_solve(m_h, slabs.data(), b.data(), x.data(), QRK_HOST), m_h, "computeAndSolve");
     m_haveR = false; m_isInitialized = true;
@@ -555,9 +574,9 @@ class BlockAngularBandedSparseQR {
     return x;
   }
  private:
-  void ensureHandle(Index numBlocks, const MatrixXd& border) {
+  void ensureHandle(Index numBlocks, const MatrixXd& border, Index matCols) {
     const Index m2 = border.cols();
-    if (m_h && m_nb == numBlocks && m_m2 == m2) return;
+    if (m_h && m_nb == numBlocks && m_m2 == m2 && m_matCols == matCols) return;
     qrk_destroy(m_h);
     m_h = nullptr;
     qrk_desc_t d{};
@@ -565,14 +584,15 @@ class BlockAngularBandedSparseQR {
     d.block_rows = BlockRows; d.block_cols = BlockCols; d.block_overlap = BlockOverlap;
     d.pivoting = QRK_PIVOT_NONE; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2;
     d.right_solver = RightSolverTag::pivoting == QRK_PIVOT_COLPIV ? QRK_RIGHT_COLPIV : QRK_RIGHT_UNPIVOTED;
+    d.n_cols = matCols;                                                                                     // m1 + m2 (0: full last slab)
     const int st = qrk_create(&d, &m_h);
-    m_nb = numBlocks; m_m2 = m2; m_rows = numBlocks * BlockRows;
-    m_cols = (numBlocks - 1) * (BlockCols - BlockOverlap) + BlockCols + m2;
+    m_nb = numBlocks; m_m2 = m2; m_matCols = matCols; m_rows = numBlocks * BlockRows;
+    m_cols = matCols > 0 ? matCols : (numBlocks - 1) * (BlockCols - BlockOverlap) + BlockCols + m2;
     if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
     detail::throw_if(st, nullptr, "BlockAngularBandedSparseQR");
   }
   qrk_handle_t m_h = nullptr;
-  Index m_nb = -1, m_m2 = 0, m_rows = 0, m_cols = 0;
+  Index m_nb = -1, m_m2 = 0, m_matCols = 0, m_rows = 0, m_cols = 0;
   bool m_isInitialized = false;
   mutable bool m_haveR = false;
   mutable MatrixRType m_R;

@@ -19,6 +19,7 @@ QRK_STATUS_CUDA_ERROR = 3
 QRK_STATUS_NO_DEVICE = 4
 QRK_STATUS_ALLOC_FAILED = 5
 QRK_STATUS_UNSUPPORTED = 6
+QRK_STATUS_PEER_TIMEOUT = 7
 
 QRK_INFO_SUCCESS, QRK_INFO_NUMERICAL_ISSUE, QRK_INFO_NO_CONVERGENCE, QRK_INFO_INVALID_INPUT = 0, 1, 2, 3
 QRK_BLOCK_DIAGONAL, QRK_BLOCK_ANGULAR, QRK_BANDED_BLOCKED = 0, 1, 2
@@ -83,6 +84,8 @@ def lib():
             "qrk_packed_factors": [vp, vp, vp, C.c_int],
             "qrk_apply_qt": [vp, vp, i64, vp, i64, i32, C.c_int],
             "qrk_apply_q": [vp, vp, i64, vp, i64, i32, C.c_int],
+            "qrk_apply_qt_thin": [vp, vp, i64, vp, i64, i32, C.c_int],
+            "qrk_apply_q_thin": [vp, vp, i64, vp, i64, i32, C.c_int],
             "qrk_solve": [vp, vp, i64, vp, i64, i32, C.c_int],
             "qrk_launch_count": [vp, C.POINTER(i64)],
             "qrk_set_border": [vp, vp, i64, C.c_int], "qrk_angular_set_world": [vp, i32],
@@ -90,7 +93,7 @@ def lib():
             "qrk_angular_merge": [vp, vp, i32, C.c_int],
             "qrk_angular_xchg_buffer": [vp, C.POINTER(vp), C.POINTER(i64)],
             "qrk_angular_p2p_attach": [vp, C.POINTER(vp), i32, i32],
-            "qrk_angular_p2p_status": [vp, C.POINTER(i32)],
+            "qrk_angular_p2p_status": [vp, C.POINTER(i32)], "qrk_angular_p2p_set_timeout": [vp, C.c_double],
             "qrk_ipc_export": [vp, vp], "qrk_ipc_import": [vp, C.POINTER(vp)], "qrk_ipc_close": [vp],
             "qrk_bind_host_thread_to_device": [i32, C.POINTER(i32), C.POINTER(i32)],
             "qrk_host_alloc": [C.POINTER(vp), i64, i32], "qrk_host_free": [vp],

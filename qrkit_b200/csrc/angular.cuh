@@ -383,13 +383,23 @@ angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__
 // into every peer's exchange buffer over NVLink (buffers mapped with cudaIpcOpenMemHandle), followed by a flag per
 // (step parity, source rank).  Buffer layout (identical on every rank): [2][G][Tri::N] doubles, then [2][G] uint64 flags.
 // A rank can run at most one step ahead of a peer (it waits for the peer's flag of the current step), so two parities
-// suffice.  The spin is bounded (~2 s): on a timeout *err is set and the step finishes with whatever arrived.
+// suffice.  The spin is bounded (timeout_ns of %globaltimer, default 10 s, qrk_angular_p2p_set_timeout): on a timeout *err is
+// set (sticky until the next attach) and the merged triangle is POISONED with NaN, so that x2, x1, R2 and the root record of
+// this and every later step are NaN on the ranks that saw it — never a plausible-looking wrong answer; the host entry points
+// that synchronise (qrk_synchronize, qrk_rank, host-memspace solves) report QRK_STATUS_PEER_TIMEOUT.
 struct AngularXchg {
   double* const* peers = nullptr;   // device array of G pointers: peers[g] = rank g's exchange buffer as mapped here
   int world = 0, rank = 0;
   unsigned long long* seq = nullptr; // device-resident step counter (the kernel advances it: a captured launch replays correctly)
   int* err = nullptr;
+  unsigned long long timeout_ns = 10000000000ull;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int M2, int TPB>
 __device__ __forceinline__ void merge_triangle_list(const double* tris, int count, double (&T)[Tri<M2>::N], double* scratch,
@@ -463,14 +473,15 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
     if (threadIdx.x < G) {
       const volatile unsigned long long* mine =
           reinterpret_cast<const volatile unsigned long long*>(xc.peers[xc.rank] + (size_t)2 * G * N) + (size_t)par * G + threadIdx.x;
-      const long long t0 = clock64();
+      const unsigned long long t0 = global_timer_ns();
       while (*mine != seq) {
-        if (clock64() - t0 > (1LL << 32)) { *xc.err = 1; break; }
+        if (global_timer_ns() - t0 > xc.timeout_ns) { atomicExch(xc.err, 1); break; }
       }
       __threadfence_system();
     }
     __syncthreads();
     if (threadIdx.x == 0) *xc.seq = seq;
+    const bool broken = *reinterpret_cast<volatile int*>(xc.err) != 0;   // this step or an earlier one lost a peer
     // ---- the G triangles in rank order: the same data, the same order, the same arithmetic on every rank
     if (G <= 32) {                            // one triangle per lane of warp 0: a single cooperative warp merge
       const double* src = xc.peers[xc.rank] + (size_t)par * G * N;
@@ -481,6 +492,11 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
       }
     } else {
       merge_triangle_list<M2, TPB>(xc.peers[xc.rank] + (size_t)par * G * N, G, T, scratch, true);
+    }
+    if (broken) {
+      const double poison = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+      for (int i = 0; i < N; i++) T[i] = poison;
     }
   }
   if (threadIdx.x != 0) return;

@@ -40,6 +40,7 @@ struct AngularArgs {
   int xchg_world = 0, xchg_rank = 0;
   unsigned long long* xchg_seq = nullptr;
   int* xchg_err = nullptr;
+  unsigned long long xchg_timeout_ns = 0;   // 0: the kernel's default (10 s)
 };
 
 struct AngularVTable {

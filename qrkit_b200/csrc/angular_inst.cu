@@ -136,6 +136,7 @@ cudaError_t backsolve(const AngularArgs& a, cudaStream_t s) {
 cudaError_t root(const AngularArgs& a, cudaStream_t s) {
   AngularXchg xc;
   xc.peers = a.xchg_peers; xc.world = a.xchg_world; xc.rank = a.xchg_rank; xc.seq = a.xchg_seq; xc.err = a.xchg_err;
+  if (a.xchg_timeout_ns) xc.timeout_ns = a.xchg_timeout_ns;
   if (a.root_mode == 2)
     angular_root_kernel<M2, 512, true><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
                                                          a.perm_tail, a.m1, xc);

@@ -63,6 +63,9 @@ namespace {
     }                                             \
   } while (0)
 
+struct DeviceGuard;
+int peer_exchange_status(qrk_solver* h);   // QRK_STATUS_PEER_TIMEOUT once the fused exchange lost a peer (call after a stream sync)
+
 struct DeviceGuard {
   int prev = -1;
   // Also clears a stale non-sticky error another library left in this thread (NCCL's lazy communicator set-up leaves
@@ -253,6 +256,7 @@ void free_dev(qrk_solver* h) {
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
   F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wpart); F(h->d_xchg); F(h->d_xchg_peers); F(h->d_xchg_err); F(h->d_xchg_seq); F(h->d_wperm); F(h->d_wiscal);
+  F(h->d_q2); F(h->d_q2tau); F(h->d_q2sign); F(h->d_q2scr); F(h->d_qtmp); F(h->d_qthin); F(h->d_q2iscr);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
   h->classes.clear();
@@ -472,7 +476,7 @@ int angular_root_and_back(qrk_solver* h, AngularArgs& a, bool have_rhs, double* 
   if (h->world > 1) {
     a.root_mode = 2;
     a.xchg_peers = h->d_xchg_peers; a.xchg_world = h->world; a.xchg_rank = h->xchg_rank; a.xchg_err = h->d_xchg_err;
-    a.xchg_seq = h->d_xchg_seq;
+    a.xchg_seq = h->d_xchg_seq; a.xchg_timeout_ns = h->xchg_timeout_ns;
   }
   a.keep_rhs_only = keep_rhs_only;
   QRK_TRY_CUDA(h, h->avt->root(a, h->stream));
@@ -745,8 +749,125 @@ int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
   return wide_back(h, true, d_x);
 }
 
+
+// ---- matrixQ() of the block-angular solver: Q = Q1 [I 0; 0 Q2] (BlockAngularSparseQR.h:598-644) ---------------------------
+// The dense right block's Q2 acts on the complement rows [m1, n) of the left factor's FullQ layout.
+//  * dense right-block path: the stored factorisation (one Householder QR, or the blocked first stage followed by the
+//    ColPiv reflectors of its triangle) is applied as it is for solve(b).
+//  * fused TSQR path: the tree keeps no reflectors, so Q2 is built on demand from the residual panel kept by compute():
+//    an unpivoted Householder QR of Abot in the column order P2 the root chose (R is unique up to row signs for a fixed
+//    column order; the signs are aligned with the stored R2 so that Q^T A P_c = R holds entry by entry).
+int ensure_q2(qrk_solver* h) {
+  if (h->wide || h->q2_ready) return QRK_STATUS_OK;
+  QRK_REQUIRE(h, h->have_abot, "matrixQ() of the block-angular solver needs compute(): the fused compute_solve() does not keep the residual panel");
+  QRK_REQUIRE(h, h->root_done, "the TSQR root has not run yet (multi-GPU: call qrk_angular_merge first)");
+  const long long N = h->n_rows - h->sum_cols;
+  const int M = h->m2;
+  if (!h->d_q2) {
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_q2, std::max<long long>(1, N * M) * sizeof(double)));
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_q2tau, M * sizeof(double)));
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_q2sign, M * sizeof(double)));
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_q2scr, (2 * M + 2) * sizeof(double)));
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_q2iscr, (M + 1) * sizeof(int)));
+  }
+  std::vector<int> p2(M);
+  QRK_TRY_CUDA(h, cudaMemcpyAsync(p2.data(), h->d_root_i, M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < M; c++)
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_q2 + (long long)c * N, h->d_abot + (long long)p2[c] * N, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  QRK_TRY_CUDA(h, cudaMemsetAsync(h->d_q2tau, 0, M * sizeof(double), h->stream));
+  DenseBorder d;
+  d.A = h->d_q2; d.ld = N; d.N = N; d.Nrule = N; d.M = M; d.nrhs = 0; d.pivot = 0;
+  d.upd = h->d_q2scr; d.dir = h->d_q2scr + M; d.scal = h->d_q2scr + 2 * M; d.tau = h->d_q2tau;
+  d.perm = h->d_q2iscr; d.iscal = h->d_q2iscr + M;
+  if (N > 0) {
+    int st = wide_unblocked(h, d);
+    if (st != QRK_STATUS_OK) return st;
+  }
+  dense_diag_sign_kernel<<<1, 64, 0, h->stream>>>(h->d_q2, N, h->d_root, M, (int)std::min<long long>(N, M), h->d_q2sign);
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  h->launches++;
+  h->q2_ready = true;
+  return QRK_STATUS_OK;
+}
+
+// vec (the n - m1 complement rows of one column) <- Q2^T vec (transpose) or Q2 vec
+int apply_q2(qrk_solver* h, double* vec, bool transpose) {
+  const int M = h->m2;
+  if (!h->wide) {
+    DenseBorder d;
+    d.A = h->d_q2; d.ld = h->n_rows - h->sum_cols; d.N = d.ld; d.Nrule = d.N; d.M = M; d.nrhs = 0; d.pivot = 0; d.tau = h->d_q2tau;
+    d.upd = d.dir = d.scal = nullptr; d.perm = d.iscal = nullptr;
+    if (d.N <= 0) return QRK_STATUS_OK;
+    if (transpose) {
+      dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(d, vec);
+      dense_scale_head_kernel<<<1, 64, 0, h->stream>>>(vec, h->d_q2sign, (int)std::min<long long>(d.N, M));
+    } else {
+      dense_scale_head_kernel<<<1, 64, 0, h->stream>>>(vec, h->d_q2sign, (int)std::min<long long>(d.N, M));
+      dense_apply_q_kernel<1024><<<1, 1024, 0, h->stream>>>(d, vec);
+    }
+    h->launches += 2;
+    QRK_TRY_CUDA(h, cudaGetLastError());
+    return QRK_STATUS_OK;
+  }
+  DenseBorder d = wide_desc(h, 1);
+  if (d.N <= 0) return QRK_STATUS_OK;
+  const bool two_stage = h->wide_blocked && d.pivot;
+  if (two_stage) d.tau = h->d_wtau1;
+  double* head = h->d_wtri + (size_t)M * M;        // the right-hand side column of the triangle: scratch for the second stage
+  const DenseBorder t = wide_tri_desc(h, 1);
+  if (transpose) {
+    dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(d, vec);
+    h->launches++;
+    if (two_stage) {
+      QRK_TRY_CUDA(h, cudaMemcpyAsync(head, vec, M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(t, head);
+      QRK_TRY_CUDA(h, cudaMemcpyAsync(vec, head, M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      h->launches++;
+    }
+  } else {
+    if (two_stage) {
+      QRK_TRY_CUDA(h, cudaMemcpyAsync(head, vec, M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      dense_apply_q_kernel<1024><<<1, 1024, 0, h->stream>>>(t, head);
+      QRK_TRY_CUDA(h, cudaMemcpyAsync(vec, head, M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      h->launches++;
+    }
+    dense_apply_q_kernel<1024><<<1, 1024, 0, h->stream>>>(d, vec);
+    h->launches++;
+  }
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  return QRK_STATUS_OK;
+}
+
+// matrixQ().transpose() * B / matrixQ() * B for a block-angular handle (device pointers, FullQ layout of the left factor)
+int angular_apply(qrk_solver* h, int op, const double* d_B, long long ldb, double* d_X, long long ldx, int nrhs) {
+  if (h->left_banded) {
+    h->err = "matrixQ() products with a banded left solver are not provided (the two-phase banded Q1 has an extended complement)";
+    return QRK_STATUS_UNSUPPORTED;
+  }
+  QRK_REQUIRE(h, h->world == 1, "matrixQ() products of a multi-GPU block-angular handle are not provided (Q2 spans all ranks' rows)");
+  int st = ensure_q2(h);
+  if (st != QRK_STATUS_OK) return st;
+  const long long m1 = h->sum_cols, n = h->n_rows;
+  if (op == OP_APPLY_QT) {
+    st = run_op(h, OP_APPLY_QT, d_B, ldb, d_X, ldx, nrhs);                       // Q1^T v (:616-618)
+    for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) st = apply_q2(h, d_X + j * ldx + m1, true);   // Q2^T on rows [m1, n) (:619-624)
+    return st;
+  }
+  // Q v = Q1 [v1; Q2 v2] (:633-642): the bottom rows change before Q1 sees them, so work on a copy
+  const long long ldt = (n + 1) & ~1LL;
+  st = ensure_buffer(h, h->d_qtmp, h->cap_qtmp, (size_t)ldt * nrhs);
+  if (st != QRK_STATUS_OK) return st;
+  QRK_TRY_CUDA(h, cudaMemcpy2DAsync(h->d_qtmp, ldt * sizeof(double), d_B, ldb * sizeof(double), n * sizeof(double), nrhs,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+  for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) st = apply_q2(h, h->d_qtmp + j * ldt + m1, false);
+  if (st != QRK_STATUS_OK) return st;
+  return run_op(h, OP_APPLY_Q, h->d_qtmp, ldt, d_X, ldx, nrhs);
+}
+
 int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x, bool keep_abot) {
   QRK_REQUIRE(h, h->d_border, "no border set: call qrk_set_border first (BlockMatrix1x2 right block)");
+  h->q2_ready = false;
   if (h->wide) return wide_run(h, A_in, d_b, d_x);
   AngularArgs a = angular_args(h);
   a.A_in = A_in;
@@ -829,6 +950,14 @@ std::vector<int> banded_r_outer(const qrk_solver* h) {
   return outer;
 }
 
+int peer_exchange_status(qrk_solver* h) {
+  if (!h->d_xchg_err || h->xchg_rank < 0) return QRK_STATUS_OK;
+  int flag = 0;
+  if (cudaMemcpy(&flag, h->d_xchg_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { (void)cudaGetLastError(); return QRK_STATUS_CUDA_ERROR; }
+  if (flag) { h->err = "fused peer exchange: a peer never delivered its triangle within the timeout; results are NaN-poisoned until the next qrk_angular_p2p_attach"; return QRK_STATUS_PEER_TIMEOUT; }
+  return QRK_STATUS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -844,6 +973,7 @@ const char* qrk_status_string(int status) {
     case QRK_STATUS_NO_DEVICE: return "no CUDA device (qrkit_b200 has no CPU fallback)";
     case QRK_STATUS_ALLOC_FAILED: return "device allocation failed";
     case QRK_STATUS_UNSUPPORTED: return "unsupported configuration";
+    case QRK_STATUS_PEER_TIMEOUT: return "fused peer exchange timed out: a peer GPU never delivered its triangle (results are NaN)";
     default: return "unknown status";
   }
 }
@@ -1087,7 +1217,7 @@ int qrk_synchronize(qrk_handle_t h) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
   DeviceGuard g(h->device);
   QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
-  return QRK_STATUS_OK;
+  return peer_exchange_status(h);
 }
 
 int qrk_total_values(qrk_handle_t h, int64_t* n) {
@@ -1281,6 +1411,7 @@ int qrk_factorize_solve(qrk_handle_t h, const double* b, double* x, int memspace
   if (memspace == QRK_HOST) {
     QRK_TRY_CUDA(h, cudaMemcpyAsync(x, h->d_x, h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+    return peer_exchange_status(h);
   }
   return QRK_STATUS_OK;
 }
@@ -1366,6 +1497,7 @@ int qrk_rank(qrk_handle_t h, int64_t* rank) {
     QRK_TRY_CUDA(h, cudaMemcpyAsync(&r2, h->d_root_i + h->m2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
     *rank += r2;
+    return peer_exchange_status(h);
   }
   return QRK_STATUS_OK;
 }
@@ -1514,13 +1646,32 @@ int qrk_matrix_q(qrk_handle_t h, int32_t* outer, int32_t* inner, double* values,
 }
 
 // ---- Q^T B, Q B, solve ----------------------------------------------------------------------------
+constexpr int OP_APPLY_QT_THIN = 10, OP_APPLY_Q_THIN = 11;   // Q1^T B (n_cols rows out) / Q1 Y (n_cols rows in): the thin factor
+
 static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double* X, int64_t ldx, int32_t nrhs, int memspace) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
   QRK_REQUIRE(h, B && X && nrhs >= 0, "B / X is null or nrhs < 0");
-  const long long in_rows = h->n_rows;
-  const long long out_rows = (op == OP_SOLVE) ? h->n_cols : h->n_rows;
+  const bool thin = op == OP_APPLY_QT_THIN || op == OP_APPLY_Q_THIN;
+  const long long in_rows = (op == OP_APPLY_Q_THIN) ? h->n_cols : h->n_rows;
+  const long long out_rows = (op == OP_SOLVE || op == OP_APPLY_QT_THIN) ? h->n_cols : h->n_rows;
   QRK_REQUIRE(h, ldb >= in_rows && ldx >= out_rows, "leading dimension smaller than the number of rows");
+  const bool banded_q1 = h->bvt != nullptr;               // banded solver, or block angular with a banded left solver
+  if (banded_q1 && (op == OP_APPLY_QT || op == OP_APPLY_Q)) {
+    // The two-phase banded factorisation represents Q as an isometry into an EXTENDED complement (overlap rows of every
+    // group enter as virtual zero rows, banded.cuh): there is no n x n orthogonal matrix to multiply with.  The thin factor
+    // Q1 = A R^-1 (what solve() and the LM caller use) is exact: qrk_apply_qt_thin / qrk_apply_q_thin.
+    h->err = "matrixQ() as an n x n operator is not provided for a banded factor; use qrk_apply_qt_thin / qrk_apply_q_thin (Q1 = A R^-1)";
+    return QRK_STATUS_UNSUPPORTED;
+  }
+  if (thin && !banded_q1 && h->desc.q_format != QRK_FULL_Q) {
+    h->err = "the thin-factor products need the FullQ index layout (thin part first)";
+    return QRK_STATUS_UNSUPPORTED;
+  }
+  if (op == OP_APPLY_Q_THIN && ang(h) && h->left_banded) {
+    h->err = "qrk_apply_q_thin is not provided for a block-angular handle with a banded left solver";
+    return QRK_STATUS_UNSUPPORTED;
+  }
   DeviceGuard g(h->device);
   const double* d_B = B;
   double* d_X = X;
@@ -1535,34 +1686,66 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
                                       cudaMemcpyHostToDevice, h->stream));
     d_B = h->d_b; d_X = h->d_x;
   }
-  if (op == OP_SOLVE) {
+  int st = QRK_STATUS_OK;
+  if (thin && !banded_q1) {
+    // thin products through the full operator on a scratch copy: Q1^T B = (Q^T B)[0:n_cols], Q1 Y = Q [Y; 0]
+    const long long ldt = (h->n_rows + 1) & ~1LL;
+    st = ensure_buffer(h, h->d_qthin, h->cap_qthin, (size_t)ldt * nrhs);
+    if (st != QRK_STATUS_OK) return st;
+    const int full_op = (op == OP_APPLY_QT_THIN) ? OP_APPLY_QT : OP_APPLY_Q;
+    const double* src = d_B;
+    long long lds = dldb;
+    double* dst = d_X;
+    long long ldd = dldx;
+    if (op == OP_APPLY_QT_THIN) { dst = h->d_qthin; ldd = ldt; }
+    else {
+      QRK_TRY_CUDA(h, cudaMemsetAsync(h->d_qthin, 0, (size_t)ldt * nrhs * sizeof(double), h->stream));
+      QRK_TRY_CUDA(h, cudaMemcpy2DAsync(h->d_qthin, ldt * sizeof(double), d_B, dldb * sizeof(double), h->n_cols * sizeof(double), nrhs,
+                                        cudaMemcpyDeviceToDevice, h->stream));
+      src = h->d_qthin; lds = ldt;
+    }
+    if (h->n_rows > h->sum_rows) { copy_tail_kernel<<<64, 256, 0, h->stream>>>(src, lds, dst, ldd, nrhs, h->sum_rows, h->n_rows); h->launches++; }
+    st = ang(h) ? angular_apply(h, full_op, src, lds, dst, ldd, nrhs) : run_op(h, full_op, src, lds, dst, ldd, nrhs);
+    if (st != QRK_STATUS_OK) return st;
+    if (op == OP_APPLY_QT_THIN)
+      QRK_TRY_CUDA(h, cudaMemcpy2DAsync(d_X, dldx * sizeof(double), h->d_qthin, ldt * sizeof(double), h->n_cols * sizeof(double), nrhs,
+                                        cudaMemcpyDeviceToDevice, h->stream));
+  } else if (thin && ang(h)) {
+    // banded left solver: [Q1thin^T b ; (Q2^T of the extended complement)[0:m2]] — what _solve_impl forms before the triangular solves
+    const long long n = h->w_ld, m1 = h->sum_cols;
+    const int M = h->m2;
+    double* rhs_col = h->d_wx + (long long)M * n;
+    for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) {
+      st = banded_left_apply_qt(h, d_B + j * dldb, h->n_rows, rhs_col, 1);
+      if (st == QRK_STATUS_OK) st = apply_q2(h, rhs_col + m1, true);
+      if (st == QRK_STATUS_OK)
+        QRK_TRY_CUDA(h, cudaMemcpyAsync(d_X + j * dldx, rhs_col, (size_t)(m1 + M) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  } else if (op == OP_SOLVE) {
     if (h->n_cols > h->sum_cols && !ang(h))   // y.bottomRows(...).setZero() (:272)
       QRK_TRY_CUDA(h, cudaMemset2DAsync(d_X + h->sum_cols, dldx * sizeof(double), 0, (h->n_cols - h->sum_cols) * sizeof(double),
                                         nrhs, h->stream));
-  } else if (h->n_rows > h->sum_rows && !h->bvt) {
+  } else if (!thin && h->n_rows > h->sum_rows && !h->bvt) {
     copy_tail_kernel<<<64, 256, 0, h->stream>>>(d_B, dldb, d_X, dldx, nrhs, h->sum_rows, h->n_rows);
     h->launches++;
   }
-  int st = QRK_STATUS_OK;
-  if (h->bvt && !(ang(h) && op == OP_SOLVE)) {
-    // Q^T b by the window sweep over the stored reflectors (BandedBlockedSparseQR.h:655-670 applies the YTY blocks in
-    // the same order), then the banded back substitution (:299-304).  Q^T b: thin part [0, n_cols), zeros after it.
-    // matrixQ() * v: Q1 * v[0:n_cols] (zero complement), the reflectors in reverse order.
+  if (thin && !(banded_q1 && !ang(h))) {
+    // done above
+  } else if (h->bvt && !ang(h)) {
+    // Q1^T b by the window sweep over the stored reflectors (BandedBlockedSparseQR.h:655-670 applies the YTY blocks in
+    // the same order) and the chase reflectors; solve: + the banded back substitution (:299-304).
+    // Q1 y: the same reflectors in reverse order on [y; 0].
     for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) {
       BandedArgs a = banded_args(h);
       cudaError_t e;
-      if (op == OP_APPLY_Q) {
+      if (op == OP_APPLY_Q_THIN) {
         a.y = const_cast<double*>(d_B + j * dldb);   // read only: the thin part of the input
         a.x = d_X + j * dldx;
         e = h->bvt->apply_q(a, h->stream);
         h->launches += banded_launches_per_call();
       } else {
         a.b = d_B + j * dldb;
-        if (op == OP_APPLY_QT) {
-          a.y = d_X + j * dldx;      // thin part; the window sweep works on [0 (overlap rows); A], whose annihilated-row
-                                     // components do not map one-to-one onto the n_rows - n_cols complement: left zero
-          if (h->n_rows > h->sum_cols) cudaMemsetAsync(d_X + j * dldx + h->sum_cols, 0, (h->n_rows - h->sum_cols) * sizeof(double), h->stream);
-        }
+        if (op == OP_APPLY_QT_THIN) a.y = d_X + j * dldx;
         e = h->bvt->apply_qt(a, h->stream);
         h->launches += banded_launches_per_call();
         if (e == cudaSuccess && op == OP_SOLVE) { a.x = d_X + j * dldx; e = h->bvt->backsolve(a, h->stream); h->launches++; }
@@ -1577,6 +1760,8 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
       if (memspace == QRK_HOST) h->pending_x = X;
       return QRK_STATUS_OK;
     }
+  } else if (ang(h)) {
+    st = angular_apply(h, op, d_B, dldb, d_X, dldx, nrhs);
   } else {
     st = run_op(h, op, d_B, dldb, d_X, dldx, nrhs);
   }
@@ -1585,11 +1770,18 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     QRK_TRY_CUDA(h, cudaMemcpy2DAsync(X, ldx * sizeof(double), h->d_x, dldx * sizeof(double), out_rows * sizeof(double), nrhs,
                                       cudaMemcpyDeviceToHost, h->stream));
     QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int pst = peer_exchange_status(h)) return pst;
   }
   h->info = QRK_INFO_SUCCESS;   // m_info = Success (:278)
   return QRK_STATUS_OK;
 }
 
+int qrk_apply_qt_thin(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace) {
+  return op_entry(h, OP_APPLY_QT_THIN, B, ldb, Y, ldy, nrhs, memspace);
+}
+int qrk_apply_q_thin(qrk_handle_t h, const double* Y, int64_t ldy, double* X, int64_t ldx, int32_t nrhs, int memspace) {
+  return op_entry(h, OP_APPLY_Q_THIN, Y, ldy, X, ldx, nrhs, memspace);
+}
 int qrk_apply_qt(qrk_handle_t h, const double* B, int64_t ldb, double* Y, int64_t ldy, int32_t nrhs, int memspace) {
   return op_entry(h, OP_APPLY_QT, B, ldb, Y, ldy, nrhs, memspace);
 }
@@ -1713,6 +1905,12 @@ int qrk_angular_p2p_attach(qrk_handle_t h, void* const* peer_buffers, int32_t wo
   QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_seq, 0, sizeof(unsigned long long)));
   QRK_TRY_CUDA(h, cudaMemset(h->d_xchg, 0, h->xchg_bytes));       // flags back to 0: attach restarts the step count on every rank
   h->xchg_rank = rank;
+  return QRK_STATUS_OK;
+}
+
+int qrk_angular_p2p_set_timeout(qrk_handle_t h, double seconds) {
+  if (!h || !h->avt || !(seconds > 0.0)) return QRK_STATUS_INVALID_ARGUMENT;
+  h->xchg_timeout_ns = (unsigned long long)(seconds * 1e9);
   return QRK_STATUS_OK;
 }
 

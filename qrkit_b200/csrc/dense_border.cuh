@@ -190,6 +190,36 @@ __global__ void __launch_bounds__(TPB) dense_apply_qt_kernel(DenseBorder d, doub
   }
 }
 
+// v <- Q2 v: H_0 ... H_{size-1} v (matrixQ() * v of the right solver, BlockAngularSparseQR.h:568-572), one CTA
+template <int TPB>
+__global__ void __launch_bounds__(TPB) dense_apply_q_kernel(DenseBorder d, double* vec) {
+  __shared__ double sred[TPB / 32];
+  const int tid = threadIdx.x;
+  const int size = (int)(d.N < d.M ? d.N : d.M);
+  for (int k = size - 1; k >= 0; k--) {
+    const double* v = d.A + (long long)k * d.ld;
+    double dot = 0.0;
+    for (long long i = k + 1 + tid; i < d.N; i += TPB) dot = fma(v[i], vec[i], dot);
+    dot = block_sum<TPB>(dot, sred) + vec[k];
+    const double w = d.tau[k] * dot;
+    __syncthreads();
+    for (long long i = k + 1 + tid; i < d.N; i += TPB) vec[i] = fma(-v[i], w, vec[i]);
+    if (tid == 0) vec[k] -= w;
+    __syncthreads();
+  }
+}
+
+// Row signs that make a second Householder factorisation of the same matrix agree with a stored R2: sign[k] = -1 where the
+// diagonals differ in sign (R is unique up to row signs; Q D with D = diag(sign) then satisfies (Q D)(D R) = A P)
+__global__ void dense_diag_sign_kernel(const double* __restrict__ A, long long ld, const double* __restrict__ R2, int M, int size,
+                                       double* __restrict__ sign) {
+  for (int k = threadIdx.x; k < M; k += blockDim.x)
+    sign[k] = (k < size && A[(long long)k * ld + k] * R2[(long long)k * M + k] < 0.0) ? -1.0 : 1.0;
+}
+__global__ void dense_scale_head_kernel(double* __restrict__ vec, const double* __restrict__ sign, int M) {
+  for (int k = threadIdx.x; k < M; k += blockDim.x) vec[k] *= sign[k];
+}
+
 // rank (Eigen ColPivHouseholderQR::rank(): |R_ii| > |maxpivot| eps diagonalSize among the nonzero pivots), the root
 // record [R2 | z2 | y2 | x2] / [P2 | rank2] shared with the TSQR path, colsPermutation()[m1 + c] = m1 + P2[c]
 // (BlockAngularSparseQR.h:498-503), y2 = R2[0:rank,0:rank]^-1 z2[0:rank] (:211-217), x2 = P2 y2.

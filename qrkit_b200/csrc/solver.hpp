@@ -76,6 +76,15 @@ struct qrk_solver {
   int* d_xchg_err = nullptr;
   unsigned long long* d_xchg_seq = nullptr;   // step counter, advanced by the root kernel itself
   int xchg_rank = -1;                  // >= 0 once attached
+  unsigned long long xchg_timeout_ns = 0;   // 0: default
+  // Q2 of the fused TSQR path, built on demand for matrixQ() products (the TSQR tree keeps no reflectors): Householder QR of
+  // the kept residual panel in the column order P2, plus the row signs that align it with the stored R2
+  double *d_q2 = nullptr, *d_q2tau = nullptr, *d_q2sign = nullptr, *d_q2scr = nullptr, *d_qtmp = nullptr;
+  int* d_q2iscr = nullptr;
+  size_t cap_qtmp = 0;
+  double* d_qthin = nullptr;           // scratch of the thin-factor products (qrk_apply_qt_thin / qrk_apply_q_thin)
+  size_t cap_qthin = 0;
+  bool q2_ready = false;
   double* pending_x = nullptr;
   int pending_space = 0;
   int pending_keep_rhs_only = 0;

@@ -230,6 +230,14 @@ class BlockDiagonalSparseQR:
         """matrixQ() * B"""
         return self._apply(lib().qrk_apply_q, B, self.rows())
 
+    def applyQtThin(self, B):
+        """(matrixQ().transpose() * B).topRows(cols()): Q1^T B with the thin factor Q1 = (A P) R^-1 (qrk_apply_qt_thin)"""
+        return self._apply(lib().qrk_apply_qt_thin, B, self.cols())
+
+    def applyQThin(self, Y):
+        """matrixQ() * [Y; 0]: Q1 Y (qrk_apply_q_thin)"""
+        return self._apply(lib().qrk_apply_q_thin, Y, self.rows())
+
     def solve(self, B):
         return self._apply(lib().qrk_solve, B, self.cols())
 

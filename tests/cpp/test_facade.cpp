@@ -43,10 +43,17 @@ int main() {
     A.insertBack(b);
   }
   DiagQR solver;
-  solver.compute(A);
+  try {
+    solver.compute(A);
+  } catch (const std::exception& e) {
+    if (ndev >= 1) throw;
+    // no device: compute() must refuse loudly (there is no CPU fallback), never return as if it had factorised
+    std::printf("no CUDA device: compute() threw \"%s\"; info() = %d\n", e.what(), (int)solver.info());
+    return (std::string(e.what()).find("no CPU fallback") != std::string::npos && solver.info() == InvalidInput) ? 77 : 1;
+  }
   if (ndev < 1) {
-    std::printf("no CUDA device: info() = %d (%s)\n", (int)solver.info(), solver.lastErrorMessage().c_str());
-    return solver.info() == InvalidInput ? 77 : 1;
+    std::printf("FAILED: compute() returned without a CUDA device\n");
+    return 1;
   }
   CHECK(solver.info() == Success, "info() == Success");
   CHECK(solver.rows() == rows && solver.cols() == cols && solver.rank() == cols, "rows / cols / rank");

@@ -58,8 +58,14 @@ def _check(qk, oracle, nb, br, bc, ov, suggested=2, lo=0.5, hi=5.0):
     assert rel(s2.solve(b), x_ref) <= 1e-10
     x_true = vector(n_cols, seed=9)
     assert rel(s2.solve(Ad @ x_true), x_true) <= 1e-10
-    # Q^T b: the thin part equals the oracle's up to the row signs of R
-    y = s2.applyQt(b)
+    # Q1^T b (the thin factor, the only Q product a banded handle has): equals the oracle's thin part up to the row signs of R;
+    # the n x n products refuse instead of returning a non-orthogonal result
+    with pytest.raises(qk.QrkError):
+        s2.applyQt(b)
+    with pytest.raises(qk.QrkError):
+        s2.applyQ(b)
+    y = s2.applyQtThin(b)
+    assert y.shape == (n_cols,)
     if oracle_q_ok:
         yref = ref.apply_q(b, transpose=True)
         sg = np.sign(np.diag(R)) * np.sign(np.diag(Rref))
@@ -67,11 +73,9 @@ def _check(qk, oracle, nb, br, bc, ov, suggested=2, lo=0.5, hi=5.0):
     assert rel(np.linalg.solve(R, y[:n_cols]), x_ref) <= 1e-9
     assert abs(np.linalg.norm(y[:n_cols]) ** 2 + np.linalg.norm(Ad @ x_ref - b) ** 2 - np.linalg.norm(b) ** 2) <= 1e-11 * np.linalg.norm(b) ** 2
     assert np.array_equal(s2.colsPermutation(), np.arange(n_cols, dtype=np.int32))
-    # matrixQ() * v on the thin part (zero complement): Q1 (R x) = A x, and Q1 Q1^T b = A x_ls (projection on range(A))
-    v = np.zeros(n_rows)
-    v[:n_cols] = R @ x_true
-    assert rel(s2.applyQ(v), Ad @ x_true) <= 1e-11
-    assert rel(s2.applyQ(y), Ad @ x_ref) <= 1e-9
+    # Q1 y: Q1 (R x) = A x, and Q1 Q1^T b = A x_ls (projection on range(A))
+    assert rel(s2.applyQThin(R @ x_true), Ad @ x_true) <= 1e-11
+    assert rel(s2.applyQThin(y), Ad @ x_ref) <= 1e-9
 
 
 @pytest.mark.parametrize("br,bc,ov", [(16, 24, 16), (7, 4, 2), (7, 2, 0), (8, 8, 4), (12, 8, 4), (4, 6, 4)])

@@ -55,10 +55,23 @@ def _check(qk, oracle, vals, r, c, J2, b, piv, tol_x=TOL_X):
     assert rel(s2.solve(b), x_ref) <= tol_x
     x_true = vector(m1 + m2, seed=77)
     assert rel(s2.solve(A @ x_true), x_true) <= tol_x
-    # Q1 accessors still refer to the left factor
+    # matrixQ().transpose() * v = [I 0; 0 Q2^T] Q1^T v (BlockAngularSparseQR.h:607-625): thin part of the left factor, then the
+    # right solver's Q2^T on the complement rows; its first m2 entries equal the reference's up to the row signs of R2
     y = s2.applyQt(b)
     yref = ref.apply_qt(b)
     assert rel(y[:m1], yref[:m1]) <= TOL_R
+    assert rel(np.abs(y[m1:m1 + m2]), np.abs(yref[m1:m1 + m2])) <= 1e-10
+    assert abs(np.linalg.norm(y) - np.linalg.norm(b)) <= 1e-13 * np.linalg.norm(b)      # Q is orthogonal on all n rows
+    assert rel(s2.applyQ(y), b) <= 1e-13                                                  # Q Q^T = I
+    if nb * r <= 4000:
+        # the reference's own identities (test/test-qrkit.cpp:251-254) on the full n x n operator: Q^T (A P) = R, Q R = A P
+        n = nb * r
+        Rfull = np.zeros((n, m1 + m2)); Rfull[:m1 + m2, :] = Rt
+        assert rel(s2.applyQt(np.asfortranarray(AP)), Rfull) <= 1e-13
+        assert rel(s2.applyQ(np.asfortranarray(Rfull)), AP) <= 1e-13
+    # the fused compute_solve() keeps no residual panel: the Q2 stage cannot be formed, and the call says so
+    with pytest.raises(qk.QrkError):
+        s1.applyQt(b)
 
 
 @pytest.mark.parametrize("n", [500, 2000, 10000])
@@ -145,8 +158,12 @@ def test_banded_left_block_vs_lapack(qk, br, bc, ov, nb, m2, right):
     assert rel(s.solve(A @ x_true), x_true) <= 1e-10
     s2 = qk.BlockAngularSparseQR(right_solver=right)
     assert rel(s2.compute_solve(mat, b), x_ls) <= 1e-10
-    y = s.applyQt(b)                                            # the left factor's Q^T, thin part
+    y = s.applyQtThin(b)                                        # [Q1thin^T b; z2]: the vector _solve_impl back-substitutes
+    assert y.shape == (m1 + m2,)
     assert rel(R[:m1, :m1].T @ y[:m1], A1.T @ b) <= 1e-11
+    assert rel(R.T @ y, AP.T @ b) <= 1e-10                      # R^T (Q_thin^T b) = (A P)^T b
+    with pytest.raises(qk.QrkError):                            # no n x n Q for a banded left factor: refused, not approximated
+        s.applyQt(b)
 
 
 def test_reference_test4_with_its_banded_left_solver(qk):

@@ -134,6 +134,11 @@ def test_mixed_blocks_vs_oracle(qk, oracle, piv):
     P = solver.colsPermutation()
     y = solver.applyQ(np.asfortranarray(R.toarray()))
     assert rel(y, A[:, P]) <= TOL_QR
+    # the thin factor Q1 = (A P) R^-1: Q1^T b = (Q^T b)[0:n_cols], Q1 (R x) = A P x
+    n_cols = int(bc.sum())
+    assert np.array_equal(solver.applyQtThin(b), solver.applyQt(b)[:n_cols])
+    xs = vector(n_cols, seed=23)
+    assert rel(solver.applyQThin(R.toarray()[:n_cols, :] @ xs), A[:, P] @ xs) <= TOL_QR
 
 
 @pytest.mark.parametrize("qformat", [0, 1])
