@@ -464,11 +464,28 @@ def main():
             ms_e2e = max(per_rank)
         assert torch.equal(hx[: w * CC].cuda(), dx[: w * CC]), "host and device paths disagree"
         L.qrk_destroy(h)
+        # the platform's ceiling for this step: the same bytes as ONE plain pinned H2D copy per buffer, all ranks at once
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dA.copy_(hA, non_blocking=True); db.copy_(hb, non_blocking=True)
+        c1.record()
+        barrier()
+        ms_copy = c0.elapsed_time(c1) / 3
+        copy_rates = [(hA.numel() + hb.numel()) * 8 / (ms_copy * 1e-3) / 1e9]
+        if world > 1:
+            t = torch.tensor(copy_rates, dtype=torch.float64, device="cuda")
+            allt = torch.empty(world, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allt, t)
+            copy_rates = [float(v) for v in allt.cpu()]
         h2d = int(hA.numel() * 8 + hb.numel() * 8)
         e2e = {"value": world * nb * R / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(hx.numel() * 8), "ms_per_step": ms_e2e, "steps": e_steps,
                "per_rank_ms_per_step": per_rank, "per_rank_h2d_gbs": [h2d / (m * 1e-3) / 1e9 for m in per_rank],
                "host_numa_node_per_rank": numa_nodes, "host_cpus_bound": int(ncpu.value),
+               "plain_h2d_copy_gbs_per_rank": copy_rates,
+               "h2d_ceiling_note": "plain cudaMemcpyAsync of the same pinned A and b on every rank at the same time: what the host / PCIe fabric gives N concurrent uploads; the e2e step can not beat it",
                "note": "qrk_compute_solve(QRK_HOST): pinned host A, b -> device, fused kernel, x -> host, per step; the library pipelines the three stages in 16 MB chunks over three streams, so the step is bound by the PCIe upload of A and b; host buffers from qrk_host_alloc (pinned, allocated on the GPU-local NUMA node)"}
         del hA, hb, hx
         for p_ in (pA, pb, px):

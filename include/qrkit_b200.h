@@ -102,7 +102,8 @@ typedef struct {
   int32_t block_overlap;   /* banded: column overlap of consecutive blocks (_BlockOverlap, BandedBlockedSparseQR.h:122); else 0 */
   int32_t right_solver;    /* block angular: qrk_right_solver, the RightSolver template argument (BlockAngularSparseQR.h:79) */
   int32_t left_solver;     /* block angular: qrk_left_solver, the LeftSolver template argument (BlockAngularSparseQR.h:79) */
-  int32_t reserved[2];
+  int32_t reserved[2];     /* [0]: banded: SuggestedBlockCols template argument of BandedBlockedSparseQR (:122), 0 = its default 2 —
+                              it only shapes the windows the reference merges, i.e. the stored pattern of matrixR(); [1]: 0 */
 } qrk_desc_t;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -260,8 +261,10 @@ QRK_API int qrk_ipc_close(void* device_ptr);
  *                                     EXTENDED complement (every group's overlap rows enter as virtual zero rows), so there
  *                                     is no n x n orthogonal matrix to multiply with (the reference's complement depends on
  *                                     its own window blocking and is not unique either)
- *   qrk_matrix_r(_nnz)                R as CSC with its natural band pattern (values as the reference up to row signs;
- *                                     the reference additionally stores explicit zeros of its merged windows, :484-491)
+ *   qrk_matrix_r(_nnz)                R as CSC in the reference's exact stored pattern: per merged window (the blocks its block
+ *                                     detection + mergeBlocks yield for this slab geometry, SparseQRUtils.h:186-253, 308-385) the
+ *                                     dense rectangle of solved rows x window columns, explicit zeros included (:484-491);
+ *                                     values as the reference up to row signs
  *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation
  * Supported (block_rows, block_cols, overlap): (16,24,16), (7,4,2), (7,2,0), (8,8,4), (12,8,4), (4,6,4). */
 

@@ -60,6 +60,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     obj_dir = os.path.join(_PKG, "build")
     os.makedirs(obj_dir, exist_ok=True)
     compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    compile_flags += os.environ.get("QRK_NVCC_EXTRA", "").split()      # development switch, e.g. -DQRK_WY_ROWPANEL (A/B builds)
 
     def compile_one(tu):
         name, src, extra = tu

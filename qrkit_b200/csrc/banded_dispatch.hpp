@@ -3,6 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <vector>
+
 namespace qrk {
 
 struct BandedArgs {
@@ -36,6 +39,8 @@ struct BandedVTable {
 };
 
 const BandedVTable* banded_vtable(int br, int bc, int ov);
+// structure.cpp: the reference's merged windows for a slab geometry, {idxRow, idxCol, numRows, numCols} each
+void banded_reference_windows(long long nb, int br, int bc, int ov, int last_cols, int suggested, std::vector<int32_t>& out4);
 int banded_launches_per_call();
 // rows of the complement output of apply_qt: nb (OV + BR - BC) window rows + groups * OV chase rows + (BC - last_cols)
 long long banded_comp_rows(long long nb, int br, int bc, int ov, int group, int last_cols);   // kernels per factor / apply call (for the launch counter)   // nullptr when the shape is not instantiated

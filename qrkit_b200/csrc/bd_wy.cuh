@@ -64,7 +64,10 @@ struct WyGeom {
     ld = rp + 4;
   }
 };
-constexpr int kWyScratch = 160;   // panel warp scratch: 2 x 16 step buffers, 8x8 Gram, 8x8 S = V^T V
+// panel warp scratch: two step buffers of the column-per-lane panel (raw pivot column 4 x (RQ + 2), pivot row 8, norm partials 4;
+// RQ = 32 rows per lane at most) and the 8x8 S = V^T V; the cooperative look-ahead apply reuses it for its partial W (W x 64)
+constexpr int kWyStepBuf = 4 * (32 + 2) + 12;
+constexpr int kWyScratch = 2 * kWyStepBuf + 64;
 constexpr int kWyPB = 96;   // diagonal tile of V (unit lower triangular 8x8), column stride 12 (= 12 mod 16)
 
 __host__ __device__ inline size_t wy_smem_bytes(int r, int c) {
@@ -72,10 +75,11 @@ __host__ __device__ inline size_t wy_smem_bytes(int r, int c) {
   const size_t d = (size_t)g.cp * g.ld + g.ld + 2 * kWyPB + 2 * 64 + kWyScratch + 2 * (size_t)g.cp;
   return d * 8 + 16;
 }
-// rows per lane of the panel warp (template parameter MR): 1, 2 or 4; 0 = block too tall for this kernel
+// panel rows per lane in units of 8 (template parameter MR; the panel warp holds 8 MR rows of ONE column per lane, the
+// apply warps 4 MR row tiles): 1..4; 0 = block too tall for this kernel
 __host__ __device__ inline int wy_mr(int r, int c) {
   const WyGeom g(r, c);
-  return g.rp <= 32 ? 1 : g.rp <= 64 ? 2 : g.rp <= 128 ? 4 : 0;
+  return g.rp <= 32 ? 1 : g.rp <= 64 ? 2 : g.rp <= 96 ? 3 : g.rp <= 128 ? 4 : 0;
 }
 // Team size.  The panel chain is serial (one warp), the other warps only apply finished panels, and the kernel is
 // latency bound: what counts is how many blocks are resident per SM.  Small blocks are limited by registers x threads,
@@ -84,6 +88,8 @@ __host__ __device__ inline int wy_warps(int r, int c) {
   const int cp = WyGeom(r, c).cp;
   return cp <= 24 ? 1 : cp <= 48 ? 2 : 4;
 }
+
+__device__ __forceinline__ bool lane_is(int j, int q, int jj, int qq) { return j == jj && q == qq; }
 
 // fragment slot -> row inside an 8-row tile: k-step h, slot q  (see header)
 __device__ __forceinline__ int wy_kappa(int q, int h) { return h ? 4 + ((q + 2) & 3) : q; }
@@ -505,6 +511,150 @@ __device__ __forceinline__ void wy_factor_panel_gram(double* sA, int ld, int rp,
   WY_TRACE(5);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column-per-lane panel (-DQRK_WY_COLPANEL).  Lane (j = lane >> 2, q = lane & 3) holds column j of the panel, local rows 4 i + q
+// (i < RQ = 8 MR) — its OWN column only, so the two things a Householder step must share travel through shared memory
+// instead of a warp-wide reduction:
+//   * the RAW pivot column (published by the four lanes that own it as soon as the previous step has updated it), its
+//     partial tail norms, and the pivot row;
+//   * nothing else: every lane forms the dot product of the raw tail with its own column over its own rows, and two
+//     shuffles (xor 1, 2) finish it.  The scalar chain (rsqrt / reciprocal with Newton steps, all lanes redundantly) runs
+//     beside those dot products: tau v^T a_j = -(dd a_Kj + t_j) / beta needs only the raw dot t_j.
+// Lanes of the already finished columns j < K take part in the same dot product: their result is S_jK = v_j^T v_K, the
+// entry of V^T V the T factor needs (dlarft), so T costs no extra pass.  One __syncwarp per step (the step buffers
+// alternate).  Per step and lane: 2 RQ shared loads, 3 RQ FMAs, 2 shuffles, one scalar chain — against ONE batched
+// 32-lane reduce-scatter (9 dependent shuffle rounds) + gather per step of the row-per-lane panel above.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MR>
+__device__ __noinline__ void wy_factor_panel_cpl(double* sA, int ld, int rp, int p, double* PB0, double* sT, double* scratch,
+                                                 double* sTau, int lane) {
+  constexpr int RQ = 8 * MR, TS = RQ + 2;
+  constexpr int ROWB = 4 * (32 + 2);              // pivot row (8 columns) at ROWB, the 4 norm partials at ROWB + 8
+  const int nrow = rp - p;                        // a multiple of 8
+  const int nq = nrow >> 2;                       // valid rows per lane; the rest of a[] is zero and stays zero
+  const int j = lane >> 2, q = lane & 3;
+  double* sS = scratch + 2 * kWyStepBuf;          // 8 x 8, strictly upper part used
+  WY_TRACE(0);
+  double a[RQ];
+  {
+    const double* base = sA + (size_t)(p + j) * ld + p + q;
+#pragma unroll
+    for (int i = 0; i < RQ; i++) a[i] = (i < nq) ? base[4 * i] : 0.0;
+  }
+  __syncwarp();                                   // the scratch of an earlier use (previous panel, cooperative apply) is dead
+  if (j == 0) {                                   // what step 0 reads: raw column 0, its tail norm partials ...
+    double* dst = scratch + q * TS;
+    double s0 = (q > 0) ? a[0] * a[0] : 0.0, s1 = a[1] * a[1], s2 = 0.0, s3 = 0.0;
+    *reinterpret_cast<double2*>(dst) = make_double2(a[0], a[1]);
+#pragma unroll
+    for (int i = 2; i < RQ; i += 2) {
+      *reinterpret_cast<double2*>(dst + i) = make_double2(a[i], a[i + 1]);
+      if (i & 2) { s2 = fma(a[i], a[i], s2); s3 = fma(a[i + 1], a[i + 1], s3); }
+      else { s0 = fma(a[i], a[i], s0); s1 = fma(a[i + 1], a[i + 1], s1); }
+    }
+    scratch[ROWB + 8 + q] = (s0 + s1) + (s2 + s3);
+  }
+  if (q == 0) scratch[ROWB + j] = a[0];           // ... and row 0 of the panel
+  double* tauv = sTau + p;
+  double myinv = 0.0;                             // 1 / (x0 - beta) of this lane's OWN column: the essential part is stored
+                                                  // unscaled in a[] and scaled once, at write-back
+  WY_TRACE(1);
+#pragma unroll 1
+  for (int K = 0; K < 8; K++) {
+    const double* buf = scratch + (K & 1) * kWyStepBuf;
+    const double* tailq = buf + q * TS;           // raw pivot column, rows 4 i + q
+    __syncwarp();
+    const double c0 = buf[ROWB + K], rowj = buf[ROWB + j];
+    const double2 n01 = *reinterpret_cast<const double2*>(buf + ROWB + 8), n23 = *reinterpret_cast<const double2*>(buf + ROWB + 10);
+    const double tailSq = (n01.x + n01.y) + (n23.x + n23.y);
+    const bool m0 = q > K, m1 = 4 + q > K;        // rows q and 4 + q lie below the pivot row?
+    // raw dot of the pivot column's tail with this lane's column (rows > K); rows >= 8 always take part
+    double t0, t1, t2 = 0.0, t3 = 0.0;
+    {
+      const double2 tv = *reinterpret_cast<const double2*>(tailq);
+      t0 = m0 ? tv.x * a[0] : 0.0;
+      t1 = m1 ? tv.y * a[1] : 0.0;
+    }
+#pragma unroll
+    for (int i = 2; i < RQ; i += 2) {
+      const double2 tv = *reinterpret_cast<const double2*>(tailq + i);
+      if (i & 2) { t2 = fma(tv.x, a[i], t2); t3 = fma(tv.y, a[i + 1], t3); }
+      else { t0 = fma(tv.x, a[i], t0); t1 = fma(tv.y, a[i + 1], t1); }
+    }
+    double t = (t0 + t1) + (t2 + t3);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    const WyRefl h = wy_reflector(c0, tailSq);    // Eigen makeHouseholder; runs beside the dot products
+    const double sj = -fma(h.dd, rowj, t) * h.ib; // tau v^T a_j
+    const double add = (j > K) ? -(sj * h.inv) : 0.0;
+    // columns j > K: a -= (tau v^T a_j) v, v = [1; inv * tail]; the others see add = 0 (a + 0 * tail: unchanged)
+    {
+      const double2 tv = *reinterpret_cast<const double2*>(tailq);
+      a[0] = fma(tv.x, m0 ? add : 0.0, a[0]);
+      a[1] = fma(tv.y, m1 ? add : 0.0, a[1]);
+    }
+#pragma unroll
+    for (int i = 2; i < RQ; i += 2) {
+      const double2 tv = *reinterpret_cast<const double2*>(tailq + i);
+      a[i] = fma(tv.x, add, a[i]);
+      a[i + 1] = fma(tv.y, add, a[i + 1]);
+    }
+    if (q == (K & 3)) {                           // the pivot row: R_Kj = a_Kj - tau v^T a_j (j > K), beta on the diagonal
+      const double old = (K >> 2) ? a[1] : a[0];
+      const double nv = (j > K) ? old - sj : (j == K) ? h.beta : old;
+      if (K >> 2) a[1] = nv; else a[0] = nv;
+    }
+    if (j == K) myinv = h.inv;
+    if (j < K && q == 0) sS[j * 8 + K] = myinv * fma(h.inv, t, rowj);   // S_jK = v_j[K] + v_j[K+1:]^T v_K[K+1:], v_j = myinv * a
+    if (j == K && q == 0) tauv[K] = h.tau;
+    if (K < 7) {                                  // publish what step K + 1 reads
+      double* nb = scratch + ((K + 1) & 1) * kWyStepBuf;
+      if (j == K + 1) {
+        double* dst = nb + q * TS;
+        double s0 = (q > K + 1) ? a[0] * a[0] : 0.0, s1 = (4 + q > K + 1) ? a[1] * a[1] : 0.0, s2 = 0.0, s3 = 0.0;
+        *reinterpret_cast<double2*>(dst) = make_double2(a[0], a[1]);
+#pragma unroll
+        for (int i = 2; i < RQ; i += 2) {
+          *reinterpret_cast<double2*>(dst + i) = make_double2(a[i], a[i + 1]);
+          if (i & 2) { s2 = fma(a[i], a[i], s2); s3 = fma(a[i + 1], a[i + 1], s3); }
+          else { s0 = fma(a[i], a[i], s0); s1 = fma(a[i + 1], a[i + 1], s1); }
+        }
+        nb[ROWB + 8 + q] = (s0 + s1) + (s2 + s3);
+      }
+      if (q == ((K + 1) & 3)) nb[ROWB + j] = ((K + 1) >> 2) ? a[1] : a[0];
+    }
+  }
+  WY_TRACE(2);
+  // packed columns back in place: R above / on the diagonal, the essential parts (scaled now) below; unit-lower diagonal tile of V
+  {
+    const double e0 = (q > j) ? a[0] * myinv : a[0], e1 = (4 + q > j) ? a[1] * myinv : a[1];
+    double* base = sA + (size_t)(p + j) * ld + p + q;
+    base[0] = e0; base[4] = e1;
+#pragma unroll
+    for (int i = 2; i < RQ; i++) if (i < nq) base[4 * i] = a[i] * myinv;
+    PB0[j * 12 + q] = (q < j) ? 0.0 : (q == j) ? 1.0 : e0;
+    PB0[j * 12 + 4 + q] = (4 + q < j) ? 0.0 : (4 + q == j) ? 1.0 : e1;
+  }
+  __syncwarp();
+  // T (upper triangular, Q = I - V T V^T): T_kk = tau_k, T[0:k,k] = -tau_k T[0:k,0:k] S[0:k,k]   (LAPACK dlarft /
+  // Eigen make_block_householder_triangular_factor); lane i owns row i
+  if (lane < 8) {
+    double Tr[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < k; m++) sum = fma(Tr[m], sS[m * 8 + k], sum);
+      const double tk = tauv[k];
+      Tr[k] = (k < lane) ? 0.0 : (k == lane) ? tk : -tk * sum;
+      sT[lane * 8 + k] = Tr[k];
+    }
+  }
+  __syncwarp();
+  WY_TRACE(5);
+}
+
 // ---- apply panel p to one 8-column tile (or to the right-hand side), by ONE warp ---------------------------------
 template <int MR>
 __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld, int rp, int p, int jt, bool is_rhs,
@@ -525,17 +675,17 @@ __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld,
   }
   // W^T = A2^T V   (8 columns x 8 reflectors)
   const double* vcol = sA + (size_t)(p + g) * ld + p;
-  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;   // four independent chains
 #pragma unroll
   for (int t = 0; t < NT; t++) {
     if (t < nt) {
       const double v0 = (t == 0) ? PB0[g * 12 + k0] : vcol[8 * t + k0];
       const double v1 = (t == 0) ? PB0[g * 12 + k1] : vcol[8 * t + k1];
-      dmma884(c00, c01, a0[t], v0);
-      dmma884(c10, c11, a1[t], v1);
+      if (t & 1) { dmma884(e00, e01, a0[t], v0); dmma884(e10, e11, a1[t], v1); }
+      else { dmma884(c00, c01, a0[t], v0); dmma884(c10, c11, a1[t], v1); }
     }
   }
-  const double w0 = c00 + c10, w1 = c01 + c11;
+  const double w0 = (c00 + c10) + (e00 + e10), w1 = (c01 + c11) + (e01 + e11);
   // W2^T = W^T T ; output slots 2q+e hold reflector q + 4e
   const int pg = (g >> 1) + 4 * (g & 1);
   double d0 = 0.0, d1 = 0.0;
@@ -557,18 +707,84 @@ __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld,
   }
 }
 
+
+// ---- apply panel p to the NEXT panel's tile, by ALL W warps of the CTA (the look-ahead tile is on the critical path) ----
+// Warp w takes the row tiles t = w, w + W, ...: partial W^T = A2^T V over its rows -> shared memory -> every warp sums the W
+// partials, multiplies by T and updates its own row tiles.  One __syncthreads inside; every warp of the CTA must call it.
+template <int MR, int W>
+__device__ __forceinline__ void wy_apply_panel_coop(double* sA, int ld, int rp, int p, int jt, const double* PB0, const double* sT,
+                                                    double* sWpart, int warp, int lane) {
+  constexpr int NTW = (4 * MR + W - 1) / W;
+  const int q = lane & 3, g = lane >> 2;
+  const int k0 = wy_kappa(q, 0), k1 = wy_kappa(q, 1);
+  const int rho = wy_kappa(g >> 1, g & 1);
+  const int nt = (rp - p) >> 3;
+  double* col = sA + (size_t)(8 * jt + g) * ld + p;
+  double a0[NTW], a1[NTW];
+#pragma unroll
+  for (int u = 0; u < NTW; u++) {
+    const int t = warp + u * W;
+    a0[u] = (t < nt) ? col[8 * t + k0] : 0.0;
+    a1[u] = (t < nt) ? col[8 * t + k1] : 0.0;
+  }
+  const double* vcol = sA + (size_t)(p + g) * ld + p;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+  for (int u = 0; u < NTW; u++) {
+    const int t = warp + u * W;
+    if (t < nt) {
+      const double v0 = (t == 0) ? PB0[g * 12 + k0] : vcol[8 * t + k0];
+      const double v1 = (t == 0) ? PB0[g * 12 + k1] : vcol[8 * t + k1];
+      dmma884(c00, c01, a0[u], v0);
+      dmma884(c10, c11, a1[u], v1);
+    }
+  }
+  *reinterpret_cast<double2*>(sWpart + warp * 64 + 2 * lane) = make_double2(c00 + c10, c01 + c11);
+  __syncthreads();
+  double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const double2 pw = *reinterpret_cast<const double2*>(sWpart + w * 64 + 2 * lane);
+    w0 += pw.x; w1 += pw.y;
+  }
+  const int pg = (g >> 1) + 4 * (g & 1);
+  double d0 = 0.0, d1 = 0.0;
+  dmma884(d0, d1, w0, sT[(2 * q) * 8 + pg]);
+  dmma884(d0, d1, w1, sT[(2 * q + 1) * 8 + pg]);
+  d0 = -d0; d1 = -d1;
+  const double* vq0 = sA + (size_t)(p + q) * ld + p + rho;
+  const double* vq1 = sA + (size_t)(p + q + 4) * ld + p + rho;
+#pragma unroll
+  for (int u = 0; u < NTW; u++) {
+    const int t = warp + u * W;
+    if (t < nt) {
+      const double b0 = (t == 0) ? PB0[q * 12 + rho] : vq0[8 * t];
+      const double b1 = (t == 0) ? PB0[(q + 4) * 12 + rho] : vq1[8 * t];
+      dmma884(a0[u], a1[u], d0, b0);
+      dmma884(a0[u], a1[u], d1, b1);
+      col[8 * t + k0] = a0[u]; col[8 * t + k1] = a1[u];
+    }
+  }
+}
+
 // ---- kernel: grid.x = blocks of this size class -----------------------------------------------------------------
 // Measured on B200 (profiles/r01_wy_gram_panel_experiment.txt): the Gram-downdated panel shortens a column step from
 // ~1100 to ~830 cycles but its two wide reductions (G: 36 sums, S: 28 sums) cost 2.2-3.1 k cycles each, so config 5 runs
 // at 7.3 ms instead of 6.6 ms: the per-column all-reduce stays the default; -DQRK_WY_GRAM selects the other variant.
-#ifdef QRK_WY_GRAM
-#define WY_FACTOR_PANEL wy_factor_panel_gram   // one Gram reduction per panel
+// Measured on B200, config 5 per class (profiles/r02_wy_panel_variants.md): with the cooperative look-ahead apply and the tile
+// queue below, the row-per-lane panel gives 6.25 ms, the column-per-lane panel 6.75 ms (its step has no warp-wide reduction
+// but ~315 instructions, two shared-memory passes over the pivot column and 4 RQ FP64 instructions: 1.65 k cycles against
+// 1.1 k), the round-1 schedule 6.63 ms.  The row-per-lane panel stays the default.
+#if defined(QRK_WY_GRAM)
+#define WY_FACTOR_PANEL wy_factor_panel_gram   // row-per-lane, one Gram reduction per panel (experiment)
+#elif defined(QRK_WY_COLPANEL)
+#define WY_FACTOR_PANEL wy_factor_panel_cpl    // column-per-lane, no warp-wide reduction (experiment)
 #else
-#define WY_FACTOR_PANEL wy_factor_panel        // one all-reduce per column
+#define WY_FACTOR_PANEL wy_factor_panel        // row-per-lane, one all-reduce per column (default)
 #endif
 
 // resident CTAs per SM the register allocation must leave room for (shared memory allows about as many)
-__host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr == 4 ? 12 : mr == 2 ? 16 : 20) / w; }
+__host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr >= 3 ? 12 : mr == 2 ? 16 : 20) / w; }
 
 template <int MR, int W, bool SOLVE>
 __global__ void __launch_bounds__(32 * W, wy_min_ctas(MR, W))
@@ -637,29 +853,45 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   const int P = cp >> 3;
   const int n_tiles = P + (SOLVE ? 1 : 0);
   const int rot = (W > 1) ? s_rot : 0;
+  __shared__ int s_next_tile;
   if (warp == rot) WY_FACTOR_PANEL<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
     const int p = 8 * pi, buf = pi & 1;
     const bool has_next = pi + 1 < P;
-    const int onext = (pi + 1 + rot) % W;
-    for (int jt = pi + 1; jt < n_tiles; jt++) {
-      int wsel;
-      if (W == 1) wsel = 0;
-      else if (has_next) wsel = (jt == pi + 1) ? onext : (onext + 1 + (jt - pi - 2) % (W > 1 ? W - 1 : 1)) % W;
-      else wsel = (jt - pi - 1 + rot) % W;
-      if (wsel != warp) continue;
-      WY_TRACE(6);
-      wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
-      WY_TRACE(7);
-      if (W > 1 && has_next && jt == pi + 1) {
-        __syncwarp();
-        WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+    if (W == 1) {
+      for (int jt = pi + 1; jt < n_tiles; jt++) {
+        wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
+        if (has_next && jt == pi + 1) {
+          __syncwarp();
+          WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+        }
       }
-    }
-    if (W == 1 && has_next) {
       __syncwarp();
+      continue;
+    }
+    // (a) the look-ahead tile (the next panel's columns) by all warps, rows split; (b) its owner factors it at once while the
+    // other warps take the remaining tiles (and the right-hand side) from a queue, the owner joins them when it is done
+    int first = pi + 1;
+    if (has_next) {
+      WY_TRACE(6);
+      wy_apply_panel_coop<MR, W>(sA, ld, rp, p, pi + 1, sPB + buf * kWyPB, sT + buf * 64, sS, warp, lane);
+      WY_TRACE(7);
+      first = pi + 2;
+    }
+    if (tid == 0) s_next_tile = first;
+    __syncthreads();
+    const int onext = (pi + 1 + rot) % W;
+    if (has_next && warp == onext)
       WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
+    WY_TRACE(3);
+    for (;;) {
+      int jt = 0;
+      if (lane == 0) jt = atomicAdd(&s_next_tile, 1);
+      jt = __shfl_sync(0xffffffffu, jt, 0);
+      if (jt >= n_tiles) break;
+      wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
+      WY_TRACE(4);
     }
     WY_TRACE(8);
     __syncthreads();

@@ -218,6 +218,9 @@ cudaError_t launch_wy_factor(bool solve, const BlockIndex& bi, const SizeClass& 
   switch (key) {
     case 11: return launch_wy_factor_mw<1, 1>(solve, bi, sc, A, packed, tau, b, x, s);
     case 21: return launch_wy_factor_mw<2, 1>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 31: return launch_wy_factor_mw<3, 1>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 32: return launch_wy_factor_mw<3, 2>(solve, bi, sc, A, packed, tau, b, x, s);
+    case 34: return launch_wy_factor_mw<3, 4>(solve, bi, sc, A, packed, tau, b, x, s);
     case 41: return launch_wy_factor_mw<4, 1>(solve, bi, sc, A, packed, tau, b, x, s);
     case 12: return launch_wy_factor_mw<1, 2>(solve, bi, sc, A, packed, tau, b, x, s);
     case 14: return launch_wy_factor_mw<1, 4>(solve, bi, sc, A, packed, tau, b, x, s);
@@ -918,38 +921,62 @@ int banded_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x
   return QRK_STATUS_OK;
 }
 
-// natural band pattern of R as CSC: column j holds rows [gmin(j), j]
-__global__ void export_banded_r_kernel(const double* __restrict__ rband, const int* __restrict__ outer, int* __restrict__ inner,
+// matrixR() of the banded solver in the reference's exact compressed layout (BandedBlockedSparseQR.h:484-491, 511-512): window i
+// (idxCol, numCols) contributes the dense rectangle rows [idxCol, idxCol + solvedRows) x columns [idxCol, idxCol + numCols) —
+// EVERY coefficient of it is a stored entry, the zeros below the diagonal and beyond the band included; solvedRows = the
+// distance to the next window's first column, or numRows for the last window (its rows below the triangle are stored zeros
+// too).  The windows are the reference's merged blocks (banded_reference_windows).  Values: the band R where it lives, 0 else.
+__global__ void export_banded_r_kernel(const double* __restrict__ rband, const int* __restrict__ outer, const int* __restrict__ inner,
                                        double* __restrict__ vals, long long n_cols, long long nb, int bc, int step) {
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_cols; j += (long long)gridDim.x * blockDim.x) {
-    const int p0 = outer[j], cnt = outer[j + 1] - p0;
-    const long long g0 = j - cnt + 1;
-    for (int q = 0; q < cnt; q++) {
-      const long long g = g0 + q;
-      long long w = g / step;
-      if (w > nb - 1) w = nb - 1;
-      inner[p0 + q] = (int)g;
-      vals[p0 + q] = rband[g * bc + (j - w * step)];
+    for (int p = outer[j]; p < outer[j + 1]; p++) {
+      const long long g = inner[p];
+      double v = 0.0;
+      if (g <= j) {                                         // g <= j < n_cols
+        long long w = g / step;
+        if (w > nb - 1) w = nb - 1;
+        const long long off = j - w * step;
+        if (off < bc) v = rband[g * bc + off];
+      }
+      vals[p] = v;
+    }
+  }
+}
+
+// column pointers and row indices of that layout (host; the banded columns only — a border adds its own)
+void banded_r_pattern(const qrk_solver* h, std::vector<int>& outer, std::vector<int>* inner) {
+  const long long n = h->sum_cols;
+  const std::vector<int32_t>& win = h->b_windows;
+  const size_t nw = win.size() / 4;
+  outer.assign(n + 1, 0);
+  auto solved = [&](size_t i) -> long long { return i + 1 < nw ? (long long)win[4 * (i + 1) + 1] - win[4 * i + 1] : (long long)win[4 * i + 2]; };
+  for (size_t i = 0; i < nw; i++) {                          // count per column
+    const long long c0 = win[4 * i + 1], nc = win[4 * i + 3], sr = solved(i);
+    for (long long c = c0; c < c0 + nc && c < n; c++) outer[c + 1] += (int)sr;
+  }
+  for (long long j = 0; j < n; j++) outer[j + 1] += outer[j];
+  if (!inner) return;
+  inner->assign((size_t)outer[n], 0);
+  std::vector<int> fill(outer.begin(), outer.end() - 1);
+  for (size_t i = 0; i < nw; i++) {                          // windows in order: row ranges ascend, so every column stays sorted
+    const long long c0 = win[4 * i + 1], nc = win[4 * i + 3], sr = solved(i);
+    for (long long c = c0; c < c0 + nc && c < n; c++) {
+      int* dst = inner->data() + fill[c];
+      for (long long r = 0; r < sr; r++) dst[r] = (int)(c0 + r);
+      fill[c] += (int)sr;
     }
   }
 }
 
 std::vector<int> banded_r_outer(const qrk_solver* h) {
-  const long long n = h->sum_cols, S = h->b_step, BC = h->uc, nb = h->nb;   // the banded columns (a border adds its own)
-  std::vector<int> outer(n + 1, 0);
-  long long acc = 0;
-  for (long long j = 0; j < n; j++) {
-    // rows g <= j whose window covers column j: w(g) >= wmin, w(g) = min(g / S, nb - 1)
-    long long wmin = (j - BC) >= 0 ? (j - BC) / S + 1 : 0;
-    if (wmin > nb - 1) wmin = nb - 1;
-    const long long gmin = wmin * S;
-    outer[j] = (int)acc;
-    acc += j - gmin + 1;
-  }
-  outer[n] = (int)acc;
+  std::vector<int> outer;
+  banded_r_pattern(h, outer, nullptr);
   return outer;
 }
 
+}  // namespace
+
+namespace {
 int peer_exchange_status(qrk_solver* h) {
   if (!h->d_xchg_err || h->xchg_rank < 0) return QRK_STATUS_OK;
   int flag = 0;
@@ -1047,6 +1074,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     h->b_step = h->uc - h->b_ov;
     h->bvt = banded_vtable(h->ur, h->uc, h->b_ov);
     if (!h->bvt) return fail(QRK_STATUS_UNSUPPORTED);
+    if (desc->reserved[0] < 0) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->n_rows = h->sum_rows;
     // n_cols defaults to the full width of the last slab; a narrower last slab (the reference's pattern gives the last
     // block block_cols - overlap columns, SparseQRUtils.h:284) is selected by passing n_cols explicitly
@@ -1055,6 +1083,9 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     if (h->n_cols > full || h->n_cols <= (h->nb - 1) * (long long)h->b_step) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->sum_cols = h->n_cols;
     if (h->n_rows < h->n_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    // the reference's windows for this geometry: they fix the stored pattern of matrixR() (explicit zeros included)
+    banded_reference_windows(h->nb, h->ur, h->uc, h->b_ov, (int)(h->n_cols - (h->nb - 1) * (long long)h->b_step),
+                             desc->reserved[0] > 0 ? desc->reserved[0] : 2, h->b_windows);
     if (desc->n_rows > 0 && desc->n_rows != h->n_rows) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->info = QRK_INFO_SUCCESS;      // landscape slabs are normal here
   }
@@ -1600,8 +1631,10 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
   if (h->bvt) {
     if (want_q) { h->err = "banded matrixQ() as an explicit sparse matrix is not provided"; e = cudaErrorNotSupported; }
     else {
-      const std::vector<int> ho = banded_r_outer(h);
+      std::vector<int> ho, hi;
+      banded_r_pattern(h, ho, &hi);
       cudaMemcpyAsync(d_outer, ho.data(), ho.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      cudaMemcpyAsync(d_inner, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
       export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->sum_cols, h->nb, h->uc, h->b_step);
       e = cudaGetLastError();
       if (ang(h) && e == cudaSuccess) {     // R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:285-308) with a banded R1

@@ -110,6 +110,7 @@ struct qrk_solver {
   double *d_rband = nullptr;           // band R: n_cols x block_cols
   double *d_btau = nullptr;            // tau: num_blocks x block_cols
   double *d_ythin = nullptr;           // (Q^T b)[0:n_cols]
+  std::vector<int32_t> b_windows;      // the reference's merged windows {idxRow, idxCol, numRows, numCols}: the stored pattern of matrixR()
   int b_group = 1;                     // slabs per parallel group of the two-phase banded factorisation (banded.cuh)
   double *d_gband = nullptr, *d_gy = nullptr, *d_cvec = nullptr, *d_ctau = nullptr;   // group triangles / chase reflectors
   size_t cap_gy = 0;                   // doubles in d_gy (one vector of groups x W per right-hand side column)

@@ -78,6 +78,24 @@ int emit(const std::vector<Block>& blocks, int32_t* out, int64_t capacity, int64
 
 }  // namespace
 
+namespace qrk {
+// The windows BandedBlockedSparseQR::factorize walks (BandedBlockedSparseQR.h:463-508) for nb dense slabs of br x bc shifted by
+// bc - ov columns, the last one last_cols wide: what BlockBandedMatrixInfo::operator() detects on such a matrix (one block per
+// slab, SparseQRUtils.h:186-253) after mergeBlocks (:308-385) with maxColStep = bc - ov.  out4: {idxRow, idxCol, numRows, numCols}.
+void banded_reference_windows(long long nb, int br, int bc, int ov, int last_cols, int suggested, std::vector<int32_t>& out4) {
+  const int step = bc - ov;
+  std::vector<Block> v;
+  v.reserve((size_t)nb);
+  for (long long k = 0; k < nb; k++)
+    v.push_back({(int32_t)(k * br), (int32_t)(k * step), br, (k < nb - 1) ? bc : last_cols});
+  merge_blocks(v, step, suggested);
+  out4.resize(4 * v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    out4[4 * i] = v[i].row; out4[4 * i + 1] = v[i].col; out4[4 * i + 2] = v[i].nrows; out4[4 * i + 3] = v[i].ncols;
+  }
+}
+}  // namespace qrk
+
 extern "C" {
 
 int qrk_order_as_banded_as_possible(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner,

@@ -50,7 +50,11 @@ def _check(qk, oracle, nb, br, bc, ov, suggested=2, lo=0.5, hi=5.0):
     assert rel(x1, x_ref) <= 1e-10
     s2 = qk.BandedBlockedSparseQR(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov)
     assert s2.rows() == n_rows and s2.cols() == n_cols and s2.rank() == n_cols and s2.info() == qk.QRK_INFO_SUCCESS
-    R = s2.matrixR().toarray()[:n_cols, :]
+    # matrixR(): the reference's exact stored pattern — per merged window the dense rectangle of solved rows x window columns,
+    # explicit zeros included (BandedBlockedSparseQR.h:484-491): index arrays bit-exact against the oracle
+    Rs, Rrs = s2.matrixR(), ref.matrixR()
+    assert np.array_equal(Rs.outer, Rrs.outer) and np.array_equal(Rs.inner, Rrs.inner), "banded R: CSC index arrays must be bit-exact"
+    R = Rs.toarray()[:n_cols, :]
     assert np.allclose(np.tril(R, -1), 0.0)
     assert rel(sign_normalize_rows(R), sign_normalize_rows(Rref)) <= 1e-12
     Ad = A.toarray()
