@@ -69,8 +69,17 @@ typedef enum {
 /* The dense right-block solver of BlockAngularSparseQR (template parameter RightSolver, BlockAngularSparseQR.h:79). */
 typedef enum {
   QRK_RIGHT_COLPIV = 0,    /* Eigen::ColPivHouseholderQR<MatrixXd> (test/test-qrkit.cpp:46-48, examples/ellipse_fitting.cpp:35) */
-  QRK_RIGHT_UNPIVOTED = 1  /* BlockedThinDenseQR<MatrixXd, N> / Eigen::HouseholderQR: no column pivoting, P2 = identity,
+  QRK_RIGHT_UNPIVOTED = 1, /* BlockedThinDenseQR<MatrixXd, N> / Eigen::HouseholderQR: no column pivoting, P2 = identity,
                               rank() = cols (BlockedThinDenseQR.h:132); R2 equals the reference's up to row signs */
+  QRK_RIGHT_THIN_SPARSE = 2 /* BlockedThinSparseQR<SparseMatrix, SuggestedBlockCols> on the (dense) border (BlockedThinSparseQR.h:105-166,
+                              198-283; test/test-qrkit.cpp:54-57, 329-362): ColPivHouseholderQR inside every panel of
+                              SuggestedBlockCols columns (desc.reserved[1], 0 = the reference's 2) with Eigen's per-panel
+                              nonzero-pivot rule; columns whose pivot is "zero" are deferred to the end of P2 (:250-255, 150-158);
+                              rank() = the nonzero pivots (:281).  With full column rank R2, P2 and x equal the reference's.
+                              Rank-deficient borders: the reference's R collides (its R columns restart at m_nonzeroPivots + bc);
+                              here the deferred columns receive every later reflector and take the trailing columns of R, so
+                              A P = Q R holds and x is the basic solution; solve() / matrixQ() products on a STORED factorisation
+                              that deferred columns are refused (use the fused qrk_compute_solve) */
 } qrk_right_solver;
 
 /* The left solver of BlockAngularSparseQR (template parameter LeftSolver, BlockAngularSparseQR.h:79). */
@@ -103,7 +112,8 @@ typedef struct {
   int32_t right_solver;    /* block angular: qrk_right_solver, the RightSolver template argument (BlockAngularSparseQR.h:79) */
   int32_t left_solver;     /* block angular: qrk_left_solver, the LeftSolver template argument (BlockAngularSparseQR.h:79) */
   int32_t reserved[2];     /* [0]: banded: SuggestedBlockCols template argument of BandedBlockedSparseQR (:122), 0 = its default 2 —
-                              it only shapes the windows the reference merges, i.e. the stored pattern of matrixR(); [1]: 0 */
+                              it only shapes the windows the reference merges, i.e. the stored pattern of matrixR();
+                              [1]: block angular with QRK_RIGHT_THIN_SPARSE: SuggestedBlockCols of BlockedThinSparseQR, 0 = 2 */
 } qrk_desc_t;
 
 /* ---- library ------------------------------------------------------------------------------- */

@@ -293,7 +293,8 @@ class BandedOracle:
 # ------------------------------------------------------------------------------ block angular
 class BlockAngularOracle:
     """Reference-faithful BlockAngularSparseQR (BlockAngularSparseQR.h:459-514) with a dense border.
-    right_kind: 0 = ColPivHouseholderQR<MatrixXd>, 1 = BlockedThinDenseQR<MatrixXd, panel>."""
+    right_kind: 0 = ColPivHouseholderQR<MatrixXd>, 1 = BlockedThinDenseQR<MatrixXd, panel>,
+    2 = BlockedThinSparseQR<SparseMatrix, panel> on a dense border (per-panel ColPiv, zero-pivot columns deferred)."""
 
     def __init__(self, J2, *, br=None, bc=None, values=None, left_colpiv=True, A_csc=None, blocks=None,
                  right_kind=0, panel=2):

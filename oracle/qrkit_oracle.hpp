@@ -738,6 +738,75 @@ inline DenseQR dense_blocked_thin_compute(const Dense& A, int panel) {
   return q;
 }
 
+// BlockedThinSparseQR::compute (BlockedThinSparseQR.h:105-166) with updateBlockInfo (:198-236) and factorize (:238-283), on a
+// DENSE input (the border of the reference's test 6, test/test-qrkit.cpp:329-362, is fully dense):
+//  * analyzePattern (:168-196): ColumnDensity and AsBandedAsPossible are stable sorts by stored entries per column / first
+//    stored column per row; a fully dense matrix keeps both orders, so m_outputPerm_c and m_rowPerm start as the identity;
+//  * updateBlockInfo: every column's last stored row is rows-1, so a panel always spans rows [m_nonzeroPivots, rows);
+//  * factorize: ColPivHouseholderQR of the panel, its Y / T (computeBlockedRepresentation, BlockedThinQRBase.h:321-333),
+//    updateMat on EVERY column from the panel's first one (:308-319), R column m_nonzeroPivots + bc = rows above the diagonal
+//    position from the updated matrix (pivoted column) + the panel's triangle (:270-279), nonzero pivots appended to
+//    m_nnzColPermIdxs, the others deferred to m_zeroColPermIdxs (:250-255), final P = [nonzero pivots ; deferred] (:150-158).
+// Rank-deficient panels: the reference restarts R columns it has already written (startVec(m_nonzeroPivots + bc) collides with
+// the deferred columns of the previous panel) and never applies later panels to a deferred column, i.e. its R is not a
+// factor of A P there.  This restatement keeps everything the reference defines (pivot order, nonzero-pivot rule, deferral
+// order, rank = m_nonzeroPivots) and gives the deferred columns what A P = Q R requires: every later block reflector is applied
+// to them and they occupy the trailing columns of R.  With full column rank the two coincide entry by entry.
+inline DenseQR dense_blocked_thin_sparse_compute(const Dense& A, int panel) {
+  DenseQR q; q.rows = A.rows; q.cols = A.cols; q.thin = true;
+  Dense M = A;                                                  // m_pmatDense
+  std::vector<int> nnzIdx, zeroIdx;
+  std::vector<int> zeroBlock;                                   // number of YTY blocks already applied to a deferred column
+  Dense R(A.rows, A.cols);                                      // full columns of Q^T A P, position order
+  int nzp = 0, solved = 0;
+  while (solved < M.cols) {
+    int newCols = panel;                                        // updateBlockInfo :198-236
+    if (solved + newCols >= M.cols) newCols = M.cols - solved;
+    const int idxRow = nzp, numRows = M.rows - nzp;
+    Dense P = M.block(idxRow, solved, numRows, newCols);        // factorize :238-283
+    const int size = std::min(numRows, newCols);
+    std::vector<double> tau(std::max(size, 1), 0.0);
+    std::vector<int> perm(newCols);
+    const int nzp_p = colpiv_householder_qr(P.v.data(), numRows, newCols, tau.data(), perm.data());
+    for (int c = 0; c < nzp_p; c++) nnzIdx.push_back(solved + perm[c]);
+    for (int c = nzp_p; c < newCols; c++) { zeroIdx.push_back(solved + perm[c]); zeroBlock.push_back((int)q.blocks.size() + 1); }
+    YTYBlock blk;
+    blk.Y = Dense::identity(numRows, newCols);
+    for (int bc = 0; bc < newCols; bc++) for (int rr = bc + 1; rr < numRows; rr++) blk.Y(rr, bc) = P(rr, bc);
+    std::vector<double> tauc(newCols, 0.0);
+    for (int k = 0; k < size; k++) tauc[k] = tau[k];
+    blk.T = block_householder_t_factor(blk.Y.v.data(), numRows, numRows, newCols, tauc.data());
+    for (auto& t : blk.T.v) t = -t;
+    blk.row = idxRow; blk.col = solved; blk.numZeros = 0;
+    std::vector<double> t1(newCols), t2(newCols);
+    for (int j = solved; j < M.cols; j++) {                     // updateMat :308-319
+      double* cj = M.col(j) + idxRow;
+      for (int k = 0; k < newCols; k++) { double s = 0; for (int i = 0; i < numRows; i++) s += blk.Y(i, k) * cj[i]; t1[k] = s; }
+      for (int k = 0; k < newCols; k++) { double s = 0; for (int l = 0; l < newCols; l++) s += blk.T(l, k) * t1[l]; t2[k] = s; }
+      for (int i = 0; i < numRows; i++) { double s = 0; for (int k = 0; k < newCols; k++) s += blk.Y(i, k) * t2[k]; cj[i] += s; }
+    }
+    q.blocks.push_back(blk);
+    for (int bc = 0; bc < nzp_p; bc++) {                        // R columns of the nonzero pivots (:270-279)
+      const int pos = nzp + bc;
+      for (int br = 0; br < nzp; br++) R(br, pos) = M(br, solved + perm[bc]);
+      for (int br = 0; br <= bc; br++) R(nzp + br, pos) = P(br, bc);
+    }
+    nzp += nzp_p;
+    solved += newCols;
+  }
+  for (size_t z = 0; z < zeroIdx.size(); z++) {                 // deferred columns: the remaining reflectors, then the tail of R
+    std::vector<double> col(M.col(zeroIdx[z]), M.col(zeroIdx[z]) + M.rows);
+    std::vector<YTYBlock> rest(q.blocks.begin() + zeroBlock[z], q.blocks.end());
+    ytysequence_apply(rest, col.data(), true);
+    for (int r = 0; r < M.rows; r++) R(r, nzp + (int)z) = col[r];
+  }
+  q.perm = nnzIdx;
+  q.perm.insert(q.perm.end(), zeroIdx.begin(), zeroIdx.end());
+  q.packed = R;
+  q.rank = nzp;                                                 // rank() = m_nonzeroPivots
+  return q;
+}
+
 inline void dense_qr_apply_qt(const DenseQR& q, double* v) {
   if (q.thin) ytysequence_apply(q.blocks, v, true);
   else apply_qt_inplace(q.packed.v.data(), q.rows, q.cols, q.tau.data(), v, q.rows, 1);
@@ -773,7 +842,7 @@ inline void angular_finish(AngularQR& f, const Dense& J2in, int right_kind, int 
   f.J2 = J2in;                                               // solveRightBlock :361-369 (left row perm = identity)
   for (int j = 0; j < m2; j++) angular_left_apply_qt(f, f.J2.col(j));
   Dense Abot = f.J2.block(m1, 0, n - m1, m2);
-  f.right = right_kind == 0 ? dense_colpiv_compute(Abot) : dense_blocked_thin_compute(Abot, panel);
+  f.right = right_kind == 0 ? dense_colpiv_compute(Abot) : right_kind == 2 ? dense_blocked_thin_sparse_compute(Abot, panel) : dense_blocked_thin_compute(Abot, panel);
   const Sparse& R1 = f.left_banded ? f.leftBanded.R : f.leftBD.R;
   Sparse& R = f.R;                                            // makeR :285-308
   R.row_major = false; R.rows = n; R.cols = m1 + m2; R.outer.assign(m1 + m2 + 1, 0);
@@ -820,6 +889,7 @@ inline std::vector<double> angular_solve(const AngularQR& f, const double* b) {
   const int cols = f.m1 + f.m2;
   y.resize(std::max(f.n, cols), 0.0);
   sparse_upper_solve(f.R, f.rank, y.data());
+  std::fill(y.begin() + f.rank, y.end(), 0.0);              // y.bottomRows(y.rows() - rank).setZero() (:216)
   std::vector<double> x(cols);
   for (int j = 0; j < cols; j++) x[f.colPerm[j]] = y[j];
   return x;

@@ -502,7 +502,7 @@ DenseBorder wide_desc(qrk_solver* h, int nrhs) {
   DenseBorder d;
   d.A = h->d_wx + h->sum_cols;            // the complement rows of Q1^T [J2 | b] (rows [m1, n) for a block-diagonal left block)
   d.ld = h->w_ld; d.N = h->w_N; d.Nrule = h->n_rows - h->sum_cols; d.M = h->m2; d.nrhs = nrhs;
-  d.pivot = h->desc.right_solver == QRK_RIGHT_UNPIVOTED ? 0 : 1;
+  d.pivot = h->desc.right_solver == QRK_RIGHT_UNPIVOTED ? 0 : h->desc.right_solver == QRK_RIGHT_THIN_SPARSE ? 2 : 1;
   d.upd = h->d_wupd; d.dir = h->d_wdir; d.tau = h->d_wtau2; d.perm = h->d_wperm; d.scal = h->d_wscal; d.iscal = h->d_wiscal;
   return d;
 }
@@ -560,6 +560,68 @@ int wide_unblocked(qrk_solver* h, const DenseBorder& d) {
     if (ncols > 0) dense_upd_kernel<128><<<ncols, 128, 0, h->stream>>>(d, k);
     h->launches += ncols > 0 ? 2 : 1;
   }
+  QRK_TRY_CUDA(h, cudaGetLastError());
+  return QRK_STATUS_OK;
+}
+
+
+// BlockedThinSparseQR as the right solver (BlockedThinSparseQR.h:105-166): panels of `s` column positions; inside a panel
+// Eigen's ColPivHouseholderQR column by column (dense_piv_kernel restricted to the panel, dense_upd_kernel on EVERY column to
+// the right — updateMat(idxCol, cols), :264 — the right-hand side and the deferred columns included).  The panel's nonzero-pivot
+// count comes back to the host once per panel; columns with a zero pivot are rotated behind the unprocessed ones (:250-255),
+// so that "position = diagonal row" keeps holding for the next panel, which starts at row m_nonzeroPivots (:234).
+int wide_thin_sparse(qrk_solver* h, DenseBorder d) {
+  const int M = d.M;
+  const int s = h->desc.reserved[1] > 0 ? h->desc.reserved[1] : 2;
+  thin_init_kernel<<<1, 256, 0, h->stream>>>(d);
+  h->launches++;
+  h->thin_deferred = false;
+  int nzp = 0, u1 = M;                      // [0, nzp) done, [nzp, u1) unprocessed in their original order, [u1, M) deferred
+  double* tmp = nullptr;
+  while (nzp < u1 && nzp < d.N) {
+    const int k0 = nzp, left = u1 - k0;
+    const int pc = (left <= s) ? left : s;  // updateBlockInfo (:198-236): the last panel takes what is left
+    d.pend = k0 + pc;
+    thin_panel_prep_kernel<<<1, 256, 0, h->stream>>>(d, k0, pc);
+    h->launches++;
+    const int steps = (int)std::min<long long>(pc, d.N - k0);
+    for (int k = k0; k < k0 + steps; k++) {
+      dense_piv_kernel<1024><<<1, 1024, 0, h->stream>>>(d, k);
+      const int ncols = M - k - 1 + d.nrhs;
+      if (ncols > 0) dense_upd_kernel<128><<<ncols, 128, 0, h->stream>>>(d, k);
+      h->launches += ncols > 0 ? 2 : 1;
+    }
+    int nz_abs = k0 + pc;
+    QRK_TRY_CUDA(h, cudaMemcpyAsync(&nz_abs, d.iscal + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (steps < pc && nz_abs > k0 + steps) nz_abs = k0 + steps;      // fewer rows than panel columns: the rest has no pivot
+    const int z = k0 + pc - nz_abs;
+    if (z > 0) {                            // defer: zero below their own step, then [nz_abs, nz_abs + z) -> [u1 - z, u1)
+      h->thin_deferred = true;
+      for (int c = nz_abs; c < k0 + pc; c++) thin_clear_below_kernel<<<32, 256, 0, h->stream>>>(d, c, std::min(c, k0 + steps - 1));
+      const int moved = u1 - (nz_abs + z);  // unprocessed columns that shift left by z
+      if (moved > 0) {
+        if (!tmp) QRK_TRY_CUDA(h, cudaMalloc(&tmp, (size_t)s * d.N * sizeof(double)));
+        QRK_TRY_CUDA(h, cudaMemcpy2DAsync(tmp, d.N * sizeof(double), d.A + (long long)nz_abs * d.ld, d.ld * sizeof(double), d.N * sizeof(double), z,
+                                          cudaMemcpyDeviceToDevice, h->stream));
+        for (int c = nz_abs + z; c < u1; c++)
+          QRK_TRY_CUDA(h, cudaMemcpyAsync(d.A + (long long)(c - z) * d.ld, d.A + (long long)c * d.ld, d.N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        QRK_TRY_CUDA(h, cudaMemcpy2DAsync(d.A + (long long)(u1 - z) * d.ld, d.ld * sizeof(double), tmp, d.N * sizeof(double), d.N * sizeof(double), z,
+                                          cudaMemcpyDeviceToDevice, h->stream));
+        std::vector<int> perm(M);
+        QRK_TRY_CUDA(h, cudaMemcpyAsync(perm.data(), d.perm, M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::rotate(perm.begin() + nz_abs, perm.begin() + nz_abs + z, perm.begin() + u1);
+        QRK_TRY_CUDA(h, cudaMemcpyAsync(d.perm, perm.data(), M * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+      }
+      u1 -= z;
+    }
+    nzp = nz_abs;
+  }
+  QRK_TRY_CUDA(h, cudaMemcpyAsync(d.iscal, &nzp, sizeof(int), cudaMemcpyHostToDevice, h->stream));   // rank() = m_nonzeroPivots (:281)
+  QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (tmp) cudaFree(tmp);
   QRK_TRY_CUDA(h, cudaGetLastError());
   return QRK_STATUS_OK;
 }
@@ -692,7 +754,9 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
   const DenseBorder d = wide_desc(h, d_b ? 1 : 0);
   h->wide_blocked = false;
   if (d.N > 0) {
-    if (wide_can_block(d)) {
+    if (d.pivot == 2) {
+      st = wide_thin_sparse(h, d);
+    } else if (wide_can_block(d)) {
       h->wide_blocked = true;
       st = wide_blocked_qr(h, d);
       if (st == QRK_STATUS_UNSUPPORTED) {   // the panel cluster could not be launched: the column-by-column path instead
@@ -730,6 +794,10 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
 }
 
 int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
+  if (h->thin_deferred) {
+    h->err = "BlockedThinSparseQR right solver: the factorisation deferred zero-pivot columns; solve() on the stored factors is not provided, use the fused compute_solve()";
+    return QRK_STATUS_UNSUPPORTED;
+  }
   const long long n = h->w_ld;
   const int M = h->m2;
   double* rhs_col = h->d_wx + (long long)M * n;
@@ -737,7 +805,7 @@ int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
   if (st != QRK_STATUS_OK) return st;
   DenseBorder d = wide_desc(h, 1);
   if (d.N > 0) {
-    const bool two_stage = h->wide_blocked && d.pivot;
+    const bool two_stage = h->wide_blocked && d.pivot == 1;
     if (two_stage) d.tau = h->d_wtau1;
     dense_apply_qt_kernel<1024><<<1, 1024, 0, h->stream>>>(d, rhs_col + h->sum_cols);   // Q2^T on the bottom rows (:619-624)
     h->launches++;
@@ -815,7 +883,11 @@ int apply_q2(qrk_solver* h, double* vec, bool transpose) {
   }
   DenseBorder d = wide_desc(h, 1);
   if (d.N <= 0) return QRK_STATUS_OK;
-  const bool two_stage = h->wide_blocked && d.pivot;
+  if (h->thin_deferred) {
+    h->err = "BlockedThinSparseQR right solver: the factorisation deferred zero-pivot columns; matrixQ() products are not provided for it";
+    return QRK_STATUS_UNSUPPORTED;
+  }
+  const bool two_stage = h->wide_blocked && d.pivot == 1;
   if (two_stage) d.tau = h->d_wtau1;
   double* head = h->d_wtri + (size_t)M * M;        // the right-hand side column of the triangle: scratch for the second stage
   const DenseBorder t = wide_tri_desc(h, 1);
@@ -1094,9 +1166,10 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     h->m2 = desc->border_cols;
     h->avt = angular_vtable(h->m2);
     if (desc->q_format != QRK_FULL_Q || h->m2 < 1 || h->m2 > 4096) return fail(QRK_STATUS_UNSUPPORTED);
-    if (desc->right_solver != QRK_RIGHT_COLPIV && desc->right_solver != QRK_RIGHT_UNPIVOTED) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    if (desc->right_solver != QRK_RIGHT_COLPIV && desc->right_solver != QRK_RIGHT_UNPIVOTED && desc->right_solver != QRK_RIGHT_THIN_SPARSE) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    if (desc->reserved[1] < 0) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->left_banded = left_banded;
-    if (!uniform || !h->avt || left_banded || !h->avt->shape_ok(h->ur, h->uc) || desc->right_solver == QRK_RIGHT_UNPIVOTED) {   // dense_border.cuh
+    if (!uniform || !h->avt || left_banded || !h->avt->shape_ok(h->ur, h->uc) || desc->right_solver != QRK_RIGHT_COLPIV) {   // dense_border.cuh
       h->avt = nullptr;
       h->wide = true;
     }

@@ -21,7 +21,9 @@ struct DenseBorder {
   long long ld, N;
   long long Nrule;   // rows of the matrix Eigen's rules refer to (= N, or the tall residual's rows when A is its M x M triangle)
   int M, nrhs;
-  int pivot;         // 1: ColPivHouseholderQR (Eigen's pivot rule), 0: HouseholderQR / BlockedThinDenseQR (no pivoting)
+  int pivot;         // 1: ColPivHouseholderQR (Eigen's pivot rule), 0: HouseholderQR / BlockedThinDenseQR (no pivoting),
+                     // 2: BlockedThinSparseQR — ColPiv inside the panel [.., pend) only, per-panel nonzero-pivot rule (iscal[1])
+  int pend = 0;      // pivot == 2: end (exclusive) of the current panel's column positions
   double *upd, *dir, *tau;
   int* perm;         // P2: perm[c] = original border column at position c
   double* scal;      // [0] threshold_helper, [1] maxpivot
@@ -69,6 +71,39 @@ __global__ void __launch_bounds__(256) dense_prep_kernel(DenseBorder d) {
   }
 }
 
+// BlockedThinSparseQR (BlockedThinSparseQR.h:238-246): start of the panel at positions [k0, k0 + pc) — the dense block Ji spans
+// rows [k0, N), so the panel's ColPivHouseholderQR sees the column norms over those rows, its threshold_helper
+// (max norm * eps)^2 / rows and its own nonzero-pivot count (kept as a position in iscal[1]; k0 + pc = "all nonzero so far")
+__global__ void __launch_bounds__(256) thin_panel_prep_kernel(DenseBorder d, int k0, int pc) {
+  __shared__ double sred[8];
+  __shared__ double smax;
+  if (threadIdx.x == 0) smax = 0.0;
+  for (int c = 0; c < pc; c++) {
+    const double* col = d.A + (long long)(k0 + c) * d.ld;
+    double s = 0.0;
+    for (long long i = k0 + threadIdx.x; i < d.N; i += 256) s = fma(col[i], col[i], s);
+    s = block_sum<256>(s, sred);
+    if (threadIdx.x == 0) { const double nrm = sqrt(s); d.upd[k0 + c] = nrm; d.dir[k0 + c] = nrm; smax = fmax(smax, nrm); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double me = smax * DBL_EPSILON;
+    d.scal[0] = me * me / (double)(d.N - k0);
+    d.iscal[1] = k0 + pc;
+  }
+}
+// P2 = identity, maxpivot = 0, nonzero pivots = 0 (before the first panel)
+__global__ void thin_init_kernel(DenseBorder d) {
+  for (int j = threadIdx.x; j < d.M; j += blockDim.x) { d.perm[j] = j; d.tau[j] = 0.0; }
+  if (threadIdx.x == 0) { d.scal[0] = 0.0; d.scal[1] = 0.0; d.iscal[0] = 0; d.iscal[1] = 0; }
+}
+// a deferred (zero-pivot) column at position c whose own reflector step was `step`: below that row the transformed column is
+// zero (H x = beta e1); the stored reflector is dropped so that later panels see data, not a Householder vector
+__global__ void thin_clear_below_kernel(DenseBorder d, int c, int step) {
+  double* col = d.A + (long long)c * d.ld;
+  for (long long i = step + 1 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.N; i += (long long)gridDim.x * blockDim.x) col[i] = 0.0;
+}
+
 // step k, part 1: first maximum of upd[k..M), swap, reflector of column k (Eigen makeHouseholderInPlace)
 template <int TPB>
 __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
@@ -79,8 +114,9 @@ __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double bv = -1.0;
   int bj = 0x7fffffff;
+  const int jend = (d.pivot == 2) ? d.pend : d.M;
   if (!d.pivot) { bv = 0.0; bj = k; }
-  else for (int j = k + tid; j < d.M; j += TPB) {
+  else for (int j = k + tid; j < jend; j += TPB) {
     const double u = d.upd[j];
     if (u > bv) { bv = u; bj = j; }                    // strict '>': the first maximum wins inside a thread
   }
@@ -96,7 +132,9 @@ __global__ void __launch_bounds__(TPB) dense_piv_kernel(DenseBorder d, int k) {
     for (int w = 1; w < TPB / 32; w++)
       if (sval[w] > bv || (sval[w] == bv && sidx[w] < bj)) { bv = sval[w]; bj = sidx[w]; }
     const int size = (int)(d.Nrule < d.M ? d.Nrule : d.M);
-    if (d.pivot && d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.Nrule - k)) d.iscal[0] = k;
+    if (d.pivot == 2) {                                  // the panel's own ColPivHouseholderQR: m_nonzero_pivots, as a position
+      if (d.iscal[1] == jend && bv * bv < d.scal[0] * (double)(d.N - k)) d.iscal[1] = k;
+    } else if (d.pivot && d.iscal[0] == size && bv * bv < d.scal[0] * (double)(d.Nrule - k)) d.iscal[0] = k;
     if (bj != k) {
       double t = d.upd[k]; d.upd[k] = d.upd[bj]; d.upd[bj] = t;
       t = d.dir[k]; d.dir[k] = d.dir[bj]; d.dir[bj] = t;
@@ -233,7 +271,7 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
   {                                      // rank: |R_ii| > |maxpivot| eps size among the nonzero pivots, counted in parallel
     const double thresh = fabs(d.scal[1]) * (DBL_EPSILON * (double)size);
     int cnt = 0;
-    if (d.pivot) for (int i = tid; i < d.iscal[0]; i += TPB) cnt += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
+    if (d.pivot == 1) for (int i = tid; i < d.iscal[0]; i += TPB) cnt += (fabs(d.A[(long long)i * d.ld + i]) > thresh) ? 1 : 0;
     if (tid == 0) s_rank = 0;
     __syncthreads();
     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(TPB) dense_finish_kernel(DenseBorder d, const 
     __syncthreads();
     if (tid == 0) {
       if (!d.pivot) s_rank = M;            // BlockedThinDenseQR: m_nonzeroPivots = m_R.cols() (BlockedThinDenseQR.h:132)
+      if (d.pivot == 2) s_rank = d.iscal[0];   // BlockedThinSparseQR: rank() = m_nonzeroPivots, summed over the panels (:281)
       root_i[M] = s_rank;
     }
   }

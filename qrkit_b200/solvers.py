@@ -291,12 +291,14 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
     """BlockAngularSparseQR<LeftSolver, RightSolver> (BlockAngularSparseQR.h:79-281).  mat.left is a SparseBlockDiagonal
     (LeftSolver = BlockDiagonalSparseQR: narrow borders go through the fused TSQR kernels, Eigen's ColPiv rule at the root) or a
     BandedSlabs (LeftSolver = BandedBlockedSparseQR, the pair of test/test-qrkit.cpp:44-48); right_solver: 0 =
-    ColPivHouseholderQR<MatrixXd>, 1 = BlockedThinDenseQR / HouseholderQR (unpivoted)."""
+    ColPivHouseholderQR<MatrixXd>, 1 = BlockedThinDenseQR / HouseholderQR (unpivoted), 2 = BlockedThinSparseQR (ColPiv inside
+    panels of `right_panel` columns, zero-pivot columns deferred; test/test-qrkit.cpp:54-57)."""
 
     def __init__(self, mat: BlockMatrix1x2 | None = None, *, pivoting=QRK_PIVOT_COLPIV, device=0, stream=None, world=1,
-                 right_solver=0):
+                 right_solver=0, right_panel=0):
         self._world = world
-        self._right_solver = right_solver      # 0: ColPivHouseholderQR<MatrixXd>, 1: BlockedThinDenseQR / HouseholderQR (unpivoted)
+        self._right_solver = right_solver      # 0: ColPivHouseholderQR<MatrixXd>, 1: BlockedThinDenseQR / HouseholderQR (unpivoted), 2: BlockedThinSparseQR
+        self._right_panel = right_panel        # SuggestedBlockCols of BlockedThinSparseQR (0 = the reference's 2)
         super().__init__(None, pivoting=pivoting, q_format=QRK_FULL_Q, device=device, stream=stream)
         if mat is not None:
             self.compute(mat)
@@ -304,7 +306,7 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
     def _ensure_handle_angular(self, mat: BlockMatrix1x2):
         left, m2 = mat.left, mat.right.shape[1]
         banded = isinstance(left, BandedSlabs)      # LeftSolver = BandedBlockedSparseQR (test/test-qrkit.cpp:44-48)
-        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2, self._right_solver,
+        key = ("angular", left.num_blocks, left.block_rows, left.block_cols, m2, self._right_solver, self._right_panel,
                (left.overlap, left.n_cols) if banded else None)
         if self._h and key == self._shape_key:
             return
@@ -314,6 +316,7 @@ class BlockAngularSparseQR(BlockDiagonalSparseQR):
         d.block_rows, d.block_cols = left.block_rows, left.block_cols
         d.pivoting, d.q_format, d.border_cols = self._pivoting, QRK_FULL_Q, m2
         d.right_solver = self._right_solver
+        d.reserved[1] = self._right_panel
         if banded:
             d.left_solver, d.block_overlap, d.n_cols, d.pivoting = 1, left.overlap, left.n_cols + m2, QRK_PIVOT_NONE
         h = C.c_void_p()

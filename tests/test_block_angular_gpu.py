@@ -437,3 +437,62 @@ def test_config3_full_size_properties(qk, oracle):
     g2 = np.einsum("nij,ni->j", Jb, res)
     scale = np.abs(J2).max() * np.linalg.norm(rhs)
     assert np.abs(g1).max() <= 1e-9 * scale and np.abs(g2).max() <= 1e-7 * scale
+
+
+@pytest.mark.parametrize("panel", [2, 3])
+@pytest.mark.parametrize("nb,r,c,m2", [(40, 7, 2, 9), (64, 8, 4, 16), (200, 2, 1, 5)])
+def test_thin_sparse_right_solver_vs_oracle(qk, oracle, nb, r, c, m2, panel):
+    """RightSolver = BlockedThinSparseQR<.., SuggestedBlockCols = panel> (test/test-qrkit.cpp:54-57, 329-362): ColPiv inside
+    every panel of the border, full column rank.  P_c bit-exact, R index arrays bit-exact, R2 up to row signs, x to 1e-10."""
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    b = vector(nb * r, seed=5)
+    m1 = nb * c
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True, right_kind=2, panel=panel)
+    s = qk.BlockAngularSparseQR(mat, pivoting=1, right_solver=2, right_panel=panel)
+    assert s.rank() == ref.rank == m1 + m2 and s.info() == qk.QRK_INFO_SUCCESS
+    P = s.colsPermutation()
+    assert np.array_equal(P, ref.colsPermutation()), "per-panel pivot order must be bit-exact"
+    assert not np.array_equal(P[m1:], m1 + np.arange(m2)), "the case should exercise pivoting inside a panel"
+    R, Rr = s.matrixR(), ref.matrixR()
+    assert np.array_equal(R.outer, Rr.outer) and np.array_equal(R.inner, Rr.inner)
+    Rd, Rrd = R.toarray(), Rr.toarray()
+    assert rel(Rd[:m1, :], Rrd[:m1, :]) <= TOL_R
+    assert rel(_sign_fix(Rd[m1:m1 + m2, m1:], Rrd[m1:m1 + m2, m1:]), Rrd[m1:m1 + m2, m1:]) <= TOL_R * 10
+    x_ref = ref.solve(b)
+    assert rel(s.solve(b), x_ref) <= TOL_X
+    assert rel(qk.BlockAngularSparseQR(pivoting=1, right_solver=2, right_panel=panel).compute_solve(mat, b), x_ref) <= TOL_X
+    A = np.hstack([blocks_to_dense(vals, np.full(nb, r), np.full(nb, c)), J2])
+    assert rel(s.solve(b), np.linalg.lstsq(A, b, rcond=None)[0]) <= TOL_X
+
+
+def test_thin_sparse_right_solver_rank_deficient_border(qk, oracle):
+    """BlockedThinSparseQR's zero-pivot deferral (BlockedThinSparseQR.h:250-255, 150-158): border columns that are exactly zero
+    are detected inside their panel, moved to the end of P2 and excluded from the rank; x is the basic solution (zero on the
+    deferred columns).  Deferral order, P_c and rank bit-exact against the oracle; A P = Q R through R^T R = (A P)^T (A P)."""
+    nb, r, c, m2, panel = 50, 7, 2, 11, 2
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2)
+    J2[:, 2] = 0.0; J2[:, 5] = 0.0; J2[:, 7] = 0.0           # first / second column of their panels (a panel that is ALL zero
+                                                             # is not flagged by Eigen's rule: its threshold is 0 and 0 < 0 fails)
+    b = vector(nb * r, seed=5)
+    m1 = nb * c
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True, right_kind=2, panel=panel)
+    s = qk.BlockAngularSparseQR(pivoting=1, right_solver=2, right_panel=panel)
+    x = s.compute_solve(mat, b)
+    assert s.rank() == ref.rank == m1 + m2 - 3
+    P = s.colsPermutation()
+    assert np.array_equal(P, ref.colsPermutation())
+    assert list(P[-3:] - m1) == [2, 5, 7]                     # deferral order = panel order
+    Rd = s.matrixR().toarray()[:m1 + m2, :]
+    A = np.hstack([blocks_to_dense(vals, np.full(nb, r), np.full(nb, c)), J2])
+    AP = A[:, P]
+    assert rel(Rd.T @ Rd, AP.T @ AP) <= 1e-12
+    assert np.all(x[m1 + np.array([2, 5, 7])] == 0.0)
+    keep = np.setdiff1d(np.arange(m1 + m2), m1 + np.array([2, 5, 7]))
+    assert rel(x[keep], np.linalg.lstsq(A[:, keep], b, rcond=None)[0]) <= TOL_X
+    assert rel(x, ref.solve(b)) <= TOL_X
+    with pytest.raises(qk.QrkError):                            # stored-factor products are refused once columns were deferred
+        s.solve(b)
