@@ -255,6 +255,10 @@ QRK_API int qrk_angular_p2p_status(qrk_handle_t h, int32_t* timed_out);
 QRK_API int qrk_ipc_export(const void* device_ptr, void* handle64);
 QRK_API int qrk_ipc_import(const void* handle64, void** device_ptr);
 QRK_API int qrk_ipc_close(void* device_ptr);
+/* One process driving several GPUs (no IPC needed: every cudaMalloc allocation is addressable once peer access is on):
+ * cudaDeviceEnablePeerAccess(peer) issued on `device`; already enabled / device == peer is not an error.  Then pass the
+ * handles' qrk_angular_xchg_buffer pointers straight to qrk_angular_p2p_attach (QRKit.hpp: ShardedBlockAngularSparseQR). */
+QRK_API int qrk_enable_peer_access(int32_t device, int32_t peer);
 
 /* ---- banded blocked (BandedBlockedSparseQR.h:122-344) ---------------------------------------------------------------
  * A handle of kind QRK_BANDED_BLOCKED describes num_blocks block rows of block_rows x block_cols; block row k sits at

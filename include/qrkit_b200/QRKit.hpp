@@ -14,11 +14,14 @@
 // All arithmetic happens in libqrkit_b200.so on the GPU; there is no CPU fallback: without a CUDA device
 // every solver reports info() == InvalidInput and lastErrorMessage() says so.
 #pragma once
+#include <algorithm>
 #include <cassert>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <exception>
+#include <thread>
 #include <vector>
 
 #include "../qrkit_b200.h"
@@ -598,6 +601,190 @@ class BlockAngularBandedSparseQR {
   mutable MatrixRType m_R;
   mutable PermutationType m_outputPerm_c;
   std::string m_lastError;
+};
+
+// ---- multi-GPU, one host process -------------------------------------------------------------------------------
+// The reference's block loop is serial (BlockDiagonalSparseQR.h:432); the blocks are independent, so G GPUs each take a
+// contiguous range of them.  One handle per device, one host thread per handle for the (blocking) host-memory calls.
+namespace detail {
+// contiguous block range of shard g: balanced, every boundary a multiple of 2 blocks (16-byte alignment of odd-sized slices)
+inline void shard_range(Index nb, int G, int g, Index& lo, Index& hi) {
+  const Index units = (nb + 1) / 2;
+  lo = std::min<Index>(nb, (units * g / G) * 2);
+  hi = std::min<Index>(nb, (units * (g + 1) / G) * 2);
+}
+template <typename F>
+inline void for_each_shard(int G, F f) {        // f(g) on its own thread; the first exception is rethrown on the caller's thread
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err((size_t)G);
+  for (int g = 0; g < G; g++) th.emplace_back([&, g]() { try { f(g); } catch (...) { err[(size_t)g] = std::current_exception(); } });
+  for (auto& t : th) t.join();
+  for (auto& e : err) if (e) std::rethrow_exception(e);
+}
+}  // namespace detail
+
+// BlockDiagonalSparseQR over several GPUs: NO collective on the data path — x, R and the permutations stay sharded on the
+// devices and are concatenated on the host (global offsets = prefix sums of the block sizes).
+template <typename BlockQRSolverTag>
+class ShardedBlockDiagonalSparseQR {
+ public:
+  using Blk = typename BlockQRSolverTag::MatrixType;
+  using MatrixType = SparseBlockDiagonal<Blk>;
+  explicit ShardedBlockDiagonalSparseQR(const std::vector<int>& devices) : m_dev(devices), m_h(devices.size(), nullptr) {
+    detail::require(!devices.empty(), "ShardedBlockDiagonalSparseQR: no devices");
+  }
+  ~ShardedBlockDiagonalSparseQR() { for (auto h : m_h) qrk_destroy(h); }
+  ShardedBlockDiagonalSparseQR(const ShardedBlockDiagonalSparseQR&) = delete;
+  ShardedBlockDiagonalSparseQR& operator=(const ShardedBlockDiagonalSparseQR&) = delete;
+
+  void compute(const MatrixType& mat) {
+    ensureHandles(mat);
+    const double* values = mat.size() ? mat[0].data() : nullptr;
+    detail::for_each_shard(G(), [&](int g) { detail::throw_if(qrk_compute(m_h[(size_t)g], values + m_lo[(size_t)g] * R * C, QRK_HOST), m_h[(size_t)g], "compute"); });
+  }
+  VectorXd solve(const VectorXd& b) const {
+    detail::require((Index)b.size() == m_rows, "solve: b.size() != rows()");
+    VectorXd x((size_t)m_cols);
+    detail::for_each_shard(G(), [&](int g) {
+      const Index lo = m_lo[(size_t)g], nbg = m_lo[(size_t)g + 1] - lo;
+      detail::throw_if(qrk_solve(m_h[(size_t)g], b.data() + lo * R, nbg * R, x.data() + lo * C, nbg * C, 1, QRK_HOST), m_h[(size_t)g], "solve");
+    });
+    return x;
+  }
+  VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {      // the fused pass on every shard
+    ensureHandles(mat);
+    detail::require((Index)b.size() == m_rows, "computeAndSolve: b.size() != rows()");
+    VectorXd x((size_t)m_cols);
+    const double* values = mat.size() ? mat[0].data() : nullptr;
+    detail::for_each_shard(G(), [&](int g) {
+      const Index lo = m_lo[(size_t)g];
+      detail::throw_if(qrk_compute_solve(m_h[(size_t)g], values + lo * R * C, b.data() + lo * R, x.data() + lo * C, QRK_HOST), m_h[(size_t)g], "computeAndSolve");
+    });
+    return x;
+  }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index rank() const { Index r = 0; for (auto h : m_h) { int64_t rg = 0; qrk_rank(h, &rg); r += rg; } return r; }
+  PermutationMatrix colsPermutation() const {                              // shard-local indices shifted by the shard's first column
+    PermutationMatrix p;
+    p.indices().resize((size_t)m_cols);
+    for (int g = 0; g < G(); g++) {
+      const Index lo = m_lo[(size_t)g], nbg = m_lo[(size_t)g + 1] - lo;
+      if (nbg == 0) continue;
+      detail::throw_if(qrk_cols_permutation(m_h[(size_t)g], p.indices().data() + lo * C, QRK_HOST), m_h[(size_t)g], "colsPermutation");
+      for (Index j = lo * C; j < (lo + nbg) * C; j++) p.indices()[(size_t)j] += (int)(lo * C);
+    }
+    return p;
+  }
+  int shards() const { return G(); }
+
+ private:
+  enum { R = Blk::RowsAtCompileTime, C = Blk::ColsAtCompileTime };
+  int G() const { return (int)m_dev.size(); }
+  void ensureHandles(const MatrixType& mat) {
+    if (m_nb == mat.size()) return;
+    for (auto& h : m_h) { qrk_destroy(h); h = nullptr; }
+    m_nb = mat.size(); m_rows = m_nb * R; m_cols = m_nb * C;
+    m_lo.assign((size_t)G() + 1, 0);
+    for (int g = 0; g < G(); g++) {
+      Index lo, hi;
+      detail::shard_range(m_nb, G(), g, lo, hi);
+      m_lo[(size_t)g] = lo; m_lo[(size_t)g + 1] = hi;
+      qrk_desc_t d{};
+      d.kind = QRK_BLOCK_DIAGONAL; d.device = m_dev[(size_t)g]; d.num_blocks = hi - lo; d.block_rows = R; d.block_cols = C;
+      d.pivoting = BlockQRSolverTag::pivoting; d.q_format = QRK_FULL_Q;
+      detail::throw_if(qrk_create(&d, &m_h[(size_t)g]), nullptr, "ShardedBlockDiagonalSparseQR");
+    }
+  }
+  std::vector<int> m_dev;
+  std::vector<qrk_handle_t> m_h;
+  std::vector<Index> m_lo;
+  Index m_nb = -1, m_rows = 0, m_cols = 0;
+};
+
+// BlockAngularSparseQR over several GPUs (narrow border, fused TSQR path): every GPU factors its block range, applies Q1^T to
+// its rows of [J2 | b] and reduces them to one m2 x (m2+1) triangle; the triangles cross NVLink INSIDE the TSQR root kernel
+// (peer stores + flags, qrk_angular_p2p_attach), every GPU merges them in rank order — bit-identical shared parameters — and
+// back-substitutes its own x1.  The ONE exchange step of BlockAngularSparseQR.h:361-369, no host round trip.
+template <typename BlockQRSolverLeftTag>
+class ShardedBlockAngularSparseQR {
+ public:
+  using Blk = typename BlockQRSolverLeftTag::MatrixType;
+  using MatrixType = BlockMatrix1x2<SparseBlockDiagonal<Blk>, MatrixXd>;
+  explicit ShardedBlockAngularSparseQR(const std::vector<int>& devices) : m_dev(devices), m_h(devices.size(), nullptr) {
+    detail::require(devices.size() >= 2, "ShardedBlockAngularSparseQR: needs at least two shards (use BlockAngularSparseQR for one GPU)");
+  }
+  ~ShardedBlockAngularSparseQR() { for (auto h : m_h) qrk_destroy(h); }
+  ShardedBlockAngularSparseQR(const ShardedBlockAngularSparseQR&) = delete;
+  ShardedBlockAngularSparseQR& operator=(const ShardedBlockAngularSparseQR&) = delete;
+
+  // x = [x1 (all shards, in block order) ; x2]
+  VectorXd computeAndSolve(const MatrixType& mat, const VectorXd& b) {
+    ensureHandles(mat);
+    const auto& L = mat.leftBlock();
+    const MatrixXd& J2 = mat.rightBlock();
+    detail::require((Index)b.size() == m_rows && J2.rows() == m_rows, "computeAndSolve: b.size() / border rows != rows()");
+    const double* values = L.size() ? L[0].data() : nullptr;
+    VectorXd x((size_t)m_cols);
+    std::vector<VectorXd> xg((size_t)G());
+    detail::for_each_shard(G(), [&](int g) {
+      const Index lo = m_lo[(size_t)g], nbg = m_lo[(size_t)g + 1] - lo;
+      qrk_handle_t h = m_h[(size_t)g];
+      xg[(size_t)g] = VectorXd((size_t)(nbg * C + m_m2));
+      detail::throw_if(qrk_set_border(h, J2.data() + lo * R, J2.rows(), QRK_HOST), h, "border");      // this shard's rows of every border column
+      detail::throw_if(qrk_compute_solve(h, values + lo * R * C, b.data() + lo * R, xg[(size_t)g].data(), QRK_HOST), h, "computeAndSolve");
+    });
+    for (int g = 0; g < G(); g++) {
+      const Index lo = m_lo[(size_t)g], nbg = m_lo[(size_t)g + 1] - lo;
+      std::copy(xg[(size_t)g].begin(), xg[(size_t)g].begin() + nbg * C, x.begin() + lo * C);
+    }
+    const Index m1 = m_cols - m_m2, last = m_lo[1] - m_lo[0];
+    std::copy(xg[0].begin() + last * C, xg[0].end(), x.begin() + m1);                                  // x2: the same bits on every shard
+    m_x2_identical = true;
+    for (int g = 1; g < G(); g++) {
+      const Index nbg = m_lo[(size_t)g + 1] - m_lo[(size_t)g];
+      for (Index j = 0; j < m_m2; j++) m_x2_identical = m_x2_identical && xg[(size_t)g][(size_t)(nbg * C + j)] == x[(size_t)(m1 + j)];
+    }
+    return x;
+  }
+  bool sharedParametersIdentical() const { return m_x2_identical; }
+  Index rows() const { return m_rows; }
+  Index cols() const { return m_cols; }
+  Index rank() const { int64_t r2 = 0, r = 0; for (int g = 0; g < G(); g++) { qrk_rank(m_h[(size_t)g], &r); r2 = r - (m_lo[(size_t)g + 1] - m_lo[(size_t)g]) * C; } return (m_cols - m_m2) + r2; }
+  int shards() const { return G(); }
+
+ private:
+  enum { R = Blk::RowsAtCompileTime, C = Blk::ColsAtCompileTime };
+  int G() const { return (int)m_dev.size(); }
+  void ensureHandles(const MatrixType& mat) {
+    const auto& L = mat.leftBlock();
+    const Index m2 = mat.rightBlock().cols();
+    if (m_nb == L.size() && m_m2 == m2) return;
+    for (auto& h : m_h) { qrk_destroy(h); h = nullptr; }
+    m_nb = L.size(); m_m2 = m2; m_rows = mat.rows(); m_cols = mat.cols();
+    m_lo.assign((size_t)G() + 1, 0);
+    std::vector<void*> bufs((size_t)G(), nullptr);
+    for (int g = 0; g < G(); g++) {
+      Index lo, hi;
+      detail::shard_range(m_nb, G(), g, lo, hi);
+      m_lo[(size_t)g] = lo; m_lo[(size_t)g + 1] = hi;
+      qrk_desc_t d{};
+      d.kind = QRK_BLOCK_ANGULAR; d.device = m_dev[(size_t)g]; d.num_blocks = hi - lo; d.block_rows = R; d.block_cols = C;
+      d.pivoting = BlockQRSolverLeftTag::pivoting; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2; d.right_solver = QRK_RIGHT_COLPIV;
+      detail::throw_if(qrk_create(&d, &m_h[(size_t)g]), nullptr, "ShardedBlockAngularSparseQR");
+      detail::throw_if(qrk_angular_set_world(m_h[(size_t)g], G()), m_h[(size_t)g], "set_world (the fused TSQR path takes 1..8 border columns)");
+      int64_t bytes = 0;
+      detail::throw_if(qrk_angular_xchg_buffer(m_h[(size_t)g], &bufs[(size_t)g], &bytes), m_h[(size_t)g], "xchg_buffer");
+    }
+    for (int g = 0; g < G(); g++)
+      for (int p = 0; p < G(); p++) detail::throw_if(qrk_enable_peer_access(m_dev[(size_t)g], m_dev[(size_t)p]), nullptr, "peer access between the shards' devices");
+    for (int g = 0; g < G(); g++) detail::throw_if(qrk_angular_p2p_attach(m_h[(size_t)g], bufs.data(), G(), g), m_h[(size_t)g], "p2p_attach");
+  }
+  std::vector<int> m_dev;
+  std::vector<qrk_handle_t> m_h;
+  std::vector<Index> m_lo;
+  Index m_nb = -1, m_m2 = 0, m_rows = 0, m_cols = 0;
+  bool m_x2_identical = false;
 };
 
 }  // namespace QRKit_b200

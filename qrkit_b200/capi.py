@@ -94,6 +94,7 @@ def lib():
             "qrk_angular_xchg_buffer": [vp, C.POINTER(vp), C.POINTER(i64)],
             "qrk_angular_p2p_attach": [vp, C.POINTER(vp), i32, i32],
             "qrk_angular_p2p_status": [vp, C.POINTER(i32)], "qrk_angular_p2p_set_timeout": [vp, C.c_double],
+            "qrk_enable_peer_access": [i32, i32],
             "qrk_ipc_export": [vp, vp], "qrk_ipc_import": [vp, C.POINTER(vp)], "qrk_ipc_close": [vp],
             "qrk_bind_host_thread_to_device": [i32, C.POINTER(i32), C.POINTER(i32)],
             "qrk_host_alloc": [C.POINTER(vp), i64, i32], "qrk_host_free": [vp],

@@ -599,19 +599,21 @@ int wide_thin_sparse(qrk_solver* h, DenseBorder d) {
     if (z > 0) {                            // defer: zero below their own step, then [nz_abs, nz_abs + z) -> [u1 - z, u1)
       h->thin_deferred = true;
       for (int c = nz_abs; c < k0 + pc; c++) thin_clear_below_kernel<<<32, 256, 0, h->stream>>>(d, c, std::min(c, k0 + steps - 1));
-      const int moved = u1 - (nz_abs + z);  // unprocessed columns that shift left by z
+      // [nz_abs, nz_abs + z) go to the very end, everything behind them (the unprocessed columns and the columns deferred
+      // earlier, which stay in deferral order: m_zeroColPermIdxs, :253-255) shifts left by z
+      const int moved = M - (nz_abs + z);
       if (moved > 0) {
         if (!tmp) QRK_TRY_CUDA(h, cudaMalloc(&tmp, (size_t)s * d.N * sizeof(double)));
         QRK_TRY_CUDA(h, cudaMemcpy2DAsync(tmp, d.N * sizeof(double), d.A + (long long)nz_abs * d.ld, d.ld * sizeof(double), d.N * sizeof(double), z,
                                           cudaMemcpyDeviceToDevice, h->stream));
-        for (int c = nz_abs + z; c < u1; c++)
+        for (int c = nz_abs + z; c < M; c++)
           QRK_TRY_CUDA(h, cudaMemcpyAsync(d.A + (long long)(c - z) * d.ld, d.A + (long long)c * d.ld, d.N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        QRK_TRY_CUDA(h, cudaMemcpy2DAsync(d.A + (long long)(u1 - z) * d.ld, d.ld * sizeof(double), tmp, d.N * sizeof(double), d.N * sizeof(double), z,
+        QRK_TRY_CUDA(h, cudaMemcpy2DAsync(d.A + (long long)(M - z) * d.ld, d.ld * sizeof(double), tmp, d.N * sizeof(double), d.N * sizeof(double), z,
                                           cudaMemcpyDeviceToDevice, h->stream));
         std::vector<int> perm(M);
         QRK_TRY_CUDA(h, cudaMemcpyAsync(perm.data(), d.perm, M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
-        std::rotate(perm.begin() + nz_abs, perm.begin() + nz_abs + z, perm.begin() + u1);
+        std::rotate(perm.begin() + nz_abs, perm.begin() + nz_abs + z, perm.end());
         QRK_TRY_CUDA(h, cudaMemcpyAsync(d.perm, perm.data(), M * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
       }
@@ -1270,7 +1272,7 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
     if (cudaMalloc(&h->d_wx, std::max<size_t>(1, (size_t)h->w_ld * (M + 1)) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wupd, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wdir, M * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wtau2, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wscal, 2 * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_wperm, M * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wiscal, 2 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->d_wtau1, M * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_wT, 64 * ((M + 7) / 8) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wtri, M * (M + 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_wpart, ((M + 1 + 7) / 8 + 1) * (size_t)kWideRowSplit * 64 * sizeof(double)) != cudaSuccess ||
@@ -2050,6 +2052,21 @@ int qrk_ipc_import(const void* handle64, void** device_ptr) {
 int qrk_ipc_close(void* device_ptr) {
   if (!device_ptr) return QRK_STATUS_INVALID_ARGUMENT;
   return cudaIpcCloseMemHandle(device_ptr) == cudaSuccess ? QRK_STATUS_OK : QRK_STATUS_CUDA_ERROR;
+}
+
+int qrk_enable_peer_access(int32_t device, int32_t peer) {
+  int ndev = 0;
+  qrk_device_count(&ndev);
+  if (ndev <= 0) return QRK_STATUS_NO_DEVICE;
+  if (device < 0 || device >= ndev || peer < 0 || peer >= ndev) return QRK_STATUS_INVALID_ARGUMENT;
+  if (device == peer) return QRK_STATUS_OK;
+  DeviceGuard g(device);
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, device, peer) != cudaSuccess || !can) { (void)cudaGetLastError(); return QRK_STATUS_UNSUPPORTED; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return QRK_STATUS_CUDA_ERROR; }
+  (void)cudaGetLastError();
+  return QRK_STATUS_OK;
 }
 
 int qrk_launch_count(qrk_handle_t h, int64_t* launches) {

@@ -169,6 +169,42 @@ int main() {
     BlockAngularBandedSparseQR<7, 4, 2, BlockedThinDenseQR<MatrixXd, 2>> ab2;
     CHECK(rel(ab2.computeAndSolve(slabs, nbb, Bb, ba), xa) <= 1e-10, "banded-left angular, unpivoted right solver: computeAndSolve recovers x  (1e-10)");
   }
+  // one host process, several GPUs (two shards on device 0 when the box has one GPU): contiguous block ranges per shard
+  {
+    const std::vector<int> devs = {0, ndev > 1 ? 1 : 0, 0};
+    const Index nbs = 1001;                                     // odd: ragged last shard
+    SparseBlockDiagonal<Block7x2> As(nbs * r, nbs * c);
+    for (Index i = 0; i < nbs; i++) { Block7x2 bb; for (int j = 0; j < c; j++) for (int k = 0; k < r; k++) bb(k, j) = synth(41, i, k, j); As.insertBack(bb); }
+    VectorXd bs((size_t)(nbs * r));
+    for (size_t i = 0; i < bs.size(); i++) bs[i] = synth(43, i, 0, 0, -1.0, 1.0);
+    DiagQR one;
+    const VectorXd x_one = one.computeAndSolve(As, bs);
+    ShardedBlockDiagonalSparseQR<ColPivHouseholderQR<Block7x2>> sh(devs);
+    const VectorXd x_sh = sh.computeAndSolve(As, bs);
+    CHECK(x_sh == x_one, "sharded block-diagonal computeAndSolve over 3 shards: bit-identical to one handle");
+    sh.compute(As);
+    CHECK(rel(sh.solve(bs), x_one) <= 1e-13 && sh.rank() == nbs * c, "sharded block-diagonal compute() + solve() (1e-13), rank");
+    const auto Ps = sh.colsPermutation(); const auto& Po = one.colsPermutation();
+    bool same = true;
+    for (Index j = 0; j < nbs * c; j++) same = same && Ps.indices()[(size_t)j] == Po.indices()[(size_t)j];
+    CHECK(same, "sharded colsPermutation() = the single-handle permutation (global column indices)");
+    // block angular, 5 border columns: the triangles cross over peer memory inside the TSQR root kernel
+    typedef Matrix<2, 1> Block2x1;
+    const Index np = 4000;
+    SparseBlockDiagonal<Block2x1> Ja(np * 2, np);
+    for (Index i = 0; i < np; i++) { Block2x1 bb; bb(0, 0) = synth(51, i, 0, 0); bb(1, 0) = synth(51, i, 1, 0); Ja.insertBack(bb); }
+    MatrixXd Jb(np * 2, 5);
+    for (Index i = 0; i < np * 2; i++) for (int j = 0; j < 5; j++) Jb(i, j) = synth(53, i, j, 0);
+    VectorXd ba((size_t)(np * 2));
+    for (size_t i = 0; i < ba.size(); i++) ba[i] = synth(55, i, 0, 0, -1.0, 1.0);
+    BlockMatrix1x2<SparseBlockDiagonal<Block2x1>, MatrixXd> Ma(Ja, Jb);
+    BlockAngularSparseQR<ColPivHouseholderQR<Block2x1>> a1;
+    const VectorXd xa1 = a1.computeAndSolve(Ma, ba);
+    ShardedBlockAngularSparseQR<ColPivHouseholderQR<Block2x1>> ash(std::vector<int>{0, ndev > 1 ? 1 : 0});
+    const VectorXd xas = ash.computeAndSolve(Ma, ba);
+    CHECK(rel(xas, xa1) <= 1e-10 && ash.sharedParametersIdentical(), "sharded block-angular computeAndSolve (fused peer exchange): x (1e-10), x2 bit-identical on the shards");
+    CHECK(ash.rank() == np + 5, "sharded block-angular rank");
+  }
   std::printf(failures ? "FAILED (%d)\n" : "All passed.\n", failures);
   return failures ? 1 : 0;
 }

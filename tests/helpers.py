@@ -155,3 +155,11 @@ def slabs_to_sparse(slabs, nb, br, bc, ov):
     rows = (np.arange(nb)[:, None, None] * br + ii[None]).reshape(-1)
     cols = (np.arange(nb)[:, None, None] * s + jj[None]).reshape(-1)
     return sp.csc_matrix((S.reshape(-1), (rows, cols)), shape=(nb * br, (nb - 1) * s + bc))
+
+
+def oracle_banded_q_is_exact(nb, windows):
+    """Geometries for which the reference's banded Q (and therefore the oracle's, which restates it) is an exact factor of A:
+    no slabs were merged (one window per slab), or the chain has at most two windows (no merged window in the middle).  For the
+    others `activeRows = bi.numRows + ...` (BandedBlockedSparseQR.h:497) undercounts the rows a merged middle window hands on in
+    the 2-segment YTY layout; R is unaffected.  Enumerated in tests/test_oracle.py::test_oracle_banded_q_geometries."""
+    return len(windows) == nb or len(windows) <= 2

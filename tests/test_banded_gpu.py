@@ -42,8 +42,14 @@ def _check(qk, oracle, nb, br, bc, ov, suggested=2, lo=0.5, hi=5.0):
     b = vector(n_rows, seed=3)
     x_ref = np.linalg.lstsq(A.toarray(), b, rcond=None)[0]
     x_orc = ref.solve(b)
-    oracle_q_ok = rel(x_orc, x_ref) <= 1e-9      # the reference's 2-segment YTY bookkeeping (numZeros, :497-500) does not hold
-    if oracle_q_ok:                               # for every merged-window geometry; R always does (checked below)
+    # The reference's Q bookkeeping (one 2-segment YTY block per window, rows [idxCol, idxCol + numCols) + the rest after
+    # numZeros, BandedBlockedSparseQR.h:479, 497-500) maps window rows to vector rows correctly only while no MERGED window sits
+    # in the middle of the chain: a middle window's next step counts bi.numRows, not its active rows (:497).  Pinned on the CPU
+    # in tests/test_oracle.py::test_oracle_banded_q_geometries; R never depends on it (checked below for every geometry).
+    from helpers import oracle_banded_q_is_exact
+    oracle_q_ok = rel(x_orc, x_ref) <= 1e-9
+    assert oracle_q_ok == oracle_banded_q_is_exact(nb, blocks), "the LAPACK fallback may only be taken for the pinned geometries"
+    if oracle_q_ok:
         x_ref = x_orc
     s1 = qk.BandedBlockedSparseQR(block_rows=br, block_cols=bc, overlap=ov)
     x1 = s1.compute_solve(slabs, b, nb)
@@ -145,8 +151,25 @@ def test_config4_properties(qk, nb):
     x_true = vector(n_cols, seed=11)
     s = qk.BandedBlockedSparseQR(block_rows=br, block_cols=bc, overlap=ov)
     x = s.compute_solve(slabs, A @ x_true, nb)
-    assert rel(x, x_true) <= 1e-9
+    assert rel(x, x_true) <= 1e-10
     b = vector(n_rows, seed=12)
     x = s.compute_solve(slabs, b, nb)
     g = A.T @ (A @ x - b)
-    assert np.abs(g).max() <= 1e-9 * np.abs(A.T @ b).max()
+    assert np.abs(g).max() <= 1e-10 * np.abs(A.T @ b).max()
+    # the whole factorisation against the oracle (the reference's windowed recurrence over its merged 72 x 40 windows): R equal
+    # up to row signs at 1e-12 relative Frobenius over ALL stored entries, index arrays bit-exact, x at 1e-10
+    from oracle import oracle as orc
+    ref = orc.BandedOracle(A.tocsc(), reference_style_windows(nb, br, bc, ov, 2))
+    s2 = qk.BandedBlockedSparseQR(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov)
+    R, Rr = s2.matrixR(), ref.matrixR()
+    assert np.array_equal(R.outer, Rr.outer) and np.array_equal(R.inner, Rr.inner)
+    cols_of = np.repeat(np.arange(n_cols), np.diff(R.outer))
+    diag = R.inner == cols_of
+    sg = np.sign(R.values[diag]) * np.sign(Rr.val[diag])                  # per-row sign, read off the diagonals
+    on_rows = R.inner < n_cols                                         # the last window also stores zero rows below the triangle
+    flip = np.ones(len(R.values)); flip[on_rows] = sg[R.inner[on_rows]]
+    assert rel(R.values * flip, Rr.val) <= 1e-12
+    x_orc = ref.solve(b)
+    if rel(x_orc, x) > 1e-10:      # the reference's 2-segment YTY bookkeeping of Q does not hold for this merged-window geometry
+        x_orc = None               # (see test_oracle_banded_q_geometries); R, which does not depend on it, is compared above
+    assert x_orc is None or rel(x, x_orc) <= 1e-10

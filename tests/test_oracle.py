@@ -266,3 +266,28 @@ def test_block_angular_ellipse(oracle):
     assert np.array_equal(P[:n], np.arange(n)) and sorted(P[n:]) == list(range(n, n + 5))
     out = oracle.angular_reference_uniform(n, 2, 1, J1, J2, b)
     assert rel(out["x"], x) <= 1e-14
+
+
+@pytest.mark.parametrize("br,bc,ov", [(16, 24, 16), (7, 4, 2), (7, 2, 0), (8, 8, 4), (12, 8, 4), (4, 6, 4)])
+@pytest.mark.parametrize("nb", [1, 2, 3, 5, 11, 40])
+def test_oracle_banded_q_geometries(oracle, br, bc, ov, nb):
+    """Where the reference's banded Q is an exact factor and where it is not (a reference limitation the oracle restates
+    faithfully, BandedBlockedSparseQR.h:497-500): x = R^-1 (Q^T b)[0:n] equals LAPACK's least-squares solution exactly for the
+    geometries helpers.oracle_banded_q_is_exact names, and is visibly wrong (> 1e-3) for the others; R equals LAPACK's up to
+    row signs for ALL of them."""
+    from helpers import oracle_banded_q_is_exact, reference_style_windows, sign_normalize_rows, slabs_to_sparse
+    slabs = uniform_blocks(nb, br, bc)
+    A = slabs_to_sparse(slabs, nb, br, bc, ov)
+    if A.shape[0] < A.shape[1]:
+        pytest.skip("fewer rows than columns")
+    windows = reference_style_windows(nb, br, bc, ov, 2)
+    ref = oracle.BandedOracle(A, windows)
+    Ad = A.toarray()
+    R = ref.matrixR().toarray()[:A.shape[1], :]
+    assert rel(sign_normalize_rows(R), sign_normalize_rows(np.linalg.qr(Ad, mode="r"))) <= 1e-12
+    b = vector(A.shape[0], seed=3)
+    err = rel(ref.solve(b), np.linalg.lstsq(Ad, b, rcond=None)[0])
+    if oracle_banded_q_is_exact(nb, windows):
+        assert err <= 1e-10
+    else:
+        assert err > 1e-3
