@@ -280,7 +280,20 @@ QRK_API int qrk_enable_peer_access(int32_t device, int32_t peer);
  *                                     dense rectangle of solved rows x window columns, explicit zeros included (:484-491);
  *                                     values as the reference up to row signs
  *   qrk_rank (= cols, :514), qrk_cols_permutation (identity), qrk_rows_permutation
- * Supported (block_rows, block_cols, overlap): (16,24,16), (7,4,2), (7,2,0), (8,8,4), (12,8,4), (4,6,4). */
+ * Slab shapes (block_rows, block_cols, overlap) with the fast two-phase kernels: (16,24,16), (7,4,2), (7,2,0), (8,8,4), (12,8,4),
+ * (4,6,4); every other shape runs on the general window chain below (same results, sequential, with an exact n x n Q). */
+
+/* BandedBlockedSparseQR on a GENERAL banded matrix (the analyzePattern else-branch, BandedBlockedSparseQR.h:408-426: row ordering +
+ * block detection): the caller orders the rows (qrk_order_as_banded_as_possible), detects the blocks (qrk_detect_band_starts, or
+ * qrk_detect_blocks for the reference's merged windows), extracts them (qrk_extract_blocks: dense, column-major, back to back =
+ * the `values` of qrk_compute / qrk_compute_solve) and creates the handle from the block list {idxRow, idxCol, numRows, numCols}:
+ * rows contiguous and in order, first columns non-decreasing.  Any block sizes, overlaps and column steps; windows run
+ * sequentially on one SM (banded_generic.cuh), so this path is general, not fast.  qrk_apply_qt / qrk_apply_q are an exact
+ * n x n Q here: [thin part (n_cols) ; complement (n_rows - n_cols, window order)].  matrixR(): the reference's stored pattern
+ * for the windows mergeBlocks makes of this block list (suggested_block_cols: 0 = 2).  The same general chain (one window per
+ * slab) serves qrk_create for slab shapes outside the instantiated list. */
+QRK_API int qrk_create_banded_general(const int32_t* blocks, int64_t num_blocks, int64_t n_rows, int64_t n_cols, int32_t device,
+                                      int32_t suggested_block_cols, qrk_handle_t* out);
 
 /* ---- pattern analysis on the host (no GPU needed; qrkit_b200/csrc/structure.cpp) ---------------------- */
 /* SparseQROrdering::AsBandedAsPossible (SparseQROrdering.h:53-120): rows of a row-major (CSR) pattern stably sorted by
@@ -297,6 +310,11 @@ QRK_API int qrk_order_column_density(int64_t cols, const int32_t* csc_outer, int
 QRK_API int qrk_detect_blocks(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner,
                               int32_t suggested_block_cols, int32_t* blocks, int64_t capacity, int64_t* num_blocks,
                               int64_t* nonzero_q_estimate);
+/* The same detection WITHOUT mergeBlocks: one block per distinct band start (first stored column), rows in order — the
+ * window chain qrk_create_banded_general factors (its own windows need not be portrait: rows still to be finalised are
+ * carried from window to window). */
+QRK_API int qrk_detect_band_starts(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner, int32_t* blocks,
+                                   int64_t capacity, int64_t* num_blocks);
 /* fromBlockDiagonalPattern (SparseQRUtils.h:255-272) and fromBlockBandedPattern (:274-302, merge included). */
 QRK_API int qrk_block_diagonal_pattern(int64_t rows, int64_t cols, int32_t block_rows, int32_t block_cols, int32_t* blocks,
                                        int64_t capacity, int64_t* num_blocks);

@@ -105,6 +105,8 @@ def lib():
             "qrk_order_as_banded_as_possible": [i64, i64, vp, vp, vp, C.POINTER(i32)],
             "qrk_order_column_density": [i64, vp, vp],
             "qrk_detect_blocks": [i64, i64, vp, vp, i32, vp, i64, C.POINTER(i64), C.POINTER(i64)],
+            "qrk_detect_band_starts": [i64, i64, vp, vp, vp, i64, C.POINTER(i64)],
+            "qrk_create_banded_general": [vp, i64, i64, i64, i32, i32, C.POINTER(vp)],
             "qrk_block_diagonal_pattern": [i64, i64, i32, i32, vp, i64, C.POINTER(i64)],
             "qrk_block_banded_pattern": [i64, i64, i32, i32, i32, i32, vp, i64, C.POINTER(i64)],
             "qrk_extract_blocks": [i64, i64, vp, vp, vp, vp, vp, i64, vp],

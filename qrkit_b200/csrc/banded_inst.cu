@@ -1,5 +1,6 @@
 // banded_inst.cu — instantiations of the block-banded kernels.
 #include "banded.cuh"
+#include "banded_generic.cuh"
 #include "banded_dispatch.hpp"
 
 namespace qrk {
@@ -68,7 +69,51 @@ cudaError_t backsolve_t(const BandedArgs& a, cudaStream_t s) {
 QRK_BANDED_SHAPES(X)
 #undef X
 
+
+// ---- the general window chain: the same four operations on BandedArgs::gen --------------------------------------------
+template <typename K>
+cudaError_t gen_opt_in(K kernel, size_t smem) {
+  return smem > 48 * 1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) : cudaSuccess;
+}
+cudaError_t gen_factor(const BandedArgs& a, cudaStream_t s) {
+  GenArgs g = *a.gen;
+  g.A_in = a.A_in; g.b = a.b; g.y = a.y; g.comp = a.comp;
+  const size_t smem = gen_smem_factor(g.max_rows, g.max_cols);
+  cudaError_t e = gen_opt_in(banded_generic_factor_kernel, smem);
+  if (e != cudaSuccess) return e;
+  banded_generic_factor_kernel<<<1, kGenThreads, smem, s>>>(g);
+  return cudaGetLastError();
+}
+cudaError_t gen_apply_qt(const BandedArgs& a, cudaStream_t s) {
+  const GenArgs g = *a.gen;
+  const size_t smem = gen_smem_apply(g.max_rows, g.max_cols);
+  cudaError_t e = gen_opt_in(banded_generic_apply_kernel<true>, smem);
+  if (e != cudaSuccess) return e;
+  banded_generic_apply_kernel<true><<<(unsigned)a.ncols, kGenThreads, smem, s>>>(g, a.b, a.ldb, a.y, a.ldy, a.comp, a.ldcomp, nullptr, 0);
+  return cudaGetLastError();
+}
+cudaError_t gen_apply_q(const BandedArgs& a, cudaStream_t s) {
+  const GenArgs g = *a.gen;
+  const size_t smem = gen_smem_apply(g.max_rows, g.max_cols);
+  cudaError_t e = gen_opt_in(banded_generic_apply_kernel<false>, smem);
+  if (e != cudaSuccess) return e;
+  banded_generic_apply_kernel<false><<<(unsigned)a.ncols, kGenThreads, smem, s>>>(g, nullptr, 0, a.y, a.ldy, a.comp, a.ldcomp, a.x, a.ldx);
+  return cudaGetLastError();
+}
+cudaError_t gen_backsolve(const BandedArgs& a, cudaStream_t s) {
+  banded_generic_backsolve_kernel<<<1, kGenThreads, 0, s>>>(*a.gen, a.y, a.x);
+  return cudaGetLastError();
+}
+const BandedVTable kGenericVT = {0, 0, 0, gen_factor, gen_apply_qt, gen_apply_q, gen_backsolve};
+
 }  // namespace
+
+const BandedVTable* banded_generic_vtable() { return &kGenericVT; }
+size_t banded_generic_smem_bytes(int max_rows, int max_cols) { return gen_smem_factor(max_rows, max_cols); }
+cudaError_t banded_generic_export_r(const GenArgs& g, const int* d_col0, const int* d_outer, const int* d_inner, double* d_vals, cudaStream_t s) {
+  banded_generic_export_r_kernel<<<148 * 4, 256, 0, s>>>(g, d_col0, d_outer, d_inner, d_vals);
+  return cudaGetLastError();
+}
 
 const BandedVTable* banded_vtable(int br, int bc, int ov) {
 #define X(BR, BC, OV) if (br == BR && bc == BC && ov == OV) return &kT_##BR##_##BC##_##OV;

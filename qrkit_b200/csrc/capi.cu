@@ -259,6 +259,7 @@ void free_dev(qrk_solver* h) {
   F(h->d_tau); F(h->d_perm); F(h->d_b); F(h->d_x);
   F(h->d_rband); F(h->d_btau); F(h->d_ythin); F(h->d_gband); F(h->d_gy); F(h->d_cvec); F(h->d_ctau);
   F(h->d_wx); F(h->d_wupd); F(h->d_wdir); F(h->d_wtau2); F(h->d_wscal); F(h->d_wtau1); F(h->d_wT); F(h->d_wtri); F(h->d_wpart); F(h->d_xchg); F(h->d_xchg_peers); F(h->d_xchg_err); F(h->d_xchg_seq); F(h->d_wperm); F(h->d_wiscal);
+  F(h->d_gwin); F(h->d_gcol0); F(h->d_gpacked); F(h->d_gtau); F(h->d_gcomp);
   F(h->d_q2); F(h->d_q2tau); F(h->d_q2sign); F(h->d_q2scr); F(h->d_qtmp); F(h->d_qthin); F(h->d_q2iscr);
   F(h->d_border_own); F(h->d_atop); F(h->d_y1); F(h->d_abot); F(h->d_partials); F(h->d_tri); F(h->d_root); F(h->d_root_i);
   for (auto& sc : h->classes) if (sc.d_ids) cudaFree(sc.d_ids);
@@ -978,6 +979,7 @@ BandedArgs banded_args(qrk_solver* h) {
   a.nb = h->nb; a.packed = h->d_values; a.tau = h->d_btau; a.rband = h->d_rband; a.y = h->d_ythin;
   a.last_cols = (int)(h->sum_cols - (h->nb - 1) * (long long)h->b_step);   // sum_cols = the banded columns (n_cols includes a border)
   a.group = h->b_group; a.gband = h->d_gband; a.gy = h->d_gy; a.cvec = h->d_cvec; a.ctau = h->d_ctau;
+  if (h->bgen) a.gen = &h->g_args;
   return a;
 }
 
@@ -1051,6 +1053,65 @@ std::vector<int> banded_r_outer(const qrk_solver* h) {
 }  // namespace
 
 namespace {
+
+// The general window chain (banded_generic.cuh) from a list of dense blocks {idxRow, idxCol, numRows, numCols}: rows contiguous
+// and in order, first columns non-decreasing, every window tall enough to finalise the rows the next one starts after.
+// in_cols[i]: columns of block i as stored in the input values (block i at voff[i], column-major numRows x in_cols).
+int build_generic_chain(qrk_solver* h, const std::vector<int32_t>& b4, const std::vector<long long>& voff, const std::vector<int>& in_cols) {
+  const size_t nw = b4.size() / 4;
+  h->g_win.assign(nw, GenWindow());
+  long long row = 0, poff = 0, toff = 0, coff = 0;
+  int carry = 0, prev_end = 0, max_rows = 1, max_cols = 1;
+  for (size_t i = 0; i < nw; i++) {
+    GenWindow& w = h->g_win[i];
+    w.row0 = b4[4 * i]; w.col0 = b4[4 * i + 1]; w.nrows = b4[4 * i + 2];
+    const int ncols_blk = b4[4 * i + 3];
+    if (w.row0 != row || w.nrows <= 0 || ncols_blk <= 0 || w.col0 < 0 || (i > 0 && w.col0 < h->g_win[i - 1].col0)) {
+      h->err = "banded window chain: blocks must cover the rows contiguously, in order, with non-decreasing first columns";
+      return QRK_STATUS_INVALID_ARGUMENT;
+    }
+    if (i > 0 && w.col0 > prev_end) { h->err = "banded window chain: a column range is covered by no block"; return QRK_STATUS_INVALID_ARGUMENT; }
+    w.ncols_in = in_cols[i];
+    w.ncols = std::max(ncols_blk, prev_end - w.col0);      // wide enough for the carried rows' columns (:502)
+    w.carry = carry;
+    const int rows = carry + w.nrows;
+    w.steps = std::min(rows, w.ncols);
+    const bool last = i + 1 == nw;
+    w.solved = last ? w.steps : b4[4 * (i + 1) + 1] - w.col0;
+    if (w.solved > w.steps || (last && (w.steps != w.ncols || w.col0 + w.ncols != h->sum_cols))) {
+      h->err = "banded window chain: a window has fewer rows than the columns it must finalise (structurally rank deficient)";
+      return QRK_STATUS_INVALID_ARGUMENT;
+    }
+    w.voff = voff[i]; w.poff = poff; w.toff = toff; w.coff = coff;
+    poff += (long long)rows * w.ncols; toff += w.steps; coff += rows - w.steps;
+    carry = w.steps - w.solved;
+    prev_end = w.col0 + w.ncols;
+    row += w.nrows;
+    max_rows = std::max(max_rows, rows); max_cols = std::max(max_cols, w.ncols);
+  }
+  if (row != h->n_rows || coff != h->n_rows - h->sum_cols) { h->err = "banded window chain: the blocks do not add up to the matrix"; return QRK_STATUS_INVALID_ARGUMENT; }
+  if (banded_generic_smem_bytes(max_rows, max_cols) > kMaxSmem - 2048) {
+    h->err = "banded window chain: a window does not fit the shared memory of one SM";
+    return QRK_STATUS_UNSUPPORTED;
+  }
+  std::vector<int> col0(nw + 1);
+  for (size_t i = 0; i < nw; i++) col0[i] = h->g_win[i].col0;
+  col0[nw] = (int)h->sum_cols;
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_gwin, nw * sizeof(GenWindow)));
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_gcol0, (nw + 1) * sizeof(int)));
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_gpacked, std::max<long long>(poff, 1) * sizeof(double)));
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_gtau, std::max<long long>(toff, 1) * sizeof(double)));
+  QRK_TRY_CUDA(h, cudaMalloc(&h->d_gcomp, std::max<long long>(coff, 1) * sizeof(double)));
+  QRK_TRY_CUDA(h, cudaMemcpy(h->d_gwin, h->g_win.data(), nw * sizeof(GenWindow), cudaMemcpyHostToDevice));
+  QRK_TRY_CUDA(h, cudaMemcpy(h->d_gcol0, col0.data(), (nw + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  GenArgs& g = h->g_args;
+  g.win = h->d_gwin; g.nwin = (int)nw; g.max_rows = max_rows; g.max_cols = max_cols;
+  g.packed = h->d_gpacked; g.tau = h->d_gtau; g.n_rows = h->n_rows; g.n_cols = h->sum_cols;
+  h->bgen = true;
+  h->bvt = banded_generic_vtable();
+  return QRK_STATUS_OK;
+}
+
 int peer_exchange_status(qrk_solver* h) {
   if (!h->d_xchg_err || h->xchg_rank < 0) return QRK_STATUS_OK;
   int flag = 0;
@@ -1090,7 +1151,22 @@ int qrk_device_count(int* count) {
   return QRK_STATUS_OK;
 }
 
-int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
+static int create_impl(const qrk_desc_t* desc, const int32_t* gen_blocks, qrk_handle_t* out);
+
+int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) { return create_impl(desc, nullptr, out); }
+
+int qrk_create_banded_general(const int32_t* blocks, int64_t num_blocks, int64_t n_rows, int64_t n_cols, int32_t device,
+                              int32_t suggested_block_cols, qrk_handle_t* out) {
+  if (!blocks || num_blocks < 1 || n_rows < 1 || n_cols < 1 || !out) return QRK_STATUS_INVALID_ARGUMENT;
+  std::vector<int32_t> rows((size_t)num_blocks), cols((size_t)num_blocks);
+  for (int64_t i = 0; i < num_blocks; i++) { rows[(size_t)i] = blocks[4 * i + 2]; cols[(size_t)i] = blocks[4 * i + 3]; }
+  qrk_desc_t d = qrk_desc_t();
+  d.kind = QRK_BANDED_BLOCKED; d.device = device; d.num_blocks = num_blocks; d.rows = rows.data(); d.cols = cols.data();
+  d.n_rows = n_rows; d.n_cols = n_cols; d.reserved[0] = suggested_block_cols;
+  return create_impl(&d, blocks, out);
+}
+
+static int create_impl(const qrk_desc_t* desc, const int32_t* gen_blocks, qrk_handle_t* out) {
   if (!desc || !out) return QRK_STATUS_INVALID_ARGUMENT;
   *out = nullptr;
   if (desc->kind != QRK_BLOCK_DIAGONAL && desc->kind != QRK_BLOCK_ANGULAR && desc->kind != QRK_BANDED_BLOCKED) return QRK_STATUS_UNSUPPORTED;
@@ -1140,14 +1216,26 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   }
   h->n_rows = desc->n_rows > 0 ? desc->n_rows : h->sum_rows;
   h->n_cols = desc->n_cols > 0 ? desc->n_cols : h->sum_cols;
-  if (banded) {
+  if (banded && gen_blocks) {
+    // a general chain of dense blocks (BandedBlockedSparseQR.h:408-426 after row ordering and block detection)
+    if (desc->reserved[0] < 0 || desc->n_rows != h->sum_rows || desc->n_cols < 1 || desc->n_rows < desc->n_cols) return fail(QRK_STATUS_INVALID_ARGUMENT);
+    h->n_rows = desc->n_rows; h->n_cols = desc->n_cols; h->sum_cols = h->n_cols;
+    h->info = QRK_INFO_SUCCESS;
+    DeviceGuard gg(h->device);
+    std::vector<int32_t> b4(gen_blocks, gen_blocks + 4 * h->nb);
+    banded_reference_windows_from_blocks(b4, desc->reserved[0] > 0 ? desc->reserved[0] : 2, h->b_windows);
+    const int stg = build_generic_chain(h, b4, h->h_voff, h->h_cols);
+    if (stg != QRK_STATUS_OK) return fail(stg);
+  } else if (banded) {
     // nb block rows of block_rows x block_cols, consecutive blocks shifted by S = block_cols - overlap columns
     // (BlockBandedMatrixInfo::fromBlockBandedPattern, SparseQRUtils.h:274-302)
     if (!uniform || h->nb < 1) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->b_ov = desc->block_overlap;
     h->b_step = h->uc - h->b_ov;
+    if (h->b_step <= 0 || h->b_ov < 0) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->bvt = banded_vtable(h->ur, h->uc, h->b_ov);
-    if (!h->bvt) return fail(QRK_STATUS_UNSUPPORTED);
+    if (std::getenv("QRK_BANDED_GENERIC")) h->bvt = nullptr;            // test switch: the general window chain for every shape
+    if (!h->bvt && left_banded) return fail(QRK_STATUS_UNSUPPORTED);    // the block-angular combination needs an instantiated shape
     if (desc->reserved[0] < 0) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->n_rows = h->sum_rows;
     // n_cols defaults to the full width of the last slab; a narrower last slab (the reference's pattern gives the last
@@ -1162,6 +1250,20 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
                              desc->reserved[0] > 0 ? desc->reserved[0] : 2, h->b_windows);
     if (desc->n_rows > 0 && desc->n_rows != h->n_rows) return fail(QRK_STATUS_INVALID_ARGUMENT);
     h->info = QRK_INFO_SUCCESS;      // landscape slabs are normal here
+    if (!h->bvt) {                   // a slab shape that is not instantiated: the general window chain, one window per slab
+      DeviceGuard gg(h->device);
+      std::vector<int32_t> b4((size_t)h->nb * 4);
+      std::vector<long long> voff((size_t)h->nb);
+      std::vector<int> in_cols((size_t)h->nb);
+      const int last_cols = (int)(h->n_cols - (h->nb - 1) * (long long)h->b_step);
+      for (long long k = 0; k < h->nb; k++) {
+        b4[4 * k] = (int32_t)(k * h->ur); b4[4 * k + 1] = (int32_t)(k * h->b_step); b4[4 * k + 2] = h->ur;
+        b4[4 * k + 3] = (k == h->nb - 1) ? last_cols : h->uc;
+        voff[(size_t)k] = k * (long long)h->ur * h->uc; in_cols[(size_t)k] = b4[4 * k + 3];
+      }
+      const int stg = build_generic_chain(h, b4, voff, in_cols);
+      if (stg != QRK_STATUS_OK) return fail(stg);
+    }
   }
   if (angular) {
     // left block: uniform small blocks covering all rows, FullQ; border: 1..8 dense columns
@@ -1246,7 +1348,9 @@ int qrk_create(const qrk_desc_t* desc, qrk_handle_t* out) {
   cudaMemsetAsync(h->d_tau, 0, std::max<long long>(h->n_cols, 1) * sizeof(double), h->stream);
   iota_kernel<<<256, 256, 0, h->stream>>>(h->d_perm, h->n_cols);   // m_outputPerm_c.setIdentity (:417)
   h->launches++;
-  if (banded) {
+  if (banded && h->bgen) {
+    if (cudaMalloc(&h->d_ythin, (size_t)h->sum_cols * sizeof(double)) != cudaSuccess) return fail(QRK_STATUS_ALLOC_FAILED);
+  } else if (banded) {
     // slabs per parallel group (banded.cuh): enough groups to fill the GPU with one warp each, few enough that the
     // overlap rows the chase re-eliminates at every group boundary stay a small fraction (OV per group * S columns)
     h->b_group = (int)std::max<long long>(8, std::min<long long>(64, h->nb / 2048));
@@ -1635,6 +1739,7 @@ int qrk_rows_permutation(qrk_handle_t h, int32_t* indices, int memspace) {
 int qrk_packed_factors(qrk_handle_t h, double* packed, double* tau, int memspace) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
   if (!h->factorized) return QRK_STATUS_NOT_FACTORIZED;
+  if (h->bgen) { h->err = "qrk_packed_factors: the general banded window chain keeps its reflectors per window, not in the block-COO layout"; return QRK_STATUS_UNSUPPORTED; }
   DeviceGuard g(h->device);
   const cudaMemcpyKind kind = memspace == QRK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (packed) QRK_TRY_CUDA(h, cudaMemcpyAsync(packed, h->d_values, h->total_values * sizeof(double), kind, h->stream));
@@ -1710,8 +1815,11 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
       banded_r_pattern(h, ho, &hi);
       cudaMemcpyAsync(d_outer, ho.data(), ho.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
       cudaMemcpyAsync(d_inner, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-      export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->sum_cols, h->nb, h->uc, h->b_step);
-      e = cudaGetLastError();
+      if (h->bgen) e = banded_generic_export_r(h->g_args, h->d_gcol0, d_outer, d_inner, d_vals, h->stream);
+      else {
+        export_banded_r_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_rband, d_outer, d_inner, d_vals, h->sum_cols, h->nb, h->uc, h->b_step);
+        e = cudaGetLastError();
+      }
       if (ang(h) && e == cudaSuccess) {     // R = [R1, Atop P2; 0, R2] (makeR, BlockAngularSparseQR.h:285-308) with a banded R1
         export_angular_border_kernel<<<148, 256, 0, h->stream>>>(h->d_wx, h->w_ld, h->d_root, h->d_root_i, h->sum_cols, h->m2, (long long)ho.back(),
                                                                  d_outer, d_inner, d_vals);
@@ -1765,7 +1873,7 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
   const long long out_rows = (op == OP_SOLVE || op == OP_APPLY_QT_THIN) ? h->n_cols : h->n_rows;
   QRK_REQUIRE(h, ldb >= in_rows && ldx >= out_rows, "leading dimension smaller than the number of rows");
   const bool banded_q1 = h->bvt != nullptr;               // banded solver, or block angular with a banded left solver
-  if (banded_q1 && (op == OP_APPLY_QT || op == OP_APPLY_Q)) {
+  if (banded_q1 && !h->bgen && (op == OP_APPLY_QT || op == OP_APPLY_Q)) {
     // The two-phase banded factorisation represents Q as an isometry into an EXTENDED complement (overlap rows of every
     // group enter as virtual zero rows, banded.cuh): there is no n x n orthogonal matrix to multiply with.  The thin factor
     // Q1 = A R^-1 (what solve() and the LM caller use) is exact: qrk_apply_qt_thin / qrk_apply_q_thin.
@@ -1846,7 +1954,12 @@ static int op_entry(qrk_handle_t h, int op, const double* B, int64_t ldb, double
     for (int j = 0; j < nrhs && st == QRK_STATUS_OK; j++) {
       BandedArgs a = banded_args(h);
       cudaError_t e;
-      if (op == OP_APPLY_Q_THIN) {
+      if (h->bgen && (op == OP_APPLY_QT || op == OP_APPLY_Q)) {
+        // the general window chain has an exact n x n Q: [thin part ; complement in window order] (banded_generic.cuh)
+        if (op == OP_APPLY_QT) { a.b = d_B + j * dldb; a.y = d_X + j * dldx; a.comp = d_X + j * dldx + h->sum_cols; e = h->bvt->apply_qt(a, h->stream); }
+        else { a.y = const_cast<double*>(d_B + j * dldb); a.comp = const_cast<double*>(d_B + j * dldb + h->sum_cols); a.x = d_X + j * dldx; e = h->bvt->apply_q(a, h->stream); }
+        h->launches++;
+      } else if (op == OP_APPLY_Q_THIN) {
         a.y = const_cast<double*>(d_B + j * dldb);   // read only: the thin part of the input
         a.x = d_X + j * dldx;
         e = h->bvt->apply_q(a, h->stream);

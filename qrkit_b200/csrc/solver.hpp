@@ -114,6 +114,13 @@ struct qrk_solver {
   std::vector<int32_t> b_windows;      // the reference's merged windows {idxRow, idxCol, numRows, numCols}: the stored pattern of matrixR()
   int b_group = 1;                     // slabs per parallel group of the two-phase banded factorisation (banded.cuh)
   double *d_gband = nullptr, *d_gy = nullptr, *d_cvec = nullptr, *d_ctau = nullptr;   // group triangles / chase reflectors
+  // the general window chain (banded_generic.cuh): block sizes / overlaps at run time, an exact n x n Q
+  bool bgen = false;
+  std::vector<qrk::GenWindow> g_win;
+  qrk::GenArgs g_args;                 // device pointers of the chain (win, packed, tau), sizes
+  qrk::GenWindow* d_gwin = nullptr;
+  int* d_gcol0 = nullptr;
+  double *d_gpacked = nullptr, *d_gtau = nullptr, *d_gcomp = nullptr;
   size_t cap_gy = 0;                   // doubles in d_gy (one vector of groups x W per right-hand side column)
 
   // ---- staging buffers for host-memspace calls ----

@@ -94,6 +94,21 @@ void banded_reference_windows(long long nb, int br, int bc, int ov, int last_col
     out4[4 * i] = v[i].row; out4[4 * i + 1] = v[i].col; out4[4 * i + 2] = v[i].nrows; out4[4 * i + 3] = v[i].ncols;
   }
 }
+// The same for a general list of detected blocks (one per distinct band start): mergeBlocks with maxColStep = the largest
+// step between consecutive first columns, as BlockBandedMatrixInfo::operator() computes it (SparseQRUtils.h:213-220).
+void banded_reference_windows_from_blocks(const std::vector<int32_t>& in4, int suggested, std::vector<int32_t>& out4) {
+  std::vector<Block> v(in4.size() / 4);
+  int maxColStep = 0;
+  for (size_t i = 0; i < v.size(); i++) {
+    v[i] = {in4[4 * i], in4[4 * i + 1], in4[4 * i + 2], in4[4 * i + 3]};
+    if (i > 0) maxColStep = std::max(maxColStep, (int)(v[i].col - v[i - 1].col));
+  }
+  merge_blocks(v, maxColStep, suggested);
+  out4.resize(4 * v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    out4[4 * i] = v[i].row; out4[4 * i + 1] = v[i].col; out4[4 * i + 2] = v[i].nrows; out4[4 * i + 3] = v[i].ncols;
+  }
+}
 }  // namespace qrk
 
 extern "C" {
@@ -123,8 +138,8 @@ int qrk_order_column_density(int64_t cols, const int32_t* csc_outer, int32_t* pe
   return QRK_STATUS_OK;
 }
 
-int qrk_detect_blocks(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner, int32_t suggested_block_cols,
-                      int32_t* blocks, int64_t capacity, int64_t* num_blocks, int64_t* nonzero_q_estimate) {
+static int detect_impl(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner, int32_t suggested_block_cols, bool merge,
+                       int32_t* blocks, int64_t capacity, int64_t* num_blocks, int64_t* nonzero_q_estimate) {
   if (rows < 0 || cols < 0 || !csr_outer) return QRK_STATUS_INVALID_ARGUMENT;
   std::vector<int32_t> first, last;
   row_extents(rows, cols, csr_outer, csr_inner, first, last);
@@ -152,9 +167,19 @@ int qrk_detect_blocks(int64_t rows, int64_t cols, const int32_t* csr_outer, cons
     found.push_back({(int32_t)j, first[j], h, width[first[j]]});
     nzq += (int64_t)h * h;
   }
-  merge_blocks(found, maxColStep, suggested_block_cols);
+  if (merge) merge_blocks(found, maxColStep, suggested_block_cols);
   if (nonzero_q_estimate) *nonzero_q_estimate = nzq;
   return emit(found, blocks, capacity, num_blocks);
+}
+
+int qrk_detect_blocks(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner, int32_t suggested_block_cols,
+                      int32_t* blocks, int64_t capacity, int64_t* num_blocks, int64_t* nonzero_q_estimate) {
+  return detect_impl(rows, cols, csr_outer, csr_inner, suggested_block_cols, true, blocks, capacity, num_blocks, nonzero_q_estimate);
+}
+
+int qrk_detect_band_starts(int64_t rows, int64_t cols, const int32_t* csr_outer, const int32_t* csr_inner, int32_t* blocks, int64_t capacity,
+                           int64_t* num_blocks) {
+  return detect_impl(rows, cols, csr_outer, csr_inner, 0, false, blocks, capacity, num_blocks, nullptr);
 }
 
 int qrk_block_diagonal_pattern(int64_t rows, int64_t cols, int32_t block_rows, int32_t block_cols, int32_t* blocks, int64_t capacity,

@@ -396,6 +396,34 @@ class BandedBlockedSparseQR(BlockDiagonalSparseQR):
         if self._stream is not None:
             check(lib().qrk_set_stream(self._h, C.c_void_p(int(self._stream))), self._h)
 
+    @classmethod
+    def from_sparse(cls, A, *, merged=False, suggested_block_cols=2, device=0, stream=None):
+        """compute(const SparseMatrix&) on a GENERAL banded matrix — the analyzePattern else-branch of the reference
+        (BandedBlockedSparseQR.h:408-426): AsBandedAsPossible row ordering, block detection, dense extraction of the blocks, then the
+        general window chain (qrk_create_banded_general).  merged=True factors the reference's merged windows instead of one
+        window per band start (same R; bigger windows).  rowsPermutation() returns the ordering; as in the reference, solve() expects
+        the right-hand side already permuted (test/test-qrkit.cpp:235)."""
+        from . import structure
+        perm, has = structure.as_banded_as_possible(A)
+        Ar = A.tocsr()
+        if has:
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(len(perm), dtype=np.int32)
+            Ar = Ar[inv, :]
+        blocks = structure.detect_blocks(Ar, suggested_block_cols)[0] if merged else structure.detect_band_starts(Ar)
+        values = structure.extract_blocks(A, blocks, perm if has else None)
+        self = cls(block_rows=0, block_cols=0, overlap=0, device=device, stream=stream)
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().qrk_create_banded_general(_ptr(blocks), len(blocks), A.shape[0], A.shape[1], device, suggested_block_cols, C.byref(h)))
+        self._h, self._shape_key = h, ("banded-general", len(blocks))
+        if stream is not None:
+            check(lib().qrk_set_stream(self._h, C.c_void_p(int(stream))), self._h)
+        check(lib().qrk_compute(self._h, _ptr(values), QRK_HOST), self._h)
+        check(lib().qrk_analyze_pattern(self._h, _ptr(np.ascontiguousarray(perm, dtype=np.int32))), self._h)   # rowsPermutation()
+        self.blocks, self.values = blocks, values
+        return self
+
     def _nb(self, slabs, num_blocks):
         br, bc, _ = self._geom
         return int(num_blocks) if num_blocks is not None else len(slabs) // (br * bc)

@@ -59,6 +59,12 @@ def detect_blocks(A, suggested_block_cols=2):
     return out[:n.value], nzq.value
 
 
+def detect_band_starts(A):
+    """The same detection without mergeBlocks: one block per distinct band start (qrk_detect_band_starts)."""
+    A, outer, inner = _csr(A)
+    return _blocks_call(lib().qrk_detect_band_starts, A.shape[0], A.shape[1], _p(outer), _p(inner))
+
+
 def block_diagonal_pattern(rows, cols, block_rows, block_cols):
     return _blocks_call(lib().qrk_block_diagonal_pattern, rows, cols, block_rows, block_cols)
 

@@ -13,7 +13,7 @@
 
 using namespace QRKit;
 typedef Eigen::Matrix<double, 7, 2> Block7x2;
-static_assert(sizeof(Block7x2) >= 14 * sizeof(double), "inline storage");
+static_assert(sizeof(Block7x2) == 14 * sizeof(double), "fixed-size blocks are packed: std::vector<Block> is the block-COO value array");
 typedef BlockDiagonalSparseQR_B200<Eigen::ColPivHouseholderQR<Block7x2> > DiagQR;
 typedef BlockAngularSparseQR_B200<DiagQR, Eigen::ColPivHouseholderQR<Eigen::MatrixXd> > AngularQR;
 typedef Eigen::SparseMatrix<double, Eigen::ColMajor, int> SpMat;

@@ -134,10 +134,95 @@ def test_reference_overlapping_pattern(qk, oracle):
     assert rel(s.solve(A @ x_true), x_true) <= 1e-10               # test/test-qrkit.cpp:255
 
 
-def test_unsupported_shape_is_reported(qk):
-    with pytest.raises(qk.QrkError) as e:
-        qk.BandedBlockedSparseQR(np.ones(5 * 3 * 2), num_blocks=2, block_rows=5, block_cols=3, overlap=1)
-    assert e.value.status == 6
+def _full_q_checks(qk, s, Ad, b):
+    """The general window chain has an exact n x n Q: Q^T v = [thin part ; complement], ||Q^T v|| = ||v||, Q Q^T = I,
+    Q^T A = [R ; 0] and Q [R ; 0] = A (the reference's identities, test/test-qrkit.cpp:251-254)."""
+    n_rows, n_cols = Ad.shape
+    y = s.applyQt(b)
+    assert y.shape == (n_rows,)
+    assert abs(np.linalg.norm(y) - np.linalg.norm(b)) <= 1e-13 * np.linalg.norm(b)
+    assert rel(s.applyQ(y), b) <= 1e-13
+    assert np.array_equal(y[:n_cols], s.applyQtThin(b))
+    R = s.matrixR().toarray()
+    Rfull = np.zeros((n_rows, n_cols)); Rfull[:n_cols] = np.triu(R[:n_cols])
+    assert rel(s.applyQt(np.asfortranarray(Ad)), Rfull) <= 1e-13
+    assert rel(s.applyQ(np.asfortranarray(Rfull)), Ad) <= 1e-13
+
+
+@pytest.mark.parametrize("br,bc,ov,nb", [(5, 3, 1, 2), (5, 3, 1, 37), (9, 5, 2, 25), (20, 30, 20, 12), (3, 7, 5, 30), (6, 6, 0, 10)])
+def test_slab_shapes_outside_the_instantiated_list(qk, oracle, br, bc, ov, nb):
+    """Any (block_rows, block_cols, overlap): shapes without a templated kernel run on the general window chain
+    (banded_generic.cuh) — same checks as the fast path, plus the exact n x n Q this path provides."""
+    slabs = uniform_blocks(nb, br, bc)
+    A = slabs_to_sparse(slabs, nb, br, bc, ov)
+    Ad = A.toarray()
+    n_rows, n_cols = Ad.shape
+    assert n_rows >= n_cols
+    b = vector(n_rows, seed=3)
+    x_ref = np.linalg.lstsq(Ad, b, rcond=None)[0]
+    s = qk.BandedBlockedSparseQR(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov)
+    assert s.rows() == n_rows and s.cols() == n_cols and s.rank() == n_cols and s.info() == qk.QRK_INFO_SUCCESS
+    assert rel(s.solve(b), x_ref) <= 1e-10
+    assert rel(qk.BandedBlockedSparseQR(block_rows=br, block_cols=bc, overlap=ov).compute_solve(slabs, b, nb), x_ref) <= 1e-10
+    ref = oracle.BandedOracle(A, reference_style_windows(nb, br, bc, ov, 2))
+    Rs, Rrs = s.matrixR(), ref.matrixR()
+    assert np.array_equal(Rs.outer, Rrs.outer) and np.array_equal(Rs.inner, Rrs.inner)
+    assert rel(sign_normalize_rows(Rs.toarray()[:n_cols]), sign_normalize_rows(Rrs.toarray()[:n_cols])) <= 1e-12
+    _full_q_checks(qk, s, Ad, b)
+
+
+@pytest.mark.parametrize("br,bc,ov", [(16, 24, 16), (7, 4, 2), (7, 2, 0)])
+def test_general_chain_equals_the_two_phase_kernels(qk, oracle, monkeypatch, br, bc, ov):
+    """QRK_BANDED_GENERIC routes an instantiated shape through the general chain: same x, same R (up to row signs)."""
+    nb = 23
+    slabs = uniform_blocks(nb, br, bc)
+    Ad = slabs_to_sparse(slabs, nb, br, bc, ov).toarray()
+    b = vector(Ad.shape[0], seed=3)
+    fast = qk.BandedBlockedSparseQR(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov)
+    monkeypatch.setenv("QRK_BANDED_GENERIC", "1")
+    gen = qk.BandedBlockedSparseQR(slabs, num_blocks=nb, block_rows=br, block_cols=bc, overlap=ov)
+    assert rel(gen.solve(b), fast.solve(b)) <= 1e-11
+    Rg, Rf = gen.matrixR(), fast.matrixR()
+    assert np.array_equal(Rg.outer, Rf.outer) and np.array_equal(Rg.inner, Rf.inner)
+    n = Ad.shape[1]
+    assert rel(sign_normalize_rows(Rg.toarray()[:n]), sign_normalize_rows(Rf.toarray()[:n])) <= 1e-12
+    _full_q_checks(qk, gen, Ad, b)
+
+
+@pytest.mark.parametrize("merged", [False, True])
+def test_reference_test3_general_sparse_input_with_shuffled_rows(qk, oracle, merged):
+    """The reference's banded test (test/test-qrkit.cpp:63-96, 208-258): the overlapping 7-row / 2+2-column pattern with its rows
+    SHUFFLED, given as a general sparse matrix.  compute() = AsBandedAsPossible ordering + block detection + extraction + the
+    general window chain; then, as the reference does, b is permuted with rowsPermutation() before solve() (:235).
+    x against LAPACK and the oracle, R against the oracle (index arrays bit-exact, values up to row signs), Q R = P A."""
+    from helpers import overlapping_banded_matrix
+    from qrkit_b200 import structure
+    num_params, num_res = 64, 7 * 32                               # 32 block rows of 7 rows (columns 2i, 2i+1 (+2 overlap entries))
+    A0 = overlapping_banded_matrix(num_params, num_res).tocsr()
+    rng = np.random.default_rng(7)
+    shuffle = rng.permutation(num_res)
+    A = A0[shuffle, :].tocsc()                                     # std::random_shuffle of the rows (:90-95)
+    s = qk.BandedBlockedSparseQR.from_sparse(A, merged=merged)
+    perm = s.rowsPermutation()                                     # indices()[orig row] = new row
+    PA = np.zeros((num_res, num_params)); PA[perm, :] = A.toarray()
+    first = np.array([np.nonzero(r)[0][0] for r in PA])
+    assert np.all(np.diff(first) >= 0), "rows ordered by their first stored column"
+    x_true = vector(num_params, seed=9)
+    b = A @ x_true
+    Pb = np.empty(num_res); Pb[perm] = b
+    assert rel(s.solve(Pb), x_true) <= 1e-10                       # :255
+    bl = vector(num_res, seed=3)
+    Pbl = np.empty(num_res); Pbl[perm] = bl
+    assert rel(s.solve(Pbl), np.linalg.lstsq(A.toarray(), bl, rcond=None)[0]) <= 1e-10
+    # the oracle on the ordered matrix with the reference's merged windows
+    import scipy.sparse as sp
+    PAs = sp.csc_matrix(PA)
+    windows, _ = structure.detect_blocks(PAs, 2)
+    ref = oracle.BandedOracle(PAs, windows)
+    Rs, Rrs = s.matrixR(), ref.matrixR()
+    assert np.array_equal(Rs.outer, Rrs.outer) and np.array_equal(Rs.inner, Rrs.inner)
+    assert rel(sign_normalize_rows(Rs.toarray()[:num_params]), sign_normalize_rows(Rrs.toarray()[:num_params])) <= 1e-12
+    _full_q_checks(qk, s, PA, Pbl)
 
 
 @pytest.mark.parametrize("nb", [20_000, 100_000])
