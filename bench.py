@@ -256,7 +256,7 @@ def run_sharded(args, L, piv, rank, world, local_rank):
                          "roofline_frac": algorithmic_bytes_per_block(R, CC, piv) * NB / (ms * 1e-3) / 1e9 / (peak * world),
                          "l2": "4 rotating handle + buffer sets per rank (4 x 640/N MB): no step re-reads lines left in L2 by the previous one"}
     # ---- config 3 with its exchange step, config 5 by bytes
-    a = _ap.Namespace(steps=max(args.steps, 20), warmup=5, points=1_000_000, mixed_blocks=100_000, scaling="strong", graphs=False)
+    a = _ap.Namespace(steps=max(args.steps, 20), warmup=5, points=1_000_000, mixed_blocks=100_000, scaling="strong", graphs=True)
     ex = {}
     for scaling in ("strong", "weak"):
         a.scaling = scaling
@@ -273,6 +273,10 @@ def run_sharded(args, L, piv, rank, world, local_rank):
                                "fused_p2p_us": None if not f else f["ms_per_step"] * 1e3,
                                "x2_identical": bool(line["x2_identical_on_all_ranks"] and f.get("x_identical_to_nccl_path", False)),
                                "rows_per_s_nccl": line["value"], "rows_per_s_fused": f.get("value"),
+                               # the same steps replayed from a CUDA graph (kernels + collective captured once): at N > 1 the eager
+                               # loop is bound by the host issuing the calls of a ~40 us step, not by the devices
+                               "nccl_graph_us": None if not line.get("cuda_graph_replay") else line["cuda_graph_replay"]["ms_per_step"] * 1e3,
+                               "fused_p2p_graph_us": None if not f or f.get("cuda_graph_replay_ms_per_step") is None else f["cuda_graph_replay_ms_per_step"] * 1e3,
                                "collective": line["collective"], "roofline_frac_nccl": line["roofline"]["frac"],
                                "roofline_frac_fused": None if not f else 248.0 * (f["value"] / 2) / 1e9 / line["roofline"]["peak"]}
     out["angular_exchange"] = ex

@@ -1655,21 +1655,29 @@ static int compute_solve_host_pipelined(qrk_solver* h, const double* values, con
   QRK_TRY_CUDA(h, cudaEventRecord(ev0, h->stream));            // earlier work on the handle's stream comes first
   QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_in, ev0, 0));
   QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_out, ev0, 0));
+  // a failure in the middle must not leave copies in flight into the caller's buffers: drain all three streams first
+  auto bail = [&](cudaError_t e, const char* what) {
+    cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_out);
+    (void)cudaGetLastError();
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? QRK_STATUS_ALLOC_FAILED : QRK_STATUS_CUDA_ERROR;
+  };
+#define QRK_PIPE(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(e__, #expr); } while (0)
   for (int i = 0; i < nchunks; i++) {
     const long long b0 = i * chunk, cnt = std::min(chunk, h->nb - b0);
     cudaEvent_t ev_in = h->pipe_events[2 * i], ev_k = h->pipe_events[2 * i + 1];
-    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_values + b0 * r * c, values + b0 * r * c, (size_t)cnt * r * c * sizeof(double),
-                                    cudaMemcpyHostToDevice, h->s_in));
-    QRK_TRY_CUDA(h, cudaMemcpyAsync(h->d_b + b0 * r, b + b0 * r, (size_t)cnt * r * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
-    QRK_TRY_CUDA(h, cudaEventRecord(ev_in, h->s_in));
-    QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->stream, ev_in, 0));
-    QRK_TRY_CUDA(h, launch_small_factor_dyn(r, c, piv, true, h->d_values + b0 * r * c, h->d_values + b0 * r * c, h->d_tau + b0 * c,
-                                            h->d_perm + b0 * c, h->d_b + b0 * r, h->d_x + b0 * c, cnt, h->stream, b0));
+    QRK_PIPE(cudaMemcpyAsync(h->d_values + b0 * r * c, values + b0 * r * c, (size_t)cnt * r * c * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    QRK_PIPE(cudaMemcpyAsync(h->d_b + b0 * r, b + b0 * r, (size_t)cnt * r * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    QRK_PIPE(cudaEventRecord(ev_in, h->s_in));
+    QRK_PIPE(cudaStreamWaitEvent(h->stream, ev_in, 0));
+    QRK_PIPE(launch_small_factor_dyn(r, c, piv, true, h->d_values + b0 * r * c, h->d_values + b0 * r * c, h->d_tau + b0 * c,
+                                     h->d_perm + b0 * c, h->d_b + b0 * r, h->d_x + b0 * c, cnt, h->stream, b0));
     h->launches++;
-    QRK_TRY_CUDA(h, cudaEventRecord(ev_k, h->stream));
-    QRK_TRY_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_k, 0));
-    QRK_TRY_CUDA(h, cudaMemcpyAsync(x + b0 * c, h->d_x + b0 * c, (size_t)cnt * c * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+    QRK_PIPE(cudaEventRecord(ev_k, h->stream));
+    QRK_PIPE(cudaStreamWaitEvent(h->s_out, ev_k, 0));
+    QRK_PIPE(cudaMemcpyAsync(x + b0 * c, h->d_x + b0 * c, (size_t)cnt * c * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
   }
+#undef QRK_PIPE
   if (h->n_cols > h->sum_cols) std::fill(x + h->sum_cols, x + h->n_cols, 0.0);     // y.bottomRows(...).setZero() (:272)
   QRK_TRY_CUDA(h, cudaStreamSynchronize(h->s_out));
   QRK_TRY_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1801,9 +1809,16 @@ static int export_sparse(qrk_handle_t h, bool want_q, int32_t* outer, int32_t* i
       eoff[i] = acc;
       acc += want_q ? (long long)h->h_rows[i] * h->h_rows[i] : (long long)h->h_cols[i] * (h->h_cols[i] + 1) / 2;
     }
-    cudaMalloc(&d_eoff, h->nb * sizeof(long long));
-    cudaMemcpyAsync(d_eoff, eoff.data(), h->nb * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
-    cudaStreamSynchronize(h->stream);
+    cudaError_t ee = cudaMalloc(&d_eoff, h->nb * sizeof(long long));
+    if (ee == cudaSuccess) ee = cudaMemcpyAsync(d_eoff, eoff.data(), h->nb * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
+    if (ee == cudaSuccess) ee = cudaStreamSynchronize(h->stream);
+    if (ee != cudaSuccess) {                      // never launch the export kernels with a null / unfilled offset table
+      (void)cudaGetLastError();
+      if (d_eoff) cudaFree(d_eoff);
+      if (memspace == QRK_HOST) { cudaFree(d_outer); cudaFree(d_inner); cudaFree(d_vals); }
+      h->err = std::string("export: per-block offset table: ") + cudaGetErrorString(ee);
+      return ee == cudaErrorMemoryAllocation ? QRK_STATUS_ALLOC_FAILED : QRK_STATUS_CUDA_ERROR;
+    }
   }
   const BlockIndex bi = block_index(h);
   const int full_q = h->desc.q_format == QRK_FULL_Q ? 1 : 0;
