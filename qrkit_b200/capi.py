@@ -9,7 +9,7 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libqrkit_b200.so")
+LIB_PATH = os.environ.get("QRKIT_B200_LIB") or os.path.join(_PKG, "lib", "libqrkit_b200.so")   # the override is a development switch (tools/build_variant.py)
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "qrkit_b200.h")
 
 QRK_STATUS_OK = 0

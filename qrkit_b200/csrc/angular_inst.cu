@@ -11,7 +11,14 @@ namespace qrk {
 namespace {
 
 constexpr int M2 = QRK_M2;
-constexpr int TPB = 128;
+// tuning hooks for A/B builds (QRK_NVCC_EXTRA="-DQRK_ANG_TPB=.. -DQRK_ANG_U1=.. -DQRK_ANG_MINB=.."); the defaults are the measured best
+#ifndef QRK_ANG_TPB
+#define QRK_ANG_TPB 128
+#endif
+#ifndef QRK_ANG_U1
+#define QRK_ANG_U1 2
+#endif
+constexpr int TPB = QRK_ANG_TPB;
 
 // left block shapes available to the block-angular path (r > c)
 #define QRK_ANGULAR_SHAPES(X) X(2, 1) X(3, 1) X(4, 2) X(7, 2)
@@ -21,11 +28,15 @@ constexpr int TPB = 128;
 template <int R, int C>
 struct Cfg {
   static constexpr int M1 = R - C;
-  static constexpr int U = (M1 >= 2) ? 1 : 2;
+  static constexpr int U = (M1 >= 2) ? 1 : QRK_ANG_U1;
   static constexpr size_t stage_bytes = (size_t)AngularSmem<R, C, M2, TPB, U, 1>::stage_doubles * 8;
   static constexpr int NSTAGE = (2 * stage_bytes <= 96 * 1024) ? 2 : 1;
   static constexpr int regs_doubles = R * C + U * M1 * (M2 + 1) + Tri<M2>::N;
+#ifdef QRK_ANG_MINB
+  static constexpr int MINB = QRK_ANG_MINB;
+#else
   static constexpr int MINB = (regs_doubles <= 44) ? 3 : 2;
+#endif
   using Smem = AngularSmem<R, C, M2, TPB, U, NSTAGE>;
 };
 
