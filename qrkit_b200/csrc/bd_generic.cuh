@@ -282,6 +282,16 @@ bd_generic_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const doubl
 // global memory (each read once per rhs), the vector lives in shared memory.
 // op: OP_SOLVE / OP_APPLY_QT / OP_APPLY_Q as in bd_small.cuh; full_q selects the FullQ index layout.
 // ---------------------------------------------------------------------------------------------
+// column `col` of the packed block, rows lo < i < hi of this lane (i = lane + 32 m), zeros elsewhere
+template <int RPL>
+__device__ __forceinline__ void op_fetch_col(double (&dst)[RPL], const double* __restrict__ P, int r, int col, bool valid, int lo, int hi, int lane) {
+#pragma unroll
+  for (int m = 0; m < RPL; m++) {
+    const int i = lane + 32 * m;
+    dst[m] = (valid && i > lo && i < hi) ? __ldg(P + (size_t)col * r + i) : 0.0;
+  }
+}
+
 template <int WPC>   // warps per CTA
 __global__ void __launch_bounds__(32 * WPC)
 bd_generic_op_kernel(BlockIndex bi, long long nb, const double* __restrict__ packed, const double* __restrict__ tau_in,
@@ -310,6 +320,44 @@ bd_generic_op_kernel(BlockIndex bi, long long nb, const double* __restrict__ pac
     for (int i = lane; i < r; i += 32) v[i] = Bc[ro + i];
   }
   __syncwarp();
+  // The reflector columns are streamed from HBM in chunks of KB columns held in registers, the next chunk in flight while the
+  // current one is applied: the chain per reflector is then one warp reduction, not one memory round trip (blocks of up to
+  // 32 * RPL rows; taller blocks fall back to direct loads).
+  constexpr int KB = 4, RPL = 4;
+  if (r <= 32 * RPL) {
+    double cur[KB][RPL], nxt[KB][RPL];
+#define QRK_OP_FETCH1(dst, kk0_, q)                                                               \
+  { const int kkf = (kk0_) + q, kf = (op == 2) ? nv - 1 - kkf : kkf;                               \
+    op_fetch_col<RPL>(dst[q], P, r, kkf < nv ? kf : 0, kkf < nv, kf, r, lane); }
+#define QRK_OP_FETCH(dst, kk0_) QRK_OP_FETCH1(dst, kk0_, 0) QRK_OP_FETCH1(dst, kk0_, 1) QRK_OP_FETCH1(dst, kk0_, 2) QRK_OP_FETCH1(dst, kk0_, 3)
+    static_assert(KB == 4, "QRK_OP_FETCH is written out for four columns");
+    QRK_OP_FETCH(cur, 0)
+    for (int kk0 = 0; kk0 < nv; kk0 += KB) {
+      QRK_OP_FETCH(nxt, kk0 + KB)
+#pragma unroll
+      for (int q = 0; q < KB; q++) {
+        const int kk = kk0 + q;
+        if (kk < nv) {
+          const int k = (op == 2) ? nv - 1 - kk : kk;
+          const double tau = tau_in[co + k];
+          double dot = 0.0;
+#pragma unroll
+          for (int m = 0; m < RPL; m++) { const int i = lane + 32 * m; if (i < r) dot = fma(cur[q][m], v[i], dot); }
+          dot = warp_sum(dot) + v[k];
+          const double tmp = tau * dot;
+          __syncwarp();
+#pragma unroll
+          for (int m = 0; m < RPL; m++) { const int i = lane + 32 * m; if (i > k && i < r) v[i] = fma(-cur[q][m], tmp, v[i]); }
+          if (lane == 0) v[k] -= tmp;
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < KB; q++)
+#pragma unroll
+        for (int m = 0; m < RPL; m++) cur[q][m] = nxt[q][m];
+    }
+  } else {
   for (int kk = 0; kk < nv; kk++) {
     const int k = (op == 2) ? nv - 1 - kk : kk;
     const double* ck = P + (size_t)k * r;
@@ -323,13 +371,48 @@ bd_generic_op_kernel(BlockIndex bi, long long nb, const double* __restrict__ pac
     if (lane == 0) v[k] -= tmp;
     __syncwarp();
   }
+  }
   if (op == 0 /*OP_SOLVE*/) {
+    if (c <= 32 * RPL) {
+      double cur[KB][RPL], nxt[KB][RPL];
+#define QRK_OP_FETCH_R1(dst, jj0_, q)                         /* columns c-1-jj0, c-2-jj0, ...: rows <= the diagonal */ \
+  { const int jf = c - 1 - ((jj0_) + q);                                                          \
+    op_fetch_col<RPL>(dst[q], P, r, jf >= 0 ? jf : 0, jf >= 0, -1, jf + 1, lane); }
+#define QRK_OP_FETCH_R(dst, jj0_) QRK_OP_FETCH_R1(dst, jj0_, 0) QRK_OP_FETCH_R1(dst, jj0_, 1) QRK_OP_FETCH_R1(dst, jj0_, 2) QRK_OP_FETCH_R1(dst, jj0_, 3)
+      QRK_OP_FETCH_R(cur, 0)
+      for (int jj0 = 0; jj0 < c; jj0 += KB) {
+        QRK_OP_FETCH_R(nxt, jj0 + KB)
+#pragma unroll
+        for (int q = 0; q < KB; q++) {
+          const int j = c - 1 - (jj0 + q);
+          if (j >= 0) {
+            double dg = 0.0;                                         // R_jj sits in lane j % 32, slot j / 32: one broadcast per
+#pragma unroll                                                       // slot (a register array must not be indexed by j)
+            for (int m = 0; m < RPL; m++) {
+              const double dm = __shfl_sync(0xffffffffu, cur[q][m], j & 31);
+              dg = ((j >> 5) == m) ? dm : dg;
+            }
+            const double yj = v[j] / dg;
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < RPL; m++) { const int i = lane + 32 * m; if (i < j) v[i] = fma(-cur[q][m], yj, v[i]); }
+            if (lane == 0) v[j] = yj;
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < KB; q++)
+#pragma unroll
+          for (int m = 0; m < RPL; m++) cur[q][m] = nxt[q][m];
+      }
+    } else {
     for (int j = c - 1; j >= 0; --j) {
       const double yj = v[j] / P[(size_t)j * r + j];
       __syncwarp();
       if (lane == 0) v[j] = yj;
       for (int i = lane; i < j; i += 32) v[i] = fma(-P[(size_t)j * r + i], yj, v[i]);
       __syncwarp();
+    }
     }
     for (int j = lane; j < c; j += 32) Xc[perm ? perm[co + j] : co + j] = v[j];
   } else if (op == 1 /*OP_APPLY_QT*/ && full_q) {
