@@ -102,6 +102,17 @@ template <typename BlockMatrix> struct ColPivHouseholderQR { using MatrixType = 
 // dense right-block solver of BlockAngularSparseQR without column pivoting (reference src/QRKit/BlockedThinDenseQR.h:62;
 // test/test-qrkit.cpp:53-56): P2 = identity, rank() = cols; the panel width does not change R
 template <typename DenseMatrix, int SuggestedBlockCols = 2> struct BlockedThinDenseQR { using MatrixType = DenseMatrix; static constexpr int pivoting = QRK_PIVOT_NONE; };
+// rank-revealing right-block solver (reference src/QRKit/BlockedThinSparseQR.h:105-283; test/test-qrkit.cpp:54-57): ColPiv inside
+// panels of SuggestedBlockCols columns, zero-pivot columns deferred to the end of P2, rank() = the nonzero pivots
+template <typename Matrix_, int SuggestedBlockCols = 2> struct BlockedThinSparseQR {
+  using MatrixType = Matrix_;
+  static constexpr int pivoting = QRK_PIVOT_COLPIV;
+  static constexpr int thin_sparse_panel = SuggestedBlockCols;
+};
+namespace detail {
+template <typename T, typename = void> struct RightSolverKind { static constexpr int kind = T::pivoting == QRK_PIVOT_COLPIV ? QRK_RIGHT_COLPIV : QRK_RIGHT_UNPIVOTED, panel = 0; };
+template <typename T> struct RightSolverKind<T, decltype((void)T::thin_sparse_panel)> { static constexpr int kind = QRK_RIGHT_THIN_SPARSE, panel = T::thin_sparse_panel; };
+}  // namespace detail
 
 // ---- SparseBlockDiagonal (SparseBlockDiagonal.h:44-163) ------------------------------------------------
 template <typename BlockMatrixType>
@@ -406,7 +417,8 @@ class BlockAngularSparseQR {
     qrk_desc_t d{};
     d.kind = QRK_BLOCK_ANGULAR; d.num_blocks = L.size(); d.block_rows = Blk::RowsAtCompileTime; d.block_cols = Blk::ColsAtCompileTime;
     d.pivoting = BlockQRSolverLeftTag::pivoting; d.q_format = QRK_FULL_Q; d.border_cols = (int32_t)m2;
-    d.right_solver = RightSolverTag::pivoting == QRK_PIVOT_COLPIV ? QRK_RIGHT_COLPIV : QRK_RIGHT_UNPIVOTED;
+    d.right_solver = detail::RightSolverKind<RightSolverTag>::kind;
+    d.reserved[1] = detail::RightSolverKind<RightSolverTag>::panel;
     const int st = qrk_create(&d, &m_h);
     m_nb = L.size(); m_m2 = m2; m_rows = mat.rows(); m_cols = mat.cols();
     if (st == QRK_STATUS_NO_DEVICE) { m_lastError = qrk_status_string(st); m_h = nullptr; return; }
@@ -443,6 +455,58 @@ class BandedBlockedSparseQR {
     detail::require((Index)slabs.size() >= numBlocks * BlockRows * BlockCols, "BandedBlockedSparseQR::compute: slabs holds fewer than numBlocks * BlockRows * BlockCols values");
     detail::throw_if(m_h ? qrk_compute(m_h, slabs.data(), QRK_HOST) : (int)QRK_STATUS_NO_DEVICE, m_h, "compute");
     m_haveR = false; m_isInitialized = true;
+  }
+  // compute(const MatrixType&) on a GENERAL banded sparse matrix — the analyzePattern else-branch of the reference
+  // (BandedBlockedSparseQR.h:408-426): AsBandedAsPossible row ordering, block detection, dense extraction of the blocks, then
+  // the general window chain (any block sizes; BlockRows / BlockCols / BlockOverlap of this class are not used).
+  // rowsPermutation() holds the ordering; as in the reference, solve() expects the right-hand side already permuted
+  // (test/test-qrkit.cpp:235).  matrixQ() is an exact n x n operator on this path: applyQtFull / applyQFull.
+  void compute(const SparseMatrix<ColMajor>& mat) {
+    const Index n = mat.rows(), m = mat.cols();
+    // row-major pattern of the matrix
+    std::vector<StorageIndex> rp((size_t)n + 1, 0), ri((size_t)mat.nonZeros());
+    for (Index p = 0; p < mat.nonZeros(); p++) rp[(size_t)mat.inner[(size_t)p] + 1]++;
+    for (Index i = 0; i < n; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+    { std::vector<StorageIndex> fill(rp.begin(), rp.end() - 1);
+      for (Index j = 0; j < m; j++) for (StorageIndex p = mat.outer[(size_t)j]; p < mat.outer[(size_t)j + 1]; p++) ri[(size_t)fill[(size_t)mat.inner[(size_t)p]]++] = (StorageIndex)j; }
+    m_rowPerm.indices().resize((size_t)n);
+    int32_t has = 0;
+    detail::throw_if(qrk_order_as_banded_as_possible(n, m, rp.data(), ri.data(), m_rowPerm.indices().data(), &has), nullptr, "AsBandedAsPossible");
+    // pattern of P * A (new row = indices[orig row]), then one block per band start
+    std::vector<StorageIndex> prp((size_t)n + 1, 0), pri(ri.size());
+    std::vector<StorageIndex> inv((size_t)n);
+    for (Index i = 0; i < n; i++) inv[(size_t)m_rowPerm.indices()[(size_t)i]] = (StorageIndex)i;
+    for (Index i = 0; i < n; i++) prp[(size_t)i + 1] = prp[(size_t)i] + (rp[(size_t)inv[(size_t)i] + 1] - rp[(size_t)inv[(size_t)i]]);
+    for (Index i = 0; i < n; i++) std::copy(ri.begin() + rp[(size_t)inv[(size_t)i]], ri.begin() + rp[(size_t)inv[(size_t)i] + 1], pri.begin() + prp[(size_t)i]);
+    int64_t nblk = 0;
+    detail::throw_if(qrk_detect_band_starts(n, m, prp.data(), pri.data(), nullptr, 0, &nblk), nullptr, "block detection");
+    std::vector<int32_t> blocks((size_t)nblk * 4);
+    detail::throw_if(qrk_detect_band_starts(n, m, prp.data(), pri.data(), blocks.data(), nblk, &nblk), nullptr, "block detection");
+    size_t total = 0;
+    for (int64_t k = 0; k < nblk; k++) total += (size_t)blocks[4 * k + 2] * blocks[4 * k + 3];
+    std::vector<double> values(total);
+    detail::throw_if(qrk_extract_blocks(n, m, mat.outer.data(), mat.inner.data(), mat.values.data(), m_rowPerm.indices().data(), blocks.data(), nblk, values.data()),
+                     nullptr, "block extraction");
+    qrk_destroy(m_h);
+    m_h = nullptr; m_nb = -1;
+    detail::throw_if(qrk_create_banded_general(blocks.data(), nblk, n, m, 0, 0, &m_h), nullptr, "BandedBlockedSparseQR (general sparse matrix)");
+    m_rows = n; m_cols = m;
+    detail::throw_if(qrk_compute(m_h, values.data(), QRK_HOST), m_h, "compute");
+    detail::throw_if(qrk_analyze_pattern(m_h, m_rowPerm.indices().data()), m_h, "rowsPermutation");
+    m_haveR = false; m_isInitialized = true;
+  }
+  const PermutationType& rowsPermutation() const { return m_rowPerm; }
+  VectorXd applyQtFull(const VectorXd& v) const {                                                             // matrixQ().transpose() * v, n x n (general path)
+    detail::require((Index)v.size() == m_rows, "applyQtFull: v.size() != rows()");
+    VectorXd y((size_t)m_rows);
+    detail::throw_if(qrk_apply_qt(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ().transpose() * v");
+    return y;
+  }
+  VectorXd applyQFull(const VectorXd& v) const {                                                              // matrixQ() * v, n x n (general path)
+    detail::require((Index)v.size() == m_rows, "applyQFull: v.size() != rows()");
+    VectorXd y((size_t)m_rows);
+    detail::throw_if(qrk_apply_q(m_h, v.data(), m_rows, y.data(), m_rows, 1, QRK_HOST), m_h, "matrixQ() * v");
+    return y;
   }
   VectorXd computeAndSolve(const std::vector<double>& slabs, Index numBlocks, const VectorXd& b, Index matCols = 0) {
     ensureHandle(numBlocks, matCols);
@@ -511,6 +575,7 @@ class BandedBlockedSparseQR {
   bool m_isInitialized = false;
   mutable bool m_haveR = false;
   mutable MatrixRType m_R;
+  PermutationType m_rowPerm;
   std::string m_lastError;
 };
 

@@ -194,7 +194,89 @@ bd_generic_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const doubl
     double inv = 1.0 / (c0 - beta);
     double tau = (beta - c0) / beta;
     if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
-    // (b) trailing columns (and the rhs), one warp per column: col -= tau * v * (v^T col), v = [1; inv*ck[k+1:]]
+    // (b) trailing columns (and the rhs): col -= tau * v * (v^T col), v = [1; inv*ck[k+1:]].  Warp w owns the columns
+    //     k+1+w, k+1+w+W, ...; for blocks of up to 128 rows it takes them FOUR at a time with the reflector and the four
+    //     columns in registers: the four warp reductions run side by side (one shuffle latency chain per batch instead of
+    //     one per column) and lane q does the LAWN-176 norm downdate of the batch's q-th column.  Same per-lane summation
+    //     order as the one-column form below, so the results are bit-identical.
+    if (r <= 128) {
+      constexpr int RPL = 4, NBAT = 4;
+      double v[RPL];
+#pragma unroll
+      for (int m = 0; m < RPL; m++) { const int i = k + 1 + lane + 32 * m; v[m] = (i < r) ? ck[i] : 0.0; }
+      for (int j0 = k + 1 + warp; j0 < ncol_ext; j0 += NBAT * W) {
+        double cv[NBAT][RPL], dot[NBAT], piv[NBAT];
+#pragma unroll
+        for (int q = 0; q < NBAT; q++) {
+          const int j = j0 + q * W;
+          const double* cj = (j < c) ? sA + (size_t)j * r : sRhs;
+          dot[q] = 0.0;
+#pragma unroll
+          for (int m = 0; m < RPL; m++) {
+            const int i = k + 1 + lane + 32 * m;
+            cv[q][m] = (j < ncol_ext && i < r) ? cj[i] : 0.0;
+            dot[q] = fma(v[m], cv[q][m], dot[q]);
+          }
+          piv[q] = (j < ncol_ext) ? cj[k] : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q = 0; q < NBAT; q++) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+        }
+        double newk[NBAT], nsq[NBAT];
+#pragma unroll
+        for (int q = 0; q < NBAT; q++) {
+          const int j = j0 + q * W;
+          double* cj = (j < c) ? sA + (size_t)j * r : sRhs;
+          const double tmp = tau * fma(dot[q], inv, piv[q]);
+          const double tinv = tmp * inv;
+          nsq[q] = 0.0;
+#pragma unroll
+          for (int m = 0; m < RPL; m++) {
+            const int i = k + 1 + lane + 32 * m;
+            cv[q][m] = fma(-v[m], tinv, cv[q][m]);
+            if (j < ncol_ext && i < r) cj[i] = cv[q][m];
+            nsq[q] = fma(cv[q][m], cv[q][m], nsq[q]);
+          }
+          newk[q] = piv[q] - tmp;
+          if (lane == 0 && j < ncol_ext) cj[k] = newk[q];
+        }
+        if (PIV) {
+          // lane q: downdate of column j0 + q W; a column that must be recomputed gets its norm from the registers
+          bool recompute = false;
+          int jq = -1;
+#pragma unroll
+          for (int q = 0; q < NBAT; q++) if (lane == q) { jq = j0 + q * W; }
+          double myk = 0.0;
+#pragma unroll
+          for (int q = 0; q < NBAT; q++) myk = (lane == q) ? newk[q] : myk;
+          if (lane < NBAT && jq < c) {
+            const double upd = sUpd[jq];
+            if (upd != 0.0) {
+              double t = fabs(myk) / upd;
+              t = (1.0 + t) * (1.0 - t);
+              t = t < 0.0 ? 0.0 : t;
+              const double qq = upd / sDir[jq];
+              const double t2 = t * (qq * qq);
+              if (t2 <= 1.4901161193847656e-08) recompute = true;
+              else sUpd[jq] = upd * sqrt(t);
+            }
+          }
+          const unsigned need = __ballot_sync(0xffffffffu, recompute);
+          if (need) {
+#pragma unroll
+            for (int q = 0; q < NBAT; q++) {
+              if (need & (1u << q)) {
+                const double su = warp_sum(nsq[q]);
+                const int j = j0 + q * W;
+                if (lane == 0) { sDir[j] = sqrt(su); sUpd[j] = sDir[j]; }
+              }
+            }
+          }
+        }
+      }
+    } else {
     for (int j = k + 1 + warp; j < ncol_ext; j += W) {
       double* cj = (j < c) ? sA + (size_t)j * r : sRhs;
       double dot = 0.0;
@@ -229,6 +311,7 @@ bd_generic_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const doubl
           if (lane == 0) { sDir[j] = sqrt(su); sUpd[j] = sDir[j]; }
         }
       }
+    }
     }
     team_sync<W>();
     // (c) store the essential part and beta (every reader of the raw column is past the barrier)

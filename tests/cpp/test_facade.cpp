@@ -169,6 +169,54 @@ int main() {
     BlockAngularBandedSparseQR<7, 4, 2, BlockedThinDenseQR<MatrixXd, 2>> ab2;
     CHECK(rel(ab2.computeAndSolve(slabs, nbb, Bb, ba), xa) <= 1e-10, "banded-left angular, unpivoted right solver: computeAndSolve recovers x  (1e-10)");
   }
+  // BandedBlockedSparseQR::compute(const SparseMatrix&) on a general banded matrix with SHUFFLED rows (test/test-qrkit.cpp:63-96,
+  // 208-258): row ordering + block detection + the general window chain; b is permuted with rowsPermutation() before solve (:235)
+  {
+    const Index np = 40, nbk = np / 2, nr = 7 * nbk;
+    std::vector<std::vector<std::pair<Index, double>>> colsv((size_t)np);       // column -> (row, value), rows shuffled
+    std::vector<Index> shuffle((size_t)nr);
+    for (Index i = 0; i < nr; i++) shuffle[(size_t)i] = (i * 37 + 11) % nr;     // a fixed permutation (37 and nr = 140 are coprime)
+    for (Index i = 0; i < nbk; i++)
+      for (Index j = 2 * i; j < 2 * i + 2; j++) {
+        for (int k = 0; k < 7; k++) colsv[(size_t)j].push_back({shuffle[(size_t)(i * 7 + k)], synth(61, i, k, j)});
+        if (j < np - 2) colsv[(size_t)j + 2].push_back({shuffle[(size_t)(i * 7 + 6)], synth(63, i, 6, j)});
+      }
+    SparseMatrix<ColMajor> Sg;
+    Sg.m_rows = nr; Sg.m_cols = np; Sg.outer.assign((size_t)np + 1, 0);
+    for (Index j = 0; j < np; j++) {
+      std::sort(colsv[(size_t)j].begin(), colsv[(size_t)j].end());
+      for (auto& e : colsv[(size_t)j]) { Sg.inner.push_back((StorageIndex)e.first); Sg.values.push_back(e.second); }
+      Sg.outer[(size_t)j + 1] = (StorageIndex)Sg.inner.size();
+    }
+    BandedBlockedSparseQR<7, 4, 2> gen;
+    gen.compute(Sg);
+    CHECK(gen.info() == Success && gen.rows() == nr && gen.cols() == np && gen.rank() == np, "banded, general sparse input: info / rows / cols / rank");
+    VectorXd xg((size_t)np), bg((size_t)nr, 0.0);
+    for (size_t j = 0; j < xg.size(); j++) xg[j] = synth(65, j, 0, 0, -1.0, 1.0);
+    for (Index j = 0; j < np; j++) for (StorageIndex p = Sg.outer[(size_t)j]; p < Sg.outer[(size_t)j + 1]; p++) bg[(size_t)Sg.inner[(size_t)p]] += Sg.values[(size_t)p] * xg[(size_t)j];
+    const VectorXd pb = gen.rowsPermutation() * bg;
+    CHECK(rel(gen.solve(pb), xg) <= 1e-10, "banded, general sparse input with shuffled rows: solve(P b) recovers x  (1e-10)");
+    const VectorXd qt = gen.applyQtFull(pb);
+    double n1 = 0, n2 = 0;
+    for (size_t i = 0; i < qt.size(); i++) { n1 += qt[i] * qt[i]; n2 += pb[i] * pb[i]; }
+    CHECK(std::fabs(std::sqrt(n1) - std::sqrt(n2)) <= 1e-13 * std::sqrt(n2) && rel(gen.applyQFull(qt), pb) <= 1e-13, "banded, general path: n x n Q is orthogonal (||Q^T v|| = ||v||, Q Q^T v = v)");
+  }
+  // rank-revealing right solver (BlockedThinSparseQR, test/test-qrkit.cpp:54-57)
+  {
+    const Index nbt = 64;
+    SparseBlockDiagonal<Block7x2> At(nbt * r, nbt * c);
+    for (Index i = 0; i < nbt; i++) { Block7x2 bb; for (int j = 0; j < c; j++) for (int k = 0; k < r; k++) bb(k, j) = synth(71, i, k, j); At.insertBack(bb); }
+    MatrixXd Bt(nbt * r, 10);
+    for (Index i = 0; i < nbt * r; i++) for (int j = 0; j < 10; j++) Bt(i, j) = synth(73, i, j, 0);
+    VectorXd xt((size_t)(nbt * c + 10)), bt((size_t)(nbt * r), 0.0);
+    for (size_t j = 0; j < xt.size(); j++) xt[j] = synth(75, j, 0, 0, -1.0, 1.0);
+    for (Index i = 0; i < nbt; i++) for (int j = 0; j < c; j++) for (int k = 0; k < r; k++) bt[(size_t)(i * r + k)] += At[i](k, j) * xt[(size_t)(i * c + j)];
+    for (Index i = 0; i < nbt * r; i++) for (int j = 0; j < 10; j++) bt[(size_t)i] += Bt(i, j) * xt[(size_t)(nbt * c + j)];
+    BlockMatrix1x2<SparseBlockDiagonal<Block7x2>, MatrixXd> Mt(At, Bt);
+    BlockAngularSparseQR<ColPivHouseholderQR<Block7x2>, BlockedThinSparseQR<SparseMatrix<ColMajor>, 2>> ts(Mt);
+    CHECK(ts.info() == Success && ts.rank() == nbt * c + 10, "BlockedThinSparseQR right solver: info / rank");
+    CHECK(rel(ts.solve(bt), xt) <= 1e-10, "BlockedThinSparseQR right solver: solve(b) recovers x  (1e-10)");
+  }
   // one host process, several GPUs (two shards on device 0 when the box has one GPU): contiguous block ranges per shard
   {
     const std::vector<int> devs = {0, ndev > 1 ? 1 : 0, 0};

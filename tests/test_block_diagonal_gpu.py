@@ -357,9 +357,34 @@ def test_config5_full_size_properties(qk):
     torch.cuda.synchronize()
     check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h)
     check(L.qrk_synchronize(h), h)
-    assert float(torch.linalg.norm(x - x_true) / torch.linalg.norm(x_true)) <= 1e-9
+    assert float(torch.linalg.norm(x - x_true) / torch.linalg.norm(x_true)) <= 1e-10
     check(L.qrk_compute_solve(h, vp(A), vp(b_ls), vp(x), QRK_DEVICE), h)
     check(L.qrk_synchronize(h), h)
     g = rmatvec(matvec(x) - b_ls)
     assert float(g.abs().max() / rmatvec(b_ls).abs().max()) <= 1e-11
     L.qrk_destroy(h)
+    # the oracle on windows of the full-size problem, unpivoted (blocked-WY / DMMA kernel) AND ColPiv (team-per-block kernel):
+    # packed factors and tau at 1e-12, column permutations bit-exact, x at 1e-10 — 3 windows of 100 consecutive blocks each
+    from oracle import oracle as orc
+    packed = torch.empty(total, dtype=torch.float64, device="cuda")
+    tau = torch.empty(cols, dtype=torch.float64, device="cuda")
+    perm = torch.empty(cols, dtype=torch.int32, device="cuda")
+    for piv in (0, 1):
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.pivoting = 0, nb, piv
+        d.rows = br.ctypes.data_as(C.POINTER(C.c_int32)); d.cols = bc.ctypes.data_as(C.POINTER(C.c_int32))
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_compute_solve(h, vp(A), vp(b_ls), vp(x), QRK_DEVICE), h)
+        check(L.qrk_packed_factors(h, vp(packed), vp(tau), QRK_DEVICE), h)
+        check(L.qrk_cols_permutation(h, vp(perm), QRK_DEVICE), h)
+        check(L.qrk_synchronize(h), h)
+        for w0 in (0, 49_950, nb - 100):
+            ids = np.arange(w0, w0 + 100)
+            v0, v1, r0, r1, c0, c1 = int(voff[w0]), int(voff[w0 + 100]), int(roff[w0]), int(roff[w0 + 100]), int(coff[w0]), int(coff[w0 + 100])
+            ref = orc.BlockDiagonalOracle(br[ids], bc[ids], A[v0:v1].cpu().numpy(), colpiv=bool(piv))
+            pk_ref, tau_ref = ref.packed()
+            assert rel(packed[v0:v1].cpu().numpy(), pk_ref) <= TOL_R and rel(tau[c0:c1].cpu().numpy(), tau_ref) <= TOL_R
+            assert np.array_equal(perm[c0:c1].cpu().numpy() - c0, ref.colsPermutation())
+            assert rel(x[c0:c1].cpu().numpy(), ref.solve(b_ls[r0:r1].cpu().numpy())) <= TOL_X
+        L.qrk_destroy(h)
