@@ -242,7 +242,7 @@ def bench_classes(args, L, stream):
         check(L.qrk_synth_fill(vp(b), SEED_A + 5, 0, nb * r, 1, 0, -1.0, 1.0, stream))
         x = torch.empty(nb * c, dtype=torch.float64, device="cuda")
         d = QrkDesc()
-        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting = 0, nb, r, c, 0
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting = 0, nb, r, c, int(getattr(args, 'class_piv', 0))
         h = C.c_void_p()
         check(L.qrk_create(C.byref(d), C.byref(h)))
         check(L.qrk_set_stream(h, stream), h)
@@ -574,6 +574,7 @@ def main():
     ap.add_argument("--class-blocks", type=int, default=0)
     ap.add_argument("--banded-blocks", type=int, default=100_000)
     ap.add_argument("--shapes", default="")
+    ap.add_argument("--class-piv", type=int, default=0, help="classes workload: 1 = ColPivHouseholderQR per block")
     ap.add_argument("--lm-points", default="500,10000,100000,500000,1000000")
     ap.add_argument("--lm-iters", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle timings (cpu_baseline)")
