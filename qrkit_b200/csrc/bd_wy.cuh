@@ -67,7 +67,7 @@ struct WyGeom {
 // panel warp scratch: two step buffers of the column-per-lane panel (raw pivot column 4 x (RQ + 2), pivot row 8, norm partials 4;
 // RQ = 32 rows per lane at most) and the 8x8 S = V^T V; the cooperative look-ahead apply reuses it for its partial W (W x 64)
 constexpr int kWyStepBuf = 4 * (32 + 2) + 12;
-constexpr int kWyScratch = 2 * kWyStepBuf + 64;
+constexpr int kWyScratch = 2 * kWyStepBuf + 64 + 40;   // (the team-panel experiment needs 396)
 constexpr int kWyPB = 96;   // diagonal tile of V (unit lower triangular 8x8), column stride 12 (= 12 mod 16)
 
 __host__ __device__ inline size_t wy_smem_bytes(int r, int c) {
@@ -655,6 +655,119 @@ __device__ __noinline__ void wy_factor_panel_cpl(double* sA, int ld, int rp, int
   WY_TRACE(5);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Team panel (-DQRK_WY_TEAMPANEL, experiment): the column-per-lane panel spread over ALL WP warps of the CTA.  Thread
+// (warp w, lane) = (column j = lane >> 2, sub-chunk s = 4 w + (lane & 3)) holds the rows NS i + s of column j (NS = 4 WP,
+// 8 MR / WP rows per thread), so the panel's pivot rows 0..7 are all "row i = 0" of the sub-chunks s = 0..7.  Per step: the
+// raw pivot column, its tail-norm partials (one per warp) and the pivot row are published in shared memory; every thread
+// forms its dot-product partial, two shuffles reduce over the lane's four sub-chunks, the WP per-warp partials cross through
+// shared memory; the scalar chain runs beside all that.  Two CTA barriers per step.  Every warp of the CTA must call it.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MR, int WP>
+__device__ __noinline__ void wy_factor_panel_team(double* sA, int ld, int rp, int p, double* PB0, double* sT, double* scratch,
+                                                  double* sTau, int warp, int lane) {
+  static_assert(WP == 2 || WP == 4, "pivot rows 0..7 must all be row 0 of a sub-chunk");
+  constexpr int NS = 4 * WP, RQ = 8 * MR / WP, TS = RQ + 2;
+  constexpr int ROWB = 16 * (16 + 2);             // pivot row (8) at ROWB, norm partials (4) at ROWB + 8, dot partials (4 x 8) at ROWB + 12
+  static_assert(ROWB + 12 + 32 + 64 <= kWyScratch, "scratch too small for the team panel");
+  const int nrow = rp - p;
+  const int j = lane >> 2, q = lane & 3, sc = 4 * warp + q;
+  double* sS = scratch + ROWB + 44;               // 8 x 8, strictly upper part used
+  double* tail = scratch;                         // [NS][TS] raw pivot column
+  double* rowb = scratch + ROWB;
+  double* nrm = rowb + 8;
+  double* dotp = rowb + 12;
+  double a[RQ];
+  {
+    const double* base = sA + (size_t)(p + j) * ld + p + sc;
+#pragma unroll
+    for (int i = 0; i < RQ; i++) a[i] = (NS * i + sc < nrow) ? base[NS * i] : 0.0;
+  }
+  auto publish = [&](int Kn) {                    // what step Kn reads: raw column Kn, its tail-norm partial per warp, row Kn
+    if (j == Kn) {
+      double* dst = tail + sc * TS;
+      double s0 = (sc > Kn) ? a[0] * a[0] : 0.0, s1 = 0.0;
+      dst[0] = a[0];
+#pragma unroll
+      for (int i = 1; i < RQ; i++) {
+        dst[i] = a[i];
+        if (i & 1) s1 = fma(a[i], a[i], s1); else s0 = fma(a[i], a[i], s0);
+      }
+      double sn = s0 + s1;
+      sn += __shfl_xor_sync(0xfu << (4 * Kn), sn, 1);
+      sn += __shfl_xor_sync(0xfu << (4 * Kn), sn, 2);
+      if (q == 0) nrm[warp] = sn;
+    }
+    if (sc == Kn) rowb[j] = a[0];
+  };
+  __syncthreads();                                // the scratch of an earlier use is dead
+  publish(0);
+  double* tauv = sTau + p;
+  double myinv = 0.0;
+  WY_TRACE(1);
+#pragma unroll 1
+  for (int K = 0; K < 8; K++) {
+    __syncthreads();
+    const double c0 = rowb[K], rowj = rowb[j];
+    double tailSq = nrm[0] + nrm[1];
+    if (WP == 4) tailSq += nrm[2] + nrm[3];
+    double tv[RQ];
+    double t0, t1 = 0.0;
+    {
+      const double* tq = tail + sc * TS;
+#pragma unroll
+      for (int i = 0; i < RQ; i++) tv[i] = tq[i];
+      t0 = (sc > K) ? tv[0] * a[0] : 0.0;
+#pragma unroll
+      for (int i = 1; i < RQ; i++) { if (i & 1) t1 = fma(tv[i], a[i], t1); else t0 = fma(tv[i], a[i], t0); }
+    }
+    double t = t0 + t1;
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (q == 0) dotp[warp * 8 + j] = t;
+    const WyRefl h = wy_reflector(c0, tailSq);
+    __syncthreads();
+    t = dotp[j] + dotp[8 + j];
+    if (WP == 4) t += dotp[16 + j] + dotp[24 + j];
+    const double sj = -fma(h.dd, rowj, t) * h.ib;
+    const double add = (j > K) ? -(sj * h.inv) : 0.0;
+    {
+      const double old = a[0];
+      a[0] = fma(tv[0], (sc > K) ? add : 0.0, a[0]);
+      if (sc == K) a[0] = (j > K) ? old - sj : (j == K) ? h.beta : old;
+    }
+#pragma unroll
+    for (int i = 1; i < RQ; i++) a[i] = fma(tv[i], add, a[i]);
+    if (j == K) myinv = h.inv;
+    if (j < K && sc == 0) sS[j * 8 + K] = myinv * fma(h.inv, t, rowj);
+    if (j == K && sc == 0) tauv[K] = h.tau;
+    if (K < 7) publish(K + 1);
+  }
+  WY_TRACE(2);
+  {
+    const double e0 = (sc > j) ? a[0] * myinv : a[0];
+    double* base = sA + (size_t)(p + j) * ld + p + sc;
+    if (sc < nrow) base[0] = e0;
+#pragma unroll
+    for (int i = 1; i < RQ; i++) if (NS * i + sc < nrow) base[NS * i] = a[i] * myinv;
+    if (sc < 8) PB0[j * 12 + sc] = (sc < j) ? 0.0 : (sc == j) ? 1.0 : e0;
+  }
+  __syncthreads();
+  if (warp == 0 && lane < 8) {
+    double Tr[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < k; m++) sum = fma(Tr[m], sS[m * 8 + k], sum);
+      const double tk = tauv[k];
+      Tr[k] = (k < lane) ? 0.0 : (k == lane) ? tk : -tk * sum;
+      sT[lane * 8 + k] = Tr[k];
+    }
+  }
+}
+
 // ---- apply panel p to one 8-column tile (or to the right-hand side), by ONE warp ---------------------------------
 template <int MR>
 __device__ __forceinline__ void wy_apply_panel(double* sA, double* sRhs, int ld, int rp, int p, int jt, bool is_rhs,
@@ -854,6 +967,43 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   const int n_tiles = P + (SOLVE ? 1 : 0);
   const int rot = (W > 1) ? s_rot : 0;
   __shared__ int s_next_tile;
+#ifdef QRK_WY_TEAMPANEL
+  if constexpr (W == 2 || W == 4) {
+    // experiment: every panel by the whole CTA (wy_factor_panel_team), the tiles by the whole CTA from the queue: no overlap
+    wy_factor_panel_team<MR, W>(sA, ld, rp, 0, sPB, sT, sS, sTau, warp, lane);
+    __syncthreads();
+    for (int pi = 0; pi < P; pi++) {
+      const int p = 8 * pi, buf = pi & 1;
+      const bool has_next = pi + 1 < P;
+      int first = pi + 1;
+      if (has_next) {
+        WY_TRACE(6);
+        wy_apply_panel_coop<MR, W>(sA, ld, rp, p, pi + 1, sPB + buf * kWyPB, sT + buf * 64, sS, warp, lane);
+        WY_TRACE(7);
+        first = pi + 2;
+      }
+      if (tid == 0) s_next_tile = first;
+      __syncthreads();
+      WY_TRACE(3);
+      for (;;) {
+        int jt = 0;
+        if (lane == 0) jt = atomicAdd(&s_next_tile, 1);
+        jt = __shfl_sync(0xffffffffu, jt, 0);
+        if (jt >= n_tiles) break;
+        wy_apply_panel<MR>(sA, sRhs, ld, rp, p, jt, jt == P, sPB + buf * kWyPB, sT + buf * 64, lane);
+        WY_TRACE(4);
+      }
+      WY_TRACE(8);
+      __syncthreads();
+      WY_TRACE(9);
+      if (has_next) {
+        wy_factor_panel_team<MR, W>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, warp, lane);
+        __syncthreads();
+      }
+    }
+  } else
+#endif
+  {
   if (warp == rot) WY_FACTOR_PANEL<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
@@ -896,6 +1046,7 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
     WY_TRACE(8);
     __syncthreads();
     WY_TRACE(9);
+  }
   }
 
   // ---- epilogue: x = R^-1 (Q^T b)[0:c] (warp 0, y in registers), tau, packed factors ----
