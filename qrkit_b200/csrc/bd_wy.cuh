@@ -706,9 +706,14 @@ __device__ __noinline__ void wy_factor_panel_team(double* sA, int ld, int rp, in
   double* tauv = sTau + p;
   double myinv = 0.0;
   WY_TRACE(1);
+#ifdef QRK_WY_TRACE
+  long long wy_acc[6] = {0, 0, 0, 0, 0, 0};
+  long long wy_last = clock64();
+#endif
 #pragma unroll 1
   for (int K = 0; K < 8; K++) {
     __syncthreads();
+    WY_CLK(0);                                    // barrier A (publication of the previous step)
     const double c0 = rowb[K], rowj = rowb[j];
     double tailSq = nrm[0] + nrm[1];
     if (WP == 4) tailSq += nrm[2] + nrm[3];
@@ -726,8 +731,14 @@ __device__ __noinline__ void wy_factor_panel_team(double* sA, int ld, int rp, in
     t += __shfl_xor_sync(0xffffffffu, t, 1);
     t += __shfl_xor_sync(0xffffffffu, t, 2);
     if (q == 0) dotp[warp * 8 + j] = t;
+    WY_CLK(1);                                    // shared loads, dot partial, two shuffles
     const WyRefl h = wy_reflector(c0, tailSq);
+#ifdef QRK_WY_TRACE
+    if (h.tau == 123.456) wy_acc[5]++;            // keep the chain in front of the clock read
+#endif
+    WY_CLK(2);                                    // scalar chain
     __syncthreads();
+    WY_CLK(3);                                    // barrier B (dot partials of all warps)
     t = dotp[j] + dotp[8 + j];
     if (WP == 4) t += dotp[16 + j] + dotp[24 + j];
     const double sj = -fma(h.dd, rowj, t) * h.ib;
@@ -743,7 +754,11 @@ __device__ __noinline__ void wy_factor_panel_team(double* sA, int ld, int rp, in
     if (j < K && sc == 0) sS[j * 8 + K] = myinv * fma(h.inv, t, rowj);
     if (j == K && sc == 0) tauv[K] = h.tau;
     if (K < 7) publish(K + 1);
+    WY_CLK(4);                                    // update + publication
   }
+#ifdef QRK_WY_TRACE
+  for (int i = 0; i < 5; i++) WY_TRACE_VAL(12 + i, wy_acc[i]);
+#endif
   WY_TRACE(2);
   {
     const double e0 = (sc > j) ? a[0] * myinv : a[0];
@@ -1004,7 +1019,11 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
   } else
 #endif
   {
+#ifdef QRK_WY_PINPANEL
+  if (warp == 0) WY_FACTOR_PANEL<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
+#else
   if (warp == rot) WY_FACTOR_PANEL<MR>(sA, ld, rp, 0, sPB, sT, sS, sTau, lane);
+#endif
   __syncthreads();
   for (int pi = 0; pi < P; pi++) {
     const int p = 8 * pi, buf = pi & 1;
@@ -1031,10 +1050,19 @@ bd_wy_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const double* A_
     }
     if (tid == 0) s_next_tile = first;
     __syncthreads();
+#ifdef QRK_WY_PINPANEL
+    // experiment: every panel of every resident CTA on warp 0 (one SM sub-partition runs the latency-bound scalar chains, the
+    // DMMA tile streams stay on the other three); QRK_WY_PINPANEL=2: warp 0 takes no tiles either
+    const int onext = 0;
+#else
     const int onext = (pi + 1 + rot) % W;
+#endif
     if (has_next && warp == onext)
       WY_FACTOR_PANEL<MR>(sA, ld, rp, p + 8, sPB + (buf ^ 1) * kWyPB, sT + (buf ^ 1) * 64, sS, sTau, lane);
     WY_TRACE(3);
+#if defined(QRK_WY_PINPANEL) && QRK_WY_PINPANEL == 2
+    if (warp != 0 || !has_next)
+#endif
     for (;;) {
       int jt = 0;
       if (lane == 0) jt = atomicAdd(&s_next_tile, 1);

@@ -30,7 +30,7 @@ void run(int r, int c, int nb) {
   int n; cudaMemcpyFromSymbol(&n, g_wy_trace_n, sizeof(int));
   std::vector<long long> t(4096); cudaMemcpyFromSymbol(t.data(), g_wy_trace, sizeof(long long) * 4096);
   printf("block %dx%d MR=%d W=%d smem=%zu occupancy=%d CTAs/SM, %d trace records\n", r, c, MR, W, smem, occ, n);
-  const char* names[] = {"panel:start", "panel:loaded", "panel:steps done", "tiles:start", "tile:done", "panel:T done", "apply:start", "apply:end", "phase:arrive", "phase:leave", "epilogue", "staged", "  steps: partial dots", "  steps: reduce-scatter", "  steps: smem gather", "  steps: scalar chain", "  steps: update+T"};
+  const char* names[] = {"panel:start", "panel:loaded", "panel:steps done", "tiles:start", "tile:done", "panel:T done", "apply:start", "apply:end", "phase:arrive", "phase:leave", "epilogue", "staged", "  steps: acc0 (row panel: partial dots | team panel: barrier A)", "  steps: acc1 (reduce-scatter | loads + dot + shuffles)", "  steps: acc2 (smem gather | scalar chain)", "  steps: acc3 (scalar chain | barrier B)", "  steps: acc4 (update+T | update + publication)"};
   long long t0 = t[1];
   for (int i = 0; i < n && i < 2048; i++) if (t[2 * i] / 16 < 12) t0 = t[2 * i + 1] < t0 ? t[2 * i + 1] : t0;
   for (int i = 0; i < n && i < 2048; i++) {
