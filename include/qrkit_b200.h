@@ -241,7 +241,12 @@ QRK_API int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count,
  *   qrk_ipc_export / _import  cudaIpcGetMemHandle / cudaIpcOpenMemHandle (64-byte handles) for one-process-per-GPU callers;
  *                             exchange the handles with any host-side collective (torch.distributed, MPI)
  *   qrk_angular_p2p_attach    peer_buffers[g] = rank g's exchange buffer as mapped in THIS process (own buffer at [rank])
- *                             — every rank must have returned from attach (host barrier) before any rank starts a step
+ *                             — every rank must have returned from attach (host barrier) before any rank starts a step.
+ *                             Attach also loads the kernels and allocates every buffer the later compute / solve calls of
+ *                             this handle would allocate on first use (staging for host-memspace b / x / border / values, the
+ *                             stored Abot panel): cudaMalloc waits for all running kernels of a device, so a first-use
+ *                             allocation on one rank while another rank's root kernel on the SAME device waits for it
+ *                             would stall both until the timeout (several handles per device: tests, ShardedBlockAngularSparseQR)
  *   qrk_angular_p2p_set_timeout  bound of the in-kernel wait for the peers' flags, in seconds (default 10); ranks must launch
  *                             their steps within this window of each other
  *   qrk_angular_p2p_status    *timed_out = 1 if a peer never arrived.  The condition is sticky until the next attach; the

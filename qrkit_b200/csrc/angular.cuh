@@ -25,6 +25,13 @@
 
 namespace qrk {
 
+// L2 residency between K1 and K3 (see common.cuh): -DQRK_ANG_NOHINT builds the kernels without the cache policies (A/B)
+#ifdef QRK_ANG_NOHINT
+constexpr bool kAngHint = false;
+#else
+constexpr bool kAngHint = true;
+#endif
+
 // Packed upper-trapezoidal M2 x (M2+1) triangle [R_t | z], stored by rows: row k holds columns k..M2.
 template <int M2>
 struct Tri {
@@ -222,15 +229,24 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
   for (int i = 0; i < Tri<M2>::N; i++) T[i] = 0.0;
 
   const long long ntiles = (nb + TILE - 1) / TILE;
+  const uint64_t pol_in = kAngHint ? l2_policy_evict_first() : 0, pol_out = kAngHint ? l2_policy_evict_last() : 0;
   auto issue = [&](long long tile, int stage) {
     const long long tile0 = tile * TILE;
     const int count = (int)((nb - tile0 < TILE) ? (nb - tile0) : TILE);
     double* buf = smem + (size_t)stage * L::stage_doubles;
-    stage_in_async<R * C, L::SA, TPB, TILE>(buf, A_in + tile0 * (R * C), count);
+    if (kAngHint) {
+      stage_in_async_hint<R * C, L::SA, TPB, TILE>(buf, A_in + tile0 * (R * C), count, pol_in);
 #pragma unroll
-    for (int j = 0; j < M2; j++)
-      stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + j * TILE * L::SR, J2 + (long long)j * ldj + tile0 * R, count);
-    if (b) stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + M2 * TILE * L::SR, b + tile0 * R, count);
+      for (int j = 0; j < M2; j++)
+        stage_in_async_hint<R, L::SR, TPB, TILE>(buf + TILE * L::SA + j * TILE * L::SR, J2 + (long long)j * ldj + tile0 * R, count, pol_in);
+      if (b) stage_in_async_hint<R, L::SR, TPB, TILE>(buf + TILE * L::SA + M2 * TILE * L::SR, b + tile0 * R, count, pol_in);
+    } else {
+      stage_in_async<R * C, L::SA, TPB, TILE>(buf, A_in + tile0 * (R * C), count);
+#pragma unroll
+      for (int j = 0; j < M2; j++)
+        stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + j * TILE * L::SR, J2 + (long long)j * ldj + tile0 * R, count);
+      if (b) stage_in_async<R, L::SR, TPB, TILE>(buf + TILE * L::SA + M2 * TILE * L::SR, b + tile0 * R, count);
+    }
   };
 
   long long tile = blockIdx.x;
@@ -280,7 +296,10 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
           apply_qt_chain<R, C>(a, tau, col);
           double* top = (j < M2) ? atop + (long long)j * m1 + blk * C : y1 + blk * C;
 #pragma unroll
-          for (int i = 0; i < C; i++) top[i] = col[i];
+          for (int i = 0; i < C; i++) {
+            if (kAngHint) st_global_hint(top + i, col[i], pol_out);
+            else top[i] = col[i];
+          }
 #pragma unroll
           for (int i = 0; i < M1; i++) w[u * M1 + i][j] = col[C + i];
           if (abot) {
@@ -298,8 +317,13 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
     }
     fold_rows<M2, U * M1>(T, w);
     __syncthreads();
-    stage_out<R * C, L::SA, TPB, TILE>(packed + tile0 * (R * C), buf, count);
-    stage_out<C, L::ST, TPB, TILE>(tau_out + tile0 * C, sT, count);
+    if (kAngHint) {
+      stage_out_hint<R * C, L::SA, TPB, TILE>(packed + tile0 * (R * C), buf, count, pol_out);
+      stage_out_hint<C, L::ST, TPB, TILE>(tau_out + tile0 * C, sT, count, pol_out);
+    } else {
+      stage_out<R * C, L::SA, TPB, TILE>(packed + tile0 * (R * C), buf, count);
+      stage_out<C, L::ST, TPB, TILE>(tau_out + tile0 * C, sT, count);
+    }
     if (PIV) {
       for (int d = t; d < count * C; d += TPB) perm_out[tile0 * C + d] = sP[(d / C) * L::SP + (d % C)];
     }
@@ -310,6 +334,134 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
   if (t == 0) {
 #pragma unroll
     for (int i = 0; i < Tri<M2>::N; i++) partials[(long long)blockIdx.x * Tri<M2>::N + i] = T[i];
+  }
+}
+
+// K1 for 2 x 1 blocks (the ellipse-fit shape of BASELINE configs 1 and 3): every per-point slice -- the block, its two rows
+// of each border column and of b -- is ONE aligned 16-byte vector and consecutive points are consecutive in HBM, so a warp's
+// plain vector loads are already perfectly coalesced (512 contiguous bytes each).  No shared-memory staging, no barriers in
+// the loop: thread t of the grid takes points t, t + sweep, ...; U of them are folded with ONE reflector per border column,
+// which is what pays (the 5 dependent reflector-scalar chains of a fold are the latency that bounds the kernel: ncu shows
+// half of the issue slots empty on fixed-latency dependencies; U = 4 halves their number per point against the staged
+// kernel's U = 2, and the 7 U independent vector loads of an iteration are all in flight together).
+// Measured (profiles/r02_angular_2x1_kernels_ab.txt): config 3 53.7 -> 49.4 us together with the L2 policies and the direct
+// K3.  Tried and dropped: next-iteration prefetch through a private cp.async ring (50.1 us at U = 3: the load wait it
+// removes is not what bounds the step) and prefetch.global.L2 (53.9 us).
+// Requires 16-byte aligned A / J2 / b, an even ldj and 32-bit point indices (checked by the dispatcher; otherwise the
+// staged kernel runs).
+// fold_rows with the fused reflector scalars of householder_scalars (the reciprocal's seed is taken from the 20-bit norm while
+// the Newton steps of the rsqrt still run): a shorter dependent chain per border column than fold_rows' separate rsqrt + rcp
+template <int M2, int P>
+__device__ __forceinline__ void fold_rows_fused(double (&T)[Tri<M2>::N], double (&w)[P][M2 + 1]) {
+  using TR = Tri<M2>;
+#pragma unroll
+  for (int k = 0; k < M2; k++) {
+    double tailSq = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; p++) tailSq = fma(w[p][k], w[p][k], tailSq);
+    double beta, inv, tau;
+    householder_scalars(T[TR::idx(k, k)], tailSq, false, beta, inv, tau);
+    T[TR::idx(k, k)] = beta;
+    double v[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) v[p] = w[p][k] * inv;
+#pragma unroll
+    for (int j = k + 1; j <= M2; j++) {
+      double dot = T[TR::idx(k, j)];
+#pragma unroll
+      for (int p = 0; p < P; p++) dot = fma(v[p], w[p][j], dot);
+      dot *= tau;
+      T[TR::idx(k, j)] -= dot;
+#pragma unroll
+      for (int p = 0; p < P; p++) w[p][j] = fma(-v[p], dot, w[p][j]);
+    }
+  }
+}
+
+// One iteration of the direct kernel: U points of one thread.  FULL: every one of them exists (no predication at all).
+template <bool PIV, int M2, int U, bool ABOT, bool FULL>
+__device__ __forceinline__ void angular_direct_step(double (&T)[Tri<M2>::N], unsigned p0, unsigned sweep, unsigned nb, unsigned ld2,
+                                                    const double2* A2, double2* packed2, double* __restrict__ tau_out,
+                                                    int* __restrict__ perm_out, const double2* __restrict__ J2v,
+                                                    const double2* __restrict__ b2, double* __restrict__ atop,
+                                                    double* __restrict__ y1, double* __restrict__ abot, uint64_t pol_in,
+                                                    uint64_t pol_out) {
+  constexpr int W = M2 + 1;
+  const double2 zero2 = make_double2(0.0, 0.0);
+  double2 av[U], cv[U][W];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const unsigned p = p0 + u * sweep;
+    const bool live = FULL || p < nb;
+    av[u] = !live ? zero2 : kAngHint ? ld_global_hint(A2 + p, pol_in) : A2[p];
+#pragma unroll
+    for (int j = 0; j < M2; j++) cv[u][j] = !live ? zero2 : kAngHint ? ld_global_nc_hint(J2v + (j * ld2 + p), pol_in) : __ldg(J2v + (j * ld2 + p));
+    cv[u][M2] = !(live && b2) ? zero2 : kAngHint ? ld_global_nc_hint(b2 + p, pol_in) : __ldg(b2 + p);
+  }
+  double w[U][W];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const unsigned p = p0 + u * sweep;
+    if (FULL || p < nb) {
+      double a[2] = {av[u].x, av[u].y}, tau[1], inv_diag[1], dummy[2];
+      int perm[1];
+      BlockQR<2, 1, PIV, false>::run(a, tau, inv_diag, perm, dummy);
+      if (kAngHint) {
+        st_global_hint(packed2 + p, make_double2(a[0], a[1]), pol_out);
+        st_global_hint(tau_out + p, tau[0], pol_out);
+      } else {
+        packed2[p] = make_double2(a[0], a[1]);
+        tau_out[p] = tau[0];
+      }
+      if (PIV) perm_out[p] = (int)p;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        double col[2] = {cv[u][j].x, cv[u][j].y};
+        apply_qt_chain<2, 1>(a, tau, col);
+        double* top = (j < M2) ? atop + (j * nb + p) : y1 + p;
+        if (kAngHint) st_global_hint(top, col[0], pol_out);
+        else *top = col[0];
+        w[u][j] = col[1];
+        if (ABOT) abot[j * nb + p] = col[1];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; j++) w[u][j] = 0.0;
+    }
+  }
+#ifdef QRK_ANG_FOLD_SPLIT
+  fold_rows<M2, U>(T, w);
+#else
+  fold_rows_fused<M2, U>(T, w);
+#endif
+}
+
+// 32-bit point indices: the dispatcher guarantees (M2 + 1) * max(nb, ldj / 2) < 2^32.
+template <bool PIV, int M2, int TPB, int U, int MINB, bool ABOT>
+__global__ void __launch_bounds__(TPB, MINB)
+angular_factor_direct_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, int* __restrict__ perm_out,
+                             const double* __restrict__ J2, long long ldj, const double* __restrict__ b,
+                             double* __restrict__ atop, double* __restrict__ y1, double* __restrict__ abot,
+                             double* __restrict__ partials, long long nb64) {
+  __shared__ double sTri[(TPB / 32) * Tri<M2>::N];
+  double T[Tri<M2>::N];
+#pragma unroll
+  for (int i = 0; i < Tri<M2>::N; i++) T[i] = 0.0;
+  const unsigned nb = (unsigned)nb64, ld2 = (unsigned)(ldj >> 1), sweep = gridDim.x * TPB;
+  const uint64_t pol_in = kAngHint ? l2_policy_evict_first() : 0, pol_out = kAngHint ? l2_policy_evict_last() : 0;
+  const double2* A2 = reinterpret_cast<const double2*>(A_in);
+  double2* packed2 = reinterpret_cast<double2*>(packed);
+  const double2* J2v = reinterpret_cast<const double2*>(J2);
+  const double2* b2 = reinterpret_cast<const double2*>(b);
+  unsigned p0 = blockIdx.x * TPB + threadIdx.x;
+  for (; p0 + (U - 1) * sweep < nb; p0 += sweep * U)
+    angular_direct_step<PIV, M2, U, ABOT, true>(T, p0, sweep, nb, ld2, A2, packed2, tau_out, perm_out, J2v, b2, atop, y1, abot, pol_in, pol_out);
+  if (p0 < nb)
+    angular_direct_step<PIV, M2, U, ABOT, false>(T, p0, sweep, nb, ld2, A2, packed2, tau_out, perm_out, J2v, b2, atop, y1, abot, pol_in, pol_out);
+  cta_merge_tri<M2, TPB / 32>(T, sTri);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)blockIdx.x * Tri<M2>::N + i] = T[i];
   }
 }
 
@@ -454,6 +606,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
     }
   }
   cta_merge_tri<M2, TPB / 32>(T, scratch);
+  bool poisoned = false;
   if constexpr (XCHG) {                          // mode 2 (a separate instantiation: the single-GPU root keeps its code)
     // ---- this GPU's triangle -> every rank's buffer (own included), then the flag; wait for all G flags
     const unsigned long long seq = *xc.seq + 1;               // the same on every rank: every rank runs the same sequence of steps
@@ -497,6 +650,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
       const double poison = __longlong_as_double(0x7ff8000000000000ll);
 #pragma unroll
       for (int i = 0; i < N; i++) T[i] = poison;
+      poisoned = true;
     }
   }
   if (threadIdx.x != 0) return;
@@ -544,6 +698,10 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
     for (int k = j + 1; k < M2; k++) s = fma(-a[k * M2 + j], y[k], s);
     y[j] = (j < rank) ? s * inv_diag[j] : 0.0;
   }
+  if (poisoned) {       // a NaN triangle has rank 0 under the comparison above, which would zero y: keep the poison visible in x2 / x1
+#pragma unroll
+    for (int j = 0; j < M2; j++) y[j] = __longlong_as_double(0x7ff8000000000000ll);
+  }
 #pragma unroll
   for (int j = 0; j < M2; j++) root[M2 * M2 + M2 + j] = y[j];
 #pragma unroll
@@ -565,29 +723,49 @@ angular_backsolve_kernel(const double* __restrict__ packed, const int* __restric
   double* sA = smem;
   const int t = threadIdx.x;
   const long long m1 = nb * C;
-  // launched as a programmatic dependent of the root kernel (which triggers at its start): the launch latency of this grid
-  // overlaps the root; nothing is read before the root has completed
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  double x2[M2];
-#pragma unroll
-  for (int j = 0; j < M2; j++) x2[j] = root[M2 * M2 + 2 * M2 + j];
+  // Launched as a programmatic dependent of the root kernel (which triggers at its start): the CTAs that fit on the device
+  // become resident while the root runs.  packed / atop / y1 are outputs of K1, which completed before the root started, so
+  // they are fetched BEFORE the dependency wait and overlap the root's serial chain; only x2 (the root's output) is read
+  // after it.  (K1 wrote them with evict_last: they are L2 hits.)
   const long long tile0 = (long long)blockIdx.x * TPB;
   const int count = (int)((nb - tile0 < TPB) ? (nb - tile0) : TPB);
-  if (blockIdx.x == 0 && t < M2) x[m1 + t] = root[M2 * M2 + 2 * M2 + t];
+#ifdef QRK_ANG_K3_LATE
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   stage_in_async<R * C, SA, TPB>(sA, packed + tile0 * (R * C), count);
   cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  if (t >= count) return;
   const long long blk = tile0 + t;
-  double a[R * C], y[R];
-  load_group<R * C>(a, sA + t * SA);
+  const bool live = t < count;
+  double y[R], at[M2][C];
 #pragma unroll
-  for (int k = 0; k < C; k++) y[k] = __ldg(y1 + blk * C + k);
+  for (int k = 0; k < C; k++) y[k] = live ? __ldg(y1 + blk * C + k) : 0.0;
 #pragma unroll
   for (int j = 0; j < M2; j++) {
 #pragma unroll
-    for (int k = 0; k < C; k++) y[k] = fma(-__ldg(atop + (long long)j * m1 + blk * C + k), x2[j], y[k]);
+    for (int k = 0; k < C; k++) at[j][k] = live ? __ldg(atop + (long long)j * m1 + blk * C + k) : 0.0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  double a[R * C];
+  if (live) load_group<R * C>(a, sA + t * SA);
+#ifndef QRK_ANG_K3_LATE
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  // x2 is the root kernel's output: loads pinned behind the wait (volatile asm; a plain load through the __restrict__ const
+  // pointer may be hoisted above it), through L1 so that the 5 words cost one L2 request per SM rather than one per warp
+  double x2[M2];
+#pragma unroll
+  for (int j = 0; j < M2; j++) asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(x2[j]) : "l"(root + M2 * M2 + 2 * M2 + j) : "memory");
+  if (blockIdx.x == 0 && t < M2) {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(root + M2 * M2 + 2 * M2 + t) : "memory");
+    x[m1 + t] = v;
+  }
+  if (!live) return;
+#pragma unroll
+  for (int j = 0; j < M2; j++) {
+#pragma unroll
+    for (int k = 0; k < C; k++) y[k] = fma(-at[j][k], x2[j], y[k]);
   }
   double inv_diag[C];
 #pragma unroll
@@ -597,6 +775,46 @@ angular_backsolve_kernel(const double* __restrict__ packed, const int* __restric
   for (int k = 0; k < C; k++) {
     const long long dst = PERM ? (long long)perm[blk * C + k] : blk * C + k;
     x[dst] = y[k];
+  }
+}
+
+// K3 for 2 x 1 blocks: x1_p = (y1_p - Atop_p x2) / R11_p.  PPT points per thread, all their loads (7 words a point, every
+// one an output of K1 and an L2 hit thanks to K1's evict_last stores) issued before the dependency wait, so that for the CTAs
+// resident while the root runs only the 5-word x2 fetch, 6 FMAs a point and the store of x1 remain behind it.  A grid of
+// nb / (TPB * PPT) CTAs instead of nb / TPB: the back substitution is no longer bounded by the CTA launch rate.
+template <int M2, int TPB, int PPT>
+__global__ void __launch_bounds__(TPB)
+angular_backsolve_direct_kernel(const double* __restrict__ packed, const double* __restrict__ atop, const double* __restrict__ y1,
+                                const double* root, double* __restrict__ x, long long nb) {
+  const long long base = (long long)blockIdx.x * (TPB * PPT) + threadIdx.x;
+  double r11[PPT], y[PPT], at[PPT][M2];
+#pragma unroll
+  for (int i = 0; i < PPT; i++) {
+    const long long p = base + (long long)i * TPB;
+    const bool live = p < nb;
+    r11[i] = live ? __ldg(packed + 2 * p) : 1.0;
+    y[i] = live ? __ldg(y1 + p) : 0.0;
+#pragma unroll
+    for (int j = 0; j < M2; j++) at[i][j] = live ? __ldg(atop + (long long)j * nb + p) : 0.0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  double x2[M2];
+#pragma unroll
+  for (int j = 0; j < M2; j++) asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(x2[j]) : "l"(root + M2 * M2 + 2 * M2 + j) : "memory");
+  if (blockIdx.x == 0 && threadIdx.x < M2) {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(root + M2 * M2 + 2 * M2 + threadIdx.x) : "memory");
+    x[nb + threadIdx.x] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < PPT; i++) {
+    const long long p = base + (long long)i * TPB;
+    if (p < nb) {
+      double s = y[i];
+#pragma unroll
+      for (int j = 0; j < M2; j++) s = fma(-at[i][j], x2[j], s);
+      x[p] = s * fast_rcp(r11[i]);
+    }
   }
 }
 

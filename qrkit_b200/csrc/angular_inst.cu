@@ -1,4 +1,6 @@
 // angular_inst.cu — instantiations of the block-angular kernels for ONE border width (-DQRK_M2=k).
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include "angular.cuh"
 #include "angular_dispatch.hpp"
@@ -49,14 +51,69 @@ cudaError_t opt_in(K kernel, size_t smem) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// 2 x 1 blocks: the direct (unstaged) kernel when every slice is a 16-byte aligned vector
+// U points per fold and CTAs per SM: U = 4 at 168 registers (3 CTAs of 128 threads) is the measured best for the 5-column
+// border of configs 1 / 3; wider borders carry a bigger triangle and more border words per point, so they take fewer points
+// per fold to stay free of spills (ptxas -v: M2 = 6: U = 3, M2 = 7, 8: U = 2 with 2 CTAs)
+#ifndef QRK_ANG_DIRECT_U
+#define QRK_ANG_DIRECT_U (QRK_M2 <= 5 ? 4 : QRK_M2 == 6 ? 3 : 2)
+#endif
+#ifndef QRK_ANG_DIRECT_MINB
+#define QRK_ANG_DIRECT_MINB (QRK_M2 <= 6 ? 3 : 2)
+#endif
+constexpr int kDirectU = QRK_ANG_DIRECT_U, kDirectMinB = QRK_ANG_DIRECT_MINB;
+#ifndef QRK_ANG_K3_TPB
+#define QRK_ANG_K3_TPB 256
+#endif
+#ifndef QRK_ANG_K3_PPT
+#define QRK_ANG_K3_PPT 4
+#endif
+constexpr int kK3Tpb = QRK_ANG_K3_TPB, kK3Ppt = QRK_ANG_K3_PPT;
+inline bool direct_ok(const AngularArgs& a) {
+  static const bool off = std::getenv("QRK_ANG_STAGED") != nullptr;     // A/B switch: force the staged kernel
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const long long span = (long long)(M2 + 1) * std::max<long long>(a.nb, a.ldj / 2) + 8ll * 148 * 16 * TPB;    // + a sweep of headroom for the loop counter
+  return !off && a.r == 2 && a.c == 1 && al16(a.A_in) && al16(a.packed) && al16(a.J2) && al16(a.b) && (a.ldj % 2 == 0) && span < (1ll << 32);
+}
+
+template <bool PIV, bool ABOT>
+cudaError_t factor_2x1(const AngularArgs& a, cudaStream_t s) {
+  angular_factor_direct_kernel<PIV, M2, TPB, kDirectU, kDirectMinB, ABOT><<<a.grid, TPB, 0, s>>>(
+      a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
+  return cudaGetLastError();
+}
+
 template <int R, int C, bool PIV>
 cudaError_t factor_t(const AngularArgs& a, cudaStream_t s) {
   using G = Cfg<R, C>;
+  if constexpr (R == 2 && C == 1) {
+    if (direct_ok(a)) return a.abot ? factor_2x1<PIV, true>(a, s) : factor_2x1<PIV, false>(a, s);
+  }
   auto kernel = angular_factor_kernel<R, C, PIV, M2, TPB, G::U, G::NSTAGE, G::MINB>;
   const size_t smem = G::Smem::bytes;
   cudaError_t e = opt_in(kernel, smem);
   if (e != cudaSuccess) return e;
-  kernel<<<a.grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
+  int grid = a.grid;
+  if constexpr (R == 2 && C == 1) {
+    // a.grid was sized for the direct kernel's residency: the staged kernel runs one wave of ITS resident CTAs and the
+    // partial triangles it does not produce are zero (a zero triangle is the identity of the TSQR merge)
+    static int resident = 0;
+    if (resident == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, smem);
+      if (e != cudaSuccess) return e;
+      resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const long long ntiles = (a.nb + G::Smem::TILE - 1) / G::Smem::TILE;
+    grid = (int)std::max<long long>(1, std::min<long long>(std::min(grid, resident), ntiles));
+    if (grid < a.grid) {
+      e = cudaMemsetAsync(a.partials + (size_t)grid * Tri<M2>::N, 0, (size_t)(a.grid - grid) * Tri<M2>::N * sizeof(double), s);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  kernel<<<grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
   return cudaGetLastError();
 }
 
@@ -72,6 +129,12 @@ cudaError_t max_grid_t(int* grid) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, smem);
   if (e != cudaSuccess) return e;
+  if constexpr (R == 2 && C == 1) {       // the direct kernel holds more CTAs per SM; the staged one copes with any grid
+    int per_sm_direct = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_direct, angular_factor_direct_kernel<PIV, M2, TPB, kDirectU, kDirectMinB, false>, TPB, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm_direct > per_sm) per_sm = per_sm_direct;
+  }
   *grid = sms * (per_sm > 0 ? per_sm : 1);
   return cudaSuccess;
 }
@@ -102,6 +165,16 @@ cudaError_t backsolve_t(const AngularArgs& a, cudaStream_t s) {
   cfg.numAttrs = pdl ? 1 : 0;
   const double* packed = a.packed; const int* perm = a.perm; const double* atop = a.atop; const double* y1 = a.y1; const double* root = a.root;
   double* x = a.x; long long nb = a.nb;
+  if constexpr (R == 2 && C == 1) {        // (a 1-column block has the identity permutation: PERM is moot)
+    static const bool old_k3 = std::getenv("QRK_ANG_K3_TILED") != nullptr;     // A/B switch: the generic one-point-per-thread kernel
+    if (!old_k3) {
+      constexpr int T3 = kK3Tpb, P3 = kK3Ppt;
+      cfg.gridDim = dim3((unsigned)((a.nb + T3 * P3 - 1) / (T3 * P3)));
+      cfg.blockDim = dim3(T3);
+      cfg.dynamicSmemBytes = 0;
+      return cudaLaunchKernelEx(&cfg, angular_backsolve_direct_kernel<M2, T3, P3>, packed, atop, y1, root, x, nb);
+    }
+  }
   if (a.piv) return cudaLaunchKernelEx(&cfg, angular_backsolve_kernel<R, C, M2, true, TPB>, packed, perm, atop, y1, root, x, nb);
   return cudaLaunchKernelEx(&cfg, angular_backsolve_kernel<R, C, M2, false, TPB>, packed, perm, atop, y1, root, x, nb);
 }
@@ -114,6 +187,7 @@ bool shape_ok(int r, int c) {
 }
 
 int tile_blocks(int r, int c) {
+  if (r == 2 && c == 1) return TPB;       // direct kernel: a CTA sweep covers TPB points
 #define X(R_, C_) if (r == R_ && c == C_) return Cfg<R_, C_>::U * TPB;
   QRK_ANGULAR_SHAPES(X)
 #undef X
@@ -166,9 +240,18 @@ cudaError_t preload_t(bool piv) {
   cudaFuncAttributes fa;
   cudaError_t e = piv ? cudaFuncGetAttributes(&fa, angular_factor_kernel<R, C, true, M2, TPB, G::U, G::NSTAGE, G::MINB>)
                       : cudaFuncGetAttributes(&fa, angular_factor_kernel<R, C, false, M2, TPB, G::U, G::NSTAGE, G::MINB>);
+  if constexpr (R == 2 && C == 1) {
+    if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_factor_direct_kernel<true, M2, TPB, kDirectU, kDirectMinB, false>)
+                                  : cudaFuncGetAttributes(&fa, angular_factor_direct_kernel<false, M2, TPB, kDirectU, kDirectMinB, false>);
+    if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_factor_direct_kernel<true, M2, TPB, kDirectU, kDirectMinB, true>)
+                                  : cudaFuncGetAttributes(&fa, angular_factor_direct_kernel<false, M2, TPB, kDirectU, kDirectMinB, true>);
+  }
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>);
   if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, true, TPB>)
                                 : cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, false, TPB>);
+  if constexpr (R == 2 && C == 1) {
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_backsolve_direct_kernel<M2, kK3Tpb, kK3Ppt>);
+  }
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, false>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, true>);
   return e;

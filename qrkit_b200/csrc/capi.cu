@@ -2136,6 +2136,17 @@ int qrk_angular_p2p_attach(qrk_handle_t h, void* const* peer_buffers, int32_t wo
   if (!h->d_xchg_err) { QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg_err, sizeof(int))); QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_err, 0, sizeof(int))); }
   QRK_TRY_CUDA(h, cudaMemcpy(h->d_xchg_peers, peer_buffers, (size_t)world_size * sizeof(double*), cudaMemcpyHostToDevice));
   QRK_TRY_CUDA(h, h->avt->preload(h->ur, h->uc, h->desc.pivoting == QRK_PIVOT_COLPIV));   // no lazy load behind a spinning kernel
+  // ... and no lazy ALLOCATION either: cudaMalloc / cudaFree wait for every running kernel of the device, and a root kernel
+  // that spins for a peer never finishes while that peer's thread sits in cudaMalloc (two ranks on one device: a stall
+  // until the timeout).  Everything the host- and device-memspace calls of this handle allocate on first use is set up here.
+  {
+    int st = h->d_values ? QRK_STATUS_OK : ensure_own_values(h);     // (adopted caller storage stays)
+    if (st == QRK_STATUS_OK) st = ensure_buffer(h, h->d_b, h->cap_b, (size_t)h->n_rows);
+    if (st == QRK_STATUS_OK) st = ensure_buffer(h, h->d_x, h->cap_x, (size_t)h->n_cols);
+    if (st == QRK_STATUS_OK) st = ensure_buffer(h, h->d_border_own, h->cap_border, (size_t)h->n_rows * h->m2);
+    if (st != QRK_STATUS_OK) return st;
+    if (!h->d_abot) QRK_TRY_CUDA(h, cudaMalloc(&h->d_abot, std::max<long long>(1, (h->n_rows - h->sum_cols) * (long long)(h->m2 + 1)) * sizeof(double)));
+  }
   QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_err, 0, sizeof(int)));
   if (!h->d_xchg_seq) QRK_TRY_CUDA(h, cudaMalloc(&h->d_xchg_seq, sizeof(unsigned long long)));
   QRK_TRY_CUDA(h, cudaMemset(h->d_xchg_seq, 0, sizeof(unsigned long long)));

@@ -32,6 +32,42 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
+// L2 eviction-priority hints (126 MB L2): streaming inputs are read with evict_first so that they do not displace the
+// producer kernel's outputs, which are written with evict_last and are then still L2-resident when the consumer kernel of
+// the same step reads them back (block-angular K1 -> K3).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async8_hint(void* smem, const void* gmem, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_hint(double* g, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(g), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_hint(double2* g, double2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(g), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 ld_global_nc_hint(const double2* g, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(g), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ld_global_hint(const double2* g, uint64_t pol) {     // coherent path: the buffer may be written by this kernel
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(g), "l"(pol) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int K>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
@@ -59,6 +95,44 @@ __device__ __forceinline__ void stage_in_async(double* s, const double* __restri
       if (V == 2) cp_async16(s + grp * S + within, g + d);   // count*N is even whenever N is
       else cp_async8(s + grp * S + within, g + d);
     }
+  }
+}
+
+// as stage_in_async, every copy carrying an L2 cache policy
+template <int N, int S, int TPB, int TILE = TPB>
+__device__ __forceinline__ void stage_in_async_hint(double* s, const double* __restrict__ g, int count, uint64_t pol) {
+  constexpr int V = Group<N>::vec;
+  if (count == TILE) {
+    constexpr int total = TILE * N / V;
+#pragma unroll
+    for (int q0 = 0; q0 < total; q0 += TPB) {
+      const int q = q0 + threadIdx.x;
+      if (total % TPB == 0 || q < total) {
+        const int d = q * V, grp = d / N, within = d - grp * N;
+        if (V == 2) cp_async16_hint(s + grp * S + within, g + d, pol);
+        else cp_async8_hint(s + grp * S + within, g + d, pol);
+      }
+    }
+  } else {
+    const int total = count * N / V + ((count * N) % V ? 1 : 0);
+    for (int q = threadIdx.x; q < total; q += TPB) {
+      const int d = q * V, grp = d / N, within = d - grp * N;
+      if (V == 2) cp_async16_hint(s + grp * S + within, g + d, pol);
+      else cp_async8_hint(s + grp * S + within, g + d, pol);
+    }
+  }
+}
+
+// as stage_out, every store carrying an L2 cache policy
+template <int N, int S, int TPB, int TILE = TPB>
+__device__ __forceinline__ void stage_out_hint(double* __restrict__ g, const double* s, int count, uint64_t pol) {
+  constexpr int V = Group<N>::vec;
+  const int total = (count == TILE) ? TILE * N / V : count * N / V;
+#pragma unroll 4
+  for (int q = threadIdx.x; q < total; q += TPB) {
+    const int d = q * V, grp = d / N, within = d - grp * N;
+    if (V == 2) st_global_hint(reinterpret_cast<double2*>(g + d), *reinterpret_cast<const double2*>(s + grp * S + within), pol);
+    else st_global_hint(g + d, s[grp * S + within], pol);
   }
 }
 

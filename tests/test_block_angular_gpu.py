@@ -2,6 +2,8 @@
 restatement of BlockAngularSparseQR<BlockDiagonalSparseQR, ColPivHouseholderQR<MatrixXd>> (BlockAngularSparseQR.h:459-514).
 Inputs: the ellipse-fit Jacobian of bench/bench_sparse_qr_extra.cpp:79-114 (BASELINE configs 1 and 3) and random blocks
 with a dense random border (the shape of test/test-qrkit.cpp:135-165)."""
+import time
+
 import numpy as np
 import pytest
 
@@ -503,3 +505,68 @@ def test_thin_sparse_right_solver_rank_deficient_border(qk, oracle):
     assert rel(x, ref.solve(b)) <= TOL_X
     with pytest.raises(qk.QrkError):                            # stored-factor products are refused once columns were deferred
         s.solve(b)
+
+
+def test_fused_peer_exchange_timeout_poisons_and_reports(qk, oracle):
+    """A peer that never delivers its triangle: the waiting root kernel gives up after qrk_angular_p2p_set_timeout seconds,
+    x comes back NaN (never a plausible-looking partial solve), the synchronous call returns QRK_STATUS_PEER_TIMEOUT and
+    qrk_angular_p2p_status reports it; a fresh attach clears the condition and the same handles then solve correctly."""
+    import ctypes as C
+    import torch
+    from qrkit_b200 import capi
+    from qrkit_b200.capi import QRK_DEVICE, QRK_HOST, QrkDesc, check
+    L = capi.lib()
+    n, world = 2000, 2
+    per = n // world
+    J1, J2, rhs = ellipse_problem(n)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(n, 2), bc=np.full(n, 1), values=J1, left_colpiv=False, right_kind=0)
+    x_ref = ref.solve(rhs)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    hs, bufs, xbufs = [], [], []
+    for g in range(world):
+        rows = slice(2 * g * per, 2 * (g + 1) * per)
+        dJ1, dJ2 = dev(J1[rows]), dev(J2[rows, :].T)
+        d = QrkDesc()
+        d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, per, 2, 1, 0, 5
+        h = C.c_void_p()
+        check(L.qrk_create(C.byref(d), C.byref(h)))
+        check(L.qrk_angular_set_world(h, world), h)
+        check(L.qrk_set_border(h, vp(dJ2), 2 * per, QRK_DEVICE), h)
+        check(L.qrk_set_blocks(h, vp(dJ1), QRK_DEVICE), h)
+        xb, nb_ = C.c_void_p(), C.c_int64()
+        check(L.qrk_angular_xchg_buffer(h, C.byref(xb), C.byref(nb_)), h)
+        hs.append(h); bufs.append((dJ1, dJ2)); xbufs.append(xb.value)
+    peers = (C.c_void_p * world)(*xbufs)
+    for g, h in enumerate(hs):
+        check(L.qrk_angular_p2p_attach(h, peers, world, g), h)
+    assert L.qrk_angular_p2p_set_timeout(hs[0], C.c_double(0.0)) == capi.QRK_STATUS_INVALID_ARGUMENT
+    check(L.qrk_angular_p2p_set_timeout(hs[0], C.c_double(0.05)), hs[0])
+
+    # rank 1 never runs: rank 0 must come back within the timeout, not hang
+    hb = np.ascontiguousarray(rhs[:2 * per]); hx = np.zeros(per + 5); hv = np.ascontiguousarray(J1[:2 * per])
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    t0 = time.perf_counter()
+    st = L.qrk_compute_solve(hs[0], hp(hv), hp(hb), hp(hx), QRK_HOST)
+    assert time.perf_counter() - t0 < 5.0
+    assert st == capi.QRK_STATUS_PEER_TIMEOUT, (st, L.qrk_last_error(hs[0]))
+    assert np.isnan(hx[per:]).all()
+    to = C.c_int32(0)
+    check(L.qrk_angular_p2p_status(hs[0], C.byref(to)), hs[0])
+    assert to.value != 0
+
+    # recovery: re-attach both ranks (resets flags, parities and the error word), then a normal two-rank step
+    for g, h in enumerate(hs):
+        check(L.qrk_angular_p2p_attach(h, peers, world, g), h)
+    dbs = [dev(rhs[2 * g * per:2 * (g + 1) * per]) for g in range(world)]
+    dxs = [torch.zeros(per + 5, dtype=torch.float64, device="cuda") for _ in range(world)]
+    for g, h in enumerate(hs):
+        check(L.qrk_compute_solve(h, vp(bufs[g][0]), vp(dbs[g]), vp(dxs[g]), QRK_DEVICE), h)
+    for g, h in enumerate(hs):
+        check(L.qrk_angular_p2p_status(h, C.byref(to)), h)
+        assert to.value == 0
+        xg = dxs[g].cpu().numpy()
+        assert rel(xg[:per], x_ref[g * per:(g + 1) * per]) <= 1e-9
+        assert rel(xg[per:], x_ref[n:]) <= 1e-9
+    for h in hs:
+        L.qrk_destroy(h)

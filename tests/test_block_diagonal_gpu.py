@@ -388,3 +388,47 @@ def test_config5_full_size_properties(qk):
             assert np.array_equal(perm[c0:c1].cpu().numpy() - c0, ref.colsPermutation())
             assert rel(x[c0:c1].cpu().numpy(), ref.solve(b_ls[r0:r1].cpu().numpy())) <= TOL_X
         L.qrk_destroy(h)
+
+
+def test_host_alloc_is_pinned_and_feeds_the_host_path(qk, oracle):
+    """qrk_host_alloc hands out page-locked memory (cudaHostGetFlags succeeds on it) that the host-memspace one-call path
+    accepts like any host pointer; the result equals the run from pageable numpy arrays bit for bit.  qrk_bind_host_thread_to_device
+    reports the GPU's NUMA node or -1 where the platform hides the topology -- both are valid, an error status is not."""
+    import ctypes as C
+    import os
+    from qrkit_b200 import capi
+    L = capi.lib()
+    nb, r, c = 4096, 8, 4
+    vals = uniform_blocks(nb, r, c); b = vector(nb * r, seed=77)
+    s = qk.BlockDiagonalSparseQR(pivoting=0)
+    x_pageable = s.compute_solve(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), b).copy()
+
+    saved = os.sched_getaffinity(0)
+    try:
+        node, bound = C.c_int32(-7), C.c_int32(-7)
+        capi.check(L.qrk_bind_host_thread_to_device(0, C.byref(node), C.byref(bound)))
+        assert node.value >= -1 and bound.value >= 0
+        ptrs = []
+        for nbytes in (vals.nbytes, b.nbytes, nb * c * 8):
+            p = C.c_void_p()
+            capi.check(L.qrk_host_alloc(C.byref(p), nbytes, 0))
+            assert p.value
+            ptrs.append(p)
+        rt = C.CDLL("libcudart.so.12")                        # page-locked: cudaHostGetFlags only succeeds on registered memory
+        rt.cudaHostGetFlags.argtypes = [C.POINTER(C.c_uint), C.c_void_p]
+        for p in ptrs:
+            flags = C.c_uint(0)
+            assert rt.cudaHostGetFlags(C.byref(flags), p) == 0
+        assert rt.cudaHostGetFlags(C.byref(flags), vals.ctypes.data_as(C.c_void_p)) != 0      # a pageable array is not
+        hv = np.ctypeslib.as_array(C.cast(ptrs[0], C.POINTER(C.c_double)), shape=(vals.size,))
+        hb = np.ctypeslib.as_array(C.cast(ptrs[1], C.POINTER(C.c_double)), shape=(b.size,))
+        hx = np.ctypeslib.as_array(C.cast(ptrs[2], C.POINTER(C.c_double)), shape=(nb * c,))
+        hv[:] = vals; hb[:] = b; hx[:] = 0
+        capi.check(L.qrk_compute_solve(s._h, ptrs[0], ptrs[1], ptrs[2], capi.QRK_HOST), s._h)
+        assert np.array_equal(hx, x_pageable)
+        del hv, hb, hx
+        for p in ptrs:
+            capi.check(L.qrk_host_free(p))
+        assert L.qrk_host_alloc(None, 8, 0) == capi.QRK_STATUS_INVALID_ARGUMENT
+    finally:
+        os.sched_setaffinity(0, saved)
