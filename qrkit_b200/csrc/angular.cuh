@@ -429,7 +429,13 @@ __device__ __forceinline__ void angular_direct_step(double (&T)[Tri<M2>::N], uns
       for (int j = 0; j < W; j++) w[u][j] = 0.0;
     }
   }
-#ifdef QRK_ANG_FOLD_SPLIT
+#if defined(QRK_ANG_NOFOLD)
+  // measurement only (wrong results): the memory-side floor of the kernel, with the fold's dependent chains removed
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int j = 0; j < W; j++) T[j] += w[u][j];
+#elif defined(QRK_ANG_FOLD_SPLIT)
   fold_rows<M2, U>(T, w);
 #else
   fold_rows_fused<M2, U>(T, w);
@@ -578,6 +584,13 @@ __device__ __forceinline__ void merge_triangle_list(const double* tris, int coun
   cta_merge_tri<M2, TPB / 32>(T, scratch);
 }
 
+#ifdef QRK_ROOT_TRACE
+__device__ long long g_root_trace[16];
+#define QRK_ROOT_CLK(i) do { if (threadIdx.x == 0) g_root_trace[i] = clock64(); } while (0)
+#else
+#define QRK_ROOT_CLK(i) do { } while (0)
+#endif
+
 template <int M2, int TPB, bool XCHG>
 __global__ void __launch_bounds__(TPB)
 angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
@@ -587,6 +600,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   constexpr int N = TR::N;
   __shared__ double scratch[(TPB / 32) * N];
   asm volatile("griddepcontrol.launch_dependents;");   // the back-substitution grid may be scheduled now (it waits for this grid)
+  QRK_ROOT_CLK(0);
   double T[N];
 #pragma unroll
   for (int i = 0; i < N; i++) T[i] = 0.0;
@@ -605,7 +619,9 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
       fold_tri<M2>(T, S);
     }
   }
+  QRK_ROOT_CLK(1);
   cta_merge_tri<M2, TPB / 32>(T, scratch);
+  QRK_ROOT_CLK(2);
   bool poisoned = false;
   if constexpr (XCHG) {                          // mode 2 (a separate instantiation: the single-GPU root keeps its code)
     // ---- this GPU's triangle -> every rank's buffer (own included), then the flag; wait for all G flags
@@ -668,7 +684,9 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
     for (int i = 0; i < M2; i++) a[j * M2 + i] = (i <= j) ? T[TR::idx(i, j)] : 0.0;
     z[j] = T[TR::idx(j, M2)];
   }
+  QRK_ROOT_CLK(3);
   BlockQR<M2, M2, true, true>::run(a, tau, inv_diag, perm, z);
+  QRK_ROOT_CLK(4);
   // rank as Eigen's ColPivHouseholderQR::rank(): |R_ii| > |maxpivot| * eps * diagonalSize
   double maxpivot = 0.0;
 #pragma unroll
@@ -708,6 +726,7 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   for (int j = 0; j < M2; j++) {
     root[M2 * M2 + 2 * M2 + perm[j]] = y[j];   // x2[P2[j]] = y_j (dest = P_c * y, :222)
   }
+  QRK_ROOT_CLK(5);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -778,42 +797,87 @@ angular_backsolve_kernel(const double* __restrict__ packed, const int* __restric
   }
 }
 
-// K3 for 2 x 1 blocks: x1_p = (y1_p - Atop_p x2) / R11_p.  PPT points per thread, all their loads (7 words a point, every
-// one an output of K1 and an L2 hit thanks to K1's evict_last stores) issued before the dependency wait, so that for the CTAs
-// resident while the root runs only the 5-word x2 fetch, 6 FMAs a point and the store of x1 remain behind it.  A grid of
-// nb / (TPB * PPT) CTAs instead of nb / TPB: the back substitution is no longer bounded by the CTA launch rate.
-template <int M2, int TPB, int PPT>
+// K3 for 2 x 1 blocks: x1_p = (y1_p - Atop_p x2) / R11_p.  A programmatic dependent of the root: its CTAs become resident
+// while the root's serial chain runs, and everything they need except x2 is an output of K1 (complete before the root
+// started; L2 hits thanks to K1's evict_last stores).  One wave of CTAs therefore pulls its points ON CHIP before the
+// dependency wait -- PR points per thread into registers and PS more into private shared-memory slots (cp.async; each
+// thread reads back only what it copied, so no barrier) -- which holds ~90 % of a 1M-point problem (registers alone: 45 %);
+// behind the wait only the 5-word x2 fetch, 6 FMAs a point and the store of x1 remain.  Points beyond the wave's capacity are
+// swept afterwards.  (The one-point-per-thread kernel was bounded by the CTA launch rate: 7813 CTAs.)
+template <int M2, int TPB, int PR, int PS>
 __global__ void __launch_bounds__(TPB)
 angular_backsolve_direct_kernel(const double* __restrict__ packed, const double* __restrict__ atop, const double* __restrict__ y1,
-                                const double* root, double* __restrict__ x, long long nb) {
-  const long long base = (long long)blockIdx.x * (TPB * PPT) + threadIdx.x;
-  double r11[PPT], y[PPT], at[PPT][M2];
+                                const double* root, double* __restrict__ x, long long nb64) {
+  constexpr int NW = M2 + 2;                                  // words a point needs: R11, y1, Atop row
+  extern __shared__ __align__(16) double slots[];             // [PS][NW][TPB]
+  const unsigned nb = (unsigned)nb64, t = threadIdx.x;
+  constexpr unsigned BATCH = TPB * (PR + PS);
+  const unsigned base = blockIdx.x * BATCH + t;
+  // shared-memory points of the first batch
 #pragma unroll
-  for (int i = 0; i < PPT; i++) {
-    const long long p = base + (long long)i * TPB;
+  for (int i = 0; i < PS; i++) {
+    const unsigned p = base + (PR + i) * TPB;
+    if (p < nb) {
+      cp_async8(slots + (i * NW + 0) * TPB + t, packed + 2 * (size_t)p);
+      cp_async8(slots + (i * NW + 1) * TPB + t, y1 + p);
+#pragma unroll
+      for (int j = 0; j < M2; j++) cp_async8(slots + (i * NW + 2 + j) * TPB + t, atop + ((size_t)j * nb + p));
+    }
+  }
+  cp_async_commit();
+  // register points of the first batch
+  double r11[PR], y[PR], at[PR][M2];
+#pragma unroll
+  for (int i = 0; i < PR; i++) {
+    const unsigned p = base + i * TPB;
     const bool live = p < nb;
-    r11[i] = live ? __ldg(packed + 2 * p) : 1.0;
+    r11[i] = live ? __ldg(packed + 2 * (size_t)p) : 1.0;
     y[i] = live ? __ldg(y1 + p) : 0.0;
 #pragma unroll
-    for (int j = 0; j < M2; j++) at[i][j] = live ? __ldg(atop + (long long)j * nb + p) : 0.0;
+    for (int j = 0; j < M2; j++) at[i][j] = live ? __ldg(atop + ((size_t)j * nb + p)) : 0.0;
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // x2 is the root kernel's output: loads pinned behind the wait (volatile asm), through L1 (one L2 request per SM)
   double x2[M2];
 #pragma unroll
   for (int j = 0; j < M2; j++) asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(x2[j]) : "l"(root + M2 * M2 + 2 * M2 + j) : "memory");
-  if (blockIdx.x == 0 && threadIdx.x < M2) {
+  if (blockIdx.x == 0 && t < M2) {
     double v;
-    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(root + M2 * M2 + 2 * M2 + threadIdx.x) : "memory");
-    x[nb + threadIdx.x] = v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(root + M2 * M2 + 2 * M2 + t) : "memory");
+    x[nb + t] = v;
   }
 #pragma unroll
-  for (int i = 0; i < PPT; i++) {
-    const long long p = base + (long long)i * TPB;
+  for (int i = 0; i < PR; i++) {
+    const unsigned p = base + i * TPB;
     if (p < nb) {
       double s = y[i];
 #pragma unroll
       for (int j = 0; j < M2; j++) s = fma(-at[i][j], x2[j], s);
       x[p] = s * fast_rcp(r11[i]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < PS; i++) {
+    const unsigned p = base + (PR + i) * TPB;
+    if (p < nb) {
+      double s = slots[(i * NW + 1) * TPB + t];
+#pragma unroll
+      for (int j = 0; j < M2; j++) s = fma(-slots[(i * NW + 2 + j) * TPB + t], x2[j], s);
+      x[p] = s * fast_rcp(slots[(i * NW + 0) * TPB + t]);
+    }
+  }
+  // points beyond the first wave's capacity (grid capped at the resident CTAs): plain sweep
+  for (unsigned q0 = (gridDim.x + blockIdx.x) * BATCH; q0 < nb; q0 += gridDim.x * BATCH) {
+#pragma unroll
+    for (int i = 0; i < PR + PS; i++) {
+      const unsigned p = q0 + i * TPB + t;
+      if (p < nb) {
+        double s = __ldg(y1 + p);
+#pragma unroll
+        for (int j = 0; j < M2; j++) s = fma(-__ldg(atop + ((size_t)j * nb + p)), x2[j], s);
+        x[p] = s * fast_rcp(__ldg(packed + 2 * (size_t)p));
+      }
     }
   }
 }

@@ -65,10 +65,14 @@ constexpr int kDirectU = QRK_ANG_DIRECT_U, kDirectMinB = QRK_ANG_DIRECT_MINB;
 #ifndef QRK_ANG_K3_TPB
 #define QRK_ANG_K3_TPB 256
 #endif
-#ifndef QRK_ANG_K3_PPT
-#define QRK_ANG_K3_PPT 4
+#ifndef QRK_ANG_K3_PR
+#define QRK_ANG_K3_PR 4
 #endif
-constexpr int kK3Tpb = QRK_ANG_K3_TPB, kK3Ppt = QRK_ANG_K3_PPT;
+#ifndef QRK_ANG_K3_PS
+#define QRK_ANG_K3_PS 4
+#endif
+constexpr int kK3Tpb = QRK_ANG_K3_TPB, kK3Pr = QRK_ANG_K3_PR, kK3Ps = QRK_ANG_K3_PS;
+constexpr size_t kK3Smem = (size_t)kK3Ps * (M2 + 2) * kK3Tpb * sizeof(double);
 inline bool direct_ok(const AngularArgs& a) {
   static const bool off = std::getenv("QRK_ANG_STAGED") != nullptr;     // A/B switch: force the staged kernel
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
@@ -168,11 +172,23 @@ cudaError_t backsolve_t(const AngularArgs& a, cudaStream_t s) {
   if constexpr (R == 2 && C == 1) {        // (a 1-column block has the identity permutation: PERM is moot)
     static const bool old_k3 = std::getenv("QRK_ANG_K3_TILED") != nullptr;     // A/B switch: the generic one-point-per-thread kernel
     if (!old_k3) {
-      constexpr int T3 = kK3Tpb, P3 = kK3Ppt;
-      cfg.gridDim = dim3((unsigned)((a.nb + T3 * P3 - 1) / (T3 * P3)));
-      cfg.blockDim = dim3(T3);
-      cfg.dynamicSmemBytes = 0;
-      return cudaLaunchKernelEx(&cfg, angular_backsolve_direct_kernel<M2, T3, P3>, packed, atop, y1, root, x, nb);
+      auto k3 = angular_backsolve_direct_kernel<M2, kK3Tpb, kK3Pr, kK3Ps>;
+      cudaError_t e = opt_in(k3, kK3Smem);          // (a per-device attribute: every launch, like the other kernels)
+      if (e != cudaSuccess) return e;
+      static int resident = 0;                      // one wave: the CTAs that are resident together (see the kernel)
+      if (resident == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, kK3Tpb, kK3Smem);
+        if (e != cudaSuccess) return e;
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+      }
+      const long long batch = (long long)kK3Tpb * (kK3Pr + kK3Ps);
+      cfg.gridDim = dim3((unsigned)std::max<long long>(1, std::min<long long>((a.nb + batch - 1) / batch, resident)));
+      cfg.blockDim = dim3(kK3Tpb);
+      cfg.dynamicSmemBytes = kK3Smem;
+      return cudaLaunchKernelEx(&cfg, k3, packed, atop, y1, root, x, nb);
     }
   }
   if (a.piv) return cudaLaunchKernelEx(&cfg, angular_backsolve_kernel<R, C, M2, true, TPB>, packed, perm, atop, y1, root, x, nb);
@@ -250,7 +266,7 @@ cudaError_t preload_t(bool piv) {
   if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, true, TPB>)
                                 : cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, false, TPB>);
   if constexpr (R == 2 && C == 1) {
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_backsolve_direct_kernel<M2, kK3Tpb, kK3Ppt>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_backsolve_direct_kernel<M2, kK3Tpb, kK3Pr, kK3Ps>);
   }
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, false>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, true>);

@@ -169,16 +169,19 @@ __device__ __forceinline__ void wy_panel_step(double (&a)[MR][8], double* tau_ou
   double y0;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(nsq));
   const double hx = 0.5 * nsq, ac0 = fabs(c0);
-  double y = y0;
-  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  // (depth-minimised as householder_scalars, common.cuh: norm from ONE Newton step + the Heron correction, the second Newton
+  //  step only feeds 1/beta beside the chain; reciprocal seeded from the 20-bit norm and finished by one cubic step)
   double r0;
-  { const double n1 = nsq * y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(ac0 + n1)); }   // seed only
-  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
-  double norm = nsq * y;
-  norm = fma(fma(-norm, norm, nsq), 0.5 * y, norm);
+  { const double n0 = fma(nsq, y0, ac0); asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(n0)); }   // seed only
+  double y1;
+  { const double t = y0 * y0; const double e = fma(-hx, t, 0.5); y1 = fma(y0, e, y0); }
+  double norm = nsq * y1;
+  norm = fma(fma(-norm, norm, nsq), 0.5 * y1, norm);
+  double y;
+  { const double t = y1 * y1; const double e = fma(-hx, t, 0.5); y = fma(y1, e, y1); }
   const double dabs = ac0 + norm;              // |x0 - beta|
-  double rabs = r0;
-  { double e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); }
+  double rabs;
+  { const double e = fma(-dabs, r0, 1.0); rabs = fma(r0, fma(e, e, e), r0); }
   const bool pos = c0 >= 0.0;
   double beta = pos ? -norm : norm;
   double ib = pos ? -y : y;                    // 1 / beta
@@ -306,16 +309,19 @@ __device__ __forceinline__ WyRefl wy_reflector(double c0, double tailSq) {
   double y0;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(nsq));
   const double hx = 0.5 * nsq, ac0 = fabs(c0);
-  double y = y0;
-  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
+  // (depth-minimised as householder_scalars, common.cuh: norm from ONE Newton step + the Heron correction, the second Newton
+  //  step only feeds 1/beta beside the chain; reciprocal seeded from the 20-bit norm and finished by one cubic step)
   double r0;
-  { const double n1 = nsq * y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(ac0 + n1)); }   // seed only
-  { const double t = y * y; const double e = fma(-hx, t, 0.5); y = fma(y, e, y); }
-  double norm = nsq * y;
-  norm = fma(fma(-norm, norm, nsq), 0.5 * y, norm);
+  { const double n0 = fma(nsq, y0, ac0); asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(n0)); }   // seed only
+  double y1;
+  { const double t = y0 * y0; const double e = fma(-hx, t, 0.5); y1 = fma(y0, e, y0); }
+  double norm = nsq * y1;
+  norm = fma(fma(-norm, norm, nsq), 0.5 * y1, norm);
+  double y;
+  { const double t = y1 * y1; const double e = fma(-hx, t, 0.5); y = fma(y1, e, y1); }
   const double dabs = ac0 + norm;              // |x0 - beta|
-  double rabs = r0;
-  { double e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); e = fma(-dabs, rabs, 1.0); rabs = fma(rabs, e, rabs); }
+  double rabs;
+  { const double e = fma(-dabs, r0, 1.0); rabs = fma(r0, fma(e, e, e), r0); }
   const bool pos = c0 >= 0.0;
   WyRefl h;
   h.beta = pos ? -norm : norm;

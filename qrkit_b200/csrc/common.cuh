@@ -225,8 +225,14 @@ __device__ __forceinline__ double fast_rsqrt(double x, double& sqrt_out) {
 // Scalars of one Householder reflector (Eigen's makeHouseholder, [Eigen] Householder.h): x0 = pivot entry, tailSq =
 // squared norm of the entries below.  beta = -sign(x0) sqrt(x0^2 + tailSq), inv = 1/(x0 - beta) (essential part = tail * inv),
 // tau = (beta - x0)/beta; tailSq <= DBL_MIN (or `no_tail`) gives the identity: tau = 0, inv = 0, beta = x0.
-// One dependent chain: the reciprocal's MUFU seed is taken from the 20-bit square root while the Newton steps of the
-// rsqrt still run, so only the reciprocal's two Newton steps follow the accurate norm.
+// This is THE dependent chain of every column step (TSQR merges, banded chase, panel steps), so its depth is what is
+// minimised (a dependent FP64 operation costs ~18 cycles on this part; r02 root trace: 750 cycles per merged column):
+//   * the norm is taken from the rsqrt after ONE Newton step (20 -> 39 bits) and one Heron correction, which squares the error
+//     again (-> 78 bits): the second Newton step of 1/norm is only needed by tau and runs beside the chain;
+//   * the reciprocal's MUFU seed is taken from the 20-bit norm while those steps run, and is finished by ONE cubic step
+//     r0 (1 + e + e^2), e = 1 - d r0 (|e| < 2^-19 -> 2^-57 relative) instead of two Newton steps.
+// inv is ready 10 dependent operations after the rsqrt seed (14 before); all three results are correctly rounded to within
+// one ulp of the two-step version (tests: R / tau against the oracle at 1e-12).
 __device__ __forceinline__ void householder_scalars(double x0, double tailSq, bool no_tail, double& beta, double& inv, double& tau) {
   const double s = fma(x0, x0, tailSq);
   double y0;
@@ -238,20 +244,15 @@ __device__ __forceinline__ void householder_scalars(double x0, double tailSq, bo
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d0));
   }
   const double h = 0.5 * s;
-  double y = y0;
-#pragma unroll
-  for (int it = 0; it < 2; it++) {
-    const double t = y * y;
-    const double e = fma(-h, t, 0.5);
-    y = fma(y, e, y);
-  }
-  double nrm = s * y;
-  nrm = fma(fma(-nrm, nrm, s), 0.5 * y, nrm);   // one Heron correction of the square root
+  double y1;
+  { const double t = y0 * y0; const double e = fma(-h, t, 0.5); y1 = fma(y0, e, y0); }        // 39 bits
+  double nrm = s * y1;
+  nrm = fma(fma(-nrm, nrm, s), 0.5 * y1, nrm);   // Heron correction: full precision
+  double y;                                       // 1/norm to full precision (tau only; off the chain)
+  { const double t = y1 * y1; const double e = fma(-h, t, 0.5); y = fma(y1, e, y1); }
   const double d = ax + nrm;                     // |x0 - beta|
-  double e = fma(-d, r0, 1.0);
-  double r = fma(r0, e, r0);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  const double e = fma(-d, r0, 1.0);
+  const double r = fma(r0, fma(e, e, e), r0);    // r0 (1 + e + e^2)
   const bool neg = x0 < 0.0;
   const bool degenerate = no_tail || (tailSq <= DBL_MIN) || !(s < __longlong_as_double(0x7ff0000000000000LL));
   beta = degenerate ? x0 : (neg ? nrm : -nrm);
