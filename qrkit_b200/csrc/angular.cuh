@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, int* __restrict__ perm_out,
                       const double* __restrict__ J2, long long ldj, const double* __restrict__ b,
                       double* __restrict__ atop, double* __restrict__ y1, double* __restrict__ abot,
-                      double* __restrict__ partials, long long nb) {
+                      double* __restrict__ partials, long long nb, int pld) {
   static_assert(R > C, "the border merge needs residual rows (r > c)");
   using L = AngularSmem<R, C, M2, TPB, U, NSTAGE>;
   constexpr int M1 = R - C, W = M2 + 1, TILE = L::TILE;
@@ -333,7 +333,7 @@ angular_factor_kernel(const double* A_in, double* packed, double* __restrict__ t
   cta_merge_tri<M2, TPB / 32>(T, sTri);
   if (t == 0) {
 #pragma unroll
-    for (int i = 0; i < Tri<M2>::N; i++) partials[(long long)blockIdx.x * Tri<M2>::N + i] = T[i];
+    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)i * pld + blockIdx.x] = T[i];     // component-major: the root's loads coalesce
   }
 }
 
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 angular_factor_direct_kernel(const double* A_in, double* packed, double* __restrict__ tau_out, int* __restrict__ perm_out,
                              const double* __restrict__ J2, long long ldj, const double* __restrict__ b,
                              double* __restrict__ atop, double* __restrict__ y1, double* __restrict__ abot,
-                             double* __restrict__ partials, long long nb64) {
+                             double* __restrict__ partials, long long nb64, int pld) {
   __shared__ double sTri[(TPB / 32) * Tri<M2>::N];
   double T[Tri<M2>::N];
 #pragma unroll
@@ -467,7 +467,7 @@ angular_factor_direct_kernel(const double* A_in, double* packed, double* __restr
   cta_merge_tri<M2, TPB / 32>(T, sTri);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)blockIdx.x * Tri<M2>::N + i] = T[i];
+    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)i * pld + blockIdx.x] = T[i];
   }
 }
 
@@ -476,7 +476,7 @@ angular_factor_direct_kernel(const double* A_in, double* packed, double* __restr
 template <int R, int C, int M2, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
 angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
-                   double* __restrict__ y1, double* __restrict__ abot, double* __restrict__ partials, long long nb) {
+                   double* __restrict__ y1, double* __restrict__ abot, double* __restrict__ partials, long long nb, int pld) {
   constexpr int M1 = R - C, W = M2 + 1;
   constexpr int SA = Group<R * C>::stride, ST = Group<C>::stride;
   extern __shared__ __align__(16) double smem[];
@@ -526,7 +526,7 @@ angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__
   cta_merge_tri<M2, TPB / 32>(T, sTri);
   if (t == 0) {
 #pragma unroll
-    for (int i = 0; i < Tri<M2>::N; i++) partials[(long long)blockIdx.x * Tri<M2>::N + i] = T[i];
+    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)i * pld + blockIdx.x] = T[i];     // component-major: the root's loads coalesce
   }
 }
 
@@ -593,7 +593,7 @@ __device__ long long g_root_trace[16];
 
 template <int M2, int TPB, bool XCHG>
 __global__ void __launch_bounds__(TPB)
-angular_root_kernel(const double* __restrict__ tris, int count, int mode, double* __restrict__ out_tri,
+angular_root_kernel(const double* __restrict__ tris, int count, int tris_ld, int mode, double* __restrict__ out_tri,
                     double* __restrict__ root, int* __restrict__ root_i, int keep_rhs_only, int* __restrict__ perm_tail,
                     int m1, AngularXchg xc) {
   using TR = Tri<M2>;
@@ -607,15 +607,20 @@ angular_root_kernel(const double* __restrict__ tris, int count, int mode, double
   // every thread takes one triangle per round; a round is merged cooperatively (warp, then CTA)
   for (int q0 = 0; q0 < count; q0 += TPB) {
     const int q = q0 + threadIdx.x;
+    // tris_ld > 0: component-major partials of this GPU's factor kernel (entry i of triangle q at i * tris_ld + q: a warp's
+    // loads are contiguous; the triangle-major layout cost 4.7k cycles of sector traffic for 444 triangles, r02 root trace);
+    // tris_ld = 0: triangle-major (the all-gathered per-GPU triangles)
+    const double* src = tris_ld ? tris + q : tris + (size_t)q * N;
+    const size_t step = tris_ld ? (size_t)tris_ld : 1;
     if (q0 == 0) {
       if (q < count) {
 #pragma unroll
-        for (int i = 0; i < N; i++) T[i] = tris[(long long)q * N + i];
+        for (int i = 0; i < N; i++) T[i] = src[i * step];
       }
     } else {
       double S[N];
 #pragma unroll
-      for (int i = 0; i < N; i++) S[i] = (q < count) ? tris[(long long)q * N + i] : 0.0;
+      for (int i = 0; i < N; i++) S[i] = (q < count) ? src[i * step] : 0.0;
       fold_tri<M2>(T, S);
     }
   }

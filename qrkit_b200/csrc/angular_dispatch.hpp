@@ -26,6 +26,7 @@ struct AngularArgs {
   int grid = 0;            // CTAs of the factor / rhs kernel = number of partial triangles
   const double* tris = nullptr;
   int tri_count = 0;
+  int tris_ld = 0;         // > 0: component-major (entry i of triangle q at i * tris_ld + q); 0: triangle-major
   int root_mode = 1;
   int keep_rhs_only = 0;
   double* out_tri = nullptr;

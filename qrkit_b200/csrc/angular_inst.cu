@@ -83,7 +83,7 @@ inline bool direct_ok(const AngularArgs& a) {
 template <bool PIV, bool ABOT>
 cudaError_t factor_2x1(const AngularArgs& a, cudaStream_t s) {
   angular_factor_direct_kernel<PIV, M2, TPB, kDirectU, kDirectMinB, ABOT><<<a.grid, TPB, 0, s>>>(
-      a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
+      a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb, a.grid);
   return cudaGetLastError();
 }
 
@@ -113,11 +113,11 @@ cudaError_t factor_t(const AngularArgs& a, cudaStream_t s) {
     const long long ntiles = (a.nb + G::Smem::TILE - 1) / G::Smem::TILE;
     grid = (int)std::max<long long>(1, std::min<long long>(std::min(grid, resident), ntiles));
     if (grid < a.grid) {
-      e = cudaMemsetAsync(a.partials + (size_t)grid * Tri<M2>::N, 0, (size_t)(a.grid - grid) * Tri<M2>::N * sizeof(double), s);
+      e = cudaMemsetAsync(a.partials, 0, (size_t)a.grid * Tri<M2>::N * sizeof(double), s);     // (component-major: the unused columns are strided)
       if (e != cudaSuccess) return e;
     }
   }
-  kernel<<<grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb);
+  kernel<<<grid, TPB, smem, s>>>(a.A_in, a.packed, a.tau, a.perm, a.J2, a.ldj, a.b, a.atop, a.y1, a.abot, a.partials, a.nb, a.grid);
   return cudaGetLastError();
 }
 
@@ -149,7 +149,7 @@ cudaError_t rhs_t(const AngularArgs& a, cudaStream_t s) {
   const size_t smem = ((size_t)TPB * (Group<R * C>::stride + Group<C>::stride) + (TPB / 32) * Tri<M2>::N) * 8;
   cudaError_t e = opt_in(kernel, smem);
   if (e != cudaSuccess) return e;
-  kernel<<<a.grid, TPB, smem, s>>>(a.packed, a.tau, a.b, a.y1, a.abot, a.partials, a.nb);
+  kernel<<<a.grid, TPB, smem, s>>>(a.packed, a.tau, a.b, a.y1, a.abot, a.partials, a.nb, a.grid);
   return cudaGetLastError();
 }
 
@@ -239,10 +239,10 @@ cudaError_t root(const AngularArgs& a, cudaStream_t s) {
   xc.peers = a.xchg_peers; xc.world = a.xchg_world; xc.rank = a.xchg_rank; xc.seq = a.xchg_seq; xc.err = a.xchg_err;
   if (a.xchg_timeout_ns) xc.timeout_ns = a.xchg_timeout_ns;
   if (a.root_mode == 2)
-    angular_root_kernel<M2, 512, true><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
+    angular_root_kernel<M2, 512, true><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
                                                          a.perm_tail, a.m1, xc);
   else
-    angular_root_kernel<M2, 512, false><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
+    angular_root_kernel<M2, 512, false><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
                                                           a.perm_tail, a.m1, xc);
   return cudaGetLastError();
 }

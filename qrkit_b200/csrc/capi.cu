@@ -455,7 +455,7 @@ AngularArgs angular_args(qrk_solver* h) {
   const long long tile = h->avt->tile_blocks(h->ur, h->uc);
   const long long ntiles = (h->nb + tile - 1) / tile;
   a.grid = (int)std::max<long long>(1, std::min<long long>(h->a_grid, ntiles));
-  a.tris = h->d_partials; a.tri_count = a.grid;
+  a.tris = h->d_partials; a.tri_count = a.grid; a.tris_ld = a.grid;
   a.out_tri = h->d_tri; a.root = h->d_root; a.root_i = h->d_root_i;
   a.perm_tail = h->d_perm + h->sum_cols; a.m1 = (int)h->sum_cols;
   return a;
@@ -2089,7 +2089,7 @@ int qrk_angular_merge(qrk_handle_t h, const double* tris, int32_t count, int mem
     d_tris = tmp;
   }
   AngularArgs a = angular_args(h);
-  a.tris = d_tris; a.tri_count = count; a.root_mode = 1; a.keep_rhs_only = h->pending_keep_rhs_only;
+  a.tris = d_tris; a.tri_count = count; a.tris_ld = 0; a.root_mode = 1; a.keep_rhs_only = h->pending_keep_rhs_only;
   int st = QRK_STATUS_OK;
   cudaError_t e = h->avt->root(a, h->stream);
   h->launches++;
