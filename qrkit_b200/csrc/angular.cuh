@@ -180,6 +180,67 @@ __device__ __forceinline__ void cta_merge_tri(double (&T)[Tri<M2>::N], double* s
   }
 }
 
+// The same cooperative merge with NT triangles per lane (lane l owns NT * M2 rows of the stacked matrix): ONE warp merges
+// 32 * NT triangles with the shuffle traffic and the dependent chain of a 32-triangle merge -- the per-lane dot products
+// grow, the 5 reductions and reflector-scalar chains per merge do not.  Measured on the root kernel (tools/root_trace):
+// 16 warps merging at once take 5.0k cycles for what one warp does in 2.7k (they queue on the SM's shuffle port), a 4-triangle
+// merge takes 3.0k.  Result in lane 0's T[0].  (NT = 1 is warp_merge_tri; see MergeFan for what is shipped.)
+template <int M2, int NT>
+__device__ __forceinline__ void warp_merge_tri_multi(double (&T)[NT][Tri<M2>::N]) {
+  using TR = Tri<M2>;
+  const bool lead = (threadIdx.x & 31) == 0;
+#pragma unroll
+  for (int k = 0; k < M2; k++) {
+    double red[M2 + 1];
+#pragma unroll
+    for (int j = k; j <= M2; j++) {
+      double d = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        double dt = 0.0;
+#pragma unroll
+        for (int p = 0; p <= k; p++) dt = fma(T[t][TR::idx(p, k)], T[t][TR::idx(p, j)], dt);
+        d += (t == 0 && lead) ? 0.0 : dt;         // lane 0's first triangle holds the pivot rows only
+      }
+      red[j] = d;
+    }
+    double piv[M2 + 1];
+#pragma unroll
+    for (int j = k; j <= M2; j++) piv[j] = __shfl_sync(0xffffffffu, T[0][TR::idx(k, j)], 0);
+#pragma unroll
+    for (int j = k; j <= M2; j++) red[j] = warp_sum_f64(red[j]);
+    double beta, inv, tau;
+    householder_scalars(piv[k], red[k], false, beta, inv, tau);
+#pragma unroll
+    for (int j = k + 1; j <= M2; j++) {
+      const double w = tau * fma(inv, red[j], piv[j]);
+      const double z = w * inv;
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        if (t == 0 && lead) {
+          T[0][TR::idx(k, j)] -= w;
+        } else {
+#pragma unroll
+          for (int p = 0; p <= k; p++) T[t][TR::idx(p, j)] = fma(-z, T[t][TR::idx(p, k)], T[t][TR::idx(p, j)]);
+        }
+      }
+    }
+    if (lead) T[0][TR::idx(k, k)] = beta;
+  }
+}
+
+// Triangles per lane in the root's first merge level.  1 = one triangle per thread, 512 threads: the measured best IN THE STEP
+// (config 3: root 8.8 us, step 49.5 us).  4 per lane on 128 threads is 7 % faster when the root is timed alone
+// (tools/root_trace: 12.2k against 13.0k cycles) but 4.4 us slower inside the step (ncu without cache control: root 13.2 us,
+// step 53.6 us; not explained -- sharing the SM with the dependent K3 grid was excluded by giving the root the whole SM's
+// shared memory), so it stays an experiment switch: -DQRK_ANG_ROOT_NT=4 -DQRK_ANG_ROOT_TPB=128.
+template <int M2>
+#ifdef QRK_ANG_ROOT_NT
+struct MergeFan { static constexpr int NT = QRK_ANG_ROOT_NT; };
+#else
+struct MergeFan { static constexpr int NT = 1; };
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // K1: factorize the diagonal blocks, apply Q_i^T to [J2 | b], emit Atop / y1, reduce the residual rows.
 //   J2   : n x M2 column-major, leading dimension ldj (rows of block i: i*R .. i*R+R-1)
@@ -601,31 +662,50 @@ angular_root_kernel(const double* __restrict__ tris, int count, int tris_ld, int
   __shared__ double scratch[(TPB / 32) * N];
   asm volatile("griddepcontrol.launch_dependents;");   // the back-substitution grid may be scheduled now (it waits for this grid)
   QRK_ROOT_CLK(0);
+  // Every thread takes up to NT triangles (triangle q = r * TPB + t: a warp's loads of a component-major list are contiguous),
+  // each warp merges its 32 * NT triangles cooperatively, warp 0 merges the warps' results: two dependent warp merges for up
+  // to TPB * NT triangles, executed by TPB / 32 warps (few warps: the merges queue on the SM's shuffle port, see
+  // warp_merge_tri_multi).  More triangles than that are folded serially into the first one beforehand.
+  constexpr int NT = MergeFan<M2>::NT;
   double T[N];
+  {
+    double Tm[NT][N];
 #pragma unroll
-  for (int i = 0; i < N; i++) T[i] = 0.0;
-  // every thread takes one triangle per round; a round is merged cooperatively (warp, then CTA)
-  for (int q0 = 0; q0 < count; q0 += TPB) {
-    const int q = q0 + threadIdx.x;
-    // tris_ld > 0: component-major partials of this GPU's factor kernel (entry i of triangle q at i * tris_ld + q: a warp's
-    // loads are contiguous; the triangle-major layout cost 4.7k cycles of sector traffic for 444 triangles, r02 root trace);
-    // tris_ld = 0: triangle-major (the all-gathered per-GPU triangles)
-    const double* src = tris_ld ? tris + q : tris + (size_t)q * N;
-    const size_t step = tris_ld ? (size_t)tris_ld : 1;
-    if (q0 == 0) {
-      if (q < count) {
+    for (int r = 0; r < NT; r++) {
+      const int q = r * TPB + (int)threadIdx.x;
+      const double* src = tris_ld ? tris + q : tris + (size_t)q * N;
+      const size_t step = tris_ld ? (size_t)tris_ld : 1;
 #pragma unroll
-        for (int i = 0; i < N; i++) T[i] = src[i * step];
-      }
-    } else {
+      for (int i = 0; i < N; i++) Tm[r][i] = (q < count) ? src[i * step] : 0.0;
+    }
+    for (int q0 = NT * TPB; q0 < count; q0 += TPB) {
+      const int q = q0 + (int)threadIdx.x;
+      const double* src = tris_ld ? tris + q : tris + (size_t)q * N;
+      const size_t step = tris_ld ? (size_t)tris_ld : 1;
       double S[N];
 #pragma unroll
       for (int i = 0; i < N; i++) S[i] = (q < count) ? src[i * step] : 0.0;
-      fold_tri<M2>(T, S);
+      fold_tri<M2>(Tm[0], S);
     }
+    QRK_ROOT_CLK(1);
+    warp_merge_tri_multi<M2, NT>(Tm);
+#pragma unroll
+    for (int i = 0; i < N; i++) T[i] = Tm[0][i];
   }
-  QRK_ROOT_CLK(1);
-  cta_merge_tri<M2, TPB / 32>(T, scratch);
+  if (TPB > 32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++) scratch[warp * N + i] = T[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++) T[i] = (lane < TPB / 32) ? scratch[lane * N + i] : 0.0;
+      warp_merge_tri<M2>(T);
+    }
+    __syncthreads();            // scratch is reused by the exchange path
+  }
   QRK_ROOT_CLK(2);
   bool poisoned = false;
   if constexpr (XCHG) {                          // mode 2 (a separate instantiation: the single-GPU root keeps its code)

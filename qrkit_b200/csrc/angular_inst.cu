@@ -71,6 +71,12 @@ constexpr int kDirectU = QRK_ANG_DIRECT_U, kDirectMinB = QRK_ANG_DIRECT_MINB;
 #ifndef QRK_ANG_K3_PS
 #define QRK_ANG_K3_PS 4
 #endif
+// threads of the TSQR root: TPB * MergeFan::NT triangles are merged in two dependent warp merges (angular_root_kernel)
+#ifdef QRK_ANG_ROOT_TPB
+constexpr int kRootTpb = QRK_ANG_ROOT_TPB;
+#else
+constexpr int kRootTpb = 512;
+#endif
 constexpr int kK3Tpb = QRK_ANG_K3_TPB, kK3Pr = QRK_ANG_K3_PR, kK3Ps = QRK_ANG_K3_PS;
 constexpr size_t kK3Smem = (size_t)kK3Ps * (M2 + 2) * kK3Tpb * sizeof(double);
 inline bool direct_ok(const AngularArgs& a) {
@@ -239,11 +245,11 @@ cudaError_t root(const AngularArgs& a, cudaStream_t s) {
   xc.peers = a.xchg_peers; xc.world = a.xchg_world; xc.rank = a.xchg_rank; xc.seq = a.xchg_seq; xc.err = a.xchg_err;
   if (a.xchg_timeout_ns) xc.timeout_ns = a.xchg_timeout_ns;
   if (a.root_mode == 2)
-    angular_root_kernel<M2, 512, true><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
-                                                         a.perm_tail, a.m1, xc);
+    angular_root_kernel<M2, kRootTpb, true><<<1, kRootTpb, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i,
+                                                                   a.keep_rhs_only, a.perm_tail, a.m1, xc);
   else
-    angular_root_kernel<M2, 512, false><<<1, 512, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i, a.keep_rhs_only,
-                                                          a.perm_tail, a.m1, xc);
+    angular_root_kernel<M2, kRootTpb, false><<<1, kRootTpb, 0, s>>>(a.tris, a.tri_count, a.tris_ld, a.root_mode, a.out_tri, a.root, a.root_i,
+                                                                    a.keep_rhs_only, a.perm_tail, a.m1, xc);
   return cudaGetLastError();
 }
 
@@ -268,8 +274,8 @@ cudaError_t preload_t(bool piv) {
   if constexpr (R == 2 && C == 1) {
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_backsolve_direct_kernel<M2, kK3Tpb, kK3Pr, kK3Ps>);
   }
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, false>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, 512, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, kRootTpb, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_root_kernel<M2, kRootTpb, true>);
   return e;
 }
 cudaError_t preload(int r, int c, bool piv) {

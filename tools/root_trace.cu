@@ -36,10 +36,10 @@ int run(int count, int ld) {
 
 int main(int argc, char** argv) {
   const int count = argc > 1 ? atoi(argv[1]) : 444;
-  run<512>(count, 0);
   run<512>(count, count);                       // (random data: only the timing means something)
-  run<256>(count < 256 ? count : 256, 0);      // fewer warps on the SM: how much of the merge is shuffle-port contention
-  run<128>(count < 128 ? count : 128, 0);
-  run<32>(count < 32 ? count : 32, 0);
+  run<256>(count, count);
+  run<128>(count, count);                       // the shipped configuration for M2 <= 5 (4 triangles per lane)
+  run<128>(count, 0);
+  run<32>(count < 128 ? count : 128, count < 128 ? count : 128);
   return 0;
 }
