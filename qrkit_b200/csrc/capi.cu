@@ -1125,6 +1125,11 @@ int peer_exchange_status(qrk_solver* h) {
 extern "C" {
 
 int qrk_version(void) { return 100; }
+#ifdef QRK_TRI_TRACE
+__attribute__((visibility("default"))) int qrk_debug_tri_trace(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, qrk::g_tri_trace, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 const char* qrk_status_string(int status) {
   switch (status) {

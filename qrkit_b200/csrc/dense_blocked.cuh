@@ -329,6 +329,12 @@ __global__ void __launch_bounds__(256) dense_extract_tri_kernel(const double* __
 // d: A = triangle (ld = N = M), Nrule = rows of the tall residual; needs (ceil((M+nrhs)/8) + 2) * M doubles of shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTriThreads = 512;
+#ifdef QRK_TRI_TRACE
+__device__ long long g_tri_trace[16];
+#define QRK_TRI_CLK(i) do { if (k == 64 && tid == 0 && rank == 0) g_tri_trace[i] = clock64(); } while (0)
+#else
+#define QRK_TRI_CLK(i) do { } while (0)
+#endif
 
 __host__ __device__ inline size_t tri_colpiv_smem_bytes(int M, int nrhs) {
   const size_t cpc = (size_t)(M + nrhs + kDbCluster - 1) / kDbCluster;
@@ -340,6 +346,8 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double dyn[];
   __shared__ double sred[kTriThreads / 32];
+  __shared__ double candv[2][kDbCluster];      // pivot candidates of the 8 CTAs (value, index), double buffered by step parity
+  __shared__ int candi[2][kDbCluster];
   const int M = d.M, NC = M + d.nrhs, LDR = M;
   const int CPC = (NC + kDbCluster - 1) / kDbCluster;
   double* cols = dyn;                        // CPC columns of M rows: local column l is global column rank + 8 l
@@ -388,6 +396,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
 
   for (int k = 0; k < steps; k++) {
     const int par = k & 1;
+    QRK_TRI_CLK(0);
     // ---- (1) local pivot candidate: first maximum of upd over the local columns j >= k
     if (warp == 0) {
       double bv = -1.0;
@@ -402,19 +411,27 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
         const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
         if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
       }
-      if (lane == 0) { hdr[2 + par] = bv; candj[par] = bj; }
+      // pushed into every CTA of the cluster (8 remote stores by 8 lanes) instead of being fetched by every thread after the
+      // barrier: the reads behind the barrier are local (r02 trace: the 8 dependent DSMEM fetches cost 1.6k cycles per column)
+      if (lane < kDbCluster) {
+        cluster.map_shared_rank(&candv[0][0], lane)[par * kDbCluster + rank] = bv;
+        cluster.map_shared_rank(&candi[0][0], lane)[par * kDbCluster + rank] = bj;
+      }
     }
+    QRK_TRI_CLK(1);
     cluster.sync();
-    // ---- (2) global first maximum: every thread reads the 8 candidates over DSMEM (no second intra-CTA stage)
+    QRK_TRI_CLK(2);
+    // ---- (2) global first maximum over the 8 candidates (local copies)
     int big = 0x7fffffff;
     double bigv = -1.0;
 #pragma unroll
     for (int rk = 0; rk < kDbCluster; rk++) {
-      const double ov = cluster.map_shared_rank(hdr, rk)[2 + par];
-      const int oj = cluster.map_shared_rank(candj, rk)[par];
+      const double ov = candv[par][rk];
+      const int oj = candi[par][rk];
       if (ov > bigv || (ov == bigv && oj < big)) { bigv = ov; big = oj; }
     }
     if (nonzero_pivots == size && bigv * bigv < helper * (double)(d.Nrule - k)) nonzero_pivots = k;
+    QRK_TRI_CLK(3);
     // ---- (3) owner of column k: swap with the pivot column (fused with the tail norm), reflector, pushed to every CTA
     const int owner = k & (kDbCluster - 1);
     if (rank == owner) {
@@ -448,13 +465,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
       for (int w = 0; w < NW; w++) tailSq += sred[w];
       const double c0 = ck[k];
       double beta, tau, inv;
-      if (tailSq <= DBL_MIN) { tau = 0.0; beta = c0; inv = 0.0; }
-      else {
-        beta = sqrt(fma(c0, c0, tailSq));
-        if (c0 >= 0.0) beta = -beta;
-        inv = 1.0 / (c0 - beta);
-        tau = (beta - c0) / beta;
-      }
+      householder_scalars(c0, tailSq, false, beta, inv, tau);      // Eigen's makeHouseholder; one short dependent chain (common.cuh)
       __syncthreads();                                 // every thread has read ck[k] and sred
       for (int i = k + 1 + tid; i < M; i += kTriThreads) {
         const double v = ck[i] * inv;
@@ -469,65 +480,94 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTriThreads
       }
       if (tid == 0) { ck[k] = beta; d.tau[k] = tau; }
     }
+    QRK_TRI_CLK(4);
     cluster.sync();                                    // the reflector has landed in every CTA's vloc / hdr
+    QRK_TRI_CLK(5);
     const double tau = hdr[0], beta = hdr[1];
     if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
-    // ---- (5) H_k on the local columns right of k, LAWN-176 downdate of their norms.  A warp takes two local columns
-    // at a time through the same loops (two independent dependency chains).
-    for (int l0 = warp; l0 < CPC; l0 += 2 * NW) {
-      const int l1 = l0 + NW;
-      const int j0 = rank + kDbCluster * l0, j1 = rank + kDbCluster * l1;
-      const bool a0 = l0 < CPC && j0 > k && j0 < NC, a1 = l1 < CPC && j1 > k && j1 < NC;
-      if (a0 || a1) {
-        double* c0p = cols + (size_t)(a0 ? l0 : l1) * LDR;
-        double* c1p = cols + (size_t)(a1 ? l1 : l0) * LDR;     // a warp with one active column runs it twice (harmless)
-        double dot0 = 0.0, dot1 = 0.0;
+    // ---- (5) H_k on the local columns right of k, LAWN-176 downdate of their norms.  A warp takes FOUR local columns at a
+    // time through the same loops (four independent dependency chains; 49 local columns of a 384-column border are one round
+    // of the 16 warps instead of two), and the four norm downdates run in four lanes side by side instead of one after the
+    // other in lane 0.  r02 trace at k = 64: this phase 8.4k of the column's 15.7k cycles before.
+    for (int lb = warp; lb < CPC; lb += 4 * NW) {
+      int lq[4], jq[4];
+      bool act[4], any = false;
+      int lfirst = -1;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        lq[q] = lb + q * NW; jq[q] = rank + kDbCluster * lq[q];
+        act[q] = lq[q] < CPC && jq[q] > k && jq[q] < NC;
+        if (act[q] && lfirst < 0) lfirst = lq[q];
+        any = any || act[q];
+      }
+      if (!any) continue;
+      double* cp[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) cp[q] = cols + (size_t)(act[q] ? lq[q] : lfirst) * LDR;     // an idle slot re-reads an active column (never stored)
+      double dot[4] = {0.0, 0.0, 0.0, 0.0};
+      double w[4], nsq[4] = {0.0, 0.0, 0.0, 0.0}, ak[4] = {0.0, 0.0, 0.0, 0.0};
+      {
         for (int i = k + lane; i < M; i += 32) {
           const double v = vloc[i - k];
-          dot0 = fma(v, c0p[i], dot0);
-          dot1 = fma(v, c1p[i], dot1);
+#pragma unroll
+          for (int q = 0; q < 4; q++) dot[q] = fma(v, cp[q][i], dot[q]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          dot0 += __shfl_xor_sync(0xffffffffu, dot0, o);
-          dot1 += __shfl_xor_sync(0xffffffffu, dot1, o);
-        }
-        const double w0 = tau * dot0, w1 = tau * dot1;
-        const bool two = a0 && a1;
-        double nsq0 = 0.0, nsq1 = 0.0, ak0 = 0.0, ak1 = 0.0;
-        for (int i = k + lane; i < M; i += 32) {
-          const double v = vloc[i - k];
-          const double x0 = fma(-v, w0, c0p[i]);
-          const double x1 = fma(-v, w1, c1p[i]);
-          c0p[i] = x0;
-          if (two) c1p[i] = x1;
-          if (i > k) { nsq0 = fma(x0, x0, nsq0); nsq1 = fma(x1, x1, nsq1); } else { ak0 = x0; ak1 = x1; }
+#pragma unroll
+          for (int q = 0; q < 4; q++) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          nsq0 += __shfl_xor_sync(0xffffffffu, nsq0, o);
-          nsq1 += __shfl_xor_sync(0xffffffffu, nsq1, o);
+        for (int q = 0; q < 4; q++) w[q] = tau * dot[q];
+        for (int i = k + lane; i < M; i += 32) {
+          const double v = vloc[i - k];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double x = fma(-v, w[q], cp[q][i]);
+            if (act[q]) cp[q][i] = x;
+            if (i > k) nsq[q] = fma(x, x, nsq[q]); else ak[q] = x;
+          }
         }
-        if (lane == 0) {                                        // row k is lane 0's first element
-          auto downdate = [&](int l, int j, double akj, double nsq) {
-            if (j >= M) return;                                  // a right-hand side: no norm
-            const double u = upd[l];
-            if (u != 0.0) {
-              double t = fabs(akj) / u;
-              t = (1.0 + t) * (1.0 - t);
-              t = t < 0.0 ? 0.0 : t;
-              const double qd = u / dir[l];
-              const double t2 = t * (qd * qd);
-              if (t2 <= 1.4901161193847656e-08) { const double nrm = sqrt(nsq); dir[l] = nrm; upd[l] = nrm; }   // sqrt(eps)
-              else upd[l] = u * sqrt(t);
-            }
-          };
-          if (a0) downdate(l0, j0, ak0, nsq0);
-          if (a1) downdate(l1, j1, two ? ak1 : ak0, two ? nsq1 : nsq0);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) nsq[q] += __shfl_xor_sync(0xffffffffu, nsq[q], o);
+      }
+      // lane q finishes column q (row k is lane 0's first element: its entry travels by shuffle)
+      double my_ak = 0.0, my_nsq = 0.0;
+      int my_l = 0, my_j = NC;
+      bool my_act = false;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double a0 = __shfl_sync(0xffffffffu, ak[q], 0);
+        if (lane == q) { my_ak = a0; my_nsq = nsq[q]; my_l = lq[q]; my_j = jq[q]; my_act = act[q]; }
+      }
+      if (lane < 4 && my_act && my_j < M) {                      // (a right-hand side has no norm)
+        const double u = upd[my_l];
+        if (u != 0.0) {
+          // Eigen's rule (ColPivHouseholderQR.h, LAWN 176) with correctly rounded fast reciprocal / square root (common.cuh:
+          // tools/seed_accuracy: 0 ulp against IEEE on 16M samples); the values only feed pivot comparisons
+          double t = fabs(my_ak) * fast_rcp(u);
+          t = (1.0 + t) * (1.0 - t);
+          t = t < 0.0 ? 0.0 : t;
+          const double qd = u * fast_rcp(dir[my_l]);
+          const double t2 = t * (qd * qd);
+          if (t2 <= 1.4901161193847656e-08) {                    // sqrt(eps): recompute
+            double nrm;
+            (void)fast_rsqrt(my_nsq, nrm);
+            dir[my_l] = nrm; upd[my_l] = nrm;
+          } else {
+            double st;
+            (void)fast_rsqrt(t, st);
+            upd[my_l] = u * st;
+          }
         }
       }
     }
+    QRK_TRI_CLK(6);
     __syncthreads();
+    QRK_TRI_CLK(7);
   }
 
   // ---- write back: packed factors, P2, rank bookkeeping
