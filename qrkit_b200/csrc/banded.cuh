@@ -183,7 +183,7 @@ banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__
   static_assert(BC % 2 == 0 && BC + 1 <= 32, "16-byte cp.async of whole band rows; one lane per column plus the rhs");
   __shared__ __align__(16) double prow[RING][PW];       // pivot rows: BC entries + the right-hand side value
   __shared__ __align__(16) double sv[2][NO];            // published raw tail (double buffered by step parity)
-  __shared__ __align__(16) double trash[NO];
+  __shared__ __align__(16) double trash[NO * 33];       // dump slots of the non-pivot lanes, entry i of lane l at i * 33 + l
   __shared__ double hand[NO][33];                       // rows handed to the next group
   const int lane = threadIdx.x;
   const bool is_col = lane < BC, is_rhs = (lane == BC) && have_rhs;
@@ -225,9 +225,10 @@ banded_chase_kernel(const double* __restrict__ gband, const double* __restrict__
   for (long long q = 0; q < Q; q++) {
     const bool lastw = (lw == n_g - 1);
     // ---- publish lane c's raw tail (every lane stores: lane c to the buffer, the others to a dump slot -> no divergence)
-    double* dst = (lane == c) ? sv[q & 1] : trash;
+    double* dst = (lane == c) ? sv[q & 1] : trash + lane;       // (a dump word per lane and entry: no write-write overlap for racecheck)
+    const int dstep = (lane == c) ? 1 : 33;
 #pragma unroll
-    for (int i = 0; i < OV; i++) dst[i] = Bg[i];
+    for (int i = 0; i < OV; i++) dst[i * dstep] = Bg[i];
     double tq[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < OV; i++) tq[i & 3] = fma(Bg[i], Bg[i], tq[i & 3]);
@@ -549,6 +550,7 @@ banded_chase_apply_kernel(const double* __restrict__ craw, const double* __restr
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < OV; k++) u[k] = hand[k];
+          __syncwarp();                                  // every lane has read hand[] before lane 0 writes the next group's rows
         }
       } else if (r == 0) {                               // left end of a group: u is what the group to the left handed over
         __syncwarp();

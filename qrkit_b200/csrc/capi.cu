@@ -1391,6 +1391,8 @@ static int create_impl(const qrk_desc_t* desc, const int32_t* gen_blocks, qrk_ha
     cudaMemsetAsync(h->d_root, 0, (M * M + 3 * M) * sizeof(double), h->stream);
     cudaMemsetAsync(h->d_root_i, 0, (M + 1) * sizeof(int), h->stream);
     cudaMemsetAsync(h->d_wtau2, 0, M * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_wupd, 0, M * sizeof(double), h->stream);     // norm tables: read (and ignored: 0 = no downdate) before a
+    cudaMemsetAsync(h->d_wdir, 0, M * sizeof(double), h->stream);     // panel / path has computed its norms (initcheck-clean)
   } else if (angular) {
     const bool piv = desc->pivoting == QRK_PIVOT_COLPIV;
     if (h->avt->max_grid(h->ur, h->uc, piv, &h->a_grid) != cudaSuccess) return fail(QRK_STATUS_CUDA_ERROR);

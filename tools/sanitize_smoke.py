@@ -25,8 +25,8 @@ for (br, bc, ov, nbk) in [(16, 24, 16, 11), (7, 4, 2, 9), (7, 2, 0, 5), (12, 8, 
     n_rows, n_cols = nbk * br, (nbk - 1) * (bc - ov) + bc
     s = qk.BandedBlockedSparseQR(slabs, num_blocks=nbk, block_rows=br, block_cols=bc, overlap=ov)
     bvec = vector(n_rows, seed=3)
-    y = s.applyQt(bvec)
-    print("banded2", br, bc, ov, float(np.abs(s.solve(bvec)).max()), float(np.abs(s.applyQ(y)).max()), s.matrixR().toarray().shape)
+    y = s.applyQtThin(bvec)                  # (the two-phase path keeps the thin Q; the exact n x n Q is the general chain's)
+    print("banded2", br, bc, ov, float(np.abs(s.solve(bvec)).max()), float(np.abs(s.applyQThin(y)).max()), s.matrixR().toarray().shape)
 del os.environ["QRK_BANDED_GROUP"]
 # dense border: blocked compact-WY first stage (cluster panel + DMMA update) and the cluster-resident ColPiv second stage,
 # ragged last panel (m2 = 21), unpivoted right solver, solve on the stored factors
@@ -50,3 +50,29 @@ rhs = torch.empty(2 * n, dtype=torch.float64, device="cuda"); cost = torch.zeros
 capi.check(L.qrk_ellipse_assemble(px.data_ptr(), py.data_ptr(), params.data_ptr(), n, J1.data_ptr(), J2d.data_ptr(), rhs.data_ptr(), cost.data_ptr(), None))
 torch.cuda.synchronize()
 print("ellipse", float(cost.item()))
+# round 2: the 2 x 1 block-angular kernels (unstaged K1, one-wave K3 with private cp.async slots), ragged point counts that
+# leave partial iterations / batches, ColPiv and unpivoted left blocks, compute() + solve() (stored Abot panel), full Q products
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import ellipse_problem
+for npts in (5, 129, 1000, 4099):
+    J1v, J2e, rhse = ellipse_problem(npts)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(J1v, block_rows=2, block_cols=1), J2e)
+    for piv in (0, 1):
+        s = qk.BlockAngularSparseQR(pivoting=piv)
+        xf = s.compute_solve(mat, rhse)
+        s2 = qk.BlockAngularSparseQR(mat, pivoting=piv)
+        xs = s2.solve(rhse)
+        print("angular 2x1", npts, piv, float(np.abs(xf - xs).max()), s2.rank())
+    y = s2.applyQt(rhse)
+    print("angular full Q", npts, float(np.abs(s2.applyQ(y) - rhse).max()))
+# general banded chain (run-time window table) and the thin-sparse right solver
+os.environ["QRK_BANDED_GENERIC"] = "1"
+slabs = uniform_blocks(9, 9, 5)
+s = qk.BandedBlockedSparseQR(slabs, num_blocks=9, block_rows=9, block_cols=5, overlap=2)
+print("banded generic", float(np.abs(s.solve(vector(81, seed=3))).max()))
+del os.environ["QRK_BANDED_GENERIC"]
+nb, r, c, m2 = 40, 7, 2, 20
+vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); J2[:, 3] = 0.0; b = vector(nb * r, seed=5)
+mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+s = qk.BlockAngularSparseQR(pivoting=1, right_solver=2)
+print("thin sparse right solver", float(np.abs(s.compute_solve(mat, b)).max()), s.rank())     # (a deferred zero column: fused path)
