@@ -189,11 +189,8 @@ bd_generic_factor_kernel(BlockIndex bi, const int* __restrict__ ids, const doubl
     tailSq = warp_sum(tailSq);
     const double c0 = ck[k];
     const bool degenerate = (k + 1 >= r) || (tailSq <= DBL_MIN);
-    double beta = sqrt(fma(c0, c0, tailSq));
-    if (c0 >= 0.0) beta = -beta;
-    double inv = 1.0 / (c0 - beta);
-    double tau = (beta - c0) / beta;
-    if (degenerate) { inv = 0.0; tau = 0.0; beta = c0; }
+    double beta, inv, tau;                      // Eigen makeHouseholder (one short dependent chain: common.cuh)
+    householder_scalars(c0, tailSq, degenerate, beta, inv, tau);
     // (b) trailing columns (and the rhs): col -= tau * v * (v^T col), v = [1; inv*ck[k+1:]].  Warp w owns the columns
     //     k+1+w, k+1+w+W, ...; for blocks of up to 128 rows it takes them FOUR at a time with the reflector and the four
     //     columns in registers: the four warp reductions run side by side (one shuffle latency chain per batch instead of

@@ -117,14 +117,8 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
       }
       cluster_reduce_vec<8>(part, 8 - c, par, sbuf, stot, sfin, spiv);
       const double tailSq = sfin[par][0], c0 = sfin[par][28 + c];
-      double beta, tau, inv;                    // Eigen makeHouseholder
-      if (tailSq <= DBL_MIN) { tau = 0.0; beta = c0; inv = 0.0; }
-      else {
-        beta = sqrt(fma(c0, c0, tailSq));
-        if (c0 >= 0.0) beta = -beta;
-        inv = 1.0 / (c0 - beta);
-        tau = (beta - c0) / beta;
-      }
+      double beta, tau, inv;                    // Eigen makeHouseholder (one short dependent chain: common.cuh)
+      householder_scalars(c0, tailSq, false, beta, inv, tau);
       tau_r[c] = tau;
       double w[8];
 #pragma unroll

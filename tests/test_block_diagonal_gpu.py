@@ -420,6 +420,7 @@ def test_host_alloc_is_pinned_and_feeds_the_host_path(qk, oracle):
             flags = C.c_uint(0)
             assert rt.cudaHostGetFlags(C.byref(flags), p) == 0
         assert rt.cudaHostGetFlags(C.byref(flags), vals.ctypes.data_as(C.c_void_p)) != 0      # a pageable array is not
+        rt.cudaGetLastError()                                   # (clear the expected error: torch shares this runtime instance)
         hv = np.ctypeslib.as_array(C.cast(ptrs[0], C.POINTER(C.c_double)), shape=(vals.size,))
         hb = np.ctypeslib.as_array(C.cast(ptrs[1], C.POINTER(C.c_double)), shape=(b.size,))
         hx = np.ctypeslib.as_array(C.cast(ptrs[2], C.POINTER(C.c_double)), shape=(nb * c,))
