@@ -19,6 +19,7 @@
 #include "bd_wy.cuh"
 #include "dense_border.cuh"
 #include "dense_blocked.cuh"
+#include "dense_tri_reg.cuh"
 #include "bd_small.cuh"
 #include "export.cuh"
 #include "solver.hpp"
@@ -775,7 +776,12 @@ int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) 
         const DenseBorder t = wide_tri_desc(h, d.nrhs);
         const size_t smem = tri_colpiv_smem_bytes(M, d.nrhs);
         constexpr size_t kTriMaxDyn = kMaxSmem - 1024;                     // the kernel's static shared memory comes on top
-        if (smem <= kTriMaxDyn) {         // the whole triangle fits the shared memory of one 8-CTA cluster: one launch
+        static const bool no_reg = std::getenv("QRK_TRI_SMEM") != nullptr;     // A/B switch: the shared-memory resident kernel
+        if (!no_reg && tri_reg_fits(M, d.nrhs)) {                              // register-resident triangle (dense_tri_reg.cuh)
+          dense_tri_colpiv_reg_kernel<<<kDbCluster, kTrThreads, 0, h->stream>>>(t);
+          if (cudaGetLastError() == cudaSuccess) h->launches++;
+          else st = wide_unblocked(h, t);
+        } else if (smem <= kTriMaxDyn) {  // the whole triangle fits the shared memory of one 8-CTA cluster: one launch
           static bool opted[64] = {};
           QRK_TRY_CUDA(h, ensure_smem(dense_tri_colpiv_kernel, kTriMaxDyn, opted));
           dense_tri_colpiv_kernel<<<kDbCluster, kTriThreads, smem, h->stream>>>(t);

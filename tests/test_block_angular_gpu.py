@@ -570,3 +570,37 @@ def test_fused_peer_exchange_timeout_poisons_and_reports(qk, oracle):
         assert rel(xg[per:], x_ref[n:]) <= 1e-9
     for h in hs:
         L.qrk_destroy(h)
+
+
+@pytest.mark.parametrize("m2,nb", [(65, 40), (100, 60), (130, 70), (383, 128)])
+def test_register_resident_colpiv_triangle_vs_oracle(qk, oracle, m2, nb):
+    """Borders of 65..384 columns with the ColPiv right solver take the register-resident cluster kernel for the pivoted QR of
+    the border's triangle (dense_tri_reg.cuh: columns never move, pivoting exchanges logical positions): ragged widths (not a
+    multiple of 8, 32 or 64 columns; 383 = one short of the limit), the full check of _check (P2 bit-exact, R, x, Q identities)."""
+    r, c = 7, 2
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2, seed=SEED_A + 70 + m2)
+    b = vector(nb * r, seed=5)
+    _check(qk, oracle, vals, r, c, J2, b, piv=1)
+
+
+def test_register_resident_colpiv_triangle_rank_deficient(qk, oracle):
+    """The same kernel on a rank-deficient border with exact zero columns: Eigen's nonzero-pivot threshold and the first-maximum
+    rule decide rank and P2 exactly as in the oracle's restatement, the zero columns end up behind the rank in index order.
+    (Duplicated or linearly dependent columns are not used here: the pivoted QR runs on the TRIANGLE of the unpivoted first
+    stage, where their norms tie -- and their residuals vanish -- only up to rounding, so neither their order nor whether a
+    1e-13 residual counts as a pivot is defined bit for bit; the reference decides both on the tall matrix.)"""
+    r, c, nb, m2 = 7, 2, 40, 96
+    vals = uniform_blocks(nb, r, c)
+    J2 = dense_border(nb * r, m2, seed=SEED_A + 91)
+    for j in (7, 50, 51, 95):
+        J2[:, j] = 0.0
+    b = vector(nb * r, seed=9)
+    mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+    ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True, right_kind=0)
+    s = qk.BlockAngularSparseQR(mat, pivoting=1)
+    rank = nb * c + m2 - 4
+    assert s.rank() == ref.rank == rank
+    assert np.array_equal(s.colsPermutation(), ref.colsPermutation())
+    assert rel(s.solve(b), ref.solve(b)) <= 1e-9
+    assert rel(qk.BlockAngularSparseQR(pivoting=1).compute_solve(mat, b), ref.solve(b)) <= 1e-9

@@ -76,3 +76,9 @@ vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); J2[:, 3] = 0.0; 
 mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
 s = qk.BlockAngularSparseQR(pivoting=1, right_solver=2)
 print("thin sparse right solver", float(np.abs(s.compute_solve(mat, b)).max()), s.rank())     # (a deferred zero column: fused path)
+# register-resident ColPiv triangle kernel (dense_tri_reg.cuh: borders of 65..384 columns), ragged width, two zero columns
+nb, r, c, m2 = 30, 7, 2, 70
+vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); J2[:, 11] = 0.0; J2[:, 40] = 0.0; b = vector(nb * r, seed=5)
+mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+s = qk.BlockAngularSparseQR(mat, pivoting=1)
+print("register-resident triangle", s.rank(), float(np.abs(s.solve(b)).max()))
