@@ -45,11 +45,16 @@ __device__ __forceinline__ void tri_reg_update(double (&x)[kTrSlots][kTrRows], c
     act[q] = g < NC && lj[q] > k;
     dot[q] = 0.0; nsq[q] = 0.0; ak[q] = 0.0;
   }
+  // Row slots above the pivot row's slot hold finished rows of R (the reflector is zero there): they are skipped by
+  // warp-uniform branches on the slot index, so nothing in the loops is a per-element select (the first version of this
+  // kernel spent 1755 of its 4096 instructions on FSEL) and the work shrinks as k advances.
 #pragma unroll
   for (int rs = 0; rs < kTrRows; rs++) {
-    const double v = vloc[rs * 32 + lane];
+    if (rs >= krs) {
+      const double v = vloc[rs * 32 + lane];
 #pragma unroll
-    for (int q = 0; q < cnt; q++) dot[q] = fma(v, x[s0 + q][rs], dot[q]);
+      for (int q = 0; q < cnt; q++) dot[q] = fma(v, x[s0 + q][rs], dot[q]);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -57,17 +62,27 @@ __device__ __forceinline__ void tri_reg_update(double (&x)[kTrSlots][kTrRows], c
     for (int q = 0; q < cnt; q++) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
   }
 #pragma unroll
-  for (int q = 0; q < cnt; q++) dot[q] *= tau;
+  for (int q = 0; q < cnt; q++) dot[q] = act[q] ? tau * dot[q] : 0.0;      // an inactive column is "updated" by zero: unchanged
 #pragma unroll
   for (int rs = 0; rs < kTrRows; rs++) {
-    const int i = rs * 32 + lane;
-    const double v = vloc[i];
+    if (rs > krs) {
+      const double v = vloc[rs * 32 + lane];
 #pragma unroll
-    for (int q = 0; q < cnt; q++) {
-      const double y = fma(-v, dot[q], x[s0 + q][rs]);
-      if (act[q]) x[s0 + q][rs] = y;
-      if (i > k) nsq[q] = fma(y, y, nsq[q]);
-      if (rs == krs) ak[q] = y;
+      for (int q = 0; q < cnt; q++) {
+        const double y = fma(-v, dot[q], x[s0 + q][rs]);
+        x[s0 + q][rs] = y;
+        nsq[q] = fma(y, y, nsq[q]);
+      }
+    } else if (rs == krs) {
+      const double v = vloc[rs * 32 + lane];
+      const bool below = lane > klane;
+#pragma unroll
+      for (int q = 0; q < cnt; q++) {
+        const double y = fma(-v, dot[q], x[s0 + q][rs]);
+        x[s0 + q][rs] = y;
+        ak[q] = y;
+        if (below) nsq[q] = fma(y, y, nsq[q]);
+      }
     }
   }
 #pragma unroll
@@ -223,9 +238,8 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTrThreads)
             double tailSq = 0.0, ck = 0.0;
 #pragma unroll
             for (int rs = 0; rs < kTrRows; rs++) {
-              const int i = rs * 32 + lane;
-              if (i > k) tailSq = fma(x[s][rs], x[s][rs], tailSq);
-              if (rs == krs) ck = x[s][rs];
+              if (rs > krs) tailSq = fma(x[s][rs], x[s][rs], tailSq);
+              else if (rs == krs) { ck = x[s][rs]; if (lane > klane) tailSq = fma(ck, ck, tailSq); }
             }
             tailSq = warp_sum(tailSq);
             const double c0 = __shfl_sync(0xffffffffu, ck, klane);
@@ -235,8 +249,11 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTrThreads)
             for (int rs = 0; rs < kTrRows; rs++) {
               const int i = rs * 32 + lane;
               double v = 0.0;
-              if (i > k) { v = x[s][rs] * inv; x[s][rs] = v; }
-              else if (i == k) { v = 1.0; x[s][rs] = beta; }
+              if (rs > krs) { v = x[s][rs] * inv; x[s][rs] = v; }
+              else if (rs == krs) {
+                if (lane > klane) { v = x[s][rs] * inv; x[s][rs] = v; }
+                else if (lane == klane) { v = 1.0; x[s][rs] = beta; }
+              }
               vloc[i] = v;
             }
             if (lane == 0) { hdr[0] = tau; hdr[1] = beta; d.tau[k] = tau; }
@@ -261,8 +278,12 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kTrThreads)
     const double tau = hdr[0], beta = hdr[1];
     if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
     // ---- (4) H_k on the active local columns (logical position > k; right-hand sides always), norms downdated
+#ifdef QRK_TRI_TWO_GROUPS
     tri_reg_update<0, 4>(x, vloc, logj, upd, dir, tau, k, M, NC, rank, warp, lane);
     tri_reg_update<4, 3>(x, vloc, logj, upd, dir, tau, k, M, NC, rank, warp, lane);
+#else
+    tri_reg_update<0, kTrSlots>(x, vloc, logj, upd, dir, tau, k, M, NC, rank, warp, lane);      // all seven chains side by side
+#endif
     QRK_TRI_CLK(6);
     __syncthreads();
     QRK_TRI_CLK(7);
