@@ -40,11 +40,12 @@ constexpr int kDbThreads = 512;    // threads per CTA: 4096 rows per pass, RPT p
 constexpr size_t kDbPanelSmem = (size_t)28 * kDbThreads * sizeof(double);   // transposition buffer of the reductions
 
 template <int NV>
-__device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int par, double* buf, double (*stot)[28],
+__device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int par, double* buf, double (*sall)[kDbCluster][28],
                                                    double (*sfin)[36], const double (*spiv)[8]) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster.block_rank();
   // CTA level through shared memory (value j of thread t at buf[j][t], then one warp sums a row): a shuffle tree over
   // nv values would cost 10 nv SHFL per warp, and the SHFL pipe issues one warp-instruction per clock per SM
 #pragma unroll
@@ -58,16 +59,18 @@ __device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int 
     double s = s0 + s1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) stot[par][j] = s;
+    // this CTA's total PUSHED into every CTA (lane l -> CTA l): the reads behind the barrier are local (fetching the 8
+    // totals over DSMEM after the barrier cost 1.0k cycles per reduction in the trace of the sibling kernel)
+    if (lane < kDbCluster) cluster.map_shared_rank(&sall[0][0][0], lane)[(par * kDbCluster + rank) * 28 + j] = s;
   }
-  cluster.sync();                                  // every CTA's stot[par] (and rank 0's spiv[par]) is visible
+  cluster.sync();                                  // every CTA's totals (and rank 0's pivot row) have landed here
   if (tid < nv) {
     double s = 0.0;
 #pragma unroll
-    for (int rk = 0; rk < kDbCluster; rk++) s += cluster.map_shared_rank(&stot[par][0], rk)[tid];
+    for (int rk = 0; rk < kDbCluster; rk++) s += sall[par][rk][tid];          // fixed order: bit-identical on every CTA
     sfin[par][tid] = s;
   } else if (tid >= 28 && tid < 36) {
-    sfin[par][tid] = cluster.map_shared_rank(&spiv[par][0], 0)[tid - 28];
+    sfin[par][tid] = spiv[par][tid - 28];
   }
   __syncthreads();
 }
@@ -78,13 +81,14 @@ template <int RPT>
 __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads) dense_panel_kernel(DenseBlocked d, int k0, int pw) {
   namespace cg = cooperative_groups;
   extern __shared__ __align__(16) double sbuf[];      // kDbPanelSmem: 28 x 512 doubles
-  __shared__ double stot[2][28];
+  __shared__ double sall[2][kDbCluster][28];      // the 8 CTAs' totals of the current reduction (pushed by their owners)
   __shared__ double sfin[2][36];
-  __shared__ double spiv[2][8];
+  __shared__ double spiv[2][8];                   // rank 0's pivot-row entries (pushed by rank 0)
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
   const int rank = (int)cluster.block_rank();
   const int row0 = rank * kDbThreads + tid;      // row (relative to k0) of pass 0
+  cluster.sync();                                 // every CTA has started: its shared memory may be written remotely
   constexpr int PASS = kDbCluster * kDbThreads;
   double a[RPT][8];
 #pragma unroll
@@ -111,11 +115,14 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
 #pragma unroll
         for (int j = c; j < 8; j++) part[j - c] = fma(x, a[i][j], part[j - c]);
       }
-      if (row0 == c) {                          // rank 0, thread c owns the pivot row
+      if (rank == 0 && tid < 32) {              // rank 0, thread c owns the pivot row: its entries into every CTA (lane l -> CTA l)
 #pragma unroll
-        for (int j = c; j < 8; j++) spiv[par][j] = a[0][j];
+        for (int j = c; j < 8; j++) {
+          const double pv = __shfl_sync(0xffffffffu, a[0][j], c);
+          if (tid < kDbCluster) cluster.map_shared_rank(&spiv[0][0], tid)[par * 8 + j] = pv;
+        }
       }
-      cluster_reduce_vec<8>(part, 8 - c, par, sbuf, stot, sfin, spiv);
+      cluster_reduce_vec<8>(part, 8 - c, par, sbuf, sall, sfin, spiv);
       const double tailSq = sfin[par][0], c0 = sfin[par][28 + c];
       double beta, tau, inv;                    // Eigen makeHouseholder (one short dependent chain: common.cuh)
       householder_scalars(c0, tailSq, false, beta, inv, tau);
@@ -156,26 +163,37 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
         for (int c = 0; c < j; c++) { g[e] = fma(vj, a[i][c], g[e]); e++; }   // rel >= j > c: a[i][c] is V[rel][c]
       }
     }
-    cluster_reduce_vec<28>(g, 28, pw & 1, sbuf, stot, sfin, spiv);
+    cluster_reduce_vec<28>(g, 28, pw & 1, sbuf, sall, sfin, spiv);
   }
-  if (rank == 0 && tid == 0) {                  // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j],  T[j][j] = tau_j
+  if (rank == 0 && tid < 8) {                   // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j],  T[j][j] = tau_j
+    // row i of T depends only on row i: lane i builds it in registers (one thread with an 8 x 8 local array and rolled
+    // loops spent ~3 us per panel in local-memory round trips)
     const double* G = sfin[pw & 1];
-    double T[8][8];
-    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) T[i][j] = 0.0;
+    const int i = tid;
+    double Trow[8];
+#pragma unroll
     for (int j = 0; j < 8; j++) {
-      if (j >= pw) break;
-      const double tj = tau_r[j];
-      T[j][j] = tj;
-      const int e0 = j * (j - 1) / 2;           // G[c][j] sits at G[e0 + c]
-      for (int i = 0; i < j; i++) {
-        double s = 0.0;
-        for (int l = i; l < j; l++) s = fma(T[i][l], G[e0 + l], s);
-        T[i][j] = -tj * s;
+      double val = 0.0;
+      if (j < pw) {
+        if (j == i) val = tau_r[j];
+        else if (j > i) {
+          double sum = 0.0;
+#pragma unroll
+          for (int l = 0; l < j; l++) if (l >= i) sum = fma(Trow[l], G[j * (j - 1) / 2 + l], sum);     // G[c][j] sits at G[e0 + c]
+          val = -tau_r[j] * sum;
+        }
       }
+      Trow[j] = val;
     }
     double* Tg = d.T + 64 * (k0 / 8);
-    for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) Tg[i + 8 * j] = T[i][j];
-    for (int j = 0; j < pw; j++) d.tau[k0 + j] = tau_r[j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) Tg[i + 8 * j] = Trow[j];
+    if (i < pw) {
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (j == i) t = tau_r[j];
+      d.tau[k0 + i] = t;
+    }
   }
 #pragma unroll
   for (int i = 0; i < RPT; i++) {
