@@ -1135,6 +1135,9 @@ int qrk_version(void) { return 100; }
 __attribute__((visibility("default"))) int qrk_debug_tri_trace(long long* out16) {
   return cudaMemcpyFromSymbol(out16, qrk::g_tri_trace, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
 }
+__attribute__((visibility("default"))) int qrk_debug_panel_trace(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, qrk::g_panel_trace, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
 #endif
 
 const char* qrk_status_string(int status) {

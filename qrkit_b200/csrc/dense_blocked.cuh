@@ -77,6 +77,13 @@ __device__ __forceinline__ void cluster_reduce_vec(double (&v)[NV], int nv, int 
 
 // Panel [k0, k0 + pw) of the matrix, rows [k0, N).  One cluster of 8 CTAs; thread t of CTA rank owns the rows
 // k0 + rank * 512 + t + 4096 i, i < RPT.
+#ifdef QRK_TRI_TRACE
+__device__ long long g_panel_trace[16];
+#define QRK_PANEL_CLK(i) do { if (k0 == 64 && threadIdx.x == 0 && blockIdx.x == 0) g_panel_trace[i] = clock64(); } while (0)
+#else
+#define QRK_PANEL_CLK(i) do { } while (0)
+#endif
+
 template <int RPT>
 __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads) dense_panel_kernel(DenseBlocked d, int k0, int pw) {
   namespace cg = cooperative_groups;
@@ -88,7 +95,9 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
   const int tid = threadIdx.x;
   const int rank = (int)cluster.block_rank();
   const int row0 = rank * kDbThreads + tid;      // row (relative to k0) of pass 0
+  QRK_PANEL_CLK(0);
   cluster.sync();                                 // every CTA has started: its shared memory may be written remotely
+  QRK_PANEL_CLK(1);
   constexpr int PASS = kDbCluster * kDbThreads;
   double a[RPT][8];
 #pragma unroll
@@ -100,9 +109,11 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
   double tau_r[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) tau_r[c] = 0.0;
+  QRK_PANEL_CLK(2);
 
 #pragma unroll
   for (int c = 0; c < 8; c++) {
+    if (c == 1) QRK_PANEL_CLK(3);
     if (c < pw) {                               // uniform
       const int par = c & 1;
       double part[8];
@@ -147,6 +158,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
     }
   }
 
+  QRK_PANEL_CLK(4);
   // ---- G = V^T V (strictly upper part), V unit lower trapezoidal: G[c][j] = V[j][c] + sum_{r > j} V[r][c] V[r][j]
   {
     double g[28];
@@ -165,6 +177,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
     }
     cluster_reduce_vec<28>(g, 28, pw & 1, sbuf, sall, sfin, spiv);
   }
+  QRK_PANEL_CLK(5);
   if (rank == 0 && tid < 8) {                   // T[0:j, j] = -tau_j T[0:j, 0:j] G[0:j, j],  T[j][j] = tau_j
     // row i of T depends only on row i: lane i builds it in registers (one thread with an 8 x 8 local array and rolled
     // loops spent ~3 us per panel in local-memory round trips)
@@ -195,6 +208,7 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
       d.tau[k0 + i] = t;
     }
   }
+  QRK_PANEL_CLK(6);
 #pragma unroll
   for (int i = 0; i < RPT; i++) {
     const long long r = (long long)k0 + row0 + (long long)PASS * i;
@@ -203,7 +217,9 @@ __global__ void __cluster_dims__(kDbCluster, 1, 1) __launch_bounds__(kDbThreads)
       for (int j = 0; j < 8; j++) if (j < pw) d.A[(long long)(k0 + j) * d.ld + r] = a[i][j];
     }
   }
+  QRK_PANEL_CLK(7);
   cluster.sync();                               // no CTA exits while its shared memory may still be read remotely
+  QRK_PANEL_CLK(8);
 }
 
 // entry (r, j) of the unit lower trapezoidal V of panel k0 (stored below the diagonal of the panel columns)

@@ -18,3 +18,9 @@ t = list(out)
 names = ["step start", "local candidates", "cluster.sync 1", "global max over DSMEM", "owner: swap, reflector, push", "cluster.sync 2", "update + downdate", "__syncthreads"]
 for i in range(1, 8): print(f"{t[i]-t[i-1]:7d} cycles  {names[i]}")
 print("total", t[7]-t[0])
+L.qrk_debug_panel_trace.argtypes = [C.POINTER(C.c_longlong)]
+print("panel rc", L.qrk_debug_panel_trace(out))
+t = list(out)
+pn = ["start", "first cluster.sync", "panel loaded", "column 0", "columns 1..7", "G = V^T V reduction", "T factor", "panel stored", "last cluster.sync"]
+for i in range(1, 9): print(f"{t[i]-t[i-1]:7d} cycles  {pn[i]}")
+print("panel total", t[8]-t[0])
