@@ -918,7 +918,16 @@ __device__ __forceinline__ void wy_apply_panel_coop(double* sA, int ld, int rp, 
 #endif
 
 // resident CTAs per SM the register allocation must leave room for (shared memory allows about as many)
-__host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr >= 3 ? 12 : mr == 2 ? 16 : 20) / w; }
+#ifndef QRK_WY_WARPS_MR3
+#define QRK_WY_WARPS_MR3 12
+#endif
+#ifndef QRK_WY_WARPS_MR2
+#define QRK_WY_WARPS_MR2 16
+#endif
+#ifndef QRK_WY_WARPS_MR1
+#define QRK_WY_WARPS_MR1 20
+#endif
+__host__ __device__ constexpr int wy_min_ctas(int mr, int w) { return (mr >= 3 ? QRK_WY_WARPS_MR3 : mr == 2 ? QRK_WY_WARPS_MR2 : QRK_WY_WARPS_MR1) / w; }
 
 template <int MR, int W, bool SOLVE>
 __global__ void __launch_bounds__(32 * W, wy_min_ctas(MR, W))
