@@ -229,6 +229,26 @@ __device__ __forceinline__ void warp_merge_tri_multi(double (&T)[NT][Tri<M2>::N]
   }
 }
 
+// CTA merge by ONE warp (NWARPS triangles per lane): all (NWARPS * 32) thread triangles travel through shared memory
+// (all: NWARPS * 32 * Tri::N doubles, entry i of thread t at i * threads + t), warp 0 merges them.  Result in thread 0.
+template <int M2, int NWARPS>
+__device__ __forceinline__ void cta_merge_tri_one_warp(double (&T)[Tri<M2>::N], double* all) {
+  constexpr int N = Tri<M2>::N, TH = NWARPS * 32;
+#pragma unroll
+  for (int i = 0; i < N; i++) all[i * TH + threadIdx.x] = T[i];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double Tm[NWARPS][N];
+#pragma unroll
+    for (int t = 0; t < NWARPS; t++)
+#pragma unroll
+      for (int i = 0; i < N; i++) Tm[t][i] = all[i * TH + t * 32 + threadIdx.x];
+    warp_merge_tri_multi<M2, NWARPS>(Tm);
+#pragma unroll
+    for (int i = 0; i < N; i++) T[i] = Tm[0][i];
+  }
+}
+
 // Triangles per lane in the root's first merge level.  1 = one triangle per thread, 512 threads: the measured best IN THE STEP
 // (config 3: root 8.8 us, step 49.5 us).  4 per lane on 128 threads is 7 % faster when the root is timed alone
 // (tools/root_trace: 12.2k against 13.0k cycles) but 4.4 us slower inside the step (ncu without cache control: root 13.2 us,
@@ -510,7 +530,15 @@ angular_factor_direct_kernel(const double* A_in, double* packed, double* __restr
                              const double* __restrict__ J2, long long ldj, const double* __restrict__ b,
                              double* __restrict__ atop, double* __restrict__ y1, double* __restrict__ abot,
                              double* __restrict__ partials, long long nb64, int pld) {
-  __shared__ double sTri[(TPB / 32) * Tri<M2>::N];
+  // Epilogue: the CTA's 128 thread triangles are merged by ONE warp, four per lane (cta_merge_tri_one_warp), for borders of
+  // up to 5 columns: 3 merging warps per SM instead of 12 followed by a second level (config 3: 49.5 -> 48.7 us;
+  // -DQRK_ANG_K1_TWO_LEVEL restores the two-level merge for A/B).  Wider borders keep the two-level merge (registers).
+#ifdef QRK_ANG_K1_TWO_LEVEL
+  constexpr bool ONE_WARP = false;
+#else
+  constexpr bool ONE_WARP = Tri<M2>::N <= 20;
+#endif
+  __shared__ double sTri[ONE_WARP ? TPB * Tri<M2>::N : (TPB / 32) * Tri<M2>::N];
   double T[Tri<M2>::N];
 #pragma unroll
   for (int i = 0; i < Tri<M2>::N; i++) T[i] = 0.0;
@@ -525,7 +553,8 @@ angular_factor_direct_kernel(const double* A_in, double* packed, double* __restr
     angular_direct_step<PIV, M2, U, ABOT, true>(T, p0, sweep, nb, ld2, A2, packed2, tau_out, perm_out, J2v, b2, atop, y1, abot, pol_in, pol_out);
   if (p0 < nb)
     angular_direct_step<PIV, M2, U, ABOT, false>(T, p0, sweep, nb, ld2, A2, packed2, tau_out, perm_out, J2v, b2, atop, y1, abot, pol_in, pol_out);
-  cta_merge_tri<M2, TPB / 32>(T, sTri);
+  if constexpr (ONE_WARP) cta_merge_tri_one_warp<M2, TPB / 32>(T, sTri);
+  else cta_merge_tri<M2, TPB / 32>(T, sTri);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)i * pld + blockIdx.x] = T[i];
