@@ -133,6 +133,7 @@ def bench_angular(args, L, stream):
     J1, J2, rhs = ellipse_device(n)
     x = torch.empty(n + 5, dtype=torch.float64, device="cuda")
     out = {}
+    graph_ms = None
     for piv in (0, 1):
         d = QrkDesc()
         d.kind, d.num_blocks, d.block_rows, d.block_cols, d.pivoting, d.border_cols = capi.QRK_BLOCK_ANGULAR, n, 2, 1, piv, 5
@@ -147,6 +148,17 @@ def bench_angular(args, L, stream):
         ms = time_steps(step, args.steps, args.warmup)
         l1 = C.c_int64(); L.qrk_launch_count(h, C.byref(l1))
         out[piv] = (ms, (l1.value - l0.value) // (args.steps + args.warmup))
+        if piv == 0 and getattr(args, "graphs", True):
+            # the same step replayed from a CUDA graph (the library's calls are stream-ordered and capture-safe): what the three
+            # launches cost when their dependencies are resolved on the device instead of through the stream
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                    step()
+                graph_ms = time_steps(g.replay, args.steps, args.warmup)
+            except Exception as e:
+                print(json.dumps({"graph_capture_failed": str(e)[:200]}), file=sys.stderr, flush=True)
         L.qrk_destroy(h)
     peak, src = measured_peaks()
     ms, launches = out[0]
@@ -158,6 +170,9 @@ def bench_angular(args, L, stream):
                          "algorithmic_bytes_per_point": bytes_per_point, "peak_source": src},
             "colpiv_left": {"ms_per_step": out[1][0], "value": 2 * n / (out[1][0] * 1e-3)},
             "steps": args.steps, "warmup": args.warmup, "dtype": "f64"}
+    if graph_ms is not None:
+        line["cuda_graph_replay"] = {"ms_per_step": graph_ms, "value": 2 * n / (graph_ms * 1e-3),
+                                     "roofline_frac": bytes_per_point * n / (graph_ms * 1e-3) / 1e9 / peak}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_angular(min(n, args.cpu_points))
     return line
