@@ -329,9 +329,23 @@ def bench_angular_wide(args, L, stream):
         l0 = C.c_int64(); L.qrk_launch_count(h, C.byref(l0))
         ms = time_steps(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), steps, 1)
         l1 = C.c_int64(); L.qrk_launch_count(h, C.byref(l1))
-        L.qrk_destroy(h)
         res[name] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "launches_per_step": (l1.value - l0.value) // (steps + 1),
                      "border_qr_gflops": flops / (ms * 1e-3) / 1e9}
+        if getattr(args, "graphs", True) and name != "banded_left_colpiv":
+            # ~245 launches on two streams per step: the same step replayed from a CUDA graph (fork / join of the look-ahead
+            # stream captured with it)
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                    check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h)
+                res[name]["cuda_graph_replay_ms_per_step"] = time_steps(g.replay, steps, 1)
+                del g
+            except Exception as e:
+                res[name]["cuda_graph_replay_ms_per_step"] = None
+                print(json.dumps({"wide_graph_capture_failed": name, "error": str(e)[:200]}), file=sys.stderr, flush=True)
+                torch.cuda.synchronize()
+        L.qrk_destroy(h)
     line = {"workload": f"block-angular, reference test 4/5 sizes: {nb} blocks {r}x{c} + dense {n}x{m2} border; blocked compact-WY (DMMA) first stage, ColPiv on the triangle in one cluster launch",
             "metric": "rows/s", "value": res["colpiv"]["value"], "ms_per_step": res["colpiv"]["ms_per_step"],
             "right_solver": res, "dtype": "f64",
