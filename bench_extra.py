@@ -327,9 +327,9 @@ def bench_angular_wide(args, L, stream):
         check(L.qrk_set_stream(h, stream), h)
         check(L.qrk_set_border(h, vp(J2), n, QRK_DEVICE), h)
         l0 = C.c_int64(); L.qrk_launch_count(h, C.byref(l0))
-        ms = time_steps(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), steps, 1)
+        ms = time_steps(lambda: check(L.qrk_compute_solve(h, vp(A), vp(b), vp(x), QRK_DEVICE), h), steps, 3)      # (3 warm-ups: eager, capture, first replay)
         l1 = C.c_int64(); L.qrk_launch_count(h, C.byref(l1))
-        res[name] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "launches_per_step": (l1.value - l0.value) // (steps + 1),
+        res[name] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "launches_per_step": (l1.value - l0.value) // (steps + 3),
                      "border_qr_gflops": flops / (ms * 1e-3) / 1e9}
         if getattr(args, "graphs", True) and name != "banded_left_colpiv":
             # ~245 launches on two streams per step: the same step replayed from a CUDA graph (fork / join of the look-ahead

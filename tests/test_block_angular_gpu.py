@@ -604,3 +604,26 @@ def test_register_resident_colpiv_triangle_rank_deficient(qk, oracle):
     assert np.array_equal(s.colsPermutation(), ref.colsPermutation())
     assert rel(s.solve(b), ref.solve(b)) <= 1e-9
     assert rel(qk.BlockAngularSparseQR(pivoting=1).compute_solve(mat, b), ref.solve(b)) <= 1e-9
+
+
+@pytest.mark.parametrize("m2,right", [(24, 0), (96, 0), (40, 1)])
+def test_wide_border_step_replayed_from_cuda_graph(qk, oracle, m2, right):
+    """The wide-border step is captured into a CUDA graph the second time a handle sees the same buffers and replayed from
+    then on (capi.cu: wide_run).  Four successive compute_solve calls on ONE handle with different matrices and right-hand
+    sides (host memspace: the handle's staging buffers are the stable device pointers): every result is bit-identical to a
+    fresh handle's eager first call on the same data, and the first one matches the oracle."""
+    r, c, nb = 7, 2, 60
+    s = qk.BlockAngularSparseQR(pivoting=1, right_solver=right)
+    for it in range(4):
+        vals = uniform_blocks(nb, r, c, seed=SEED_A + 3 * it)
+        J2 = dense_border(nb * r, m2, seed=SEED_A + 500 + it)
+        b = vector(nb * r, seed=40 + it)
+        mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+        x = s.compute_solve(mat, b).copy()
+        x_fresh = qk.BlockAngularSparseQR(pivoting=1, right_solver=right).compute_solve(mat, b)
+        assert np.array_equal(x, x_fresh), f"call {it}: graph replay differs from the eager step"
+        assert s.rank() == nb * c + m2
+        if it == 0:
+            ref = oracle.BlockAngularOracle(J2, br=np.full(nb, r), bc=np.full(nb, c), values=vals, left_colpiv=True,
+                                            right_kind=right, **({"panel": 2} if right == 1 else {}))
+            assert rel(x, ref.solve(b)) <= TOL_X
