@@ -224,8 +224,9 @@ QRK_API int qrk_solve(qrk_handle_t h, const double* B, int64_t ldb, double* X, i
 /* J2: n x m2 column-major with leading dimension ld (BlockMatrix1x2::rightBlock()).  Host: copied to the
  * device on the handle's stream; device: borrowed until the next compute returns. */
 QRK_API int qrk_set_border(qrk_handle_t h, const double* J2, int64_t ld, int memspace);
-/* Borders wider than 8 columns run as ~250 small launches per compute: from the second call with the same device buffers
- * (values, rhs, x, border, stream) the handle replays them from a CUDA graph it captured itself.  Set QRK_NO_GRAPH=1 to keep
+/* Launch-bound block-angular steps (borders wider than 8 columns: ~250 small launches per compute; the three-launch TSQR step
+ * of a narrow border on one GPU): from the second call with the same device buffers (values, rhs, x, border, stream) the
+ * handle replays them from a CUDA graph it captured itself.  Set QRK_NO_GRAPH=1 to keep
  * every call eager; a stream that the CALLER is capturing is never captured again by the library. */
 /* Multi-GPU (one handle per GPU, each owning a contiguous range of diagonal blocks and the matching rows of
  * J2 and b): with world_size > 1 the compute/solve calls stop after the per-GPU m2 x (m2+1) TSQR triangle;

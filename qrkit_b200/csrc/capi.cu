@@ -253,7 +253,7 @@ BlockIndex block_index(const qrk_solver* h) {
 }
 
 void free_dev(qrk_solver* h) {
-  if (h->wg_exec) { cudaGraphExecDestroy(h->wg_exec); h->wg_exec = nullptr; }
+  for (auto* g : {&h->sg_wide, &h->sg_tsqr}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
   auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   F(h->d_rows); F(h->d_cols); F(h->d_voff); F(h->d_roff); F(h->d_coff);
   if (h->own_values) F(h->d_values);
@@ -803,47 +803,55 @@ int wide_run_eager(qrk_solver* h, const double* A_in, const double* d_b, double*
   return wide_back(h, d_b != nullptr, d_x);
 }
 
-// The wide-border step is ~250 small launches on two streams (panel, look-ahead update, trailing update per 8 columns): launch
-// bound.  The second time a handle sees the same buffers (values, rhs, x, border, stream) the step is captured into a CUDA
-// graph -- the look-ahead stream's fork / join is captured with it -- and replayed from then on (reference test 4 / 5 sizes:
-// 4.0 -> 3.6 ms, 2.0 -> 1.7 ms).  The first call stays eager: it makes the lazy allocations and takes the fallbacks (a cluster
-// that cannot be placed) that must not happen inside a capture.  Not captured: a stream the CALLER is capturing, the
-// BlockedThinSparseQR right solver (one host read-back per panel), QRK_NO_GRAPH=1; any capture failure turns it off for the handle.
-void wide_graph_drop(qrk_solver* h) {
-  if (h->wg_exec) { cudaGraphExecDestroy(h->wg_exec); h->wg_exec = nullptr; }
-  h->wg_seen = 0;
+// Launch-bound steps are replayed from CUDA graphs.  The wide-border step is ~250 small launches on two streams (panel,
+// look-ahead update, trailing update per 8 columns); the narrow-border TSQR step is three dependent launches whose gaps are a
+// tenth of the step.  The second time a handle sees the same buffers (values, rhs, x, border, stream) the step is captured --
+// a second stream's fork / join and a programmatic dependent launch are captured with it -- and replayed from then on
+// (reference test 4 / 5 sizes: 4.0 -> 3.6 ms, 2.0 -> 1.75 ms; config 3: 49.0 -> 46.8 us).  The first call stays eager: it
+// makes the lazy allocations and takes the fallbacks (a cluster that cannot be placed) that must not happen inside a capture.
+// Not captured: a stream the CALLER is capturing, steps with a host read-back (BlockedThinSparseQR right solver) or that end
+// at the per-GPU triangle (NCCL form), QRK_NO_GRAPH=1; any capture failure turns the graph off for the handle.
+void step_graph_drop(qrk_solver::StepGraph& g) {
+  if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  g.seen = 0;
 }
 
-int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
+template <class Eager, class Flag>
+int step_graph_run(qrk_solver* h, qrk_solver::StepGraph& g, const void* const (&key)[8], bool allowed, Flag&& flag, Eager&& eager) {
   static const bool no_graph = std::getenv("QRK_NO_GRAPH") != nullptr;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (no_graph || h->wg_off || h->desc.right_solver == QRK_RIGHT_THIN_SPARSE ||
-      cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
-    return wide_run_eager(h, A_in, d_b, d_x);
-  const void* key[6] = {A_in, d_b, d_x, h->d_border, reinterpret_cast<const void*>(static_cast<intptr_t>(h->ld_border)), h->stream};
-  const bool same = std::memcmp(key, h->wg_key, sizeof(key)) == 0;
-  if (same && h->wg_exec) {
-    QRK_TRY_CUDA(h, cudaGraphLaunch(h->wg_exec, h->stream));
-    h->launches += h->wg_launches;
-    h->wide_blocked = h->wg_wide_blocked;
+  if (no_graph || g.off || !allowed || cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return eager();
+  const bool same = std::memcmp(key, g.key, sizeof(g.key)) == 0;
+  if (same && g.exec) {
+    QRK_TRY_CUDA(h, cudaGraphLaunch(g.exec, h->stream));
+    h->launches += g.launches;
+    flag(g.flag, false);                   // restore the host-side state the eager step leaves behind
     return QRK_STATUS_OK;
   }
-  if (!same) { wide_graph_drop(h); std::memcpy(h->wg_key, key, sizeof(key)); }
-  if (h->wg_seen == 0) { h->wg_seen = 1; return wide_run_eager(h, A_in, d_b, d_x); }
+  if (!same) { step_graph_drop(g); std::memcpy(g.key, key, sizeof(g.key)); }
+  if (g.seen == 0) { g.seen = 1; return eager(); }
   const long long l0 = h->launches;
-  auto give_up = [&]() { (void)cudaGetLastError(); h->wg_off = true; wide_graph_drop(h); h->launches = l0; return wide_run_eager(h, A_in, d_b, d_x); };
+  auto give_up = [&]() { (void)cudaGetLastError(); g.off = true; step_graph_drop(g); h->launches = l0; return eager(); };
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return give_up();
-  const int st = wide_run_eager(h, A_in, d_b, d_x);
+  const int st = eager();
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (st != QRK_STATUS_OK || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return give_up(); }
-  const cudaError_t ei = cudaGraphInstantiate(&h->wg_exec, graph, 0);
+  const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (ei != cudaSuccess) { h->wg_exec = nullptr; return give_up(); }
-  h->wg_launches = h->launches - l0;
-  h->wg_wide_blocked = h->wide_blocked;
-  QRK_TRY_CUDA(h, cudaGraphLaunch(h->wg_exec, h->stream));
+  if (ei != cudaSuccess) { g.exec = nullptr; return give_up(); }
+  g.launches = h->launches - l0;
+  flag(g.flag, true);                      // record it
+  QRK_TRY_CUDA(h, cudaGraphLaunch(g.exec, h->stream));
   return QRK_STATUS_OK;
+}
+
+int wide_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_x) {
+  const void* key[8] = {A_in, d_b, d_x, h->d_border, reinterpret_cast<const void*>(static_cast<intptr_t>(h->ld_border)), h->stream, nullptr, nullptr};
+  return step_graph_run(h, h->sg_wide, key, h->desc.right_solver != QRK_RIGHT_THIN_SPARSE,
+                        [&](bool& f, bool record) { if (record) f = h->wide_blocked; else h->wide_blocked = f; },
+                        [&]() { return wide_run_eager(h, A_in, d_b, d_x); });
 }
 
 int wide_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
@@ -997,17 +1005,27 @@ int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_
   QRK_REQUIRE(h, h->d_border, "no border set: call qrk_set_border first (BlockMatrix1x2 right block)");
   h->q2_ready = false;
   if (h->wide) return wide_run(h, A_in, d_b, d_x);
-  AngularArgs a = angular_args(h);
-  a.A_in = A_in;
-  a.b = d_b;
-  if (keep_abot) {
-    if (!h->d_abot) QRK_TRY_CUDA(h, cudaMalloc(&h->d_abot, std::max<long long>(1, (h->n_rows - h->sum_cols) * (long long)(h->m2 + 1)) * sizeof(double)));
-    a.abot = h->d_abot;
-  }
-  QRK_TRY_CUDA(h, h->avt->factor(a, h->stream));
-  h->launches++;
-  h->have_abot = keep_abot;
-  return angular_root_and_back(h, a, d_b != nullptr, d_x, 0);
+  if (keep_abot && !h->d_abot)
+    QRK_TRY_CUDA(h, cudaMalloc(&h->d_abot, std::max<long long>(1, (h->n_rows - h->sum_cols) * (long long)(h->m2 + 1)) * sizeof(double)));
+  auto eager = [&]() -> int {
+    AngularArgs a = angular_args(h);
+    a.A_in = A_in;
+    a.b = d_b;
+    if (keep_abot) a.abot = h->d_abot;
+    QRK_TRY_CUDA(h, h->avt->factor(a, h->stream));
+    h->launches++;
+    h->have_abot = keep_abot;
+    return angular_root_and_back(h, a, d_b != nullptr, d_x, 0);
+  };
+  // K1 -> root -> K3 replayed from a CUDA graph (see step_graph_run)
+  const void* key[8] = {A_in, d_b, d_x, h->d_border, reinterpret_cast<const void*>(static_cast<intptr_t>(h->ld_border)), h->stream,
+                        reinterpret_cast<const void*>(static_cast<intptr_t>(keep_abot ? 1 : 0)),
+                        reinterpret_cast<const void*>(static_cast<uintptr_t>(h->xchg_timeout_ns + 1000003ull * (unsigned)(h->xchg_rank + 2)))};
+  // (world > 1: also the fused exchange stays eager here -- instantiating a graph can wait for the device, and with several
+  //  ranks on ONE device a peer's root kernel may be spinning for this rank's step; callers capture the whole step themselves)
+  const bool complete = h->world == 1;
+  return step_graph_run(h, h->sg_tsqr, key, complete,
+                        [&](bool& f, bool record) { if (record) f = keep_abot; else { h->have_abot = f; h->root_done = true; } }, eager);
 }
 
 // solve(b) on a stored factorisation: Q1^T b, TSQR redone over [Abot | b_bot], root, back substitution
@@ -1480,8 +1498,7 @@ int qrk_destroy(qrk_handle_t h) {
 int qrk_set_stream(qrk_handle_t h, void* cuda_stream) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
   h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
-  if (h->wg_exec) { cudaGraphExecDestroy(h->wg_exec); h->wg_exec = nullptr; }
-  h->wg_seen = 0;
+  for (auto* g : {&h->sg_wide, &h->sg_tsqr}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
   return QRK_STATUS_OK;
 }
 

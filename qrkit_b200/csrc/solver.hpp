@@ -97,12 +97,16 @@ struct qrk_solver {
   // M x (M + 1) triangle the ColPiv second stage works on; wide_blocked: the last compute() took that path
   double *d_wtau1 = nullptr, *d_wT = nullptr, *d_wtri = nullptr, *d_wpart = nullptr;   // d_wpart: partial W = V^T A2 per (column block, row range)
   bool wide_blocked = false;
-  // the wide-border step (~250 launches on two streams) replayed from a CUDA graph once the same buffers come a second time
-  cudaGraphExec_t wg_exec = nullptr;
-  const void* wg_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int wg_seen = 0;
-  bool wg_off = false, wg_wide_blocked = false;
-  long long wg_launches = 0;
+  // a launch-bound step replayed from a CUDA graph once the same buffers come a second time (capi.cu: step_graph_run):
+  // the wide-border step (~250 launches on two streams) and the three-launch TSQR step of the narrow border
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int seen = 0;
+    bool off = false, flag = false;
+    long long launches = 0;
+  };
+  StepGraph sg_wide, sg_tsqr;
   bool thin_deferred = false;          // QRK_RIGHT_THIN_SPARSE: the last factorisation deferred zero-pivot columns (stored-factor products refused)
   // dense right-block path: leading dimension of d_wx (rows of [thin part ; complement] of Q1^T [J2 | b]) and the number of
   // complement rows the right block is factored on.  Block-diagonal left: n_rows and n_rows - m1; banded left: m1 + the
