@@ -82,3 +82,13 @@ vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); J2[:, 11] = 0.0;
 mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
 s = qk.BlockAngularSparseQR(mat, pivoting=1)
 print("register-resident triangle", s.rank(), float(np.abs(s.solve(b)).max()))
+# steps replayed from library-captured CUDA graphs: three calls on one handle (eager, capture + launch, replay)
+nb, r, c, m2 = 30, 7, 2, 24
+vals = uniform_blocks(nb, r, c); J2 = dense_border(nb * r, m2); b = vector(nb * r, seed=5)
+mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(vals, block_rows=r, block_cols=c), J2)
+s = qk.BlockAngularSparseQR(pivoting=1)
+print("wide step graph", [float(np.abs(s.compute_solve(mat, b)).max()) for _ in range(3)])
+J1v, J2e, rhse = ellipse_problem(777)
+mat = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(J1v, block_rows=2, block_cols=1), J2e)
+s = qk.BlockAngularSparseQR(pivoting=0)
+print("tsqr step graph", [float(np.abs(s.compute_solve(mat, rhse)).max()) for _ in range(3)])
