@@ -253,7 +253,7 @@ BlockIndex block_index(const qrk_solver* h) {
 }
 
 void free_dev(qrk_solver* h) {
-  for (auto* g : {&h->sg_wide, &h->sg_tsqr}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
+  for (auto* g : {&h->sg_wide, &h->sg_tsqr, &h->sg_solve}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
   auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   F(h->d_rows); F(h->d_cols); F(h->d_voff); F(h->d_roff); F(h->d_coff);
   if (h->own_values) F(h->d_values);
@@ -1032,12 +1032,18 @@ int angular_run(qrk_solver* h, const double* A_in, const double* d_b, double* d_
 int angular_solve_stored(qrk_solver* h, const double* d_b, double* d_x) {
   if (h->wide) return wide_solve_stored(h, d_b, d_x);
   QRK_REQUIRE(h, h->have_abot, "solve() after a fused compute_solve(): the residual panel was not kept; call compute() first");
-  AngularArgs a = angular_args(h);
-  a.b = d_b;
-  a.abot = h->d_abot;
-  QRK_TRY_CUDA(h, h->avt->rhs(a, h->stream));
-  h->launches++;
-  return angular_root_and_back(h, a, true, d_x, 1);
+  auto eager = [&]() -> int {
+    AngularArgs a = angular_args(h);
+    a.b = d_b;
+    a.abot = h->d_abot;
+    QRK_TRY_CUDA(h, h->avt->rhs(a, h->stream));
+    h->launches++;
+    return angular_root_and_back(h, a, true, d_x, 1);
+  };
+  // the reference's own calling pattern is compute(J) followed by solve(b): the three launches of solve() are replayed from a
+  // CUDA graph like those of the fused step (step_graph_run)
+  const void* key[8] = {d_b, d_x, h->d_abot, h->d_values, h->stream, nullptr, nullptr, nullptr};
+  return step_graph_run(h, h->sg_solve, key, h->world == 1, [&](bool&, bool record) { if (!record) h->root_done = true; }, eager);
 }
 
 
@@ -1498,7 +1504,7 @@ int qrk_destroy(qrk_handle_t h) {
 int qrk_set_stream(qrk_handle_t h, void* cuda_stream) {
   if (!h) return QRK_STATUS_INVALID_ARGUMENT;
   h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
-  for (auto* g : {&h->sg_wide, &h->sg_tsqr}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
+  for (auto* g : {&h->sg_wide, &h->sg_tsqr, &h->sg_solve}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
   return QRK_STATUS_OK;
 }
 

@@ -106,7 +106,7 @@ struct qrk_solver {
     bool off = false, flag = false;
     long long launches = 0;
   };
-  StepGraph sg_wide, sg_tsqr;
+  StepGraph sg_wide, sg_tsqr, sg_solve;
   bool thin_deferred = false;          // QRK_RIGHT_THIN_SPARSE: the last factorisation deferred zero-pivot columns (stored-factor products refused)
   // dense right-block path: leading dimension of d_wx (rows of [thin part ; complement] of Q1^T [J2 | b]) and the number of
   // complement rows the right block is factored on.  Block-diagonal left: n_rows and n_rows - m1; banded left: m1 + the

@@ -650,3 +650,12 @@ def test_tsqr_step_replayed_from_cuda_graph(qk, oracle, piv):
     assert rel(x, ref.solve(rhs)) <= TOL_X
     s.compute(mat)
     assert rel(s.solve(rhs), ref.solve(rhs)) <= TOL_X
+    # the reference's own calling pattern, compute(J) then solve(b), four rounds on the same handle: both calls replay
+    for it in range(4):
+        J1b = J1 * (1.0 + 0.02 * it); rhsb = rhs - 0.05 * it
+        matb = qk.BlockMatrix1x2(qk.SparseBlockDiagonal(J1b, block_rows=2, block_cols=1), J2)
+        s.compute(matb)
+        xs = s.solve(rhsb).copy()
+        fresh = qk.BlockAngularSparseQR(matb, pivoting=piv)
+        assert np.array_equal(xs, fresh.solve(rhsb)), f"round {it}: replayed compute() + solve() differs from the eager pair"
+        assert np.array_equal(s.solve(rhsb), xs)                     # a second solve on the same factorisation
