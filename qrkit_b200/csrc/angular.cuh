@@ -620,6 +620,55 @@ angular_rhs_kernel(const double* __restrict__ packed, const double* __restrict__
   }
 }
 
+// Solve-only K1 for 2 x 1 blocks (the reference's own calling pattern is compute(J) followed by solve(b)): the unstaged
+// counterpart of angular_rhs_kernel -- per point one vector load each of the packed block and of b, the scalar tau and the
+// M2 stored residual entries; U points folded with one reflector per border column; the CTA merged by one warp where the
+// triangle allows (as in angular_factor_direct_kernel).  Same partial-triangle layout (component-major).
+template <int M2, int TPB, int U, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+angular_rhs_direct_kernel(const double* __restrict__ packed, const double* __restrict__ tau_in, const double* __restrict__ b,
+                          double* __restrict__ y1, double* __restrict__ abot, double* __restrict__ partials, long long nb64, int pld) {
+  constexpr int W = M2 + 1;
+  constexpr bool ONE_WARP = Tri<M2>::N <= 20;
+  __shared__ double sTri[ONE_WARP ? TPB * Tri<M2>::N : (TPB / 32) * Tri<M2>::N];
+  double T[Tri<M2>::N];
+#pragma unroll
+  for (int i = 0; i < Tri<M2>::N; i++) T[i] = 0.0;
+  const unsigned nb = (unsigned)nb64, sweep = gridDim.x * TPB;
+  const double2* P2 = reinterpret_cast<const double2*>(packed);
+  const double2* B2 = reinterpret_cast<const double2*>(b);
+  for (unsigned p0 = blockIdx.x * TPB + threadIdx.x; p0 < nb; p0 += sweep * U) {
+    double2 av[U], bv[U];
+    double tv[U], w[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned p = p0 + u * sweep;
+      const bool live = p < nb;
+      av[u] = live ? __ldg(P2 + p) : make_double2(0.0, 0.0);
+      bv[u] = live ? __ldg(B2 + p) : make_double2(0.0, 0.0);
+      tv[u] = live ? __ldg(tau_in + p) : 0.0;
+#pragma unroll
+      for (int j = 0; j < M2; j++) w[u][j] = live ? __ldg(abot + ((size_t)j * nb + p)) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned p = p0 + u * sweep;
+      const double a[2] = {av[u].x, av[u].y}, tau[1] = {tv[u]};
+      double col[2] = {bv[u].x, bv[u].y};
+      apply_qt_chain<2, 1>(a, tau, col);
+      w[u][M2] = (p < nb) ? col[1] : 0.0;
+      if (p < nb) { y1[p] = col[0]; abot[(size_t)M2 * nb + p] = col[1]; }
+    }
+    fold_rows_fused<M2, U>(T, w);
+  }
+  if constexpr (ONE_WARP) cta_merge_tri_one_warp<M2, TPB / 32>(T, sTri);
+  else cta_merge_tri<M2, TPB / 32>(T, sTri);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < Tri<M2>::N; i++) partials[(size_t)i * pld + blockIdx.x] = T[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: TSQR root.  mode 0: merge `count` triangles into out_tri (the per-GPU triangle; multi-GPU step 1).
 //     mode 1: merge, then ColPiv + rank + x2 (single GPU, or after the NCCL all-gather of G triangles).

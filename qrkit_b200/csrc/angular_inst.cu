@@ -151,6 +151,14 @@ cudaError_t max_grid_t(int* grid) {
 
 template <int R, int C>
 cudaError_t rhs_t(const AngularArgs& a, cudaStream_t s) {
+  if constexpr (R == 2 && C == 1) {
+    static const bool off = std::getenv("QRK_ANG_STAGED") != nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (!off && al16(a.packed) && al16(a.b) && (long long)(M2 + 2) * a.nb + 8ll * 148 * 16 * TPB < (1ll << 32)) {
+      angular_rhs_direct_kernel<M2, TPB, kDirectU, kDirectMinB><<<a.grid, TPB, 0, s>>>(a.packed, a.tau, a.b, a.y1, a.abot, a.partials, a.nb, a.grid);
+      return cudaGetLastError();
+    }
+  }
   auto kernel = angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>;
   const size_t smem = ((size_t)TPB * (Group<R * C>::stride + Group<C>::stride) + (TPB / 32) * Tri<M2>::N) * 8;
   cudaError_t e = opt_in(kernel, smem);
@@ -269,6 +277,9 @@ cudaError_t preload_t(bool piv) {
                                   : cudaFuncGetAttributes(&fa, angular_factor_direct_kernel<false, M2, TPB, kDirectU, kDirectMinB, true>);
   }
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_rhs_kernel<R, C, M2, TPB, minb<R, C>()>);
+  if constexpr (R == 2 && C == 1) {
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, angular_rhs_direct_kernel<M2, TPB, kDirectU, kDirectMinB>);
+  }
   if (e == cudaSuccess) e = piv ? cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, true, TPB>)
                                 : cudaFuncGetAttributes(&fa, angular_backsolve_kernel<R, C, M2, false, TPB>);
   if constexpr (R == 2 && C == 1) {
